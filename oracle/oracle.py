@@ -1,0 +1,306 @@
+"""ctypes wrapper over oracle/libgulon_oracle.so (the C restatement of the reference).
+
+TEST INFRASTRUCTURE ONLY -- see the header of gulon_oracle.c.  Imported by tests/,
+__graft_entry__.smoke() and bench.py's CPU-baseline legs; never by gulon_b200/.
+PARITY UNPINNED (no JVM in this image, no golden vectors in the reference).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libgulon_oracle.so")
+
+TIE_LITERAL, TIE_LOWEST = 0, 1
+TOPK_LITERAL, TOPK_CANONICAL = 0, 1
+
+
+def build(force=False):
+    src = os.path.join(_HERE, "gulon_oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_SO)
+        _lib.go_jr_next_float.restype = C.c_float
+        _lib.go_distance_sq.restype = C.c_float
+        _lib.go_objective.restype = C.c_double
+        _lib.go_heap_new.restype = C.c_void_p
+    return _lib
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+i64 = C.c_int64
+i32 = C.c_int32
+
+
+def num_threads():
+    return int(lib().go_num_threads())
+
+
+class JRandom:
+    """java.util.Random."""
+
+    def __init__(self, seed):
+        self._s = C.c_uint64(0)
+        lib().go_jr_init(C.byref(self._s), i64(seed))
+
+    def next_int(self, bound=None):
+        if bound is None:
+            return int(i32(lib().go_jr_next_int(C.byref(self._s))).value)
+        return int(lib().go_jr_next_int_bound(C.byref(self._s), i32(bound)))
+
+    def next_boolean(self):
+        return bool(lib().go_jr_next_boolean(C.byref(self._s)))
+
+    def next_float(self):
+        return float(lib().go_jr_next_float(C.byref(self._s)))
+
+
+def subvectors(D, M):
+    frm = np.zeros(M, np.int32)
+    dim = np.zeros(M, np.int32)
+    dmax = lib().go_subvectors(int(D), int(M), _p(frm), _p(dim))
+    return frm, dim, int(dmax)
+
+
+def offsets(Cm):
+    Cm = _f32(Cm)
+    K, dim = Cm.shape
+    off = np.zeros(K, np.float32)
+    lib().go_offsets(_p(Cm), K, dim, i64(dim), _p(off))
+    return off
+
+
+def assign(X, frm, dim, Cm, batch=0, tie_mode=TIE_LITERAL, nthreads=1, prev=None, stats=None):
+    """KMeans.assign (batch=0, whole array) / parAssign (batch=25000)."""
+    X = _f32(X)
+    Cm = _f32(Cm)
+    N, ld = X.shape
+    K = Cm.shape[0]
+    out = np.zeros(N, np.int32) if prev is None else np.ascontiguousarray(prev, np.int32).copy()
+    st = np.zeros(2, np.int64)
+    lib().go_assign(_p(X), i64(N), i64(ld), int(frm), int(dim), _p(Cm), i64(Cm.shape[1]), K,
+                    i64(batch), int(tie_mode), int(nthreads), _p(out), _p(st))
+    if stats is not None:
+        stats += st
+    return out
+
+
+def from_assignment(X, frm, dim, a, K, return_counts=False):
+    X = _f32(X)
+    N, ld = X.shape
+    a = np.ascontiguousarray(a, np.int32)
+    Cm = np.zeros((K, dim), np.float32)
+    cnt = np.zeros(K, np.int32)
+    lib().go_from_assignment(_p(X), i64(N), i64(ld), int(frm), int(dim), _p(a), K, _p(Cm), i64(dim),
+                             _p(cnt))
+    return (Cm, cnt) if return_counts else Cm
+
+
+def kmeans_init(X, frm, dim, K, seed=0):
+    X = _f32(X)
+    N, ld = X.shape
+    Cm = np.zeros((K, dim), np.float32)
+    rows = np.zeros(K, np.int32)
+    lib().go_kmeans_init(_p(X), i64(N), i64(ld), int(frm), int(dim), K, i32(seed), _p(Cm), i64(dim),
+                         _p(rows))
+    return Cm, rows
+
+
+def compute_clusters(X, frm, dim, K, max_iter, seed=0, tie_mode=TIE_LITERAL, nthreads=1):
+    X = _f32(X)
+    N, ld = X.shape
+    Cm = np.zeros((K, dim), np.float32)
+    nu = i32(0)
+    conv = i32(0)
+    rep = np.zeros((max_iter + 2, 4), np.float32)
+    fa = np.zeros(N, np.int32)
+    st = np.zeros(2, np.int64)
+    lib().go_compute_clusters(_p(X), i64(N), i64(ld), int(frm), int(dim), K, int(max_iter),
+                              i32(seed), int(tie_mode), int(nthreads), _p(Cm), i64(dim),
+                              C.byref(nu), C.byref(conv), _p(rep), _p(fa), _p(st))
+    return dict(centroids=Cm, updates=nu.value, converged=bool(conv.value),
+                report=rep[:nu.value].copy(), assignments=fa, tie_stats=st)
+
+
+def pq_train(X, M, K, max_iter, tie_mode=TIE_LITERAL, nthreads=1):
+    X = _f32(X)
+    N, ld = X.shape
+    _, _, dmax = subvectors(ld, M)
+    cb = np.zeros((M, K, dmax), np.float32)
+    nu = np.zeros(M, np.int32)
+    conv = np.zeros(M, np.int32)
+    lib().go_pq_train(_p(X), i64(N), i64(ld), int(ld), int(M), int(K), int(max_iter), int(tie_mode),
+                      int(nthreads), _p(cb), _p(nu), _p(conv))
+    return cb, nu, conv
+
+
+def pq_encode(X, cb, tie_mode=TIE_LITERAL, nthreads=1, stats=None):
+    X = _f32(X)
+    cb = _f32(cb)
+    N, D = X.shape
+    M, K, _ = cb.shape
+    codes = np.zeros((M, N), np.uint8)
+    st = np.zeros(2, np.int64)
+    lib().go_pq_encode(_p(X), i64(N), i64(D), int(D), M, K, _p(cb), int(tie_mode), int(nthreads),
+                       _p(codes), _p(st))
+    if stats is not None:
+        stats += st
+    return codes
+
+
+def pq_decode(codes, cb, D):
+    codes = np.ascontiguousarray(codes, np.uint8)
+    cb = _f32(cb)
+    M, N = codes.shape
+    K = cb.shape[1]
+    out = np.zeros((N, D), np.float32)
+    lib().go_pq_decode(_p(codes), i64(N), i64(N), int(D), M, K, _p(cb), _p(out), i64(D))
+    return out
+
+
+def prepare_query(queries, cb):
+    queries = _f32(queries)
+    cb = _f32(cb)
+    Q, D = queries.shape
+    M, K, _ = cb.shape
+    lut = np.zeros((Q, M, K), np.float32)
+    lib().go_prepare_query(_p(queries), i64(Q), i64(D), int(D), M, K, _p(cb), _p(lut))
+    return lut
+
+
+def batch_query(lut, codes, k, frm=0, until=None, topk_mode=TOPK_CANONICAL, nthreads=1):
+    lut = _f32(lut)
+    codes = np.ascontiguousarray(codes, np.uint8)
+    Q, M, K = lut.shape
+    N = codes.shape[1]
+    until = N if until is None else until
+    ids = np.full((Q, max(k, 1)), -1, np.int32)
+    ds = np.full((Q, max(k, 1)), np.inf, np.float32)
+    sz = np.zeros(Q, np.int32)
+    lib().go_batch_query(_p(lut), i64(Q), M, K, _p(codes), i64(N), i64(frm), i64(until), int(k),
+                         int(topk_mode), int(nthreads), _p(ids), _p(ds), _p(sz))
+    return ids[:, :k], ds[:, :k], sz
+
+
+def pq_query(queries, cb, codes, k, frm=0, until=None, topk_mode=TOPK_CANONICAL, nthreads=1):
+    return batch_query(prepare_query(queries, cb), codes, k, frm, until, topk_mode, nthreads)
+
+
+def exact_nn(X, queries, k, frm=0, until=None, topk_mode=TOPK_CANONICAL, nthreads=1):
+    X = _f32(X)
+    queries = _f32(queries)
+    N, D = X.shape
+    Q = queries.shape[0]
+    until = N if until is None else until
+    ids = np.full((Q, max(k, 1)), -1, np.int32)
+    ds = np.full((Q, max(k, 1)), np.inf, np.float32)
+    sz = np.zeros(Q, np.int32)
+    lib().go_exact_nn(_p(X), i64(D), int(D), i64(frm), i64(until), _p(queries), i64(Q), i64(D),
+                      int(k), int(topk_mode), int(nthreads), _p(ids), _p(ds), _p(sz))
+    return ids[:, :k], ds[:, :k], sz
+
+
+def normalize(X):
+    X = _f32(X)
+    N, D = X.shape
+    out = np.zeros_like(X)
+    lib().go_normalize(_p(X), i64(N), i64(D), int(D), _p(out), i64(D))
+    return out
+
+
+def distance_sq(x, y):
+    x = _f32(x)
+    y = _f32(y)
+    return float(lib().go_distance_sq(_p(x), _p(y), int(x.shape[0])))
+
+
+def objective(X, frm, dim, Cm, a):
+    X = _f32(X)
+    Cm = _f32(Cm)
+    a = np.ascontiguousarray(a, np.int32)
+    return float(lib().go_objective(_p(X), i64(X.shape[0]), i64(X.shape[1]), int(frm), int(dim),
+                                    _p(Cm), i64(Cm.shape[1]), _p(a)))
+
+
+def grouped_query(query, centroids, offsets, strategy, limit, cb, codes, k,
+                  topk_mode=TOPK_CANONICAL):
+    query = _f32(query)
+    centroids = _f32(centroids)
+    offsets = np.ascontiguousarray(offsets, np.int32)
+    cb = _f32(cb)
+    codes = np.ascontiguousarray(codes, np.uint8)
+    P, D = centroids.shape
+    M, K, _ = cb.shape
+    N = codes.shape[1]
+    ids = np.full(max(k, 1), -1, np.int32)
+    ds = np.full(max(k, 1), np.inf, np.float32)
+    sz = i32(0)
+    probed = np.zeros(P, np.int32)
+    npb = i32(0)
+    lib().go_grouped_query(_p(query), int(D), _p(centroids), int(P), _p(offsets), int(strategy),
+                           int(limit), _p(cb), M, K, _p(codes), i64(N), i64(N), int(k),
+                           int(topk_mode), _p(ids), _p(ds), C.byref(sz), _p(probed), C.byref(npb))
+    return ids[:sz.value], ds[:sz.value], probed[:npb.value]
+
+
+class Heap:
+    """Literal TopKHeap (G/TopKHeap.scala)."""
+
+    def __init__(self, k):
+        self.k = k
+        self._h = C.c_void_p(lib().go_heap_new(int(k)))
+
+    def update(self, key, v):
+        lib().go_heap_update(self._h, i32(key), C.c_float(v))
+
+    def merge(self, other):
+        lib().go_heap_merge(self._h, other._h)
+
+    @property
+    def size(self):
+        return int(lib().go_heap_size(self._h))
+
+    def raw(self):
+        n = self.size
+        keys = np.zeros(max(n, 1), np.int32)
+        vals = np.zeros(max(n, 1), np.float32)
+        lib().go_heap_raw(self._h, _p(keys), _p(vals))
+        return keys[:n], vals[:n]
+
+    def delete(self):
+        r = i32(0)
+        if lib().go_heap_delete(self._h, C.byref(r)) != 0:
+            raise RuntimeError("heap is empty")
+        return r.value
+
+    def drain(self):
+        n = self.size
+        ids = np.zeros(max(n, 1), np.int32)
+        ds = np.zeros(max(n, 1), np.float32)
+        lib().go_heap_drain(self._h, _p(ids), _p(ds))
+        return ids[:n], ds[:n]
+
+    def __del__(self):
+        try:
+            lib().go_heap_free(self._h)
+        except Exception:
+            pass
