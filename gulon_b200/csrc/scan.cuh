@@ -1,0 +1,344 @@
+// scan.cuh -- query path: ADC lookup-table build, uint8 code scan, top-k.
+//
+// Reference: Index.prepareQuery (G/Index.scala:352-383), PQIndex.distances + batchQuery
+// (G/Index.scala:393-440), TopKHeap (G/TopKHeap.scala), MathUtils.normalize (G/MathUtils.scala:100-120).
+//
+// Exactness contract: every distance is the reference's fp32 value bit for bit --
+//   LUT[q][m][i] = (((0 + d0*d0) + d1*d1) + ...) with d = q - c, round-to-nearest, no FMA;
+//   dist[row]    = (((0 + LUT[0][c0]) + LUT[1][c1]) + ... + LUT[M-1][c_{M-1}]) in quantizer order.
+// One thread owns a row's whole sum; there is no split-M or tree reduction anywhere.
+#pragma once
+#include "common.cuh"
+#include "select.cuh"
+
+namespace gulon {
+
+// ---- MathUtils.normalize ---------------------------------------------------------------------
+// ||x|| = (float) sqrt((double) sum_i fl(x_i^2)) (sequential fp32 sum), y_i = fl(x_i / ||x||).
+// One thread per row: the sum must be sequential to match the reference.
+__global__ void normalize_rows_kernel(const float *__restrict__ X, i64 N, int D, i64 ld,
+                                      float *__restrict__ out, i64 ldo) {
+  i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const float *x = X + i * ld;
+  float sum = 0.0f;
+  for (int j = 0; j < D; j++) {
+    float v = x[j];
+    sum = __fadd_rn(sum, __fmul_rn(v, v));
+  }
+  float d = (float)sqrt((double)sum);
+  for (int j = 0; j < D; j++) out[i * ldo + j] = __fdiv_rn(x[j], d);
+}
+
+// ---- Index.prepareQuery ------------------------------------------------------------------------
+// Interleaved layout used by both scan kernels: lutI[(g*M + m)*256 + code] is a float4 holding
+// the table entries of queries 4g..4g+3 (zero for queries past nq and for codes >= K).
+// grid (G, M), block 256 (one thread per code).
+__global__ void __launch_bounds__(256) lut_build_kernel(const float *__restrict__ Q, i64 ldq,
+                                                        i64 nq, const float *__restrict__ cb,
+                                                        const int32_t *__restrict__ from,
+                                                        const int32_t *__restrict__ dim, int M,
+                                                        int K, int dmax,
+                                                        float4 *__restrict__ lutI) {
+  const int g = blockIdx.x, m = blockIdx.y, code = threadIdx.x;
+  const int f = from[m], dm = dim[m];
+  float r[4] = {0.f, 0.f, 0.f, 0.f};
+  if (code < K) {
+    const float *c = cb + ((i64)m * K + code) * dmax;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      i64 q = (i64)g * 4 + j;
+      if (q < nq) {
+        const float *qv = Q + q * ldq + f;
+        float s = 0.0f;
+        for (int t = 0; t < dm; t++) {
+          float d = __fsub_rn(qv[t], c[t]);
+          s = __fadd_rn(s, __fmul_rn(d, d));
+        }
+        r[j] = s;
+      }
+    }
+  }
+  lutI[((i64)g * M + m) * 256 + code] = make_float4(r[0], r[1], r[2], r[3]);
+}
+
+// lutI -> plain [nq][M][K] (export for gulon_prepare_query)
+__global__ void lut_export_kernel(const float4 *__restrict__ lutI, i64 nq, int M, int K,
+                                  float *__restrict__ out) {
+  i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  i64 total = nq * M * K;
+  if (t >= total) return;
+  int i = (int)(t % K);
+  int m = (int)((t / K) % M);
+  i64 q = t / ((i64)K * M);
+  float4 v = lutI[((q >> 2) * M + m) * 256 + i];
+  int j = (int)(q & 3);
+  out[t] = j == 0 ? v.x : j == 1 ? v.y : j == 2 ? v.z : v.w;
+}
+
+__device__ __forceinline__ float f4comp(const float4 &v, int j) {
+  return j == 0 ? v.x : j == 1 ? v.y : j == 2 ? v.z : v.w;
+}
+
+// ---- simple scan: materialise (distance, id) keys ---------------------------------------------
+// keys[(s*Q4 + q)][t] for t in [0, n_pad): row = from + s*split_len + t, valid while
+// t < rows_per_split_here and row < until; everything else is KEY_SENT.
+// grid (n_pad/256, Q4, S), block 256.
+__global__ void __launch_bounds__(256) adc_keys_kernel(const uint8_t *__restrict__ codes, i64 ps,
+                                                       i64 from, i64 until, i64 split_len,
+                                                       i64 take, const float4 *__restrict__ lutI,
+                                                       int M, int Q4, u64 *__restrict__ keys,
+                                                       i64 n_pad) {
+  const i64 t = (i64)blockIdx.x * 256 + threadIdx.x;
+  const int q = blockIdx.y, s = blockIdx.z;
+  const i64 b_s = from + (i64)s * split_len;
+  i64 e_s = b_s + split_len;
+  if (e_s > until) e_s = until;
+  const i64 row = b_s + t;
+  u64 key = KEY_SENT;
+  if (t < take && row < e_s) {
+    const int g = q >> 2, j = q & 3;
+    const float4 *lut = lutI + (i64)g * M * 256;
+    float d = 0.0f;
+    for (int m = 0; m < M; m++) {
+      int c = codes[(i64)m * ps + row];
+      d = __fadd_rn(d, f4comp(__ldg(lut + m * 256 + c), j));
+    }
+    key = make_key(d, (uint32_t)row);
+  }
+  keys[((i64)s * Q4 + q) * n_pad + t] = key;
+}
+
+// ---- fused scan ---------------------------------------------------------------------------------
+// Persistent kernel, one 512-thread CTA per SM.  Work item = (chunk of 8192 rows, group of 4
+// queries).  For each quantizer m the group's 256-entry float4 table slice is replicated 8x in
+// shared memory as [code][replica] so that lane l always reads replica l&7: every LDS.128 of a
+// quarter-warp touches 8 distinct 16-byte bank groups -> conflict-free at 128 B/clk regardless of
+// the codes.  Each thread owns 16 consecutive rows x 4 queries = 64 fp32 accumulators and adds
+// the table entries in quantizer order (bit-exact with the reference).  Codes stream as one
+// 128-bit load per thread per quantizer (coalesced 8 KB per CTA).  The replicated slice for
+// quantizer m+1 is written while m is gathered (double buffer, one barrier per quantizer).
+//
+// Top-k: per (split, query) a sorted list of k keys lives in global memory and is owned by
+// exactly one CTA (no atomics, no locks).  Rows whose key beats the list tail are pushed to a
+// shared-memory candidate area and merged by one warp per query with a bitonic sort.  The lists
+// are seeded by the simple path on the first rows of every split, so candidates are rare.
+namespace fscan {
+constexpr int NT = 512;
+constexpr int RPT = 16;
+constexpr int R = NT * RPT;  // 8192 rows per item
+constexpr int KMAX = 128;
+constexpr int SORTN = 512;
+constexpr int CAP = SORTN - KMAX;  // candidate slots per query and item
+constexpr int LUT_F4 = 256 * 8;    // float4 per replicated slice (32 KB)
+constexpr int SMEM_BYTES = 2 * LUT_F4 * 16 + 4 * SORTN * 8;
+constexpr int SUB_ROWS = 256;  // slow path: rows per sub-batch (<= CAP)
+
+struct Params {
+  const uint8_t *codes;
+  i64 ps;
+  i64 from, until;   // scanned range
+  i64 split_len;     // rows per split
+  i64 boot;          // rows at the head of every split already merged by the bootstrap
+  const float4 *lutI;
+  int M, G, k, S, Bs;
+  u64 *lists;        // [S][G*4][k]
+};
+
+__device__ __forceinline__ uint4 ldg_stream_u4(const void *p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float4 ldg_stream_f4(const void *p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ u64 ldcg_u64(const u64 *p) {
+  u64 r;
+  asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(r) : "l"(p));
+  return r;
+}
+
+// One warp merges the n candidates sitting at sb[k .. k+n) with the sorted list L (k keys).
+__device__ __forceinline__ void warp_merge(u64 *sb, u64 *L, int k, int n, int lane) {
+  int total = k + n;
+  int P = 2;
+  while (P < total) P <<= 1;
+  for (int i = lane; i < k; i += 32) sb[i] = ldcg_u64(L + i);
+  for (int i = total + lane; i < P; i += 32) sb[i] = KEY_SENT;
+  warp_bitonic_sort(sb, P, lane);
+  for (int i = lane; i < k; i += 32) L[i] = sb[i];
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(NT, 1) fused_scan_kernel(const Params p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float4 *lutbuf = reinterpret_cast<float4 *>(smem_raw);
+  u64 *sortbuf = reinterpret_cast<u64 *>(smem_raw + 2 * LUT_F4 * 16);
+  __shared__ int s_cnt[4];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int s = blockIdx.x / p.Bs, j = blockIdx.x % p.Bs;
+  if (s >= p.S) return;
+  const i64 b_s = p.from + (i64)s * p.split_len;
+  i64 e_s = b_s + p.split_len;
+  if (e_s > p.until) e_s = p.until;
+  const i64 lo = b_s + p.boot, hi = e_s;
+  if (lo >= hi || j >= p.G) return;
+  const i64 origin = lo & ~15LL;
+  const i64 n_chunks = (hi - origin + R - 1) / R;
+  const int n_my = (p.G - j + p.Bs - 1) / p.Bs;
+  const i64 n_items = n_chunks * n_my;
+  const int M = p.M, k = p.k;
+
+  // replicated-slice store mapping: thread writes 4 of the 8 replicas of one code
+  const int code_id = tid & 255, half = tid >> 8;
+  int fill_off[4];
+#pragma unroll
+  for (int t = 0; t < 4; t++) fill_off[t] = code_id * 8 + ((lane + 4 * half + t) & 7);
+  const int rep = lane & 7;
+
+  if (tid < 4) s_cnt[tid] = 0;
+
+  int parity = 0;
+  {
+    const int g0 = j;
+    float4 v = ldg_stream_f4(p.lutI + ((i64)g0 * M) * 256 + code_id);
+#pragma unroll
+    for (int t = 0; t < 4; t++) lutbuf[fill_off[t]] = v;
+  }
+  uint4 ccur = make_uint4(0, 0, 0, 0);
+  {
+    const i64 row0 = origin + (i64)tid * RPT;
+    if (row0 < hi) ccur = ldg_stream_u4(p.codes + row0);
+  }
+  __syncthreads();
+
+  for (i64 it = 0; it < n_items; ++it) {
+    const int g = j + (int)(it % n_my) * p.Bs;
+    const i64 row0 = origin + (it / n_my) * R + (i64)tid * RPT;
+    const bool has_next = it + 1 < n_items;
+    const int gn = has_next ? j + (int)((it + 1) % n_my) * p.Bs : g;
+    const i64 row0n = has_next ? origin + ((it + 1) / n_my) * R + (i64)tid * RPT : row0;
+
+    // list tails of the 4 queries (issued early; consumed after the quantizer loop)
+    u64 *L0 = p.lists + ((i64)s * p.G * 4 + (i64)g * 4) * k;
+    u64 tail[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) tail[q] = ldcg_u64(L0 + (i64)q * k + (k - 1));
+
+    float acc[RPT][4];
+#pragma unroll
+    for (int i = 0; i < RPT; i++) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.0f;
+
+    for (int m = 0; m < M; ++m) {
+      uint4 cnext = make_uint4(0, 0, 0, 0);
+      float4 lnext = make_float4(0.f, 0.f, 0.f, 0.f);
+      bool do_fill = false;
+      if (m + 1 < M) {
+        if (row0 < hi) cnext = ldg_stream_u4(p.codes + (i64)(m + 1) * p.ps + row0);
+        lnext = ldg_stream_f4(p.lutI + ((i64)g * M + m + 1) * 256 + code_id);
+        do_fill = true;
+      } else if (has_next) {
+        if (row0n < hi) cnext = ldg_stream_u4(p.codes + row0n);
+        lnext = ldg_stream_f4(p.lutI + ((i64)gn * M) * 256 + code_id);
+        do_fill = true;
+      }
+      const float4 *buf = lutbuf + parity * LUT_F4 + rep;
+      const uint32_t w[4] = {ccur.x, ccur.y, ccur.z, ccur.w};
+#pragma unroll
+      for (int i = 0; i < RPT; i++) {
+        const uint32_t c = (w[i >> 2] >> (8 * (i & 3))) & 0xffu;
+        const float4 v = buf[c * 8];
+        acc[i][0] = __fadd_rn(acc[i][0], v.x);
+        acc[i][1] = __fadd_rn(acc[i][1], v.y);
+        acc[i][2] = __fadd_rn(acc[i][2], v.z);
+        acc[i][3] = __fadd_rn(acc[i][3], v.w);
+      }
+      if (do_fill) {
+        float4 *dst = lutbuf + (parity ^ 1) * LUT_F4;
+#pragma unroll
+        for (int t = 0; t < 4; t++) dst[fill_off[t]] = lnext;
+      }
+      __syncthreads();
+      parity ^= 1;
+      ccur = cnext;
+    }
+
+    // ---- top-k epilogue -----------------------------------------------------------------
+    const int vlo = lo > row0 ? (int)(lo - row0 > RPT ? RPT : lo - row0) : 0;
+    const int vhi = hi - row0 >= RPT ? RPT : (hi > row0 ? (int)(hi - row0) : 0);
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const float tau = tail[q] == KEY_SENT ? __int_as_float(0x7f800000)
+                                            : ord2f((uint32_t)(tail[q] >> 32));
+      float mn = acc[0][q];
+#pragma unroll
+      for (int i = 1; i < RPT; i++) mn = fminf(mn, acc[i][q]);
+      if (mn <= tau) {
+#pragma unroll
+        for (int i = 0; i < RPT; i++) {
+          if (acc[i][q] <= tau && i >= vlo && i < vhi) {
+            const u64 key = make_key(acc[i][q], (uint32_t)(row0 + i));
+            if (key < tail[q]) {
+              int pos = atomicAdd(&s_cnt[q], 1);
+              if (pos < CAP) sortbuf[q * SORTN + k + pos] = key;
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+    const int c0 = s_cnt[0], c1 = s_cnt[1], c2 = s_cnt[2], c3 = s_cnt[3];
+    const bool overflow = c0 > CAP || c1 > CAP || c2 > CAP || c3 > CAP;
+    if (!overflow) {
+      if (warp < 4) {
+        const int n = s_cnt[warp];
+        if (n > 0) warp_merge(sortbuf + warp * SORTN, L0 + (i64)warp * k, k, n, lane);
+      }
+      __syncthreads();
+      if (tid < 4) s_cnt[tid] = 0;
+    } else {
+      // Slow path (adversarial orderings only): replay the item in sub-batches of SUB_ROWS rows
+      // so that no batch can overflow; tails are re-read after every merge.
+      for (int b = 0; b < R / SUB_ROWS; ++b) {
+        __syncthreads();
+        if (tid < 4) s_cnt[tid] = 0;
+        __syncthreads();
+        if (tid / (SUB_ROWS / RPT) == b) {
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            const u64 tl = ldcg_u64(L0 + (i64)q * k + (k - 1));
+#pragma unroll
+            for (int i = 0; i < RPT; i++) {
+              if (i >= vlo && i < vhi) {
+                const u64 key = make_key(acc[i][q], (uint32_t)(row0 + i));
+                if (key < tl) {
+                  int pos = atomicAdd(&s_cnt[q], 1);
+                  sortbuf[q * SORTN + k + pos] = key;
+                }
+              }
+            }
+          }
+        }
+        __syncthreads();
+        if (warp < 4) {
+          const int n = s_cnt[warp];
+          if (n > 0) warp_merge(sortbuf + warp * SORTN, L0 + (i64)warp * k, k, n, lane);
+        }
+      }
+      __syncthreads();
+      if (tid < 4) s_cnt[tid] = 0;
+    }
+    // the quantizer loop of the next item has >= 1 barrier before any push
+  }
+}
+}  // namespace fscan
+
+}  // namespace gulon

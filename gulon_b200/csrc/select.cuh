@@ -1,0 +1,177 @@
+// select.cuh -- exact (distance, id) top-k selection over arrays of u64 keys.
+//
+// Replaces the semantics of G/TopKHeap.scala (bounded heap fed in ascending row order) with a
+// deterministic lexicographic (distance asc, id asc) selection: the order T/TopKHeapSpec.scala:16-31
+// asserts.  Used by the simple scan path, the bootstrap of the fused scan, the shard merge
+// (TopKHeap#merge, G/TopKHeap.scala:44-53) and the exact kNN (G/Index.scala:209-229).
+//
+// One pass sorts chunks of 4096 keys in shared memory (bitonic) and keeps the first kk of each
+// chunk; passes repeat until one chunk is left.  Integer work, HBM-bound: 8 B read per key.
+#pragma once
+#include "common.cuh"
+
+namespace gulon {
+
+constexpr int SEL_CHUNK = 4096;
+constexpr int SEL_NT = 512;
+
+// Sorts n (power of two, <= 4096) keys in shared memory, ascending; all nt threads of the block.
+__device__ inline void block_bitonic_sort(u64 *s, int n, int tid, int nt) {
+  for (int size = 2; size <= n; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (int t = tid; t < (n >> 1); t += nt) {
+        int pos = 2 * t - (t & (stride - 1));
+        u64 a = s[pos], b = s[pos + stride];
+        bool up = (pos & size) == 0;
+        if ((a > b) == up) {
+          s[pos] = b;
+          s[pos + stride] = a;
+        }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// Same, for one warp (n <= 512), synchronised with __syncwarp.
+__device__ inline void warp_bitonic_sort(u64 *s, int n, int lane) {
+  for (int size = 2; size <= n; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncwarp();
+      for (int t = lane; t < (n >> 1); t += 32) {
+        int pos = 2 * t - (t & (stride - 1));
+        u64 a = s[pos], b = s[pos + stride];
+        bool up = (pos & size) == 0;
+        if ((a > b) == up) {
+          s[pos] = b;
+          s[pos + stride] = a;
+        }
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// in : [rows][in_stride] keys, in_stride a multiple of SEL_CHUNK (padding = KEY_SENT)
+// out: [rows][out_stride]; chunk c of a row writes its kk smallest keys at c*kk.
+__global__ void __launch_bounds__(SEL_NT) select_pass_kernel(const u64 *__restrict__ in,
+                                                             i64 in_stride, u64 *__restrict__ out,
+                                                             i64 out_stride, int kk) {
+  __shared__ u64 s[SEL_CHUNK];
+  const i64 row = blockIdx.y;
+  const i64 c = blockIdx.x;
+  const u64 *src = in + row * in_stride + c * SEL_CHUNK;
+  for (int t = threadIdx.x; t < SEL_CHUNK; t += SEL_NT) s[t] = src[t];
+  block_bitonic_sort(s, SEL_CHUNK, threadIdx.x, SEL_NT);
+  u64 *dst = out + row * out_stride + c * kk;
+  for (int t = threadIdx.x; t < kk; t += SEL_NT) dst[t] = s[t];
+}
+
+// keys [rows][stride] (first k of each row are the answer) -> ids / dists / sizes
+__global__ void unpack_keys_kernel(const u64 *__restrict__ keys, i64 stride, i64 rows, int k,
+                                   i64 id_offset, int32_t *__restrict__ ids,
+                                   float *__restrict__ dists, int32_t *__restrict__ sizes) {
+  i64 q = (i64)blockIdx.x * blockDim.y + threadIdx.y;
+  if (q >= rows) return;
+  int cnt = 0;
+  for (int i = threadIdx.x; i < k; i += 32) {
+    u64 key = keys[q * stride + i];
+    bool ok = key != KEY_SENT;
+    if (ids) ids[q * k + i] = ok ? (int32_t)((i64)(uint32_t)key + id_offset) : -1;
+    if (dists) dists[q * k + i] = ok ? ord2f((uint32_t)(key >> 32)) : __int_as_float(0x7f800000);
+    cnt += ok;
+  }
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if (sizes && threadIdx.x == 0) sizes[q] = cnt;
+}
+
+// lists [S][rows][k] -> keys [rows][stride] with row-major [s*k + i]; tail padded with KEY_SENT
+__global__ void gather_lists_kernel(const u64 *__restrict__ lists, int S, i64 rows, int k,
+                                    u64 *__restrict__ keys, i64 stride) {
+  i64 q = blockIdx.y;
+  for (i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x; t < stride;
+       t += (i64)gridDim.x * blockDim.x) {
+    u64 v = KEY_SENT;
+    if (t < (i64)S * k) {
+      int s = (int)(t / k), i = (int)(t % k);
+      v = lists[((i64)s * rows + q) * k + i];
+    }
+    keys[q * stride + t] = v;
+  }
+}
+
+// (ids, dists) [S][rows][k] -> keys [rows][stride]; id < 0 marks an empty slot
+__global__ void pack_results_kernel(const int32_t *__restrict__ ids,
+                                    const float *__restrict__ dists, int S, i64 rows, int k,
+                                    u64 *__restrict__ keys, i64 stride) {
+  i64 q = blockIdx.y;
+  for (i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x; t < stride;
+       t += (i64)gridDim.x * blockDim.x) {
+    u64 v = KEY_SENT;
+    if (t < (i64)S * k) {
+      int s = (int)(t / k), i = (int)(t % k);
+      i64 at = ((i64)s * rows + q) * k + i;
+      int32_t id = ids[at];
+      if (id >= 0) v = make_key(dists[at], (uint32_t)id);
+    }
+    keys[q * stride + t] = v;
+  }
+}
+
+// Runs selection passes until every row holds its k smallest keys at the front of the result.
+// keys_a: [rows][stride_a] input (stride_a multiple of SEL_CHUNK); scratch buffers ping-pong.
+// On return *result / *result_stride describe where the answer lives.
+struct Selector {
+  DevBuf ping, pong;
+  int run(u64 *keys_a, i64 stride_a, i64 rows, int k, cudaStream_t st, u64 **result,
+          i64 *result_stride, u64 *final_out = nullptr, i64 final_stride = 0) {
+    GREQUIRE(k >= 1, "k must be >= 1");
+    GREQUIRE(stride_a % SEL_CHUNK == 0, "internal: key stride not a multiple of %d", SEL_CHUNK);
+    GREQUIRE(k <= SEL_CHUNK / 2 || stride_a == SEL_CHUNK,
+             "k=%d too large: this build supports k <= %d, or any k when the scanned range has "
+             "at most %d rows", k, SEL_CHUNK / 2, SEL_CHUNK);
+    GREQUIRE(rows <= 65535 * 64LL, "internal: too many selection rows");
+    int kk = k < SEL_CHUNK ? k : SEL_CHUNK;
+    u64 *in = keys_a;
+    i64 in_stride = stride_a;
+    int phase = 0;
+    for (;;) {
+      i64 chunks = in_stride / SEL_CHUNK;
+      bool last = chunks == 1;
+      i64 out_stride = last ? (final_out ? final_stride : SEL_CHUNK)
+                            : round_up(chunks * kk, SEL_CHUNK);
+      u64 *out;
+      if (last && final_out) {
+        out = final_out;
+      } else {
+        DevBuf &b = (phase & 1) ? pong : ping;
+        GCHECK(b.ensure((size_t)rows * (size_t)out_stride * sizeof(u64)));
+        out = b.as<u64>();
+        if (!last)
+          GCU(cudaMemsetAsync(out, 0xFF, (size_t)rows * (size_t)out_stride * sizeof(u64), st));
+      }
+      // grid.y is limited to 65535: tile rows
+      for (i64 r0 = 0; r0 < rows; r0 += 65535) {
+        i64 nr = rows - r0 < 65535 ? rows - r0 : 65535;
+        dim3 grid((unsigned)chunks, (unsigned)nr);
+        GLAUNCH(select_pass_kernel, grid, SEL_NT, 0, st, in + r0 * in_stride, in_stride,
+                out + r0 * out_stride, out_stride, kk);
+      }
+      if (last) {
+        *result = out;
+        *result_stride = out_stride;
+        return GULON_OK;
+      }
+      in = out;
+      in_stride = out_stride;
+      phase++;
+    }
+  }
+  void release() {
+    ping.release();
+    pong.release();
+  }
+};
+
+}  // namespace gulon

@@ -1,0 +1,219 @@
+/*
+ * gulon_b200.h -- C ABI of libgulon_b200.so: the B200 (sm_100a) implementation of tixxit/gulon's
+ * product-quantization hot path (k-means codebook training, PQ encoding, ADC scan + top-k).
+ *
+ * The reference has no FFI seam: the hot path is plain Scala method calls inside one JVM.  Each
+ * entry point below names the Scala method it replaces (G/ = core/src/main/scala/net/tixxit/gulon/).
+ * INTEGRATION.md shows the JNI / Panama binding a gulon maintainer would add.
+ *
+ * Conventions
+ *   - every function returns a status (GULON_OK == 0, negative on error); gulon_last_error()
+ *     returns the calling thread's message for the last failure;
+ *   - matrices are flat row-major float32 with an explicit leading dimension `ld` (in floats);
+ *     the Scala facade flattens Matrix.data (jagged Array[Array[Float]], G/Matrix.scala:3) once;
+ *   - PQ codes are plane-major uint8 [M][plane_stride] (one Coder8 byte array per quantizer,
+ *     G/EncodedMatrix.scala:11-23, G/Coder.scala:129-140);
+ *   - codebooks are float32 [M][K][dmax], dmax = ceil(D/M); quantizer m uses the first dim[m]
+ *     floats of each centroid, with (from[m], dim[m]) given by the Vectors.subvectors split rule
+ *     (G/Vectors.scala:84-104) -- see gulon_subvectors();
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     GULON_ENODEVICE;
+ *   - functions suffixed _dev take DEVICE pointers (and a cudaStream_t passed as void*), are
+ *     asynchronous on that stream, and exist so that a host can keep data resident in HBM and
+ *     compose the path with its own collectives (torch.distributed / NCCL).
+ *
+ * Semantics fixed by this library where the reference is order- or RNG-dependent
+ *   - argmin ties: lowest centroid index (GULON_TIE_LOWEST).  The reference breaks exact ties with
+ *     a stateful Random(0).nextBoolean() stream (G/KMeans.scala:47,90);
+ *   - top-k ties: (distance ascending, id ascending) -- the stable order T/TopKHeapSpec.scala:16-31
+ *     asserts; the reference heap's order inside an equal-distance group is structure-dependent.
+ */
+#ifndef GULON_B200_H
+#define GULON_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GULON_VERSION 100 /* 0.1.0 */
+
+/* status codes */
+#define GULON_OK            0
+#define GULON_EINVAL       -1  /* IllegalArgumentException on the Scala side (require(...)) */
+#define GULON_ECUDA        -2
+#define GULON_ENOMEM       -3
+#define GULON_ENODEVICE    -4
+#define GULON_ECOMM        -5
+#define GULON_EUNSUPPORTED -6
+#define GULON_ESTATE       -7  /* IllegalStateException */
+
+/* argmin tie rule (G/KMeans.scala:47,90) */
+#define GULON_TIE_LOWEST  1
+
+/* centroid update rule (G/KMeans.scala:198-226) */
+#define GULON_UPDATE_RUNNING_MEAN 0 /* literal sequential running mean: bit-exact with the reference */
+#define GULON_UPDATE_SUM          1 /* per-cluster sum / count; shardable (all-reduce of sums+counts) */
+
+/* scan implementation selector for gulon_set_option("scan_impl", ...) */
+#define GULON_SCAN_AUTO   0
+#define GULON_SCAN_SIMPLE 1 /* distance materialisation + selection (any k, slow, cross-check path) */
+#define GULON_SCAN_FUSED  2 /* replicated-LUT gather kernel with in-kernel top-k (k <= 128)        */
+
+typedef struct gulon_points_s   *gulon_points_t;   /* device-resident float32 matrix (Matrix)      */
+typedef struct gulon_codebook_s *gulon_codebook_t; /* device-resident ProductQuantizer codebooks   */
+typedef struct gulon_index_s    *gulon_index_t;    /* device-resident Index.PQIndex                */
+
+/*
+ * Exchange hooks for the sharded paths (one process per GPU).  Buffers are DEVICE pointers;
+ * each hook must enqueue on `stream` (a cudaStream_t) or synchronise before returning.
+ * The Python host wires these to torch.distributed (NCCL); a JVM host would wire them to NCCL.
+ * The reference has no counterpart (single JVM).
+ */
+typedef struct gulon_comm {
+  int32_t rank, world;
+  int (*allreduce_sum_f32)(void *user, float *dev_buf, int64_t n, void *stream);
+  int (*allreduce_sum_i32)(void *user, int32_t *dev_buf, int64_t n, void *stream);
+  int (*allgather)(void *user, const void *dev_send, void *dev_recv, int64_t bytes_per_rank,
+                   void *stream);
+  void *user;
+} gulon_comm_t;
+
+/* KMeans.ProgressReport (G/KMeans.scala:119-127), delivered synchronously on the calling thread.
+ * quantizer = index of the sub-quantizer (0 for a plain k-means). */
+typedef struct gulon_progress {
+  int32_t quantizer;
+  int32_t num_iterations;
+  int32_t max_iterations;
+  float step_mean, step_stddev; /* SummaryStats of centroid displacement, G/KMeans.scala:160-168 */
+  int32_t converged;
+} gulon_progress_t;
+typedef void (*gulon_progress_fn)(void *user, const gulon_progress_t *report);
+
+/* ---- library / device ------------------------------------------------------------------- */
+int gulon_version(void);
+const char *gulon_last_error(void);
+int gulon_device_count(int32_t *n);
+int gulon_set_device(int32_t device); /* device used by the calling thread's later calls */
+int gulon_get_device(int32_t *device);
+int gulon_device_sync(void);
+int gulon_set_option(const char *name, int64_t value);
+int gulon_get_counter(const char *name, int64_t *value); /* e.g. "kernel_launches" */
+
+/* Vectors.subvectors split rule, G/Vectors.scala:84-104.  Returns dmax (>0) or a status (<0). */
+int gulon_subvectors(int32_t D, int32_t M, int32_t *from, int32_t *dim);
+
+/* ---- Matrix ----------------------------------------------------------------------------- */
+/* Copies a host matrix into HBM (G/Matrix.scala:3). */
+int gulon_points_create(const float *X, int64_t N, int32_t D, int64_t ld, gulon_points_t *out);
+/* Wraps an existing device matrix without copying (borrowed; caller keeps it alive). */
+int gulon_points_wrap_dev(const float *dX, int64_t N, int32_t D, int64_t ld, gulon_points_t *out);
+int gulon_points_info(gulon_points_t p, int64_t *N, int32_t *D, int64_t *ld, const float **dptr);
+int gulon_points_destroy(gulon_points_t p);
+
+/* MathUtils.normalize per row, G/MathUtils.scala:100-120 (cosine metric prep). In place on device. */
+int gulon_points_normalize(gulon_points_t p);
+/* Host convenience: out[i] = normalize(X[i]). */
+int gulon_normalize(const float *X, int64_t N, int32_t D, int64_t ld, float *out, int64_t ldo);
+
+/* ---- KMeans (G/KMeans.scala) -------------------------------------------------------------- */
+/*
+ * KMeans#assign (batch = 0, G/KMeans.scala:18-22,70-98) and #parAssign (batch = 25000, :57-68)
+ * over the column window [from, from+dim).  C is host float32 [K][dim].  With GULON_TIE_LOWEST
+ * the batch size does not change the result (it only scopes the reference's RNG).
+ * out: host int32 [N].
+ */
+int gulon_kmeans_assign(gulon_points_t p, int32_t from, int32_t dim, const float *C, int32_t K,
+                        int64_t batch, int32_t tie_mode, int32_t *out);
+/* KMeans.fromAssignment, G/KMeans.scala:198-226.  assign: host int32 [N]; out_C host [K][dim];
+ * out_counts (optional) host int32 [K]. Empty clusters stay all-zero. */
+int gulon_kmeans_update(gulon_points_t p, int32_t from, int32_t dim, const int32_t *assign,
+                        int32_t K, int32_t update_mode, float *out_C, int32_t *out_counts);
+/* KMeans.init, G/KMeans.scala:188-196: K rows sampled with replacement by java.util.Random(seed). */
+int gulon_kmeans_init(gulon_points_t p, int32_t from, int32_t dim, int32_t K, int32_t seed,
+                      float *out_C, int32_t *out_rows);
+/*
+ * KMeans.computeClusters, G/KMeans.scala:134-157: init -> parAssign -> loop i = 0..max_iter
+ * {fromAssignment -> parAssign -> converged = (assignments unchanged)}.  comm may be NULL (one GPU);
+ * with comm the points are this rank's row shard, update_mode must be GULON_UPDATE_SUM, and
+ * `n_total`/`row_offset` give the global row count and this shard's first global row (init samples
+ * global rows; the owner broadcasts them through allreduce).  out_C host [K][dim].
+ */
+int gulon_kmeans_train(gulon_points_t p, int32_t from, int32_t dim, int32_t K, int32_t max_iter,
+                       int32_t seed, int32_t tie_mode, int32_t update_mode,
+                       const gulon_comm_t *comm, int64_t n_total, int64_t row_offset,
+                       gulon_progress_fn report, void *user, float *out_C, int32_t *n_updates,
+                       int32_t *converged);
+
+/* ---- ProductQuantizer (G/ProductQuantizer.scala) ------------------------------------------ */
+/* ProductQuantizer.apply, :121-153: M independent k-means, seed = quantizer index (:139). */
+int gulon_pq_train(gulon_points_t p, int32_t M, int32_t K, int32_t max_iter, int32_t tie_mode,
+                   int32_t update_mode, const gulon_comm_t *comm, int64_t n_total,
+                   int64_t row_offset, gulon_progress_fn report, void *user,
+                   gulon_codebook_t *out);
+/* ProductQuantizer(numClusters, quantizers) from explicit centroids: host float32 [M][K][dmax]. */
+int gulon_codebook_create(int32_t D, int32_t M, int32_t K, const float *centroids,
+                          gulon_codebook_t *out);
+int gulon_codebook_info(gulon_codebook_t cb, int32_t *D, int32_t *M, int32_t *K, int32_t *dmax);
+int gulon_codebook_export(gulon_codebook_t cb, float *centroids); /* host [M][K][dmax] */
+int gulon_codebook_destroy(gulon_codebook_t cb);
+
+/* ProductQuantizer#encode, :25-35 (+ Coder8, G/Coder.scala:129-140). Requires K <= 256.
+ * X host [N][ld]; codes host uint8 [M][N].  Streams X through HBM in row chunks. */
+int gulon_pq_encode(gulon_codebook_t cb, const float *X, int64_t N, int64_t ld, int32_t tie_mode,
+                    uint8_t *codes);
+/* Device-resident form: dX device [N][ld], dcodes device uint8 [M][plane_stride]. */
+int gulon_pq_encode_dev(gulon_codebook_t cb, const float *dX, int64_t N, int64_t ld,
+                        int32_t tie_mode, uint8_t *dcodes, int64_t plane_stride, void *stream);
+/* ProductQuantizer#decode(EncodedMatrix), :58-78. codes host [M][N] -> out host [N][ldo]. */
+int gulon_pq_decode(gulon_codebook_t cb, const uint8_t *codes, int64_t N, int64_t plane_stride,
+                    float *out, int64_t ldo);
+
+/* ---- Index.PQIndex (G/Index.scala:385-441) ------------------------------------------------ */
+/* PQIndex(productQuantizer, data): copies host codes [M][plane_stride] into HBM. */
+int gulon_index_create(gulon_codebook_t cb, const uint8_t *codes, int64_t N, int64_t plane_stride,
+                       gulon_index_t *out);
+/* Adopts device codes (borrowed). plane_stride must be a multiple of 16 and dcodes 16-byte aligned. */
+int gulon_index_create_dev(gulon_codebook_t cb, const uint8_t *dcodes, int64_t N,
+                           int64_t plane_stride, gulon_index_t *out);
+int gulon_index_info(gulon_index_t ix, int64_t *N, int32_t *M, int32_t *K, int32_t *D);
+int gulon_index_destroy(gulon_index_t ix);
+
+/* Index.prepareQuery, G/Index.scala:352-383: lut host float32 [nq][M][K]. */
+int gulon_prepare_query(gulon_codebook_t cb, const float *queries, int64_t nq, int64_t ldq,
+                        float *lut);
+
+/*
+ * PQIndex#batchQuery(k, vectors, from, until), G/Index.scala:414-440 (+ SortedIndex.prepare,
+ * :324-331, when normalize != 0; + Result.fromHeap ordering, :83-94).
+ * queries host [nq][ldq]; out_ids host int32 [nq][k] (row ids + id_offset), out_dists host
+ * float32 [nq][k] ascending, out_sizes host int32 [nq] = min(k, until-from).  Unused slots hold
+ * id -1 / +inf.
+ */
+int gulon_pq_query(gulon_index_t ix, const float *queries, int64_t nq, int64_t ldq, int32_t k,
+                   int64_t from, int64_t until, int32_t normalize, int64_t id_offset,
+                   int32_t *out_ids, float *out_dists, int32_t *out_sizes);
+/* Device-resident form; results are packed keys-free arrays on device. */
+int gulon_pq_query_dev(gulon_index_t ix, const float *dqueries, int64_t nq, int64_t ldq, int32_t k,
+                       int64_t from, int64_t until, int32_t normalize, int64_t id_offset,
+                       int32_t *d_ids, float *d_dists, int32_t *d_sizes, void *stream);
+
+/*
+ * TopKHeap#merge across shards (G/TopKHeap.scala:44-53; T/TopKHeapSpec.scala:33-52): merges S
+ * result sets laid out [S][nq][k] (as produced by an all-gather of per-rank gulon_pq_query_dev
+ * outputs) into [nq][k] by (distance, id).  Device pointers.
+ */
+int gulon_topk_merge_dev(const int32_t *d_ids, const float *d_dists, int32_t S, int64_t nq,
+                         int32_t k, int32_t *d_out_ids, float *d_out_dists, int32_t *d_out_sizes,
+                         void *stream);
+
+/* Index.exactNearestNeighbours, G/Index.scala:209-229 (+ MathUtils.distanceSq, G/MathUtils.scala:85-95). */
+int gulon_exact_topk(gulon_points_t p, const float *queries, int64_t nq, int64_t ldq, int32_t k,
+                     int64_t from, int64_t until, int32_t *out_ids, float *out_dists,
+                     int32_t *out_sizes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GULON_B200_H */
