@@ -1,0 +1,184 @@
+"""ctypes binding of libgulon_b200.so (the C ABI declared in include/gulon_b200.h).
+
+The library is built in-tree with nvcc for sm_100a (`build()`); there is no CPU fallback: when the
+shared object is missing the import fails loudly, and when no CUDA device is visible every compute
+entry point returns GULON_ENODEVICE, raised here as `NoDeviceError`.
+"""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+SO_PATH = os.path.join(_HERE, "libgulon_b200.so")
+_SRC_DIR = os.path.join(_HERE, "csrc")
+_SOURCES = ["gulon_b200.cu"]
+_HEADERS = ["common.cuh", "kmeans.cuh", "scan.cuh", "select.cuh"]
+
+OK, EINVAL, ECUDA, ENOMEM, ENODEVICE, ECOMM, EUNSUPPORTED, ESTATE = 0, -1, -2, -3, -4, -5, -6, -7
+TIE_LOWEST = 1
+UPDATE_RUNNING_MEAN, UPDATE_SUM = 0, 1
+SCAN_AUTO, SCAN_SIMPLE, SCAN_FUSED = 0, 1, 2
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-shared",
+]
+
+
+class GulonError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("gulon_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class NoDeviceError(GulonError):
+    pass
+
+
+def _stale():
+    if not os.path.exists(SO_PATH):
+        return True
+    t = os.path.getmtime(SO_PATH)
+    deps = [os.path.join(_SRC_DIR, f) for f in _SOURCES + _HEADERS]
+    deps.append(os.path.join(_ROOT, "include", "gulon_b200.h"))
+    return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    """Compile csrc/*.cu into gulon_b200/libgulon_b200.so for sm_100a (nvcc cross-compiles)."""
+    if not force and not _stale():
+        return SO_PATH
+    nvcc = os.environ.get("NVCC") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        nvcc = "nvcc"
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", SO_PATH] + [os.path.join(_SRC_DIR, s) for s in _SOURCES]
+    if verbose:
+        cmd += ["-Xptxas", "-v"]
+        print(" ".join(cmd), file=sys.stderr)
+    subprocess.check_call(cmd, cwd=_SRC_DIR)
+    return SO_PATH
+
+
+i32, i64 = C.c_int32, C.c_int64
+vp = C.c_void_p
+
+
+class Comm(C.Structure):
+    """gulon_comm_t: exchange hooks for the sharded paths."""
+    ALLREDUCE_F32 = C.CFUNCTYPE(C.c_int, vp, vp, i64, vp)
+    ALLREDUCE_I32 = C.CFUNCTYPE(C.c_int, vp, vp, i64, vp)
+    ALLGATHER = C.CFUNCTYPE(C.c_int, vp, vp, vp, i64, vp)
+    _fields_ = [("rank", i32), ("world", i32),
+                ("allreduce_sum_f32", ALLREDUCE_F32),
+                ("allreduce_sum_i32", ALLREDUCE_I32),
+                ("allgather", ALLGATHER),
+                ("user", vp)]
+
+
+class Progress(C.Structure):
+    """gulon_progress_t == KMeans.ProgressReport (G/KMeans.scala:119-127)."""
+    _fields_ = [("quantizer", i32), ("num_iterations", i32), ("max_iterations", i32),
+                ("step_mean", C.c_float), ("step_stddev", C.c_float), ("converged", i32)]
+
+
+PROGRESS_FN = C.CFUNCTYPE(None, vp, C.POINTER(Progress))
+
+# every symbol include/gulon_b200.h declares: name -> (restype, argtypes)
+SIGNATURES = {
+    "gulon_version": (C.c_int, []),
+    "gulon_last_error": (C.c_char_p, []),
+    "gulon_device_count": (C.c_int, [C.POINTER(i32)]),
+    "gulon_set_device": (C.c_int, [i32]),
+    "gulon_get_device": (C.c_int, [C.POINTER(i32)]),
+    "gulon_device_sync": (C.c_int, []),
+    "gulon_set_option": (C.c_int, [C.c_char_p, i64]),
+    "gulon_get_counter": (C.c_int, [C.c_char_p, C.POINTER(i64)]),
+    "gulon_subvectors": (C.c_int, [i32, i32, vp, vp]),
+    "gulon_points_create": (C.c_int, [vp, i64, i32, i64, C.POINTER(vp)]),
+    "gulon_points_wrap_dev": (C.c_int, [vp, i64, i32, i64, C.POINTER(vp)]),
+    "gulon_points_info": (C.c_int, [vp, C.POINTER(i64), C.POINTER(i32), C.POINTER(i64),
+                                    C.POINTER(vp)]),
+    "gulon_points_destroy": (C.c_int, [vp]),
+    "gulon_points_normalize": (C.c_int, [vp]),
+    "gulon_normalize": (C.c_int, [vp, i64, i32, i64, vp, i64]),
+    "gulon_kmeans_assign": (C.c_int, [vp, i32, i32, vp, i32, i64, i32, vp]),
+    "gulon_kmeans_update": (C.c_int, [vp, i32, i32, vp, i32, i32, vp, vp]),
+    "gulon_kmeans_init": (C.c_int, [vp, i32, i32, i32, i32, vp, vp]),
+    "gulon_kmeans_train": (C.c_int, [vp, i32, i32, i32, i32, i32, i32, i32, C.POINTER(Comm), i64,
+                                     i64, PROGRESS_FN, vp, vp, C.POINTER(i32), C.POINTER(i32)]),
+    "gulon_pq_train": (C.c_int, [vp, i32, i32, i32, i32, i32, C.POINTER(Comm), i64, i64,
+                                 PROGRESS_FN, vp, C.POINTER(vp)]),
+    "gulon_codebook_create": (C.c_int, [i32, i32, i32, vp, C.POINTER(vp)]),
+    "gulon_codebook_info": (C.c_int, [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32),
+                                      C.POINTER(i32)]),
+    "gulon_codebook_export": (C.c_int, [vp, vp]),
+    "gulon_codebook_destroy": (C.c_int, [vp]),
+    "gulon_pq_encode": (C.c_int, [vp, vp, i64, i64, i32, vp]),
+    "gulon_pq_encode_dev": (C.c_int, [vp, vp, i64, i64, i32, vp, i64, vp]),
+    "gulon_pq_decode": (C.c_int, [vp, vp, i64, i64, vp, i64]),
+    "gulon_index_create": (C.c_int, [vp, vp, i64, i64, C.POINTER(vp)]),
+    "gulon_index_create_dev": (C.c_int, [vp, vp, i64, i64, C.POINTER(vp)]),
+    "gulon_index_info": (C.c_int, [vp, C.POINTER(i64), C.POINTER(i32), C.POINTER(i32),
+                                   C.POINTER(i32)]),
+    "gulon_index_destroy": (C.c_int, [vp]),
+    "gulon_prepare_query": (C.c_int, [vp, vp, i64, i64, vp]),
+    "gulon_pq_query": (C.c_int, [vp, vp, i64, i64, i32, i64, i64, i32, i64, vp, vp, vp]),
+    "gulon_pq_query_dev": (C.c_int, [vp, vp, i64, i64, i32, i64, i64, i32, i64, vp, vp, vp, vp]),
+    "gulon_topk_merge_dev": (C.c_int, [vp, vp, i32, i64, i32, vp, vp, vp, vp]),
+    "gulon_exact_topk": (C.c_int, [vp, vp, i64, i64, i32, i64, i64, vp, vp, vp]),
+    "gulon_rerank": (C.c_int, [vp, vp, i64, i64, vp, i32, i32, vp, vp, vp]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load the shared library (building it first if the sources are newer)."""
+    global _lib
+    if _lib is None:
+        if _stale():
+            build()
+        if not os.path.exists(SO_PATH):
+            raise ImportError("libgulon_b200.so is missing and could not be built; "
+                              "gulon_b200 has no CPU fallback")
+        L = C.CDLL(SO_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            f = getattr(L, name)
+            f.restype = res
+            f.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    """Map a negative status to the exception class the reference would throw."""
+    if rc >= 0:
+        return rc
+    msg = (lib().gulon_last_error() or b"").decode("utf-8", "replace")
+    if rc == EINVAL:
+        raise ValueError(msg)            # IllegalArgumentException (require(...))
+    if rc == ESTATE:
+        raise RuntimeError(msg)          # IllegalStateException
+    if rc == ENOMEM:
+        raise MemoryError(msg)
+    if rc == ENODEVICE:
+        raise NoDeviceError(rc, msg)
+    raise GulonError(rc, msg)
+
+
+def set_option(name, value):
+    check(lib().gulon_set_option(name.encode(), int(value)))
+
+
+def kernel_launches():
+    v = i64(0)
+    check(lib().gulon_get_counter(b"kernel_launches", C.byref(v)))
+    return int(v.value)
+
+
+def device_count():
+    n = i32(0)
+    check(lib().gulon_device_count(C.byref(n)))
+    return int(n.value)

@@ -96,8 +96,8 @@ struct DevBuf {
   }
 };
 
-inline i64 round_up(i64 x, i64 m) { return (x + m - 1) / m * m; }
-inline i64 ceil_div(i64 x, i64 m) { return (x + m - 1) / m; }
+__host__ __device__ inline i64 round_up(i64 x, i64 m) { return (x + m - 1) / m * m; }
+__host__ __device__ inline i64 ceil_div(i64 x, i64 m) { return (x + m - 1) / m; }
 
 // ---- (distance, id) keys --------------------------------------------------------------------
 // A candidate is one u64: order-preserving image of the fp32 distance in the high word, row id in

@@ -1,0 +1,1388 @@
+// gulon_b200.cu -- C ABI (include/gulon_b200.h) over the sm_100a kernels.
+//
+// Host logic only: argument checks (the reference's require(...)), handle ownership, chunking of
+// host buffers through HBM, and the driver loops of KMeans.computeClusters (G/KMeans.scala:134-157)
+// and ProductQuantizer.apply (G/ProductQuantizer.scala:121-153).  All arithmetic of the path runs
+// in the kernels of kmeans.cuh / scan.cuh / select.cuh; there is NO CPU fallback -- without a CUDA
+// device every compute entry point returns GULON_ENODEVICE.
+#include <math.h>
+
+#include <algorithm>
+#include <map>
+#include <memory>
+
+#include "common.cuh"
+#include "kmeans.cuh"
+#include "scan.cuh"
+#include "select.cuh"
+
+using namespace gulon;
+
+// ---- handles --------------------------------------------------------------------------------
+struct gulon_points_s {
+  float *d = nullptr;
+  i64 N = 0;
+  int D = 0;
+  i64 ld = 0;
+  bool owned = false;
+};
+
+struct gulon_codebook_s {
+  int D = 0, M = 0, K = 0, dmax = 0;
+  std::vector<int32_t> from, dim;
+  DevBuf cb, off, dfrom, ddim;
+  // sub-quantizers grouped by window width (the split rule yields at most two widths)
+  std::map<int, std::vector<int32_t>> by_dim;
+  std::map<int, DevBuf> d_by_dim;
+  std::mutex mu;
+  DevBuf scratch_q, scratch_lut;  // gulon_prepare_query staging
+  ~gulon_codebook_s() {
+    cb.release(); off.release(); dfrom.release(); ddim.release();
+    for (auto &kv : d_by_dim) kv.second.release();
+    scratch_q.release(); scratch_lut.release();
+  }
+};
+
+struct gulon_index_s {
+  gulon_codebook_t cb = nullptr;
+  const uint8_t *codes = nullptr;
+  i64 N = 0, ps = 0;
+  bool owned = false;
+  std::mutex mu;  // guards the scratch below: one query batch in flight per index handle
+  DevBuf lutI, keys, lists, qbuf, ids, dists, sizes, merged;
+  Selector sel;
+  ~gulon_index_s() {
+    if (owned && codes) cudaFree((void *)codes);
+    lutI.release(); keys.release(); lists.release(); qbuf.release();
+    ids.release(); dists.release(); sizes.release(); merged.release();
+    sel.release();
+  }
+};
+
+namespace {
+
+// ---- options / device -----------------------------------------------------------------------
+std::atomic<long long> g_scan_impl{GULON_SCAN_AUTO};
+std::atomic<long long> g_query_batch{0};      // 0 = auto (multiple of 16 * #SM)
+std::atomic<long long> g_simple_scratch{1LL << 30};
+std::atomic<long long> g_encode_chunk{1 << 20};  // rows per H2D chunk in gulon_pq_encode
+std::atomic<long long> g_fused_min_rows{16384};
+
+int need_device() {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    return fail(GULON_ENODEVICE,
+                "no CUDA device visible (%s): libgulon_b200 has no CPU fallback",
+                e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  }
+  return GULON_OK;
+}
+
+int sm_count() {
+  static thread_local int cached_dev = -1, cached = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev != cached_dev) {
+    int n = 148;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    cached = n;
+    cached_dev = dev;
+  }
+  return cached;
+}
+
+// ---- java.util.Random (JDK javadoc algorithm) -- seeds KMeans.init, G/KMeans.scala:188-196 ----
+struct JRandom {
+  uint64_t s;
+  explicit JRandom(int64_t seed) : s(((uint64_t)seed ^ 0x5DEECE66DULL) & ((1ULL << 48) - 1)) {}
+  int32_t next(int bits) {
+    s = (s * 0x5DEECE66DULL + 0xBULL) & ((1ULL << 48) - 1);
+    return (int32_t)(int64_t)(s >> (48 - bits));
+  }
+  int32_t next_int(int32_t bound) {
+    int32_t r = next(31);
+    const int32_t m = bound - 1;
+    if ((bound & m) == 0) return (int32_t)(((int64_t)bound * (int64_t)r) >> 31);
+    for (int32_t u = r;; u = next(31)) {
+      r = u % bound;
+      if ((int32_t)((uint32_t)u - (uint32_t)r + (uint32_t)m) >= 0) return r;
+    }
+  }
+};
+
+int split_rule(int D, int M, int32_t *from, int32_t *dim) {
+  const int ideal = (D + M - 1) / M;
+  const int full = M - (ideal * M - D);
+  for (int i = 0; i < M; i++) {
+    if (i < full) {
+      from[i] = i * ideal;
+      dim[i] = ideal;
+    } else {
+      from[i] = full * ideal + (i - full) * (ideal - 1);
+      dim[i] = ideal - 1;
+    }
+  }
+  return ideal;
+}
+
+template <typename T>
+int upload(DevBuf &b, const std::vector<T> &v, cudaStream_t st) {
+  GCHECK(b.ensure(std::max<size_t>(v.size(), 1) * sizeof(T)));
+  if (!v.empty()) {
+    GCU(cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+    GCU(cudaStreamSynchronize(st));  // v may be a temporary
+  }
+  return GULON_OK;
+}
+
+// ---- assignment launchers -------------------------------------------------------------------
+template <int DIM, typename OutT>
+int launch_assign_dim(const float *dX, i64 N, i64 ld, const float *cb, const float *off, int K,
+                      int dmax, const int32_t *dsubs, int nsub, const int32_t *dfrom, OutT *out,
+                      i64 out_stride, cudaStream_t st) {
+  constexpr int DP = (DIM + 3) & ~3;
+  int KC = K;
+  const int kc_max = (46 * 1024) / (4 * (DP + 1));
+  if (KC > kc_max) KC = kc_max;
+  const size_t smem = (size_t)KC * (DP + 1) * sizeof(float);
+  dim3 grid((unsigned)ceil_div(N, ASSIGN_TILE), (unsigned)nsub);
+  auto kern = assign_exact_kernel<DIM, OutT>;
+  GLAUNCH(kern, grid, ASSIGN_NT, smem, st, dX, N, ld, cb, off, K, dmax, dsubs, dfrom, out,
+          out_stride, KC);
+  return GULON_OK;
+}
+
+// One launch for `nsub` sub-quantizers that share the window width `dim`.
+template <typename OutT>
+int launch_assign(const float *dX, i64 N, i64 ld, const float *cb, const float *off, int K,
+                  int dmax, const int32_t *dsubs, int nsub, const int32_t *dfrom,
+                  const int32_t *ddim, int dim, OutT *out, i64 out_stride, cudaStream_t st) {
+  if (N <= 0 || nsub <= 0) return GULON_OK;
+  GREQUIRE(nsub <= 65535, "too many sub-quantizers in one launch (%d)", nsub);
+  switch (dim) {
+#define GULON_CASE(DD)                                                                           \
+  case DD:                                                                                       \
+    return launch_assign_dim<DD, OutT>(dX, N, ld, cb, off, K, dmax, dsubs, nsub, dfrom, out,     \
+                                       out_stride, st);
+    GULON_CASE(1) GULON_CASE(2) GULON_CASE(3) GULON_CASE(4) GULON_CASE(5) GULON_CASE(6)
+    GULON_CASE(7) GULON_CASE(8) GULON_CASE(9) GULON_CASE(10) GULON_CASE(11) GULON_CASE(12)
+    GULON_CASE(13) GULON_CASE(14) GULON_CASE(15) GULON_CASE(16)
+#undef GULON_CASE
+    default:
+      break;
+  }
+  const size_t smem = (size_t)AG_KB * dim * sizeof(float);
+  GREQUIRE(smem <= 200 * 1024, "window width %d too large for the generic assignment kernel", dim);
+  auto kern = assign_generic_kernel<OutT>;
+  static std::once_flag once;  // one per OutT instantiation
+  std::call_once(once, [&] {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  });
+  dim3 grid((unsigned)ceil_div(N, 128), (unsigned)nsub);
+  GLAUNCH(kern, grid, 128, smem, st, dX, N, ld, cb, off, K, dmax, dsubs, dfrom, ddim, out,
+          out_stride);
+  return GULON_OK;
+}
+
+// ---- a set of k-means problems over column windows of one matrix ---------------------------
+// Shared by gulon_kmeans_* (one window) and gulon_pq_train (M windows, G/ProductQuantizer.scala:121-148).
+struct Problems {
+  int n = 0, K = 0, dmax = 0;
+  std::vector<int32_t> from, dim;
+  DevBuf cb, off, dfrom, ddim, dsubs, diff, sums, counts, part_sum, part_cnt, tile_hist, base,
+      order, rows;
+  ~Problems() {
+    cb.release(); off.release(); dfrom.release(); ddim.release(); dsubs.release(); diff.release();
+    sums.release(); counts.release(); part_sum.release(); part_cnt.release();
+    tile_hist.release(); base.release(); order.release(); rows.release();
+  }
+  int setup(int n_, int K_, const int32_t *from_, const int32_t *dim_, cudaStream_t st) {
+    n = n_;
+    K = K_;
+    from.assign(from_, from_ + n);
+    dim.assign(dim_, dim_ + n);
+    dmax = 1;
+    for (int d : dim) dmax = std::max(dmax, d);
+    GCHECK(upload(dfrom, from, st));
+    GCHECK(upload(ddim, dim, st));
+    GCHECK(cb.ensure((size_t)n * K * dmax * sizeof(float)));
+    GCHECK(off.ensure((size_t)n * K * sizeof(float)));
+    GCHECK(diff.ensure((size_t)n * sizeof(int32_t)));
+    GCHECK(counts.ensure((size_t)n * K * sizeof(int32_t)));
+    GCHECK(dsubs.ensure((size_t)n * sizeof(int32_t)));
+    GCU(cudaMemsetAsync(cb.p, 0, (size_t)n * K * dmax * sizeof(float), st));
+    return GULON_OK;
+  }
+  int offsets(cudaStream_t st) {
+    const i64 t = (i64)n * K;
+    GLAUNCH(offsets_kernel, (unsigned)ceil_div(t, 256), 256, 0, st, cb.as<float>(),
+            ddim.as<int32_t>(), n, K, dmax, off.as<float>());
+    return GULON_OK;
+  }
+  // subs: host list of problem indices to process; grouped by width, one launch per width.
+  template <typename F>
+  int for_each_width(const std::vector<int32_t> &subs, cudaStream_t st, F f) {
+    std::map<int, std::vector<int32_t>> groups;
+    for (int32_t s : subs) groups[dim[s]].push_back(s);
+    size_t at = 0;
+    std::vector<int32_t> flat;
+    for (auto &kv : groups) flat.insert(flat.end(), kv.second.begin(), kv.second.end());
+    if (flat.empty()) return GULON_OK;
+    GCU(cudaMemcpyAsync(dsubs.p, flat.data(), flat.size() * sizeof(int32_t),
+                        cudaMemcpyHostToDevice, st));
+    GCU(cudaStreamSynchronize(st));
+    for (auto &kv : groups) {
+      GCHECK(f(kv.first, dsubs.as<int32_t>() + at, (int)kv.second.size()));
+      at += kv.second.size();
+    }
+    return GULON_OK;
+  }
+  int assign(const float *dX, i64 N, i64 ld, const std::vector<int32_t> &subs, int32_t *out,
+             i64 out_stride, cudaStream_t st) {
+    return for_each_width(subs, st, [&](int w, const int32_t *ds, int ns) {
+      return launch_assign<int32_t>(dX, N, ld, cb.as<float>(), off.as<float>(), K, dmax, ds, ns,
+                                    dfrom.as<int32_t>(), ddim.as<int32_t>(), w, out, out_stride, st);
+    });
+  }
+  // local per-cluster sums / counts (GULON_UPDATE_SUM); the caller all-reduces and finalises
+  int partial_sums(const float *dX, i64 N, i64 ld, const int32_t *assign, i64 astride,
+                   const std::vector<int32_t> &subs, cudaStream_t st) {
+    GCHECK(sums.ensure((size_t)n * K * dmax * sizeof(float)));
+    return for_each_width(subs, st, [&](int w, const int32_t *ds, int ns) -> int {
+      int W = 8;
+      auto need = [&](int ww) { return (size_t)ww * K * (w + 1) * 4; };
+      while (W > 1 && need(W) > 96 * 1024) W >>= 1;
+      GREQUIRE(need(W) <= 200 * 1024,
+               "K=%d x width=%d does not fit the shared-memory segmented sum; use "
+               "GULON_UPDATE_RUNNING_MEAN", K, w);
+      static std::once_flag once;
+      std::call_once(once, [] {
+        cudaFuncSetAttribute(update_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             200 * 1024);
+      });
+      int B = (int)std::max<i64>(1, std::min<i64>(ceil_div(296, ns), ceil_div(N, 2048)));
+      GCHECK(part_sum.ensure((size_t)ns * B * K * dmax * sizeof(float)));
+      GCHECK(part_cnt.ensure((size_t)ns * B * K * sizeof(int32_t)));
+      dim3 grid((unsigned)B, (unsigned)ns);
+      GLAUNCH(update_partial_kernel, grid, 32 * W, need(W), st, dX, N, ld, assign, astride, ds,
+              dfrom.as<int32_t>(), ddim.as<int32_t>(), K, dmax, part_sum.as<float>(),
+              part_cnt.as<int32_t>());
+      dim3 g2((unsigned)K, (unsigned)ns);
+      int bt = 32;
+      while (bt < w) bt <<= 1;
+      GLAUNCH(update_reduce_kernel, g2, bt, 0, st, part_sum.as<float>(), part_cnt.as<int32_t>(), B,
+              ds, ddim.as<int32_t>(), K, dmax, sums.as<float>(), counts.as<int32_t>());
+      return GULON_OK;
+    });
+  }
+  int finalize(const int32_t *d_active, cudaStream_t st) {
+    const i64 t = (i64)n * K * dmax;
+    GLAUNCH(update_finalize_kernel, (unsigned)ceil_div(t, 256), 256, 0, st, sums.as<float>(),
+            counts.as<int32_t>(), d_active, n, K, dmax, cb.as<float>());
+    return GULON_OK;
+  }
+  // literal running mean (GULON_UPDATE_RUNNING_MEAN): stable grouping by cluster, then one
+  // thread per (cluster, dimension) replays c <- p + (x - p) / n in row order.
+  int running_mean(const float *dX, i64 N, i64 ld, const int32_t *assign, i64 astride,
+                   const std::vector<int32_t> &subs, cudaStream_t st) {
+    GREQUIRE(N < (1LL << 31), "N too large for the running-mean update");
+    const int tiles = (int)std::max<i64>(1, ceil_div(N, RM_TILE));
+    GREQUIRE((size_t)4 * K * sizeof(int) <= 200 * 1024, "K=%d too large for the running-mean update", K);
+    static std::once_flag once;
+    std::call_once(once, [] {
+      cudaFuncSetAttribute(rm_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      cudaFuncSetAttribute(rm_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    });
+    return for_each_width(subs, st, [&](int w, const int32_t *ds, int ns) -> int {
+      GCHECK(tile_hist.ensure((size_t)ns * tiles * K * sizeof(int32_t)));
+      GCHECK(base.ensure((size_t)ns * K * sizeof(int32_t)));
+      GCHECK(part_cnt.ensure((size_t)ns * K * sizeof(int32_t)));
+      GCHECK(order.ensure((size_t)ns * std::max<i64>(N, 1) * sizeof(int32_t)));
+      dim3 g1((unsigned)tiles, (unsigned)ns);
+      GLAUNCH(rm_hist_kernel, g1, 256, (size_t)K * sizeof(int), st, assign, astride, N, ds, K,
+              tile_hist.as<int32_t>());
+      GLAUNCH(rm_scan_kernel, (unsigned)ns, 256, 0, st, tile_hist.as<int32_t>(), tiles, K,
+              part_cnt.as<int32_t>(), base.as<int32_t>());
+      dim3 g3((unsigned)ceil_div(tiles, 4), (unsigned)ns);
+      GLAUNCH(rm_scatter_kernel, g3, 128, (size_t)4 * K * sizeof(int), st, assign, astride, N, ds, K,
+              tiles, tile_hist.as<int32_t>(), base.as<int32_t>(), order.as<int32_t>(), N);
+      dim3 g4((unsigned)ceil_div((i64)K * w, 128), (unsigned)ns);
+      GLAUNCH(rm_chain_kernel, g4, 128, 0, st, dX, ld, ds, dfrom.as<int32_t>(), ddim.as<int32_t>(),
+              K, dmax, order.as<int32_t>(), N, part_cnt.as<int32_t>(), base.as<int32_t>(),
+              cb.as<float>());
+      // counts[sub][k] for callers that want them
+      GLAUNCH(scatter_counts_kernel, (unsigned)ceil_div((i64)ns * K, 256), 256, 0, st,
+              part_cnt.as<int32_t>(), ds, ns, K, counts.as<int32_t>());
+      return GULON_OK;
+    });
+  }
+};
+
+// SummaryStatsBuilder over MathUtils.distance of centroid pairs: KMeans.stepSize,
+// G/KMeans.scala:160-168 with G/MathUtils.scala:46-57,85-98 (host side, fp32 as the reference).
+void step_size(const float *prev, const float *next, int K, int dim, int ldc, float *mean,
+               float *stddev) {
+  volatile float m = 0.0f, s = 0.0f;
+  int n = 0;
+  for (int i = 0; i < K; i++) {
+    volatile float sum = 0.0f;
+    for (int j = 0; j < dim; j++) {
+      volatile float dx = next[(i64)i * ldc + j] - prev[(i64)i * ldc + j];
+      volatile float sq = dx * dx;
+      sum = sum + sq;
+    }
+    const float x = (float)sqrt((double)sum);
+    n += 1;
+    const float m0 = m;
+    volatile float t = (x - m0) / (float)n;
+    m = m0 + t;
+    volatile float a = x - m0, b = x - m;
+    volatile float ab = a * b;
+    s = s + ab;
+  }
+  *mean = m;
+  *stddev = n > 0 ? (float)sqrt((double)(s / (float)n)) : 0.0f;
+}
+
+// The driver loop of KMeans.computeClusters for `pr.n` windows at once; every window keeps its own
+// iteration counter and convergence flag exactly as an independent computeClusters call would.
+int train_problems(Problems &pr, gulon_points_t p, const int32_t *seeds, int max_iter,
+                   int update_mode, const gulon_comm_t *comm, i64 n_total, i64 row_offset,
+                   gulon_progress_fn report, void *user, int quantizer_base, int32_t *n_updates,
+                   int32_t *converged, cudaStream_t st) {
+  const int n = pr.n, K = pr.K, dmax = pr.dmax;
+  const i64 N = p->N;
+  const bool sharded = comm && comm->world > 1;
+  if (!sharded) {
+    n_total = N;
+    row_offset = 0;
+  }
+  GREQUIRE(n_total >= 1 && n_total < (1LL << 31), "k-means needs 1 <= N < 2^31 rows (N=%lld)",
+           (long long)n_total);
+  GREQUIRE(!sharded || update_mode == GULON_UPDATE_SUM,
+           "sharded k-means requires GULON_UPDATE_SUM (the running mean is order-dependent)");
+  GREQUIRE(max_iter >= 0, "max_iter must be >= 0");
+
+  // KMeans.init: K global rows sampled with replacement, one Random(seed) per window
+  std::vector<i64> rows((size_t)n * K);
+  for (int s = 0; s < n; s++) {
+    JRandom rng((int64_t)seeds[s]);
+    for (int k = 0; k < K; k++) rows[(size_t)s * K + k] = rng.next_int((int32_t)n_total);
+  }
+  GCHECK(upload(pr.rows, rows, st));
+  for (int s = 0; s < n; s++) {
+    GLAUNCH(gather_rows_kernel, (unsigned)K, 32, 0, st, p->d, p->ld, pr.from[s], pr.dim[s],
+            pr.rows.as<i64>() + (size_t)s * K, row_offset, N,
+            pr.cb.as<float>() + (size_t)s * K * dmax, dmax);
+  }
+  if (sharded) {
+    // rows live on exactly one rank; the others contributed zeros
+    GREQUIRE(comm->allreduce_sum_f32(comm->user, pr.cb.as<float>(), (i64)n * K * dmax, st) == 0,
+             "allreduce_sum_f32 hook failed");
+  }
+  GCHECK(pr.offsets(st));
+
+  DevBuf a_prev, a_next, d_active;
+  struct Guard {
+    DevBuf &a, &b, &c;
+    ~Guard() { a.release(); b.release(); c.release(); }
+  } guard{a_prev, a_next, d_active};
+  const i64 astride = std::max<i64>(N, 1);
+  GCHECK(a_prev.ensure((size_t)n * astride * sizeof(int32_t)));
+  GCHECK(a_next.ensure((size_t)n * astride * sizeof(int32_t)));
+  GCHECK(d_active.ensure((size_t)n * sizeof(int32_t)));
+
+  std::vector<int32_t> active(n);
+  for (int s = 0; s < n; s++) active[s] = s;
+  GCHECK(pr.assign(p->d, N, p->ld, active, a_prev.as<int32_t>(), astride, st));
+
+  std::vector<float> h_prev, h_next;
+  if (report) {
+    h_prev.resize((size_t)n * K * dmax);
+    h_next.resize((size_t)n * K * dmax);
+    GCU(cudaMemcpyAsync(h_prev.data(), pr.cb.p, h_prev.size() * sizeof(float),
+                        cudaMemcpyDeviceToHost, st));
+    GCU(cudaStreamSynchronize(st));
+    for (int s = 0; s < n; s++) {
+      gulon_progress_t r = {quantizer_base + s, 0, max_iter, 0.0f, 0.0f, 0};
+      report(user, &r);
+    }
+  }
+
+  std::vector<int32_t> iter(n, 0), conv(n, 0), upd(n, 0), mask(n), h_diff(n);
+  while (!active.empty()) {
+    for (int s = 0; s < n; s++) mask[s] = 0;
+    for (int32_t s : active) mask[s] = 1;
+    GCU(cudaMemcpyAsync(d_active.p, mask.data(), (size_t)n * sizeof(int32_t),
+                        cudaMemcpyHostToDevice, st));
+    // next = fromAssignment(prevAssignments)
+    if (update_mode == GULON_UPDATE_RUNNING_MEAN) {
+      GCHECK(pr.running_mean(p->d, N, p->ld, a_prev.as<int32_t>(), astride, active, st));
+    } else {
+      GCHECK(pr.partial_sums(p->d, N, p->ld, a_prev.as<int32_t>(), astride, active, st));
+      if (sharded) {
+        GREQUIRE(comm->allreduce_sum_f32(comm->user, pr.sums.as<float>(), (i64)n * K * dmax, st) == 0,
+                 "allreduce_sum_f32 hook failed");
+        GREQUIRE(comm->allreduce_sum_i32(comm->user, pr.counts.as<int32_t>(), (i64)n * K, st) == 0,
+                 "allreduce_sum_i32 hook failed");
+      }
+      GCHECK(pr.finalize(d_active.as<int32_t>(), st));
+    }
+    GCHECK(pr.offsets(st));
+    // assignments = next.parAssign(vecs); converged = Arrays.equals(prev, assignments)
+    GCHECK(pr.assign(p->d, N, p->ld, active, a_next.as<int32_t>(), astride, st));
+    GCU(cudaMemsetAsync(pr.diff.p, 0, (size_t)n * sizeof(int32_t), st));
+    if (N > 0) {
+      GCHECK(pr.for_each_width(active, st, [&](int, const int32_t *ds, int ns) -> int {
+        dim3 grid((unsigned)std::min<i64>(ceil_div(N, 1024), 1184), (unsigned)ns);
+        GLAUNCH(count_diff_kernel, grid, 256, 0, st, a_prev.as<int32_t>(), a_next.as<int32_t>(), N,
+                astride, ds, pr.diff.as<int32_t>());
+        return GULON_OK;
+      }));
+    }
+    if (sharded) {
+      GREQUIRE(comm->allreduce_sum_i32(comm->user, pr.diff.as<int32_t>(), (i64)n, st) == 0,
+               "allreduce_sum_i32 hook failed");
+    }
+    GCU(cudaMemcpyAsync(h_diff.data(), pr.diff.p, (size_t)n * sizeof(int32_t),
+                        cudaMemcpyDeviceToHost, st));
+    if (report)
+      GCU(cudaMemcpyAsync(h_next.data(), pr.cb.p, h_next.size() * sizeof(float),
+                          cudaMemcpyDeviceToHost, st));
+    GCU(cudaStreamSynchronize(st));
+    // carry the new assignments of the active windows forward (inactive windows are frozen)
+    std::vector<int32_t> still;
+    for (int32_t s : active) {
+      GCU(cudaMemcpyAsync(a_prev.as<int32_t>() + (size_t)s * astride,
+                          a_next.as<int32_t>() + (size_t)s * astride, (size_t)N * sizeof(int32_t),
+                          cudaMemcpyDeviceToDevice, st));
+      const int c = h_diff[s] == 0;
+      upd[s] += 1;
+      conv[s] = c;
+      if (report) {
+        gulon_progress_t r = {quantizer_base + s, iter[s], max_iter, 0.0f, 0.0f, c};
+        step_size(h_prev.data() + (size_t)s * K * dmax, h_next.data() + (size_t)s * K * dmax, K,
+                  pr.dim[s], dmax, &r.step_mean, &r.step_stddev);
+        report(user, &r);
+        memcpy(h_prev.data() + (size_t)s * K * dmax, h_next.data() + (size_t)s * K * dmax,
+               (size_t)K * dmax * sizeof(float));
+      }
+      iter[s] = c ? max_iter + 1 : iter[s] + 1;
+      if (iter[s] <= max_iter) still.push_back(s);
+    }
+    active.swap(still);
+  }
+  GCU(cudaStreamSynchronize(st));
+  for (int s = 0; s < n; s++) {
+    if (n_updates) n_updates[s] = upd[s];
+    if (converged) converged[s] = conv[s];
+  }
+  return GULON_OK;
+}
+
+int make_codebook(int D, int M, int K, gulon_codebook_t *out) {
+  GREQUIRE(D >= 1 && M >= 1 && K >= 1, "codebook needs D, M, K >= 1 (D=%d M=%d K=%d)", D, M, K);
+  GREQUIRE(M <= D, "more quantizers (%d) than dimensions (%d)", M, D);
+  std::unique_ptr<gulon_codebook_s> cb(new gulon_codebook_s);
+  cb->D = D;
+  cb->M = M;
+  cb->K = K;
+  cb->from.resize(M);
+  cb->dim.resize(M);
+  cb->dmax = split_rule(D, M, cb->from.data(), cb->dim.data());
+  GCHECK(upload(cb->dfrom, cb->from, 0));
+  GCHECK(upload(cb->ddim, cb->dim, 0));
+  for (int m = 0; m < M; m++) cb->by_dim[cb->dim[m]].push_back(m);
+  for (auto &kv : cb->by_dim) GCHECK(upload(cb->d_by_dim[kv.first], kv.second, 0));
+  GCHECK(cb->cb.ensure((size_t)M * K * cb->dmax * sizeof(float)));
+  GCHECK(cb->off.ensure((size_t)M * K * sizeof(float)));
+  *out = cb.release();
+  return GULON_OK;
+}
+
+int codebook_offsets(gulon_codebook_t cb, cudaStream_t st) {
+  const i64 t = (i64)cb->M * cb->K;
+  GLAUNCH(offsets_kernel, (unsigned)ceil_div(t, 256), 256, 0, st, cb->cb.as<float>(),
+          cb->ddim.as<int32_t>(), cb->M, cb->K, cb->dmax, cb->off.as<float>());
+  return GULON_OK;
+}
+
+int encode_dev(gulon_codebook_t cb, const float *dX, i64 N, i64 ld, uint8_t *dcodes, i64 ps,
+               cudaStream_t st) {
+  for (auto &kv : cb->by_dim) {
+    GCHECK(launch_assign<uint8_t>(dX, N, ld, cb->cb.as<float>(), cb->off.as<float>(), cb->K,
+                                  cb->dmax, cb->d_by_dim[kv.first].as<int32_t>(),
+                                  (int)kv.second.size(), cb->dfrom.as<int32_t>(),
+                                  cb->ddim.as<int32_t>(), kv.first, dcodes, ps, st));
+  }
+  return GULON_OK;
+}
+
+int normalize_dev(const float *dX, i64 N, int D, i64 ld, float *out, i64 ldo, cudaStream_t st) {
+  if (N <= 0) return GULON_OK;
+  GLAUNCH(normalize_rows_kernel, (unsigned)ceil_div(N, 128), 128, 0, st, dX, N, D, ld, out, ldo);
+  return GULON_OK;
+}
+
+int unpack(const u64 *keys, i64 stride, i64 rows, int k, i64 id_offset, int32_t *ids, float *dists,
+           int32_t *sizes, cudaStream_t st) {
+  if (rows <= 0) return GULON_OK;
+  dim3 block(32, 8);
+  GLAUNCH(unpack_keys_kernel, (unsigned)ceil_div(rows, 8), block, 0, st, keys, stride, rows, k,
+          id_offset, ids, dists, sizes);
+  return GULON_OK;
+}
+
+int fill_empty(i64 nq, int k, int32_t *ids, float *dists, int32_t *sizes, cudaStream_t st) {
+  if (nq <= 0) return GULON_OK;
+  GLAUNCH(fill_empty_kernel, (unsigned)ceil_div(nq * std::max(k, 1), 256), 256, 0, st, nq, k, ids,
+          dists, sizes);
+  return GULON_OK;
+}
+
+// One batch of queries (device, already normalised if the metric asks for it) over [from, until).
+// Caller holds ix->mu.
+int scan_batch(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 from, i64 until,
+               i64 id_offset, int32_t *d_ids, float *d_dists, int32_t *d_sizes, cudaStream_t st) {
+  gulon_codebook_t cb = ix->cb;
+  const int M = cb->M, K = cb->K;
+  const int G = (int)ceil_div(nq, 4), Q4 = G * 4;
+  const i64 range = until - from;
+  GCHECK(ix->lutI.ensure((size_t)G * M * 256 * sizeof(float4)));
+  dim3 lg((unsigned)G, (unsigned)M);
+  GLAUNCH(lut_build_kernel, lg, 256, 0, st, dQ, ldq, nq, cb->cb.as<float>(),
+          cb->dfrom.as<int32_t>(), cb->ddim.as<int32_t>(), M, K, cb->dmax, ix->lutI.as<float4>());
+
+  long long impl = g_scan_impl.load();
+  if (impl == GULON_SCAN_AUTO)
+    impl = (k <= fscan::KMAX && range >= g_fused_min_rows.load()) ? GULON_SCAN_FUSED
+                                                                   : GULON_SCAN_SIMPLE;
+  if (impl == GULON_SCAN_FUSED) {
+    GREQUIRE(k <= fscan::KMAX, "fused scan supports k <= %d (k=%d)", fscan::KMAX, k);
+    static std::once_flag once;
+    std::call_once(once, [] {
+      cudaFuncSetAttribute(fscan::fused_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           fscan::SMEM_BYTES);
+    });
+    const int nsm = sm_count();
+    int Bs = std::min(G, nsm);
+    int S = std::max(1, nsm / Bs);
+    // every split should hold at least a few items; boundaries are multiples of 16 rows
+    S = (int)std::max<i64>(1, std::min<i64>(S, range / (2 * fscan::R)));
+    i64 split_len = round_up(ceil_div(range, S), 16);
+    S = (int)ceil_div(range, split_len);
+    const size_t nl = (size_t)S * Q4 * k;
+    GCHECK(ix->lists.ensure(nl * sizeof(u64)));
+    GCU(cudaMemsetAsync(ix->lists.p, 0xFF, nl * sizeof(u64), st));
+    fscan::Params prm;
+    prm.codes = ix->codes;
+    prm.ps = ix->ps;
+    prm.from = from;
+    prm.until = until;
+    prm.split_len = split_len;
+    prm.boot = 0;
+    prm.lutI = ix->lutI.as<float4>();
+    prm.M = M;
+    prm.G = G;
+    prm.k = k;
+    prm.S = S;
+    prm.Bs = Bs;
+    prm.lists = ix->lists.as<u64>();
+    GLAUNCH(fscan::fused_scan_kernel, (unsigned)(S * Bs), fscan::NT, fscan::SMEM_BYTES, st, prm);
+    if (S == 1) return unpack(ix->lists.as<u64>(), k, nq, k, id_offset, d_ids, d_dists, d_sizes, st);
+    const i64 stride = round_up((i64)S * k, SEL_CHUNK);
+    GCHECK(ix->merged.ensure((size_t)Q4 * stride * sizeof(u64)));
+    dim3 gg((unsigned)ceil_div(stride, 256), (unsigned)Q4);
+    GLAUNCH(gather_lists_kernel, gg, 256, 0, st, ix->lists.as<u64>(), S, (i64)Q4, k,
+            ix->merged.as<u64>(), stride);
+    u64 *res;
+    i64 rs;
+    GCHECK(ix->sel.run(ix->merged.as<u64>(), stride, Q4, k, st, &res, &rs));
+    return unpack(res, rs, nq, k, id_offset, d_ids, d_dists, d_sizes, st);
+  }
+
+  // simple path: materialise keys for a few query groups at a time, select
+  const i64 n_pad = round_up(range, SEL_CHUNK);
+  i64 qb = g_simple_scratch.load() / (8 * n_pad);
+  qb = std::max<i64>(4, qb & ~3LL);
+  qb = std::min<i64>(qb, Q4);
+  GCHECK(ix->keys.ensure((size_t)qb * n_pad * sizeof(u64)));
+  for (i64 q0 = 0; q0 < nq; q0 += qb) {
+    const i64 nb = std::min<i64>(qb, Q4 - q0);       // padded queries in this pass
+    const i64 nreal = std::min<i64>(qb, nq - q0);
+    for (i64 y0 = 0; y0 < nb; y0 += 32768) {
+      dim3 grid((unsigned)(n_pad / 256), (unsigned)std::min<i64>(32768, nb - y0), 1);
+      GLAUNCH(adc_keys_kernel, grid, 256, 0, st, ix->codes, ix->ps, from, until, range, range,
+              ix->lutI.as<float4>() + (size_t)((q0 + y0) / 4) * M * 256, M, (int)nb,
+              ix->keys.as<u64>() + (size_t)y0 * n_pad, n_pad);
+    }
+    u64 *res;
+    i64 rs;
+    GCHECK(ix->sel.run(ix->keys.as<u64>(), n_pad, nb, k, st, &res, &rs));
+    GCHECK(unpack(res, rs, nreal, k, id_offset, d_ids + q0 * k, d_dists + q0 * k,
+                  d_sizes ? d_sizes + q0 : nullptr, st));
+  }
+  return GULON_OK;
+}
+
+int query_dev(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 from, i64 until,
+              int normalize, i64 id_offset, int32_t *d_ids, float *d_dists, int32_t *d_sizes,
+              cudaStream_t st) {
+  GREQUIRE(from <= until, "expected: from <= until (from=%lld until=%lld)", (long long)from,
+           (long long)until);
+  GREQUIRE(from >= 0 && until <= ix->N, "expected: from >= 0 && until <= length (until=%lld N=%lld)",
+           (long long)until, (long long)ix->N);
+  GREQUIRE(k >= 0, "k must be >= 0");
+  GREQUIRE(ldq >= ix->cb->D, "query leading dimension %lld < dimension %d", (long long)ldq,
+           ix->cb->D);
+  if (nq <= 0) return GULON_OK;
+  if (k == 0 || until == from) return fill_empty(nq, k, d_ids, d_dists, d_sizes, st);
+  std::lock_guard<std::mutex> lock(ix->mu);
+  const int D = ix->cb->D;
+  i64 qb = g_query_batch.load();
+  if (qb <= 0) qb = (i64)sm_count() * 16;
+  qb = round_up(qb, 4);
+  for (i64 q0 = 0; q0 < nq; q0 += qb) {
+    const i64 nb = std::min<i64>(qb, nq - q0);
+    const float *q = dQ + q0 * ldq;
+    i64 ql = ldq;
+    if (normalize) {
+      GCHECK(ix->qbuf.ensure((size_t)nb * D * sizeof(float)));
+      GCHECK(normalize_dev(q, nb, D, ldq, ix->qbuf.as<float>(), D, st));
+      q = ix->qbuf.as<float>();
+      ql = D;
+    }
+    GCHECK(scan_batch(ix, q, nb, ql, k, from, until, id_offset, d_ids + q0 * k, d_dists + q0 * k,
+                      d_sizes ? d_sizes + q0 : nullptr, st));
+  }
+  return GULON_OK;
+}
+
+}  // namespace
+
+// ============================================================================================
+extern "C" {
+
+int gulon_version(void) { return GULON_VERSION; }
+const char *gulon_last_error(void) { return err_slot().c_str(); }
+
+int gulon_device_count(int32_t *n) {
+  GREQUIRE(n, "null argument");
+  int c = 0;
+  if (cudaGetDeviceCount(&c) != cudaSuccess) {
+    cudaGetLastError();
+    c = 0;
+  }
+  *n = c;
+  return GULON_OK;
+}
+int gulon_set_device(int32_t device) {
+  GCHECK(need_device());
+  GCU(cudaSetDevice(device));
+  return GULON_OK;
+}
+int gulon_get_device(int32_t *device) {
+  GREQUIRE(device, "null argument");
+  GCHECK(need_device());
+  int d = 0;
+  GCU(cudaGetDevice(&d));
+  *device = d;
+  return GULON_OK;
+}
+int gulon_device_sync(void) {
+  GCHECK(need_device());
+  GCU(cudaDeviceSynchronize());
+  return GULON_OK;
+}
+
+int gulon_set_option(const char *name, int64_t value) {
+  GREQUIRE(name, "null option name");
+  std::string s(name);
+  if (s == "scan_impl") {
+    GREQUIRE(value >= GULON_SCAN_AUTO && value <= GULON_SCAN_FUSED, "scan_impl must be 0, 1 or 2");
+    g_scan_impl = value;
+  } else if (s == "query_batch") {
+    GREQUIRE(value >= 0, "query_batch must be >= 0");
+    g_query_batch = value;
+  } else if (s == "simple_scratch_bytes") {
+    GREQUIRE(value >= (1 << 20), "simple_scratch_bytes must be >= 1 MiB");
+    g_simple_scratch = value;
+  } else if (s == "encode_chunk_rows") {
+    GREQUIRE(value >= 1, "encode_chunk_rows must be >= 1");
+    g_encode_chunk = value;
+  } else if (s == "fused_min_rows") {
+    GREQUIRE(value >= 0, "fused_min_rows must be >= 0");
+    g_fused_min_rows = value;
+  } else {
+    return fail(GULON_EINVAL, "unknown option '%s'", name);
+  }
+  return GULON_OK;
+}
+
+int gulon_get_counter(const char *name, int64_t *value) {
+  GREQUIRE(name && value, "null argument");
+  if (std::string(name) == "kernel_launches") {
+    *value = launch_counter().load();
+    return GULON_OK;
+  }
+  return fail(GULON_EINVAL, "unknown counter '%s'", name);
+}
+
+int gulon_subvectors(int32_t D, int32_t M, int32_t *from, int32_t *dim) {
+  GREQUIRE(from && dim, "null argument");
+  GREQUIRE(M >= 1 && D >= 0, "subvectors needs M >= 1 and D >= 0 (D=%d M=%d)", D, M);
+  return split_rule(D, M, from, dim);
+}
+
+// ---- Matrix ---------------------------------------------------------------------------------
+int gulon_points_create(const float *X, int64_t N, int32_t D, int64_t ld, gulon_points_t *out) {
+  GREQUIRE(out, "null argument");
+  GREQUIRE(N >= 0 && D >= 1 && ld >= D, "bad matrix shape N=%lld D=%d ld=%lld", (long long)N, D,
+           (long long)ld);
+  GREQUIRE(X || N == 0, "null matrix");
+  GCHECK(need_device());
+  std::unique_ptr<gulon_points_s> p(new gulon_points_s);
+  p->N = N;
+  p->D = D;
+  p->ld = D;
+  p->owned = true;
+  if (N > 0) {
+    cudaError_t e = cudaMalloc(&p->d, (size_t)N * D * sizeof(float));
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return fail(GULON_ENOMEM, "cudaMalloc(%zu bytes) failed: %s", (size_t)N * D * sizeof(float),
+                  cudaGetErrorString(e));
+    }
+    e = cudaMemcpy2D(p->d, (size_t)D * 4, X, (size_t)ld * 4, (size_t)D * 4, (size_t)N,
+                     cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+      cudaFree(p->d);
+      return fail(GULON_ECUDA, "cudaMemcpy2D failed: %s", cudaGetErrorString(e));
+    }
+  }
+  *out = p.release();
+  return GULON_OK;
+}
+
+int gulon_points_wrap_dev(const float *dX, int64_t N, int32_t D, int64_t ld, gulon_points_t *out) {
+  GREQUIRE(out, "null argument");
+  GREQUIRE(N >= 0 && D >= 1 && ld >= D, "bad matrix shape N=%lld D=%d ld=%lld", (long long)N, D,
+           (long long)ld);
+  GREQUIRE(dX || N == 0, "null matrix");
+  GCHECK(need_device());
+  gulon_points_s *p = new gulon_points_s;
+  p->d = const_cast<float *>(dX);
+  p->N = N;
+  p->D = D;
+  p->ld = ld;
+  p->owned = false;
+  *out = p;
+  return GULON_OK;
+}
+
+int gulon_points_info(gulon_points_t p, int64_t *N, int32_t *D, int64_t *ld, const float **dptr) {
+  GREQUIRE(p, "null handle");
+  if (N) *N = p->N;
+  if (D) *D = p->D;
+  if (ld) *ld = p->ld;
+  if (dptr) *dptr = p->d;
+  return GULON_OK;
+}
+
+int gulon_points_destroy(gulon_points_t p) {
+  if (!p) return GULON_OK;
+  if (p->owned && p->d) cudaFree(p->d);
+  delete p;
+  return GULON_OK;
+}
+
+int gulon_points_normalize(gulon_points_t p) {
+  GREQUIRE(p, "null handle");
+  GCHECK(need_device());
+  GCHECK(normalize_dev(p->d, p->N, p->D, p->ld, p->d, p->ld, 0));
+  GCU(cudaStreamSynchronize(0));
+  return GULON_OK;
+}
+
+int gulon_normalize(const float *X, int64_t N, int32_t D, int64_t ld, float *out, int64_t ldo) {
+  GREQUIRE(out || N == 0, "null output");
+  GREQUIRE(ldo >= D, "output leading dimension %lld < D=%d", (long long)ldo, D);
+  gulon_points_t p = nullptr;
+  GCHECK(gulon_points_create(X, N, D, ld, &p));
+  int rc = gulon_points_normalize(p);
+  if (rc == GULON_OK && N > 0) {
+    cudaError_t e = cudaMemcpy2D(out, (size_t)ldo * 4, p->d, (size_t)p->ld * 4, (size_t)D * 4,
+                                 (size_t)N, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) rc = fail(GULON_ECUDA, "cudaMemcpy2D failed: %s", cudaGetErrorString(e));
+  }
+  gulon_points_destroy(p);
+  return rc;
+}
+
+// ---- KMeans ---------------------------------------------------------------------------------
+static int check_window(gulon_points_t p, int32_t from, int32_t dim, int32_t K) {
+  GREQUIRE(p, "null handle");
+  GREQUIRE(from >= 0 && dim >= 1 && (i64)from + dim <= p->D,
+           "column window [%d, %d) outside the matrix (D=%d)", from, from + dim, p->D);
+  GREQUIRE(K >= 1, "K must be >= 1 (K=%d)", K);
+  return GULON_OK;
+}
+
+int gulon_kmeans_assign(gulon_points_t p, int32_t from, int32_t dim, const float *C, int32_t K,
+                        int64_t batch, int32_t tie_mode, int32_t *out) {
+  GCHECK(check_window(p, from, dim, K));
+  GREQUIRE(C && (out || p->N == 0), "null argument");
+  GREQUIRE(tie_mode == GULON_TIE_LOWEST, "unsupported tie_mode %d (only GULON_TIE_LOWEST)", tie_mode);
+  GREQUIRE(batch >= 0, "batch must be >= 0");
+  GCHECK(need_device());
+  Problems pr;
+  GCHECK(pr.setup(1, K, &from, &dim, 0));
+  GCU(cudaMemcpy(pr.cb.p, C, (size_t)K * dim * sizeof(float), cudaMemcpyHostToDevice));
+  GCHECK(pr.offsets(0));
+  if (p->N == 0) return GULON_OK;
+  DevBuf a;
+  GCHECK(a.ensure((size_t)p->N * sizeof(int32_t)));
+  int rc = pr.assign(p->d, p->N, p->ld, {0}, a.as<int32_t>(), p->N, 0);
+  if (rc == GULON_OK) {
+    cudaError_t e = cudaMemcpy(out, a.p, (size_t)p->N * sizeof(int32_t), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) rc = fail(GULON_ECUDA, "cudaMemcpy failed: %s", cudaGetErrorString(e));
+  }
+  a.release();
+  return rc;
+}
+
+int gulon_kmeans_update(gulon_points_t p, int32_t from, int32_t dim, const int32_t *assign,
+                        int32_t K, int32_t update_mode, float *out_C, int32_t *out_counts) {
+  GCHECK(check_window(p, from, dim, K));
+  GREQUIRE((assign || p->N == 0) && out_C, "null argument");
+  GREQUIRE(update_mode == GULON_UPDATE_RUNNING_MEAN || update_mode == GULON_UPDATE_SUM,
+           "unknown update_mode %d", update_mode);
+  for (i64 i = 0; i < p->N; i++)
+    GREQUIRE(assign[i] >= 0 && assign[i] < K, "assignment %d at row %lld outside [0, %d)",
+             assign[i], (long long)i, K);
+  GCHECK(need_device());
+  Problems pr;
+  GCHECK(pr.setup(1, K, &from, &dim, 0));
+  DevBuf a;
+  GCHECK(a.ensure((size_t)std::max<i64>(p->N, 1) * sizeof(int32_t)));
+  int rc = GULON_OK;
+  if (p->N > 0) {
+    cudaError_t e = cudaMemcpy(a.p, assign, (size_t)p->N * sizeof(int32_t), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) rc = fail(GULON_ECUDA, "cudaMemcpy failed: %s", cudaGetErrorString(e));
+  }
+  if (rc == GULON_OK) {
+    if (update_mode == GULON_UPDATE_RUNNING_MEAN) {
+      rc = pr.running_mean(p->d, p->N, p->ld, a.as<int32_t>(), std::max<i64>(p->N, 1), {0}, 0);
+    } else {
+      rc = pr.partial_sums(p->d, p->N, p->ld, a.as<int32_t>(), std::max<i64>(p->N, 1), {0}, 0);
+      if (rc == GULON_OK) rc = pr.finalize(nullptr, 0);
+    }
+  }
+  if (rc == GULON_OK) {
+    cudaError_t e = cudaMemcpy(out_C, pr.cb.p, (size_t)K * dim * sizeof(float), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && out_counts)
+      e = cudaMemcpy(out_counts, pr.counts.p, (size_t)K * sizeof(int32_t), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) rc = fail(GULON_ECUDA, "cudaMemcpy failed: %s", cudaGetErrorString(e));
+  }
+  a.release();
+  return rc;
+}
+
+int gulon_kmeans_init(gulon_points_t p, int32_t from, int32_t dim, int32_t K, int32_t seed,
+                      float *out_C, int32_t *out_rows) {
+  GCHECK(check_window(p, from, dim, K));
+  GREQUIRE(out_C, "null argument");
+  GREQUIRE(p->N >= 1 && p->N < (1LL << 31), "KMeans.init needs 1 <= N < 2^31 rows");
+  GCHECK(need_device());
+  std::vector<i64> rows(K);
+  JRandom rng((int64_t)seed);
+  for (int k = 0; k < K; k++) {
+    rows[k] = rng.next_int((int32_t)p->N);
+    if (out_rows) out_rows[k] = (int32_t)rows[k];
+  }
+  DevBuf dr, dc;
+  int rc = upload(dr, rows, 0);
+  if (rc == GULON_OK) rc = dc.ensure((size_t)K * dim * sizeof(float));
+  if (rc == GULON_OK) {
+    rc = [&]() -> int {
+      GLAUNCH(gather_rows_kernel, (unsigned)K, 32, 0, 0, p->d, p->ld, from, dim, dr.as<i64>(),
+              (i64)0, p->N, dc.as<float>(), dim);
+      GCU(cudaMemcpy(out_C, dc.p, (size_t)K * dim * sizeof(float), cudaMemcpyDeviceToHost));
+      return GULON_OK;
+    }();
+  }
+  dr.release();
+  dc.release();
+  return rc;
+}
+
+int gulon_kmeans_train(gulon_points_t p, int32_t from, int32_t dim, int32_t K, int32_t max_iter,
+                       int32_t seed, int32_t tie_mode, int32_t update_mode,
+                       const gulon_comm_t *comm, int64_t n_total, int64_t row_offset,
+                       gulon_progress_fn report, void *user, float *out_C, int32_t *n_updates,
+                       int32_t *converged) {
+  GCHECK(check_window(p, from, dim, K));
+  GREQUIRE(out_C, "null argument");
+  GREQUIRE(tie_mode == GULON_TIE_LOWEST, "unsupported tie_mode %d (only GULON_TIE_LOWEST)", tie_mode);
+  GREQUIRE(update_mode == GULON_UPDATE_RUNNING_MEAN || update_mode == GULON_UPDATE_SUM,
+           "unknown update_mode %d", update_mode);
+  GCHECK(need_device());
+  Problems pr;
+  GCHECK(pr.setup(1, K, &from, &dim, 0));
+  GCHECK(train_problems(pr, p, &seed, max_iter, update_mode, comm, n_total, row_offset, report,
+                        user, 0, n_updates, converged, 0));
+  GCU(cudaMemcpy(out_C, pr.cb.p, (size_t)K * dim * sizeof(float), cudaMemcpyDeviceToHost));
+  return GULON_OK;
+}
+
+// ---- ProductQuantizer -----------------------------------------------------------------------
+int gulon_pq_train(gulon_points_t p, int32_t M, int32_t K, int32_t max_iter, int32_t tie_mode,
+                   int32_t update_mode, const gulon_comm_t *comm, int64_t n_total,
+                   int64_t row_offset, gulon_progress_fn report, void *user,
+                   gulon_codebook_t *out) {
+  GREQUIRE(p && out, "null argument");
+  GREQUIRE(tie_mode == GULON_TIE_LOWEST, "unsupported tie_mode %d (only GULON_TIE_LOWEST)", tie_mode);
+  GREQUIRE(update_mode == GULON_UPDATE_RUNNING_MEAN || update_mode == GULON_UPDATE_SUM,
+           "unknown update_mode %d", update_mode);
+  GCHECK(need_device());
+  gulon_codebook_t cb = nullptr;
+  GCHECK(make_codebook(p->D, M, K, &cb));
+  std::unique_ptr<gulon_codebook_s> hold(cb);
+  Problems pr;
+  GCHECK(pr.setup(M, K, cb->from.data(), cb->dim.data(), 0));
+  std::vector<int32_t> seeds(M);
+  for (int m = 0; m < M; m++) seeds[m] = m;  // G/ProductQuantizer.scala:139
+  GCHECK(train_problems(pr, p, seeds.data(), max_iter, update_mode, comm, n_total, row_offset,
+                        report, user, 0, nullptr, nullptr, 0));
+  GCU(cudaMemcpy(cb->cb.p, pr.cb.p, (size_t)M * K * cb->dmax * sizeof(float),
+                 cudaMemcpyDeviceToDevice));
+  GCHECK(codebook_offsets(cb, 0));
+  GCU(cudaStreamSynchronize(0));
+  *out = hold.release();
+  return GULON_OK;
+}
+
+int gulon_codebook_create(int32_t D, int32_t M, int32_t K, const float *centroids,
+                          gulon_codebook_t *out) {
+  GREQUIRE(centroids && out, "null argument");
+  GCHECK(need_device());
+  gulon_codebook_t cb = nullptr;
+  GCHECK(make_codebook(D, M, K, &cb));
+  std::unique_ptr<gulon_codebook_s> hold(cb);
+  GCU(cudaMemcpy(cb->cb.p, centroids, (size_t)M * K * cb->dmax * sizeof(float),
+                 cudaMemcpyHostToDevice));
+  GCHECK(codebook_offsets(cb, 0));
+  GCU(cudaStreamSynchronize(0));
+  *out = hold.release();
+  return GULON_OK;
+}
+
+int gulon_codebook_info(gulon_codebook_t cb, int32_t *D, int32_t *M, int32_t *K, int32_t *dmax) {
+  GREQUIRE(cb, "null handle");
+  if (D) *D = cb->D;
+  if (M) *M = cb->M;
+  if (K) *K = cb->K;
+  if (dmax) *dmax = cb->dmax;
+  return GULON_OK;
+}
+
+int gulon_codebook_export(gulon_codebook_t cb, float *centroids) {
+  GREQUIRE(cb && centroids, "null argument");
+  GCU(cudaMemcpy(centroids, cb->cb.p, (size_t)cb->M * cb->K * cb->dmax * sizeof(float),
+                 cudaMemcpyDeviceToHost));
+  return GULON_OK;
+}
+
+int gulon_codebook_destroy(gulon_codebook_t cb) {
+  delete cb;
+  return GULON_OK;
+}
+
+int gulon_pq_encode_dev(gulon_codebook_t cb, const float *dX, int64_t N, int64_t ld,
+                        int32_t tie_mode, uint8_t *dcodes, int64_t plane_stride, void *stream) {
+  GREQUIRE(cb, "null handle");
+  GREQUIRE(tie_mode == GULON_TIE_LOWEST, "unsupported tie_mode %d (only GULON_TIE_LOWEST)", tie_mode);
+  GREQUIRE(cb->K <= 256, "Coder8 needs K <= 256 (K=%d)", cb->K);
+  GREQUIRE(N >= 0 && ld >= cb->D && plane_stride >= N, "bad shapes N=%lld ld=%lld stride=%lld",
+           (long long)N, (long long)ld, (long long)plane_stride);
+  GREQUIRE((dX && dcodes) || N == 0, "null argument");
+  GCHECK(need_device());
+  return encode_dev(cb, dX, N, ld, dcodes, plane_stride, (cudaStream_t)stream);
+}
+
+int gulon_pq_encode(gulon_codebook_t cb, const float *X, int64_t N, int64_t ld, int32_t tie_mode,
+                    uint8_t *codes) {
+  GREQUIRE(cb, "null handle");
+  GREQUIRE(tie_mode == GULON_TIE_LOWEST, "unsupported tie_mode %d (only GULON_TIE_LOWEST)", tie_mode);
+  GREQUIRE(cb->K <= 256, "Coder8 needs K <= 256 (K=%d)", cb->K);
+  GREQUIRE(N >= 0 && ld >= cb->D, "bad shapes N=%lld ld=%lld", (long long)N, (long long)ld);
+  GREQUIRE((X && codes) || N == 0, "null argument");
+  GCHECK(need_device());
+  if (N == 0) return GULON_OK;
+  // Double-buffered row chunks: copy chunk c+1 to HBM while chunk c is encoded.
+  const int D = cb->D, M = cb->M;
+  const i64 chunk = std::min<i64>(N, g_encode_chunk.load());
+  const i64 cps = round_up(chunk, 16);
+  struct Res {
+    cudaStream_t st[2] = {nullptr, nullptr};
+    float *dx[2] = {nullptr, nullptr};
+    uint8_t *dc[2] = {nullptr, nullptr};
+    ~Res() {
+      for (int i = 0; i < 2; i++) {
+        if (dx[i]) cudaFree(dx[i]);
+        if (dc[i]) cudaFree(dc[i]);
+        if (st[i]) cudaStreamDestroy(st[i]);
+      }
+    }
+  } r;
+  for (int i = 0; i < 2; i++) {
+    GCU(cudaStreamCreateWithFlags(&r.st[i], cudaStreamNonBlocking));
+    GCU(cudaMalloc(&r.dx[i], (size_t)chunk * D * sizeof(float)));
+    GCU(cudaMalloc(&r.dc[i], (size_t)M * cps));
+  }
+  int b = 0;
+  for (i64 r0 = 0; r0 < N; r0 += chunk, b ^= 1) {
+    const i64 n = std::min<i64>(chunk, N - r0);
+    GCU(cudaMemcpy2DAsync(r.dx[b], (size_t)D * 4, X + r0 * ld, (size_t)ld * 4, (size_t)D * 4,
+                          (size_t)n, cudaMemcpyHostToDevice, r.st[b]));
+    GCHECK(encode_dev(cb, r.dx[b], n, D, r.dc[b], cps, r.st[b]));
+    GCU(cudaMemcpy2DAsync(codes + r0, (size_t)N, r.dc[b], (size_t)cps, (size_t)n, (size_t)M,
+                          cudaMemcpyDeviceToHost, r.st[b]));
+    // buffer pair b is reused two chunks later on the same stream, so reuse is stream-ordered
+  }
+  GCU(cudaStreamSynchronize(r.st[0]));
+  GCU(cudaStreamSynchronize(r.st[1]));
+  return GULON_OK;
+}
+
+int gulon_pq_decode(gulon_codebook_t cb, const uint8_t *codes, int64_t N, int64_t plane_stride,
+                    float *out, int64_t ldo) {
+  GREQUIRE(cb, "null handle");
+  GREQUIRE(N >= 0 && plane_stride >= N && ldo >= cb->D, "bad shapes");
+  GREQUIRE((codes && out) || N == 0, "null argument");
+  GREQUIRE(cb->K <= 256, "Coder8 needs K <= 256 (K=%d)", cb->K);
+  GCHECK(need_device());
+  if (N == 0) return GULON_OK;
+  for (int m = 0; m < cb->M; m++)
+    for (i64 i = 0; i < N; i++)
+      GREQUIRE(codes[(i64)m * plane_stride + i] < cb->K, "code %d >= K=%d (plane %d row %lld)",
+               (int)codes[(i64)m * plane_stride + i], cb->K, m, (long long)i);
+  DevBuf dc, dout;
+  int rc = [&]() -> int {
+    GCHECK(dc.ensure((size_t)cb->M * N));
+    GCHECK(dout.ensure((size_t)N * cb->D * sizeof(float)));
+    GCU(cudaMemcpy2D(dc.p, (size_t)N, codes, (size_t)plane_stride, (size_t)N, (size_t)cb->M,
+                     cudaMemcpyHostToDevice));
+    dim3 block(32, 8);
+    GLAUNCH(decode_kernel, (unsigned)ceil_div(N, 8), block, 0, 0, dc.as<uint8_t>(), N, N,
+            cb->cb.as<float>(), cb->dfrom.as<int32_t>(), cb->ddim.as<int32_t>(), cb->M, cb->K,
+            cb->dmax, dout.as<float>(), (i64)cb->D);
+    GCU(cudaMemcpy2D(out, (size_t)ldo * 4, dout.p, (size_t)cb->D * 4, (size_t)cb->D * 4, (size_t)N,
+                     cudaMemcpyDeviceToHost));
+    return GULON_OK;
+  }();
+  dc.release();
+  dout.release();
+  return rc;
+}
+
+// ---- Index.PQIndex ----------------------------------------------------------------------------
+int gulon_index_create(gulon_codebook_t cb, const uint8_t *codes, int64_t N, int64_t plane_stride,
+                       gulon_index_t *out) {
+  GREQUIRE(cb && out, "null argument");
+  GREQUIRE(N >= 0 && plane_stride >= N, "bad shapes N=%lld stride=%lld", (long long)N,
+           (long long)plane_stride);
+  GREQUIRE(codes || N == 0, "null codes");
+  GREQUIRE(cb->K <= 256, "Coder8 needs K <= 256 (K=%d)", cb->K);
+  GREQUIRE(N < (1LL << 31), "row ids are Int in the reference: N must be < 2^31");
+  GCHECK(need_device());
+  std::unique_ptr<gulon_index_s> ix(new gulon_index_s);
+  ix->cb = cb;
+  ix->N = N;
+  ix->ps = round_up(std::max<i64>(N, 1), 16);
+  ix->owned = true;
+  uint8_t *d = nullptr;
+  cudaError_t e = cudaMalloc(&d, (size_t)cb->M * ix->ps);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(GULON_ENOMEM, "cudaMalloc(%zu bytes) failed: %s", (size_t)cb->M * ix->ps,
+                cudaGetErrorString(e));
+  }
+  ix->codes = d;
+  GCU(cudaMemset(d, 0, (size_t)cb->M * ix->ps));
+  if (N > 0)
+    GCU(cudaMemcpy2D(d, (size_t)ix->ps, codes, (size_t)plane_stride, (size_t)N, (size_t)cb->M,
+                     cudaMemcpyHostToDevice));
+  *out = ix.release();
+  return GULON_OK;
+}
+
+int gulon_index_create_dev(gulon_codebook_t cb, const uint8_t *dcodes, int64_t N,
+                           int64_t plane_stride, gulon_index_t *out) {
+  GREQUIRE(cb && out, "null argument");
+  GREQUIRE(N >= 0 && plane_stride >= round_up(N, 16) && plane_stride % 16 == 0,
+           "plane_stride (%lld) must be a multiple of 16 and >= N rounded up to 16 (N=%lld)",
+           (long long)plane_stride, (long long)N);
+  GREQUIRE(dcodes || N == 0, "null codes");
+  GREQUIRE(((uintptr_t)dcodes & 15) == 0, "device codes must be 16-byte aligned");
+  GREQUIRE(cb->K <= 256, "Coder8 needs K <= 256 (K=%d)", cb->K);
+  GREQUIRE(N < (1LL << 31), "row ids are Int in the reference: N must be < 2^31");
+  GCHECK(need_device());
+  gulon_index_s *ix = new gulon_index_s;
+  ix->cb = cb;
+  ix->codes = dcodes;
+  ix->N = N;
+  ix->ps = plane_stride;
+  ix->owned = false;
+  *out = ix;
+  return GULON_OK;
+}
+
+int gulon_index_info(gulon_index_t ix, int64_t *N, int32_t *M, int32_t *K, int32_t *D) {
+  GREQUIRE(ix, "null handle");
+  if (N) *N = ix->N;
+  if (M) *M = ix->cb->M;
+  if (K) *K = ix->cb->K;
+  if (D) *D = ix->cb->D;
+  return GULON_OK;
+}
+
+int gulon_index_destroy(gulon_index_t ix) {
+  delete ix;
+  return GULON_OK;
+}
+
+int gulon_prepare_query(gulon_codebook_t cb, const float *queries, int64_t nq, int64_t ldq,
+                        float *lut) {
+  GREQUIRE(cb, "null handle");
+  GREQUIRE(nq >= 0 && ldq >= cb->D, "bad query shape nq=%lld ldq=%lld", (long long)nq,
+           (long long)ldq);
+  GREQUIRE((queries && lut) || nq == 0, "null argument");
+  GCHECK(need_device());
+  if (nq == 0) return GULON_OK;
+  std::lock_guard<std::mutex> lock(cb->mu);
+  const int M = cb->M, K = cb->K, D = cb->D;
+  const i64 qb = 4096;
+  GCHECK(cb->scratch_q.ensure((size_t)qb * D * sizeof(float) + (size_t)qb * M * K * sizeof(float)));
+  GCHECK(cb->scratch_lut.ensure((size_t)(qb / 4) * M * 256 * sizeof(float4)));
+  float *dq = cb->scratch_q.as<float>();
+  float *dl = dq + (size_t)qb * D;
+  for (i64 q0 = 0; q0 < nq; q0 += qb) {
+    const i64 nb = std::min<i64>(qb, nq - q0);
+    GCU(cudaMemcpy2DAsync(dq, (size_t)D * 4, queries + q0 * ldq, (size_t)ldq * 4, (size_t)D * 4,
+                          (size_t)nb, cudaMemcpyHostToDevice, 0));
+    dim3 lg((unsigned)ceil_div(nb, 4), (unsigned)M);
+    GLAUNCH(lut_build_kernel, lg, 256, 0, 0, dq, (i64)D, nb, cb->cb.as<float>(),
+            cb->dfrom.as<int32_t>(), cb->ddim.as<int32_t>(), M, K, cb->dmax,
+            cb->scratch_lut.as<float4>());
+    const i64 total = nb * M * K;
+    GLAUNCH(lut_export_kernel, (unsigned)ceil_div(total, 256), 256, 0, 0,
+            cb->scratch_lut.as<float4>(), nb, M, K, dl);
+    GCU(cudaMemcpyAsync(lut + q0 * M * K, dl, (size_t)total * sizeof(float),
+                        cudaMemcpyDeviceToHost, 0));
+    GCU(cudaStreamSynchronize(0));
+  }
+  return GULON_OK;
+}
+
+int gulon_pq_query_dev(gulon_index_t ix, const float *dqueries, int64_t nq, int64_t ldq, int32_t k,
+                       int64_t from, int64_t until, int32_t normalize, int64_t id_offset,
+                       int32_t *d_ids, float *d_dists, int32_t *d_sizes, void *stream) {
+  GREQUIRE(ix, "null handle");
+  GREQUIRE(nq >= 0, "nq must be >= 0");
+  GREQUIRE((dqueries && d_ids && d_dists) || nq == 0 || k == 0, "null argument");
+  GCHECK(need_device());
+  return query_dev(ix, dqueries, nq, ldq, k, from, until, normalize, id_offset, d_ids, d_dists,
+                   d_sizes, (cudaStream_t)stream);
+}
+
+int gulon_pq_query(gulon_index_t ix, const float *queries, int64_t nq, int64_t ldq, int32_t k,
+                   int64_t from, int64_t until, int32_t normalize, int64_t id_offset,
+                   int32_t *out_ids, float *out_dists, int32_t *out_sizes) {
+  GREQUIRE(ix, "null handle");
+  GREQUIRE(nq >= 0 && k >= 0, "nq and k must be >= 0");
+  GREQUIRE(ldq >= ix->cb->D, "query leading dimension %lld < dimension %d", (long long)ldq,
+           ix->cb->D);
+  GREQUIRE((queries && out_ids && out_dists) || nq == 0 || k == 0, "null argument");
+  GCHECK(need_device());
+  if (nq == 0) return GULON_OK;
+  const int D = ix->cb->D;
+  float *dq = nullptr;
+  int32_t *di = nullptr, *dz = nullptr;
+  float *dd = nullptr;
+  const size_t nk = (size_t)nq * std::max(k, 1);
+  int rc = [&]() -> int {
+    GCU(cudaMalloc(&dq, (size_t)nq * D * sizeof(float)));
+    GCU(cudaMalloc(&di, nk * sizeof(int32_t)));
+    GCU(cudaMalloc(&dd, nk * sizeof(float)));
+    GCU(cudaMalloc(&dz, (size_t)nq * sizeof(int32_t)));
+    GCU(cudaMemcpy2DAsync(dq, (size_t)D * 4, queries, (size_t)ldq * 4, (size_t)D * 4, (size_t)nq,
+                          cudaMemcpyHostToDevice, 0));
+    GCHECK(query_dev(ix, dq, nq, D, k, from, until, normalize, id_offset, di, dd, dz, 0));
+    if (k > 0) {
+      GCU(cudaMemcpyAsync(out_ids, di, (size_t)nq * k * sizeof(int32_t), cudaMemcpyDeviceToHost, 0));
+      GCU(cudaMemcpyAsync(out_dists, dd, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, 0));
+    }
+    if (out_sizes)
+      GCU(cudaMemcpyAsync(out_sizes, dz, (size_t)nq * sizeof(int32_t), cudaMemcpyDeviceToHost, 0));
+    GCU(cudaStreamSynchronize(0));
+    return GULON_OK;
+  }();
+  if (dq) cudaFree(dq);
+  if (di) cudaFree(di);
+  if (dd) cudaFree(dd);
+  if (dz) cudaFree(dz);
+  return rc;
+}
+
+int gulon_topk_merge_dev(const int32_t *d_ids, const float *d_dists, int32_t S, int64_t nq,
+                         int32_t k, int32_t *d_out_ids, float *d_out_dists, int32_t *d_out_sizes,
+                         void *stream) {
+  GREQUIRE(S >= 1 && nq >= 0 && k >= 1, "bad merge shape S=%d nq=%lld k=%d", S, (long long)nq, k);
+  GREQUIRE((d_ids && d_dists && d_out_ids && d_out_dists) || nq == 0, "null argument");
+  GCHECK(need_device());
+  if (nq == 0) return GULON_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  // process-wide scratch guarded by a mutex: merges are short
+  static std::mutex mu;
+  static DevBuf keys;
+  static Selector sel;
+  std::lock_guard<std::mutex> lock(mu);
+  const i64 stride = round_up((i64)S * k, SEL_CHUNK);
+  const i64 qb = std::max<i64>(1, (256LL << 20) / (stride * 8));
+  GCHECK(keys.ensure((size_t)std::min<i64>(qb, nq) * stride * sizeof(u64)));
+  for (i64 q0 = 0; q0 < nq; q0 += qb) {
+    const i64 nb = std::min<i64>(qb, nq - q0);
+    for (i64 y0 = 0; y0 < nb; y0 += 32768) {
+      const i64 ny = std::min<i64>(32768, nb - y0);
+      dim3 gg((unsigned)ceil_div(stride, 256), (unsigned)ny);
+      GLAUNCH(pack_results_kernel, gg, 256, 0, st, d_ids, d_dists, S, nq, k, q0 + y0,
+              keys.as<u64>() + (size_t)y0 * stride, stride);
+    }
+    u64 *res;
+    i64 rs;
+    GCHECK(sel.run(keys.as<u64>(), stride, nb, k, st, &res, &rs));
+    GCHECK(unpack(res, rs, nb, k, 0, d_out_ids + q0 * k, d_out_dists + q0 * k,
+                  d_out_sizes ? d_out_sizes + q0 : nullptr, st));
+  }
+  return GULON_OK;
+}
+
+int gulon_exact_topk(gulon_points_t p, const float *queries, int64_t nq, int64_t ldq, int32_t k,
+                     int64_t from, int64_t until, int32_t *out_ids, float *out_dists,
+                     int32_t *out_sizes) {
+  GREQUIRE(p, "null handle");
+  GREQUIRE(from <= until, "invalid range: expected from=%lld <= until=%lld", (long long)from,
+           (long long)until);
+  GREQUIRE(from >= 0 && until <= p->N, "invalid range: expected until=%lld <= vectors.length=%lld",
+           (long long)until, (long long)p->N);
+  GREQUIRE(nq >= 0 && k >= 0 && ldq >= p->D, "bad query shape");
+  GREQUIRE((queries && out_ids && out_dists) || nq == 0 || k == 0, "null argument");
+  GREQUIRE(p->N < (1LL << 31), "row ids are Int in the reference: N must be < 2^31");
+  GCHECK(need_device());
+  if (nq == 0) return GULON_OK;
+  const int D = p->D;
+  const i64 range = until - from;
+  DevBuf dq, keys, di, dd, dz;
+  Selector sel;
+  const size_t nk = (size_t)nq * std::max(k, 1);
+  int rc = [&]() -> int {
+    GCHECK(di.ensure(nk * sizeof(int32_t)));
+    GCHECK(dd.ensure(nk * sizeof(float)));
+    GCHECK(dz.ensure((size_t)nq * sizeof(int32_t)));
+    if (k == 0 || range == 0) {
+      GCHECK(fill_empty(nq, k, di.as<int32_t>(), dd.as<float>(), dz.as<int32_t>(), 0));
+    } else {
+      GREQUIRE((size_t)D * sizeof(float) <= 48 * 1024, "dimension %d too large for exact_topk", D);
+      GCHECK(dq.ensure((size_t)nq * D * sizeof(float)));
+      GCU(cudaMemcpy2DAsync(dq.p, (size_t)D * 4, queries, (size_t)ldq * 4, (size_t)D * 4,
+                            (size_t)nq, cudaMemcpyHostToDevice, 0));
+      const i64 n_pad = round_up(range, SEL_CHUNK);
+      i64 qb = std::max<i64>(1, g_simple_scratch.load() / (8 * n_pad));
+      qb = std::min<i64>(std::min<i64>(qb, nq), 32768);
+      GCHECK(keys.ensure((size_t)qb * n_pad * sizeof(u64)));
+      for (i64 q0 = 0; q0 < nq; q0 += qb) {
+        const i64 nb = std::min<i64>(qb, nq - q0);
+        dim3 grid((unsigned)(n_pad / 128), (unsigned)nb);
+        GLAUNCH(exact_keys_kernel, grid, 128, (size_t)D * sizeof(float), 0, p->d, p->ld, D, from,
+                until, dq.as<float>() + q0 * D, (i64)D, keys.as<u64>(), n_pad);
+        u64 *res;
+        i64 rs;
+        GCHECK(sel.run(keys.as<u64>(), n_pad, nb, k, 0, &res, &rs));
+        GCHECK(unpack(res, rs, nb, k, 0, di.as<int32_t>() + q0 * k, dd.as<float>() + q0 * k,
+                      dz.as<int32_t>() + q0, 0));
+      }
+    }
+    if (k > 0) {
+      GCU(cudaMemcpyAsync(out_ids, di.p, (size_t)nq * k * sizeof(int32_t), cudaMemcpyDeviceToHost, 0));
+      GCU(cudaMemcpyAsync(out_dists, dd.p, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, 0));
+    }
+    if (out_sizes)
+      GCU(cudaMemcpyAsync(out_sizes, dz.p, (size_t)nq * sizeof(int32_t), cudaMemcpyDeviceToHost, 0));
+    GCU(cudaStreamSynchronize(0));
+    return GULON_OK;
+  }();
+  dq.release(); keys.release(); di.release(); dd.release(); dz.release();
+  sel.release();
+  return rc;
+}
+
+int gulon_rerank(gulon_points_t p, const float *queries, int64_t nq, int64_t ldq,
+                 const int32_t *cand_ids, int32_t R, int32_t k, int32_t *out_ids,
+                 float *out_dists, int32_t *out_sizes) {
+  GREQUIRE(p, "null handle");
+  GREQUIRE(nq >= 0 && R >= 0 && k >= 0 && ldq >= p->D, "bad re-rank shape");
+  GREQUIRE((queries && cand_ids && out_ids && out_dists) || nq == 0 || k == 0 || R == 0,
+           "null argument");
+  GCHECK(need_device());
+  if (nq == 0) return GULON_OK;
+  const int D = p->D;
+  DevBuf dq, dc, keys, di, dd, dz;
+  Selector sel;
+  const size_t nk = (size_t)nq * std::max(k, 1);
+  int rc = [&]() -> int {
+    GCHECK(di.ensure(nk * sizeof(int32_t)));
+    GCHECK(dd.ensure(nk * sizeof(float)));
+    GCHECK(dz.ensure((size_t)nq * sizeof(int32_t)));
+    if (k == 0 || R == 0) {
+      GCHECK(fill_empty(nq, k, di.as<int32_t>(), dd.as<float>(), dz.as<int32_t>(), 0));
+    } else {
+      GREQUIRE((size_t)D * sizeof(float) <= 48 * 1024, "dimension %d too large for rerank", D);
+      GCHECK(dq.ensure((size_t)nq * D * sizeof(float)));
+      GCHECK(dc.ensure((size_t)nq * R * sizeof(int32_t)));
+      GCU(cudaMemcpy2DAsync(dq.p, (size_t)D * 4, queries, (size_t)ldq * 4, (size_t)D * 4,
+                            (size_t)nq, cudaMemcpyHostToDevice, 0));
+      GCU(cudaMemcpyAsync(dc.p, cand_ids, (size_t)nq * R * sizeof(int32_t), cudaMemcpyHostToDevice, 0));
+      const i64 n_pad = round_up(R, SEL_CHUNK);
+      i64 qb = std::max<i64>(1, g_simple_scratch.load() / (8 * n_pad));
+      qb = std::min<i64>(std::min<i64>(qb, nq), 32768);
+      GCHECK(keys.ensure((size_t)qb * n_pad * sizeof(u64)));
+      for (i64 q0 = 0; q0 < nq; q0 += qb) {
+        const i64 nb = std::min<i64>(qb, nq - q0);
+        dim3 grid((unsigned)(n_pad / 128), (unsigned)nb);
+        GLAUNCH(rerank_keys_kernel, grid, 128, (size_t)D * sizeof(float), 0, p->d, p->ld, D, p->N,
+                dq.as<float>() + q0 * D, (i64)D, dc.as<int32_t>() + q0 * R, R, keys.as<u64>(), n_pad);
+        u64 *res;
+        i64 rs;
+        GCHECK(sel.run(keys.as<u64>(), n_pad, nb, k, 0, &res, &rs));
+        GCHECK(unpack(res, rs, nb, k, 0, di.as<int32_t>() + q0 * k, dd.as<float>() + q0 * k,
+                      dz.as<int32_t>() + q0, 0));
+      }
+    }
+    if (k > 0) {
+      GCU(cudaMemcpyAsync(out_ids, di.p, (size_t)nq * k * sizeof(int32_t), cudaMemcpyDeviceToHost, 0));
+      GCU(cudaMemcpyAsync(out_dists, dd.p, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, 0));
+    }
+    if (out_sizes)
+      GCU(cudaMemcpyAsync(out_sizes, dz.p, (size_t)nq * sizeof(int32_t), cudaMemcpyDeviceToHost, 0));
+    GCU(cudaStreamSynchronize(0));
+    return GULON_OK;
+  }();
+  dq.release(); dc.release(); keys.release(); di.release(); dd.release(); dz.release();
+  sel.release();
+  return rc;
+}
+
+}  // extern "C"

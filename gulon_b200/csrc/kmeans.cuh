@@ -173,7 +173,8 @@ __global__ void count_diff_kernel(const int32_t *__restrict__ a, const int32_t *
 
 // ---- centroid update, sum/count form (GULON_UPDATE_SUM) -----------------------------------------
 // Deterministic segmented sum without atomics: every warp owns a contiguous row range and a
-// private [K][dim] accumulator in shared memory, lanes = dimensions, rows visited in order; the
+// private [K][dim] accumulator in shared memory, lanes = dimensions (lane j is the only thread
+// that ever touches column j, so there is no cross-lane hazard), rows visited in order; the
 // warps of a CTA are then folded in warp order and the CTAs by update_reduce_kernel in CTA order.
 // grid (B, nsub), block 32*W; dynamic smem W*K*(dim+1)*4 bytes.
 __global__ void update_partial_kernel(const float *__restrict__ X, i64 N, i64 ld,
@@ -217,7 +218,6 @@ __global__ void update_partial_kernel(const float *__restrict__ X, i64 N, i64 ld
           if (j < dm) acc[ai[u] * dm + j] = __fadd_rn(acc[ai[u] * dm + j], xv[u]);
           if (jb == 0 && lane == 0) cnt[ai[u]] += 1;
         }
-        __syncwarp();
       }
     }
   }
@@ -245,18 +245,28 @@ __global__ void update_reduce_kernel(const float *__restrict__ part_sum,
                                      const int32_t *__restrict__ dims, int K, int dmax,
                                      float *__restrict__ sums, int32_t *__restrict__ counts) {
   const int m = subs[blockIdx.y];
-  const int k = blockIdx.x, j = threadIdx.x;
+  const int k = blockIdx.x;
   const i64 base = (i64)blockIdx.y * B;
-  if (j < dims[m]) {
+  for (int j = threadIdx.x; j < dmax; j += blockDim.x) {
     float s = 0.0f;
-    for (int b = 0; b < B; b++) s = __fadd_rn(s, part_sum[((base + b) * K + k) * dmax + j]);
+    if (j < dims[m])
+      for (int b = 0; b < B; b++) s = __fadd_rn(s, part_sum[((base + b) * K + k) * dmax + j]);
     sums[((i64)m * K + k) * dmax + j] = s;
   }
-  if (j == 0) {
+  if (threadIdx.x == 0) {
     int c = 0;
     for (int b = 0; b < B; b++) c += part_cnt[(base + b) * K + k];
     counts[(i64)m * K + k] = c;
   }
+}
+
+// counts[subs[y]][k] = cnt[y][k]  (running-mean path keeps its counts per launch slot)
+__global__ void scatter_counts_kernel(const int32_t *__restrict__ cnt,
+                                      const int32_t *__restrict__ subs, int ns, int K,
+                                      int32_t *__restrict__ counts) {
+  const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (i64)ns * K) return;
+  counts[(i64)subs[t / K] * K + t % K] = cnt[t];
 }
 
 // centroid = sum / count (empty cluster -> all-zero, as the reference leaves it). grid covers M*K*dmax
@@ -428,6 +438,34 @@ __global__ void __launch_bounds__(128) exact_keys_kernel(const float *__restrict
       s = __fadd_rn(s, __fmul_rn(dx, dx));
     }
     key = make_key(s, (uint32_t)row);
+  }
+  keys[q * n_pad + t] = key;
+}
+
+// exact squared distances of listed candidate rows (re-rank, G/Tests.scala:24-37 +
+// G/MathUtils.scala:85-95).  grid (n_pad/128, nq), block 128; cand [nq][R], ids < 0 skipped.
+__global__ void __launch_bounds__(128) rerank_keys_kernel(const float *__restrict__ X, i64 ld,
+                                                          int D, i64 N,
+                                                          const float *__restrict__ Q, i64 ldq,
+                                                          const int32_t *__restrict__ cand, int R,
+                                                          u64 *__restrict__ keys, i64 n_pad) {
+  extern __shared__ float sq[];
+  const i64 q = blockIdx.y;
+  for (int j = threadIdx.x; j < D; j += 128) sq[j] = Q[q * ldq + j];
+  __syncthreads();
+  const i64 t = (i64)blockIdx.x * 128 + threadIdx.x;
+  u64 key = KEY_SENT;
+  if (t < R) {
+    const int32_t id = cand[q * R + t];
+    if (id >= 0 && id < N) {
+      const float *x = X + (i64)id * ld;
+      float s = 0.0f;
+      for (int j = 0; j < D; j++) {
+        const float dx = __fsub_rn(sq[j], x[j]);
+        s = __fadd_rn(s, __fmul_rn(dx, dx));
+      }
+      key = make_key(s, (uint32_t)id);
+    }
   }
   keys[q * n_pad + t] = key;
 }

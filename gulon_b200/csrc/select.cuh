@@ -101,11 +101,12 @@ __global__ void gather_lists_kernel(const u64 *__restrict__ lists, int S, i64 ro
   }
 }
 
-// (ids, dists) [S][rows][k] -> keys [rows][stride]; id < 0 marks an empty slot
+// (ids, dists) [S][rows][k] -> keys [.][stride] for result rows q_base + blockIdx.y; id < 0
+// marks an empty slot
 __global__ void pack_results_kernel(const int32_t *__restrict__ ids,
                                     const float *__restrict__ dists, int S, i64 rows, int k,
-                                    u64 *__restrict__ keys, i64 stride) {
-  i64 q = blockIdx.y;
+                                    i64 q_base, u64 *__restrict__ keys, i64 stride) {
+  const i64 q = q_base + blockIdx.y;
   for (i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x; t < stride;
        t += (i64)gridDim.x * blockDim.x) {
     u64 v = KEY_SENT;
@@ -115,8 +116,19 @@ __global__ void pack_results_kernel(const int32_t *__restrict__ ids,
       int32_t id = ids[at];
       if (id >= 0) v = make_key(dists[at], (uint32_t)id);
     }
-    keys[q * stride + t] = v;
+    keys[(i64)blockIdx.y * stride + t] = v;
   }
+}
+
+// empty result rows: id -1, distance +inf, size 0
+__global__ void fill_empty_kernel(i64 nq, int k, int32_t *__restrict__ ids,
+                                  float *__restrict__ dists, int32_t *__restrict__ sizes) {
+  const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < nq * k) {
+    if (ids) ids[t] = -1;
+    if (dists) dists[t] = __int_as_float(0x7f800000);
+  }
+  if (sizes && t < nq) sizes[t] = 0;
 }
 
 // Runs selection passes until every row holds its k smallest keys at the front of the result.

@@ -1,0 +1,162 @@
+"""Multi-GPU plumbing: one process per GPU, torch.distributed (NCCL over NVLink/NVSwitch).
+
+The reference is a single JVM; what shards here follows its own structure:
+  * scan + top-k: database rows are independent and the reference already merges per-range heaps
+    (TopKHeap#merge, G/TopKHeap.scala:44-53; GroupedIndex.query, G/Index.scala:273-281).  Each
+    rank owns a contiguous row shard of every code plane, emits [Q][k] (distance, global id) and one
+    all-gather + (distance, id) merge yields the same answer on every rank;
+  * encode: rows independent, no exchange;
+  * k-means: rows sharded; one all-reduce of per-cluster sums and counts per Lloyd iteration
+    (done inside the library through the gulon_comm_t hooks built by `TorchComm`).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _native as N
+
+
+def shard_bounds(n_total, world, align=16):
+    """Contiguous row shards [lo, hi) per rank; interior boundaries are multiples of `align` rows
+    so that every shard's code planes start 16-byte aligned."""
+    if world < 1 or n_total < 0:
+        raise ValueError("need world >= 1 and n_total >= 0")
+    per = -(-n_total // world)
+    per = -(-per // align) * align
+    return [(min(r * per, n_total), min((r + 1) * per, n_total)) for r in range(world)]
+
+
+class _RawBuffer:
+    """Zero-copy view of a raw pointer for torch.as_tensor / numpy."""
+
+    def __init__(self, ptr, n, typestr, cuda):
+        iface = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr), False), "version": 3,
+                 "strides": None}
+        if cuda:
+            self.__cuda_array_interface__ = iface
+        else:
+            self.__array_interface__ = iface
+
+
+def _view(ptr, n, typestr, device):
+    import torch
+    if device.type == "cuda":
+        return torch.as_tensor(_RawBuffer(ptr, n, typestr, True), device=device)
+    return torch.from_numpy(np.asarray(_RawBuffer(ptr, n, typestr, False)))
+
+
+class TorchComm:
+    """gulon_comm_t whose hooks call torch.distributed collectives on the buffers the library
+    hands over (device pointers with NCCL; host pointers with gloo in the CPU tests)."""
+
+    def __init__(self, group=None, device=None):
+        import torch
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() \
+                else torch.device("cpu")
+        self.device = torch.device(device)
+        self.calls = {"allreduce_f32": 0, "allreduce_i32": 0, "allgather": 0}
+
+        def ar_f32(_u, buf, n, _stream):
+            return self._allreduce(buf, n, "<f4", "allreduce_f32")
+
+        def ar_i32(_u, buf, n, _stream):
+            return self._allreduce(buf, n, "<i4", "allreduce_i32")
+
+        def ag(_u, send, recv, nbytes, _stream):
+            try:
+                s = _view(send, nbytes, "|u1", self.device)
+                r = _view(recv, nbytes * self.world, "|u1", self.device)
+                dist.all_gather_into_tensor(r, s, group=self.group)
+                self.calls["allgather"] += 1
+                return 0
+            except Exception:  # surfaced by the library as GULON_EINVAL "hook failed"
+                return 1
+
+        self._cbs = (N.Comm.ALLREDUCE_F32(ar_f32), N.Comm.ALLREDUCE_I32(ar_i32), N.Comm.ALLGATHER(ag))
+        self.struct = N.Comm(self.rank, self.world, self._cbs[0], self._cbs[1], self._cbs[2], None)
+
+    def _allreduce(self, buf, n, typestr, name):
+        try:
+            if n > 0:
+                t = _view(buf, n, typestr, self.device)
+                self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+            self.calls[name] += 1
+            return 0
+        except Exception:
+            return 1
+
+
+def merge_topk_host(ids, dists, k):
+    """(distance, id) merge of [S][Q][k] result sets on the host -- used only to cross-check the
+    device merge in tests and by the gloo tests' stand-in ops."""
+    S, Q, kk = ids.shape
+    out_i = np.full((Q, k), -1, np.int32)
+    out_d = np.full((Q, k), np.inf, np.float32)
+    out_s = np.zeros(Q, np.int32)
+    for q in range(Q):
+        i = ids[:, q, :].reshape(-1)
+        d = dists[:, q, :].reshape(-1)
+        keep = i >= 0
+        i, d = i[keep], d[keep]
+        o = np.lexsort((i, d))[:k]
+        out_i[q, :len(o)] = i[o]
+        out_d[q, :len(o)] = d[o]
+        out_s[q] = len(o)
+    return out_i, out_d, out_s
+
+
+class NativeOps:
+    """The device ops of the sharded scan: the CUDA library (the only product implementation)."""
+
+    def __init__(self, index):
+        self.index = index
+
+    def local_query(self, k, queries, id_offset):
+        return self.index.batch_query_dev(k, queries, id_offset=id_offset)
+
+    def merge(self, ids_all, dists_all, k):
+        import torch
+        S, Q, _ = ids_all.shape
+        oi = torch.empty((Q, k), dtype=torch.int32, device=ids_all.device)
+        od = torch.empty((Q, k), dtype=torch.float32, device=ids_all.device)
+        oz = torch.empty((Q,), dtype=torch.int32, device=ids_all.device)
+        N.check(N.lib().gulon_topk_merge_dev(ids_all.data_ptr(), dists_all.data_ptr(), S, Q, k,
+                                             oi.data_ptr(), od.data_ptr(), oz.data_ptr(),
+                                             torch.cuda.current_stream(ids_all.device).cuda_stream))
+        return oi, od, oz
+
+
+class ShardedPQIndex:
+    """A PQIndex whose code planes are row-sharded over the ranks of a process group.
+
+    `ops` provides `local_query(k, queries, id_offset)` -> (ids, dists, sizes) tensors and
+    `merge(ids_all [S][Q][k], dists_all, k)`; the default is the CUDA library.
+    """
+
+    def __init__(self, local_index, row_offset, group=None, ops=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.row_offset = int(row_offset)
+        self.ops = ops if ops is not None else NativeOps(local_index)
+
+    def batch_query(self, k, queries):
+        """queries: the same [Q][D] tensor on every rank.  Returns merged (ids, dists, sizes)."""
+        import torch
+        ids, ds, _ = self.ops.local_query(k, queries, self.row_offset)
+        if self.world == 1:
+            return self.ops.merge(ids.unsqueeze(0), ds.unsqueeze(0), k)
+        Q = ids.shape[0]
+        # rank-major concatenation along dim 0 == [world][Q][k]
+        ids_all = torch.empty((self.world * Q, k), dtype=ids.dtype, device=ids.device)
+        ds_all = torch.empty((self.world * Q, k), dtype=ds.dtype, device=ds.device)
+        self.dist.all_gather_into_tensor(ids_all, ids.contiguous(), group=self.group)
+        self.dist.all_gather_into_tensor(ds_all, ds.contiguous(), group=self.group)
+        return self.ops.merge(ids_all.view(self.world, Q, k), ds_all.view(self.world, Q, k), k)

@@ -213,6 +213,16 @@ int gulon_exact_topk(gulon_points_t p, const float *queries, int64_t nq, int64_t
                      int64_t from, int64_t until, int32_t *out_ids, float *out_dists,
                      int32_t *out_sizes);
 
+/*
+ * Exact fp32 re-rank of PQ candidates: for each query the candidate rows cand_ids[q][0..R) (ids < 0
+ * are skipped) are scored with MathUtils.distanceSq (G/MathUtils.scala:85-95) against the raw
+ * vectors and the k best kept, (distance, id) ascending.  This is the exact-distance step of the
+ * recall harness (G/Tests.scala:24-37) used as a production re-rank.  Host buffers.
+ */
+int gulon_rerank(gulon_points_t p, const float *queries, int64_t nq, int64_t ldq,
+                 const int32_t *cand_ids, int32_t R, int32_t k, int32_t *out_ids,
+                 float *out_dists, int32_t *out_sizes);
+
 #ifdef __cplusplus
 }
 #endif
