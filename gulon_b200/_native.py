@@ -178,6 +178,12 @@ def kernel_launches():
     return int(v.value)
 
 
+def counter(name):
+    v = i64(0)
+    check(lib().gulon_get_counter(name.encode(), C.byref(v)))
+    return int(v.value)
+
+
 def device_count():
     n = i32(0)
     check(lib().gulon_device_count(C.byref(n)))

@@ -68,6 +68,57 @@ std::atomic<long long> g_simple_scratch{1LL << 30};
 std::atomic<long long> g_encode_chunk{1 << 20};  // rows per H2D chunk in gulon_pq_encode
 std::atomic<long long> g_fused_min_rows{16384};
 
+// ---- optional per-launch timing of the dominant kernels (bench.py's roofline leg) -------------
+// With option "profile" = 1 every fused-scan / assign launch is bracketed by CUDA events on the
+// launching stream; gulon_get_counter("scan_kernel_ns" | "assign_kernel_ns" | ..._launches)
+// synchronises the pending events and returns the running totals.
+std::atomic<long long> g_profile{0};
+struct KernelTimer {
+  std::mutex mu;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+  double ns = 0;
+  long long launches = 0;
+  cudaEvent_t begin(cudaStream_t st) {
+    if (!g_profile.load()) return nullptr;
+    cudaEvent_t e0;
+    if (cudaEventCreate(&e0) != cudaSuccess) return nullptr;
+    cudaEventRecord(e0, st);
+    return e0;
+  }
+  void end(cudaEvent_t e0, cudaStream_t st) {
+    if (!e0) return;
+    cudaEvent_t e1;
+    if (cudaEventCreate(&e1) != cudaSuccess) {
+      cudaEventDestroy(e0);
+      return;
+    }
+    cudaEventRecord(e1, st);
+    std::lock_guard<std::mutex> lock(mu);
+    pending.emplace_back(e0, e1);
+  }
+  void drain() {
+    std::lock_guard<std::mutex> lock(mu);
+    for (auto &pr : pending) {
+      float ms = 0;
+      if (cudaEventSynchronize(pr.second) == cudaSuccess &&
+          cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) {
+        ns += (double)ms * 1e6;
+        launches += 1;
+      }
+      cudaEventDestroy(pr.first);
+      cudaEventDestroy(pr.second);
+    }
+    pending.clear();
+  }
+  void reset() {
+    drain();
+    std::lock_guard<std::mutex> lock(mu);
+    ns = 0;
+    launches = 0;
+  }
+};
+KernelTimer g_t_scan, g_t_assign;
+
 int need_device() {
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
@@ -149,8 +200,10 @@ int launch_assign_dim(const float *dX, i64 N, i64 ld, const float *cb, const flo
   const size_t smem = (size_t)KC * (DP + 1) * sizeof(float);
   dim3 grid((unsigned)ceil_div(N, ASSIGN_TILE), (unsigned)nsub);
   auto kern = assign_exact_kernel<DIM, OutT>;
+  cudaEvent_t ev = g_t_assign.begin(st);
   GLAUNCH(kern, grid, ASSIGN_NT, smem, st, dX, N, ld, cb, off, K, dmax, dsubs, dfrom, out,
           out_stride, KC);
+  g_t_assign.end(ev, st);
   return GULON_OK;
 }
 
@@ -590,7 +643,9 @@ int scan_batch(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 fr
     prm.S = S;
     prm.Bs = Bs;
     prm.lists = ix->lists.as<u64>();
+    cudaEvent_t ev = g_t_scan.begin(st);
     GLAUNCH(fscan::fused_scan_kernel, (unsigned)(S * Bs), fscan::NT, fscan::SMEM_BYTES, st, prm);
+    g_t_scan.end(ev, st);
     if (S == 1) return unpack(ix->lists.as<u64>(), k, nq, k, id_offset, d_ids, d_dists, d_sizes, st);
     const i64 stride = round_up((i64)S * k, SEL_CHUNK);
     GCHECK(ix->merged.ensure((size_t)Q4 * stride * sizeof(u64)));
@@ -712,6 +767,10 @@ int gulon_set_option(const char *name, int64_t value) {
   } else if (s == "encode_chunk_rows") {
     GREQUIRE(value >= 1, "encode_chunk_rows must be >= 1");
     g_encode_chunk = value;
+  } else if (s == "profile") {
+    g_profile = value ? 1 : 0;
+    g_t_scan.reset();
+    g_t_assign.reset();
   } else if (s == "fused_min_rows") {
     GREQUIRE(value >= 0, "fused_min_rows must be >= 0");
     g_fused_min_rows = value;
@@ -723,8 +782,19 @@ int gulon_set_option(const char *name, int64_t value) {
 
 int gulon_get_counter(const char *name, int64_t *value) {
   GREQUIRE(name && value, "null argument");
-  if (std::string(name) == "kernel_launches") {
+  const std::string s(name);
+  if (s == "kernel_launches") {
     *value = launch_counter().load();
+    return GULON_OK;
+  }
+  if (s == "scan_kernel_ns" || s == "scan_kernel_launches") {
+    g_t_scan.drain();
+    *value = s == "scan_kernel_ns" ? (int64_t)g_t_scan.ns : g_t_scan.launches;
+    return GULON_OK;
+  }
+  if (s == "assign_kernel_ns" || s == "assign_kernel_launches") {
+    g_t_assign.drain();
+    *value = s == "assign_kernel_ns" ? (int64_t)g_t_assign.ns : g_t_assign.launches;
     return GULON_OK;
   }
   return fail(GULON_EINVAL, "unknown counter '%s'", name);
