@@ -247,6 +247,9 @@ def main():
     launches = g.kernel_launches() - launches0
     scan_ns = N.counter("scan_kernel_ns")
     scan_launches = N.counter("scan_kernel_launches")
+    pscan_ns = N.counter("pscan_kernel_ns")
+    pscan_launches = N.counter("pscan_kernel_launches")
+    pstats = {nm: N.counter("pscan_" + nm) for nm in ("survivors", "candidates", "slow_items", "pairs")}
     g.set_option("profile", 0)
     value = Q * a.steps / (ms * 1e-3)
 
@@ -303,23 +306,36 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     roof = None
-    if scan_launches > 0:
-        QT = 4
-        groups = a.steps * -(-Q // QT)
-        alg_bytes = groups * n_local * M / scan_launches
-        sec = scan_ns * 1e-9 / scan_launches
+    use_p = pscan_launches > 0 and pscan_ns >= scan_ns
+    k_ns, k_launches = (pscan_ns, pscan_launches) if use_p else (scan_ns, scan_launches)
+    if k_launches > 0:
+        # algorithmic bytes: one pass over the scanned code planes per tile of Qt
+        # queries whose tables share shared memory (Qt = 8 pruned kernel, 4 exact kernel)
+        QT = 8 if use_p else 4
+        rows_scanned = (pstats["pairs"] / (a.steps * Q)) if use_p else n_local
+        alg_bytes = a.steps * -(-Q // QT) * rows_scanned * M / k_launches
+        sec = k_ns * 1e-9 / k_launches
         ach = alg_bytes / sec / 1e9
-        gathers = a.steps * Q * n_local * M / (scan_ns * 1e-9)
-        smem_peak = 148 * 32 * (clk["sm_mhz"] or 1965.0) * 1e6 if clk else None
+        gathers = a.steps * Q * rows_scanned * M / (k_ns * 1e-9)
+        clk_mhz = (clk or {}).get("sm_mhz") or 1965.0
+        smem_peak_bytes = 148 * 128 * clk_mhz * 1e6
         roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": None, "kernel": "fused_scan_kernel",
+                "traffic": None, "kernel": "pruned_scan_kernel" if use_p else "fused_scan_kernel",
                 "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
                 "algorithmic_bytes_per_launch": alg_bytes, "launch_seconds": sec,
-                "launches": scan_launches, "query_tile": QT,
-                "kernel_share_of_step": scan_ns * 1e-6 / ms,
-                "smem_gather": {"achieved_per_s": gathers, "peak_per_s": smem_peak,
-                                "frac": gathers / smem_peak if smem_peak else None,
-                                "note": "4-byte LUT reads; the binding resource for bit-exact fp32 ADC"}}
+                "launches": k_launches, "query_tile": QT,
+                "kernel_share_of_step": k_ns * 1e-6 / ms,
+                "other_scan_kernel_share_of_step": (scan_ns if use_p else pscan_ns) * 1e-6 / ms,
+                "smem_gather": {"bytes_per_entry": 2 if use_p else 4,
+                                "achieved_GBps": gathers * (2 if use_p else 4) / 1e9,
+                                "peak_GBps": smem_peak_bytes / 1e9,
+                                "frac": gathers * (2 if use_p else 4) / smem_peak_bytes,
+                                "note": "table reads from shared memory: the binding resource "
+                                        "(128 B/clk/SM crossbar)"}}
+        if use_p and pstats["pairs"]:
+            roof["pruning"] = {"survivor_rate": pstats["survivors"] / pstats["pairs"],
+                               "list_candidates": pstats["candidates"],
+                               "slow_path_items": pstats["slow_items"]}
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:

@@ -4,7 +4,7 @@ reference's Scala API (G/KMeans.scala, G/ProductQuantizer.scala, G/Index.scala) 
 hand-written CUDA kernels through the C ABI in include/gulon_b200.h.  No CPU fallback.
 """
 from . import _native
-from ._native import (GulonError, NoDeviceError, SCAN_AUTO, SCAN_FUSED, SCAN_SIMPLE, TIE_LOWEST,
+from ._native import (GulonError, NoDeviceError, SCAN_AUTO, SCAN_FUSED, SCAN_PRUNED, SCAN_SIMPLE, TIE_LOWEST,
                       UPDATE_RUNNING_MEAN, UPDATE_SUM, build, device_count, kernel_launches,
                       set_option)
 from .index import PQIndex, TopK, exact_nearest_neighbours, prepare_query
@@ -16,7 +16,7 @@ from .quantizer import Config as ProductQuantizerConfig
 from .vectors import DevicePoints, Matrix, Vectors, normalize, subvector_windows
 
 __all__ = [
-    "GulonError", "NoDeviceError", "SCAN_AUTO", "SCAN_FUSED", "SCAN_SIMPLE", "TIE_LOWEST",
+    "GulonError", "NoDeviceError", "SCAN_AUTO", "SCAN_FUSED", "SCAN_PRUNED", "SCAN_SIMPLE", "TIE_LOWEST",
     "UPDATE_RUNNING_MEAN", "UPDATE_SUM", "build", "device_count", "kernel_launches", "set_option",
     "PQIndex", "TopK", "exact_nearest_neighbours", "prepare_query", "KMeans", "KMeansConfig",
     "KMeansProgressReport", "Coder8", "EncodedMatrix", "ProductQuantizer", "Quantizer",

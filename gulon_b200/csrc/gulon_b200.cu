@@ -13,6 +13,7 @@
 
 #include "common.cuh"
 #include "kmeans.cuh"
+#include "pscan.cuh"
 #include "scan.cuh"
 #include "select.cuh"
 
@@ -50,12 +51,15 @@ struct gulon_index_s {
   bool owned = false;
   std::mutex mu;  // guards the scratch below: one query batch in flight per index handle
   DevBuf lutI, keys, lists, qbuf, ids, dists, sizes, merged;
-  Selector sel;
+  DevBuf qlut, mins, qp, boot_tail, plists, pstats, boot_keys;
+  Selector sel, sel_boot;
   ~gulon_index_s() {
     if (owned && codes) cudaFree((void *)codes);
     lutI.release(); keys.release(); lists.release(); qbuf.release();
     ids.release(); dists.release(); sizes.release(); merged.release();
-    sel.release();
+    qlut.release(); mins.release(); qp.release(); boot_tail.release(); plists.release();
+    pstats.release(); boot_keys.release();
+    sel.release(); sel_boot.release();
   }
 };
 
@@ -67,6 +71,10 @@ std::atomic<long long> g_query_batch{0};      // 0 = auto (multiple of 16 * #SM)
 std::atomic<long long> g_simple_scratch{1LL << 30};
 std::atomic<long long> g_encode_chunk{1 << 20};  // rows per H2D chunk in gulon_pq_encode
 std::atomic<long long> g_fused_min_rows{16384};
+std::atomic<long long> g_boot_rows{65536};       // rows scanned exactly to seed the pruned scan
+std::atomic<long long> g_pruned_min_rows{1 << 20};
+std::atomic<unsigned long long> g_pstats[3];     // survivors, list candidates, slow-path items
+std::atomic<unsigned long long> g_ppairs{0};     // (row, query) pairs offered to the pruned kernel
 
 // ---- optional per-launch timing of the dominant kernels (bench.py's roofline leg) -------------
 // With option "profile" = 1 every fused-scan / assign launch is bracketed by CUDA events on the
@@ -117,7 +125,7 @@ struct KernelTimer {
     launches = 0;
   }
 };
-KernelTimer g_t_scan, g_t_assign;
+KernelTimer g_t_scan, g_t_assign, g_t_pscan;
 
 int need_device() {
   int n = 0;
@@ -595,66 +603,175 @@ int fill_empty(i64 nq, int k, int32_t *ids, float *dists, int32_t *sizes, cudaSt
   return GULON_OK;
 }
 
+// Launches the fused exact scan of [from, until) for G query groups; lists [S][G*4][k].
+int fused_lists(gulon_index_t ix, i64 from, i64 until, int G, int k, DevBuf &lists, int *S_out,
+                cudaStream_t st) {
+  gulon_codebook_t cb = ix->cb;
+  const i64 range = until - from;
+  const int Q4 = G * 4;
+  GREQUIRE(k <= fscan::KMAX, "fused scan supports k <= %d (k=%d)", fscan::KMAX, k);
+  static std::once_flag once;
+  std::call_once(once, [] {
+    cudaFuncSetAttribute(fscan::fused_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         fscan::SMEM_BYTES);
+  });
+  const int nsm = sm_count();
+  int Bs = std::min(G, nsm);
+  int S = std::max(1, nsm / Bs);
+  // every split should hold at least a few items; boundaries are multiples of 16 rows
+  S = (int)std::max<i64>(1, std::min<i64>(S, range / (2 * fscan::R)));
+  i64 split_len = round_up(ceil_div(range, S), 16);
+  S = (int)ceil_div(range, split_len);
+  const size_t nl = (size_t)S * Q4 * k;
+  GCHECK(lists.ensure(nl * sizeof(u64)));
+  GCU(cudaMemsetAsync(lists.p, 0xFF, nl * sizeof(u64), st));
+  fscan::Params prm;
+  prm.codes = ix->codes;
+  prm.ps = ix->ps;
+  prm.from = from;
+  prm.until = until;
+  prm.split_len = split_len;
+  prm.boot = 0;
+  prm.lutI = ix->lutI.as<float4>();
+  prm.M = cb->M;
+  prm.G = G;
+  prm.k = k;
+  prm.S = S;
+  prm.Bs = Bs;
+  prm.lists = lists.as<u64>();
+  cudaEvent_t ev = g_t_scan.begin(st);
+  GLAUNCH(fscan::fused_scan_kernel, (unsigned)(S * Bs), fscan::NT, fscan::SMEM_BYTES, st, prm);
+  g_t_scan.end(ev, st);
+  *S_out = S;
+  return GULON_OK;
+}
+
+// [S][Q4][k] lists -> one sorted list per query: *keys / *stride (first k entries of each row)
+int collapse_lists(DevBuf &lists, int S, int Q4, int k, DevBuf &merged, Selector &sel, u64 **keys,
+                   i64 *stride, cudaStream_t st) {
+  if (S == 1) {
+    *keys = lists.as<u64>();
+    *stride = k;
+    return GULON_OK;
+  }
+  const i64 ms = round_up((i64)S * k, SEL_CHUNK);
+  GCHECK(merged.ensure((size_t)Q4 * ms * sizeof(u64)));
+  dim3 gg((unsigned)ceil_div(ms, 256), (unsigned)Q4);
+  GLAUNCH(gather_lists_kernel, gg, 256, 0, st, lists.as<u64>(), S, (i64)Q4, k, merged.as<u64>(), ms);
+  return sel.run(merged.as<u64>(), ms, Q4, k, st, keys, stride);
+}
+
 // One batch of queries (device, already normalised if the metric asks for it) over [from, until).
 // Caller holds ix->mu.
 int scan_batch(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 from, i64 until,
                i64 id_offset, int32_t *d_ids, float *d_dists, int32_t *d_sizes, cudaStream_t st) {
   gulon_codebook_t cb = ix->cb;
   const int M = cb->M, K = cb->K;
-  const int G = (int)ceil_div(nq, 4), Q4 = G * 4;
   const i64 range = until - from;
+  long long impl = g_scan_impl.load();
+  if (impl == GULON_SCAN_AUTO) {
+    if (k <= pscan::KMAX && M <= 1024 && range >= g_pruned_min_rows.load())
+      impl = GULON_SCAN_PRUNED;
+    else if (k <= fscan::KMAX && range >= g_fused_min_rows.load())
+      impl = GULON_SCAN_FUSED;
+    else
+      impl = GULON_SCAN_SIMPLE;
+  }
+  // query groups of 4 (float4 tables); the pruned scan works on tiles of 8 = two groups
+  const int G = impl == GULON_SCAN_PRUNED ? 2 * (int)ceil_div(nq, 8) : (int)ceil_div(nq, 4);
+  const int Q4 = G * 4;
   GCHECK(ix->lutI.ensure((size_t)G * M * 256 * sizeof(float4)));
   dim3 lg((unsigned)G, (unsigned)M);
   GLAUNCH(lut_build_kernel, lg, 256, 0, st, dQ, ldq, nq, cb->cb.as<float>(),
           cb->dfrom.as<int32_t>(), cb->ddim.as<int32_t>(), M, K, cb->dmax, ix->lutI.as<float4>());
 
-  long long impl = g_scan_impl.load();
-  if (impl == GULON_SCAN_AUTO)
-    impl = (k <= fscan::KMAX && range >= g_fused_min_rows.load()) ? GULON_SCAN_FUSED
-                                                                   : GULON_SCAN_SIMPLE;
   if (impl == GULON_SCAN_FUSED) {
-    GREQUIRE(k <= fscan::KMAX, "fused scan supports k <= %d (k=%d)", fscan::KMAX, k);
+    int S = 1;
+    GCHECK(fused_lists(ix, from, until, G, k, ix->lists, &S, st));
+    u64 *res;
+    i64 rs;
+    GCHECK(collapse_lists(ix->lists, S, Q4, k, ix->merged, ix->sel, &res, &rs, st));
+    return unpack(res, rs, nq, k, id_offset, d_ids, d_dists, d_sizes, st);
+  }
+
+  if (impl == GULON_SCAN_PRUNED) {
+    GREQUIRE(k <= pscan::KMAX, "pruned scan supports k <= %d (k=%d)", pscan::KMAX, k);
+    GREQUIRE(M <= 1024, "pruned scan supports M <= 1024 (M=%d)", M);
     static std::once_flag once;
     std::call_once(once, [] {
-      cudaFuncSetAttribute(fscan::fused_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           fscan::SMEM_BYTES);
+      cudaFuncSetAttribute(pscan::pruned_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           pscan::SMEM_BYTES);
     });
+    const int T = G / 2;
+    // 1. exact scan of the boot rows -> one sorted list per query (its tail is tau0)
+    const i64 boot = std::min<i64>(range, std::max<i64>(g_boot_rows.load(), k));
+    int Sb = 1;
+    GCHECK(fused_lists(ix, from, from + boot, G, k, ix->lists, &Sb, st));
+    u64 *bkeys;
+    i64 bstride;
+    GCHECK(collapse_lists(ix->lists, Sb, Q4, k, ix->boot_keys, ix->sel_boot, &bkeys, &bstride, st));
+    if (boot == range) return unpack(bkeys, bstride, nq, k, id_offset, d_ids, d_dists, d_sizes, st);
+    // 2. quantised lower-bound tables
+    GCHECK(ix->mins.ensure((size_t)Q4 * M * sizeof(float)));
+    GCHECK(ix->qp.ensure((size_t)Q4 * sizeof(pscan::QParam)));
+    GCHECK(ix->boot_tail.ensure((size_t)Q4 * sizeof(u64)));
+    GCHECK(ix->qlut.ensure((size_t)T * M * 256 * sizeof(uint4)));
+    GCHECK(ix->pstats.ensure(3 * sizeof(unsigned long long)));
+    GLAUNCH(pscan::qparams_kernel, (unsigned)G, 256, 0, st, ix->lutI.as<float4>(), M, K, nq, bkeys,
+            bstride, k, ix->mins.as<float>(), ix->qp.as<pscan::QParam>(), ix->boot_tail.as<u64>());
+    dim3 qg((unsigned)T, (unsigned)M);
+    GLAUNCH(pscan::qlut_build_kernel, qg, 256, 0, st, ix->lutI.as<float4>(), ix->mins.as<float>(),
+            ix->qp.as<pscan::QParam>(), M, K, ix->qlut.as<uint4>());
+    // 3. pruned scan of the remaining rows
+    const i64 pfrom = from + boot, prange = until - pfrom;
     const int nsm = sm_count();
-    int Bs = std::min(G, nsm);
+    int Bs = std::min(T, nsm);
     int S = std::max(1, nsm / Bs);
-    // every split should hold at least a few items; boundaries are multiples of 16 rows
-    S = (int)std::max<i64>(1, std::min<i64>(S, range / (2 * fscan::R)));
-    i64 split_len = round_up(ceil_div(range, S), 16);
-    S = (int)ceil_div(range, split_len);
+    S = (int)std::max<i64>(1, std::min<i64>(S, prange / (2 * pscan::R)));
+    const i64 split_len = round_up(ceil_div(prange, S), 16);
+    S = (int)ceil_div(prange, split_len);
     const size_t nl = (size_t)S * Q4 * k;
-    GCHECK(ix->lists.ensure(nl * sizeof(u64)));
-    GCU(cudaMemsetAsync(ix->lists.p, 0xFF, nl * sizeof(u64), st));
-    fscan::Params prm;
+    GCHECK(ix->plists.ensure(nl * sizeof(u64)));
+    GCU(cudaMemsetAsync(ix->plists.p, 0xFF, nl * sizeof(u64), st));
+    const bool want_stats = g_profile.load() != 0;
+    if (want_stats) GCU(cudaMemsetAsync(ix->pstats.p, 0, 3 * sizeof(unsigned long long), st));
+    pscan::Params prm;
     prm.codes = ix->codes;
     prm.ps = ix->ps;
-    prm.from = from;
+    prm.from = pfrom;
     prm.until = until;
     prm.split_len = split_len;
-    prm.boot = 0;
+    prm.qlut = ix->qlut.as<uint4>();
     prm.lutI = ix->lutI.as<float4>();
+    prm.qp = ix->qp.as<pscan::QParam>();
+    prm.boot_tail = ix->boot_tail.as<u64>();
+    prm.lists = ix->plists.as<u64>();
+    prm.stats = want_stats ? ix->pstats.as<unsigned long long>() : nullptr;
+    prm.nq = nq;
     prm.M = M;
-    prm.G = G;
+    prm.T = T;
     prm.k = k;
     prm.S = S;
     prm.Bs = Bs;
-    prm.lists = ix->lists.as<u64>();
-    cudaEvent_t ev = g_t_scan.begin(st);
-    GLAUNCH(fscan::fused_scan_kernel, (unsigned)(S * Bs), fscan::NT, fscan::SMEM_BYTES, st, prm);
-    g_t_scan.end(ev, st);
-    if (S == 1) return unpack(ix->lists.as<u64>(), k, nq, k, id_offset, d_ids, d_dists, d_sizes, st);
-    const i64 stride = round_up((i64)S * k, SEL_CHUNK);
-    GCHECK(ix->merged.ensure((size_t)Q4 * stride * sizeof(u64)));
-    dim3 gg((unsigned)ceil_div(stride, 256), (unsigned)Q4);
-    GLAUNCH(gather_lists_kernel, gg, 256, 0, st, ix->lists.as<u64>(), S, (i64)Q4, k,
-            ix->merged.as<u64>(), stride);
+    cudaEvent_t ev = g_t_pscan.begin(st);
+    GLAUNCH(pscan::pruned_scan_kernel, (unsigned)(S * Bs), pscan::NT, pscan::SMEM_BYTES, st, prm);
+    g_t_pscan.end(ev, st);
+    if (want_stats) {
+      unsigned long long h[3];
+      GCU(cudaMemcpyAsync(h, ix->pstats.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+      GCU(cudaStreamSynchronize(st));
+      for (int i = 0; i < 3; i++) g_pstats[i] += h[i];
+      g_ppairs += (unsigned long long)prange * (unsigned long long)nq;
+    }
+    // 4. boot list + split lists -> answer
+    const i64 ms = round_up((i64)(S + 1) * k, SEL_CHUNK);
+    GCHECK(ix->merged.ensure((size_t)Q4 * ms * sizeof(u64)));
+    dim3 gg((unsigned)ceil_div(ms, 256), (unsigned)Q4);
+    GLAUNCH(pscan::gather_lists2_kernel, gg, 256, 0, st, ix->plists.as<u64>(), S, (i64)Q4, k, bkeys,
+            bstride, ix->merged.as<u64>(), ms);
     u64 *res;
     i64 rs;
-    GCHECK(ix->sel.run(ix->merged.as<u64>(), stride, Q4, k, st, &res, &rs));
+    GCHECK(ix->sel.run(ix->merged.as<u64>(), ms, Q4, k, st, &res, &rs));
     return unpack(res, rs, nq, k, id_offset, d_ids, d_dists, d_sizes, st);
   }
 
@@ -698,7 +815,7 @@ int query_dev(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 fro
   const int D = ix->cb->D;
   i64 qb = g_query_batch.load();
   if (qb <= 0) qb = (i64)sm_count() * 16;
-  qb = round_up(qb, 4);
+  qb = std::min<i64>(round_up(qb, 8), 32768);
   for (i64 q0 = 0; q0 < nq; q0 += qb) {
     const i64 nb = std::min<i64>(qb, nq - q0);
     const float *q = dQ + q0 * ldq;
@@ -756,7 +873,7 @@ int gulon_set_option(const char *name, int64_t value) {
   GREQUIRE(name, "null option name");
   std::string s(name);
   if (s == "scan_impl") {
-    GREQUIRE(value >= GULON_SCAN_AUTO && value <= GULON_SCAN_FUSED, "scan_impl must be 0, 1 or 2");
+    GREQUIRE(value >= GULON_SCAN_AUTO && value <= GULON_SCAN_PRUNED, "scan_impl must be 0..3");
     g_scan_impl = value;
   } else if (s == "query_batch") {
     GREQUIRE(value >= 0, "query_batch must be >= 0");
@@ -771,6 +888,15 @@ int gulon_set_option(const char *name, int64_t value) {
     g_profile = value ? 1 : 0;
     g_t_scan.reset();
     g_t_assign.reset();
+    g_t_pscan.reset();
+    for (int i = 0; i < 3; i++) g_pstats[i] = 0;
+    g_ppairs = 0;
+  } else if (s == "boot_rows") {
+    GREQUIRE(value >= 1, "boot_rows must be >= 1");
+    g_boot_rows = value;
+  } else if (s == "pruned_min_rows") {
+    GREQUIRE(value >= 0, "pruned_min_rows must be >= 0");
+    g_pruned_min_rows = value;
   } else if (s == "fused_min_rows") {
     GREQUIRE(value >= 0, "fused_min_rows must be >= 0");
     g_fused_min_rows = value;
@@ -790,6 +916,19 @@ int gulon_get_counter(const char *name, int64_t *value) {
   if (s == "scan_kernel_ns" || s == "scan_kernel_launches") {
     g_t_scan.drain();
     *value = s == "scan_kernel_ns" ? (int64_t)g_t_scan.ns : g_t_scan.launches;
+    return GULON_OK;
+  }
+  if (s == "pscan_kernel_ns" || s == "pscan_kernel_launches") {
+    g_t_pscan.drain();
+    *value = s == "pscan_kernel_ns" ? (int64_t)g_t_pscan.ns : g_t_pscan.launches;
+    return GULON_OK;
+  }
+  if (s == "pscan_survivors" || s == "pscan_candidates" || s == "pscan_slow_items") {
+    *value = (int64_t)g_pstats[s == "pscan_survivors" ? 0 : s == "pscan_candidates" ? 1 : 2].load();
+    return GULON_OK;
+  }
+  if (s == "pscan_pairs") {
+    *value = (int64_t)g_ppairs.load();
     return GULON_OK;
   }
   if (s == "assign_kernel_ns" || s == "assign_kernel_launches") {

@@ -1,0 +1,404 @@
+// pscan.cuh -- pruned scan: a 16-bit lower-bound pass over all rows, exact fp32 re-evaluation of
+// the survivors only.  Results are identical to fscan::fused_scan_kernel (and to the reference:
+// PQIndex.distances + batchQuery, G/Index.scala:393-440) because every distance that can enter a
+// top-k list is still computed as (((0 + LUT[0][c0]) + LUT[1][c1]) + ...) in fp32, round-to-nearest.
+//
+// Why: the exact scan is bound by shared-memory bandwidth -- one 4-byte table read per (row, query,
+// quantizer).  A row can be discarded without computing its distance if a LOWER BOUND of it already
+// exceeds the query's current k-th best distance tau.  The bound used here is
+//     LB = base + delta * sum_m q[m][code_m],   q = min(qmax, floor((LUT[m][c] - min_c LUT[m][c]) / delta)),
+// base = sum_m min_c LUT[m][c]: 2 bytes per table entry, 8 queries per 128-bit shared-memory read,
+// plain 32-bit integer adds on packed pairs (fields cannot carry: bias + M * qmax <= 65535).  With
+// bias = 32767 - T, T = floor((tau * (1 + 2^-11) - base) / delta), bit 15 of a field is set iff
+// sum q > T, which implies fp32-sum > tau (the 2^-11 covers the fp32 summation error for M <= 2048
+// and the double rounding of the quantiser).  Rows whose 8 fields are all flagged are dropped; the
+// others ("survivors", ~1e-4 of the pairs once tau is warm) are re-evaluated exactly by one warp each
+// from the fp32 tables in global memory and offered to the top-k lists.  tau comes from an exact
+// scan of the first rows of the range (the "boot" rows, done by the fused kernel) and tightens as a
+// CTA's own list fills.
+#pragma once
+#include "common.cuh"
+#include "scan.cuh"
+#include "select.cuh"
+
+namespace gulon {
+namespace pscan {
+
+constexpr int NT = 512;
+constexpr int RPT = 16;
+constexpr int R = NT * RPT;     // 8192 rows per item
+constexpr int QT = 8;           // queries per tile (two groups of 4)
+constexpr int KMAX = 128;
+constexpr int SORTN = 256;      // per-query sort area: k list entries + up to CAPQ candidates
+constexpr int CAPQ = SORTN - KMAX;
+constexpr int QCAP = NT * QT;   // survivor queue entries (one row per thread in the slow path)
+constexpr int SLICE_U4 = 256 * 8;  // uint4 per replicated slice (32 KB)
+constexpr int T0 = 2048;        // quantisation units between base and the boot threshold
+constexpr int FLAG = 32768;
+constexpr int SMEM_BYTES = 2 * SLICE_U4 * 16 + QT * SORTN * 8 + QCAP * 4;
+
+struct QParam {
+  double base;       // sum_m min_c LUT[m][c]
+  double inv_delta;  // 0: nothing can be pruned (no threshold yet)
+};
+
+struct Params {
+  const uint8_t *codes;
+  i64 ps;
+  i64 from, until;  // rows scanned by this kernel (after the boot rows)
+  i64 split_len;
+  const uint4 *qlut;      // [T][M][256] 8 x u16
+  const float4 *lutI;     // [2T][M][256] exact tables (scan.cuh layout)
+  const QParam *qp;       // [T*8]
+  const u64 *boot_tail;   // [T*8] key of the boot list tail (KEY_SENT: none)
+  u64 *lists;             // [S][T*8][k]
+  unsigned long long *stats;  // [0] survivors, [1] list candidates, [2] slow-path items
+  i64 nq;
+  int M, T, k, S, Bs;
+};
+
+// ---- per-query quantisation parameters ---------------------------------------------------------
+// grid (G = 2T groups), block 256.  mins[(g*4+j)*M + m] = min_c LUT; qp / boot_tail per query.
+__global__ void __launch_bounds__(256) qparams_kernel(const float4 *__restrict__ lutI, int M, int K,
+                                                      i64 nq, const u64 *__restrict__ boot_keys,
+                                                      i64 boot_stride, int k,
+                                                      float *__restrict__ mins,
+                                                      QParam *__restrict__ qp,
+                                                      u64 *__restrict__ boot_tail) {
+  __shared__ float red[8][4];
+  const int g = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float INF = __int_as_float(0x7f800000);
+  double base = 0.0;
+  for (int m = 0; m < M; m++) {
+    float4 v = make_float4(INF, INF, INF, INF);
+    if (tid < K) v = lutI[((i64)g * M + m) * 256 + tid];
+    for (int o = 16; o > 0; o >>= 1) {
+      v.x = fminf(v.x, __shfl_xor_sync(0xffffffffu, v.x, o));
+      v.y = fminf(v.y, __shfl_xor_sync(0xffffffffu, v.y, o));
+      v.z = fminf(v.z, __shfl_xor_sync(0xffffffffu, v.z, o));
+      v.w = fminf(v.w, __shfl_xor_sync(0xffffffffu, v.w, o));
+    }
+    __syncthreads();
+    if (lane == 0) {
+      red[warp][0] = v.x; red[warp][1] = v.y; red[warp][2] = v.z; red[warp][3] = v.w;
+    }
+    __syncthreads();
+    if (tid < 4) {
+      float mn = red[0][tid];
+      for (int w = 1; w < 8; w++) mn = fminf(mn, red[w][tid]);
+      mins[((i64)g * 4 + tid) * M + m] = mn;
+      base += (double)mn;
+    }
+  }
+  if (tid < 4) {
+    const i64 q = (i64)g * 4 + tid;
+    QParam p;
+    p.base = base;
+    p.inv_delta = 0.0;
+    u64 tk = KEY_SENT;
+    if (q < nq) {
+      tk = boot_keys[q * boot_stride + (k - 1)];
+      if (tk != KEY_SENT) {
+        const double tau0 = (double)ord2f((uint32_t)(tk >> 32));
+        if (tau0 == tau0 && tau0 < 3.0e38 && base == base && base < 3.0e38) {
+          double delta = (tau0 - base) / (double)T0;
+          const double floor1 = tau0 * (1.0 / 1048576.0);
+          if (!(delta > floor1)) delta = floor1;
+          if (!(delta > 1e-30)) delta = 1e-30;
+          p.inv_delta = 1.0 / delta;
+        }
+      }
+    }
+    qp[q] = p;
+    boot_tail[q] = tk;
+  }
+}
+
+// grid (T, M), block 256 (thread = code): the 8 x u16 quantised entries of a tile.
+__global__ void __launch_bounds__(256) qlut_build_kernel(const float4 *__restrict__ lutI,
+                                                         const float *__restrict__ mins,
+                                                         const QParam *__restrict__ qp, int M, int K,
+                                                         uint4 *__restrict__ qlut) {
+  const int t = blockIdx.x, m = blockIdx.y, c = threadIdx.x;
+  const int qmax = (FLAG - 1) / M;
+  uint32_t f[QT];
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    const int g = 2 * t + h;
+    const float4 v = lutI[((i64)g * M + m) * 256 + c];
+    const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const i64 q = (i64)g * 4 + j;
+      const double d = ((double)vv[j] - (double)mins[q * M + m]) * qp[q].inv_delta;
+      int qi = 0;
+      if (c < K && d > 0.0) qi = d >= (double)qmax ? qmax : (int)floor(d);
+      f[h * 4 + j] = (uint32_t)qi;
+    }
+  }
+  qlut[((i64)t * M + m) * 256 + c] =
+      make_uint4(f[0] | (f[1] << 16), f[2] | (f[3] << 16), f[4] | (f[5] << 16), f[6] | (f[7] << 16));
+}
+
+// boot list [rows][boot_stride] + split lists [S][rows][k] -> keys [rows][stride]
+__global__ void gather_lists2_kernel(const u64 *__restrict__ lists, int S, i64 rows, int k,
+                                     const u64 *__restrict__ boot, i64 boot_stride,
+                                     u64 *__restrict__ keys, i64 stride) {
+  const i64 q = blockIdx.y;
+  for (i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x; t < stride;
+       t += (i64)gridDim.x * blockDim.x) {
+    u64 v = KEY_SENT;
+    if (t < (i64)S * k) {
+      const int s = (int)(t / k), i = (int)(t % k);
+      v = lists[((i64)s * rows + q) * k + i];
+    } else if (t < (i64)(S + 1) * k) {
+      v = boot[q * boot_stride + (t - (i64)S * k)];
+    }
+    keys[q * stride + t] = v;
+  }
+}
+
+__device__ __forceinline__ uint4 ldg_stream_u4(const void *p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+
+__global__ void __launch_bounds__(NT, 1) pruned_scan_kernel(const Params p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint4 *lutbuf = reinterpret_cast<uint4 *>(smem_raw);
+  u64 *sortbuf = reinterpret_cast<u64 *>(smem_raw + 2 * SLICE_U4 * 16);
+  uint32_t *surv = reinterpret_cast<uint32_t *>(smem_raw + 2 * SLICE_U4 * 16 + QT * SORTN * 8);
+  __shared__ int s_cnt[QT];
+  __shared__ u64 s_thr[QT];
+  __shared__ uint32_t s_bias[QT];
+  __shared__ int s_nsurv;
+  __shared__ unsigned long long s_stat[3];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int s = blockIdx.x / p.Bs, j = blockIdx.x % p.Bs;
+  if (s >= p.S) return;
+  const i64 lo = p.from + (i64)s * p.split_len;
+  i64 hi = lo + p.split_len;
+  if (hi > p.until) hi = p.until;
+  if (lo >= hi || j >= p.T) return;
+  const i64 origin = lo & ~15LL;
+  const i64 n_chunks = (hi - origin + R - 1) / R;
+  const int n_my = (p.T - j + p.Bs - 1) / p.Bs;
+  const i64 n_items = n_chunks * n_my;
+  const int M = p.M, k = p.k;
+
+  const int code_id = tid & 255, half = tid >> 8;
+  int fill_off[4];
+#pragma unroll
+  for (int t = 0; t < 4; t++) fill_off[t] = code_id * 8 + ((lane + 4 * half + t) & 7);
+  const int rep = lane & 7;
+
+  if (tid < QT) s_cnt[tid] = 0;
+  if (tid == 0) s_nsurv = 0;
+  if (tid < 3) s_stat[tid] = 0;
+
+  int parity = 0;
+  {
+    const uint4 v = ldg_stream_u4(p.qlut + ((i64)j * M) * 256 + code_id);
+#pragma unroll
+    for (int t = 0; t < 4; t++) lutbuf[fill_off[t]] = v;
+  }
+  uint4 ccur = make_uint4(0, 0, 0, 0);
+  {
+    const i64 row0 = origin + (i64)tid * RPT;
+    if (row0 < hi) ccur = ldg_stream_u4(p.codes + row0);
+  }
+  __syncthreads();
+
+  for (i64 it = 0; it < n_items; ++it) {
+    const int t = j + (int)(it % n_my) * p.Bs;
+    const i64 chunk0 = origin + (it / n_my) * R;
+    const i64 row0 = chunk0 + (i64)tid * RPT;
+    const bool has_next = it + 1 < n_items;
+    const int tn = has_next ? j + (int)((it + 1) % n_my) * p.Bs : t;
+    const i64 row0n = has_next ? origin + ((it + 1) / n_my) * R + (i64)tid * RPT : row0;
+    const bool warp_live = chunk0 + (i64)(warp * 32) * RPT < hi;  // any row of this warp in range
+
+    u64 *L0 = p.lists + ((i64)s * p.T * QT + (i64)t * QT) * k;
+    // thresholds of the tile's 8 queries (published by the barriers of the quantizer loop)
+    if (tid < QT) {
+      const i64 q = (i64)t * QT + tid;
+      const u64 tl = fscan::ldcg_u64(L0 + (i64)tid * k + (k - 1));
+      const u64 bt = p.boot_tail[q];
+      const u64 thr = tl < bt ? tl : bt;
+      s_thr[tid] = thr;
+      int T = -1;
+      if (q < p.nq) {
+        const QParam qp = p.qp[q];
+        if (thr == KEY_SENT || qp.inv_delta == 0.0) {
+          T = FLAG - 1;
+        } else {
+          const double tau = (double)ord2f((uint32_t)(thr >> 32));
+          const double x = (tau * (1.0 + 1.0 / 2048.0) - qp.base) * qp.inv_delta;
+          T = x < 0.0 ? -1 : (x >= (double)(FLAG - 1) ? FLAG - 1 : (int)floor(x));
+        }
+      }
+      s_bias[tid] = (uint32_t)(FLAG - 1 - T);
+    }
+
+    uint32_t acc[RPT][4];
+#pragma unroll
+    for (int i = 0; i < RPT; i++) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0u;
+
+    for (int m = 0; m < M; ++m) {
+      uint4 cnext = make_uint4(0, 0, 0, 0);
+      uint4 lnext = make_uint4(0, 0, 0, 0);
+      bool do_fill = false;
+      if (m + 1 < M) {
+        if (row0 < hi) cnext = ldg_stream_u4(p.codes + (i64)(m + 1) * p.ps + row0);
+        lnext = ldg_stream_u4(p.qlut + ((i64)t * M + m + 1) * 256 + code_id);
+        do_fill = true;
+      } else if (has_next) {
+        if (row0n < hi) cnext = ldg_stream_u4(p.codes + row0n);
+        lnext = ldg_stream_u4(p.qlut + ((i64)tn * M) * 256 + code_id);
+        do_fill = true;
+      }
+      if (warp_live) {
+        const uint4 *buf = lutbuf + parity * SLICE_U4 + rep;
+        const uint32_t w[4] = {ccur.x, ccur.y, ccur.z, ccur.w};
+#pragma unroll
+        for (int i = 0; i < RPT; i++) {
+          const uint32_t c = (w[i >> 2] >> (8 * (i & 3))) & 0xffu;
+          const uint4 v = buf[c * 8];
+          acc[i][0] += v.x;
+          acc[i][1] += v.y;
+          acc[i][2] += v.z;
+          acc[i][3] += v.w;
+        }
+      }
+      if (do_fill) {
+        uint4 *dst = lutbuf + (parity ^ 1) * SLICE_U4;
+#pragma unroll
+        for (int t4 = 0; t4 < 4; t4++) dst[fill_off[t4]] = lnext;
+      }
+      __syncthreads();
+      parity ^= 1;
+      ccur = cnext;
+    }
+
+    // ---- flag test -------------------------------------------------------------------------
+    const int vlo = lo > row0 ? (int)(lo - row0 > RPT ? RPT : lo - row0) : 0;
+    const int vhi = hi - row0 >= RPT ? RPT : (hi > row0 ? (int)(hi - row0) : 0);
+    const uint32_t b0 = s_bias[0] | (s_bias[1] << 16), b1 = s_bias[2] | (s_bias[3] << 16);
+    const uint32_t b2 = s_bias[4] | (s_bias[5] << 16), b3 = s_bias[6] | (s_bias[7] << 16);
+    uint32_t all = 0xffffffffu;
+#pragma unroll
+    for (int i = 0; i < RPT; i++) {
+      acc[i][0] += b0;
+      acc[i][1] += b1;
+      acc[i][2] += b2;
+      acc[i][3] += b3;
+      uint32_t x = acc[i][0] & acc[i][1] & acc[i][2] & acc[i][3];
+      if (i < vlo || i >= vhi) x = 0xffffffffu;
+      all &= x;
+    }
+    const bool any = (all & 0x80008000u) != 0x80008000u;
+
+    // survivors of the rows selected by `rowmask` -> queue
+    auto push = [&](uint32_t rowmask) {
+#pragma unroll
+      for (int i = 0; i < RPT; i++) {
+        if (((rowmask >> i) & 1u) && i >= vlo && i < vhi) {
+#pragma unroll
+          for (int w = 0; w < 4; w++) {
+            const uint32_t a = acc[i][w];
+            if (!(a & 0x8000u)) {
+              const int pos = atomicAdd(&s_nsurv, 1);
+              if (pos < QCAP) surv[pos] = ((uint32_t)(tid * RPT + i) << 3) | (uint32_t)(2 * w);
+            }
+            if (!(a & 0x80000000u)) {
+              const int pos = atomicAdd(&s_nsurv, 1);
+              if (pos < QCAP) surv[pos] = ((uint32_t)(tid * RPT + i) << 3) | (uint32_t)(2 * w + 1);
+            }
+          }
+        }
+      }
+    };
+    // exact re-evaluation of the queued survivors, CAPQ at a time, merge into the lists
+    auto drain = [&](int n) {
+      for (int b0s = 0; b0s < n; b0s += CAPQ) {
+        const int nb = n - b0s < CAPQ ? n - b0s : CAPQ;
+        for (int si = b0s + warp; si < b0s + nb; si += NT / 32) {
+          const uint32_t code = surv[si];
+          const int q = (int)(code & 7u);
+          const i64 row = chunk0 + (i64)(code >> 3);
+          const float4 *lut = p.lutI + (i64)(2 * t + (q >> 2)) * M * 256;
+          const int jq = q & 3;
+          float d = 0.0f;
+          for (int m0 = 0; m0 < M; m0 += 32) {
+            const int m = m0 + lane;
+            float v = 0.0f;
+            if (m < M) {
+              const int c = p.codes[(i64)m * p.ps + row];
+              v = f4comp(__ldg(lut + m * 256 + c), jq);
+            }
+            const int nn = M - m0 < 32 ? M - m0 : 32;
+            for (int u = 0; u < nn; u++) d = __fadd_rn(d, __shfl_sync(0xffffffffu, v, u));
+          }
+          if (lane == 0) {
+            const u64 key = make_key(d, (uint32_t)row);
+            if (key < s_thr[q]) {
+              const int pos = atomicAdd(&s_cnt[q], 1);
+              sortbuf[q * SORTN + k + pos] = key;
+            }
+          }
+        }
+        __syncthreads();
+        if (warp < QT) {
+          const int nc = s_cnt[warp];
+          if (nc > 0) {
+            u64 *L = L0 + (i64)warp * k;
+            fscan::warp_merge(sortbuf + warp * SORTN, L, k, nc, lane);
+            if (lane == 0) {
+              const u64 tl = L[k - 1];
+              const u64 bt = p.boot_tail[(i64)t * QT + warp];
+              s_thr[warp] = tl < bt ? tl : bt;
+              s_cnt[warp] = 0;
+              atomicAdd(&s_stat[1], (unsigned long long)nc);
+            }
+          }
+        }
+        __syncthreads();
+      }
+    };
+
+    if (any) push(0xffffu);
+    __syncthreads();
+    const int ns = s_nsurv;
+    if (ns > 0) {
+      if (ns <= QCAP) {
+        drain(ns);
+        if (tid == 0) s_stat[0] += (unsigned long long)ns;
+      } else {
+        // slow path: one row index per round, so that a round never exceeds the queue
+        for (int r = 0; r < RPT; r++) {
+          __syncthreads();
+          if (tid == 0) s_nsurv = 0;
+          __syncthreads();
+          if (any) push(1u << r);
+          __syncthreads();
+          const int nr = s_nsurv;
+          drain(nr);
+          if (tid == 0) s_stat[0] += (unsigned long long)nr;
+        }
+        if (tid == 0) s_stat[2] += 1;
+      }
+      __syncthreads();
+      if (tid == 0) s_nsurv = 0;
+    }
+    // the quantizer loop of the next item has >= 1 barrier before the next push
+  }
+  __syncthreads();
+  if (tid < 3 && p.stats && s_stat[tid]) atomicAdd(p.stats + tid, s_stat[tid]);
+}
+
+}  // namespace pscan
+}  // namespace gulon

@@ -60,6 +60,7 @@ extern "C" {
 #define GULON_SCAN_AUTO   0
 #define GULON_SCAN_SIMPLE 1 /* distance materialisation + selection (any k, slow, cross-check path) */
 #define GULON_SCAN_FUSED  2 /* replicated-LUT gather kernel with in-kernel top-k (k <= 128)        */
+#define GULON_SCAN_PRUNED 3 /* 16-bit lower-bound pass + exact fp32 re-evaluation of survivors      */
 
 typedef struct gulon_points_s   *gulon_points_t;   /* device-resident float32 matrix (Matrix)      */
 typedef struct gulon_codebook_s *gulon_codebook_t; /* device-resident ProductQuantizer codebooks   */

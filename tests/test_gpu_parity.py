@@ -246,12 +246,21 @@ def build_index(g, rng, n, D, M, K=256, codes=None):
     return pq, cb, codes, g.PQIndex(pq, g.EncodedMatrix(g.Coder8(n), codes))
 
 
-def check_query(g, oracle, ix, cb, codes, Q, k, frm, until, impl):
+IMPLS = ["simple", "fused", "pruned"]
+
+
+def impl_id(g, name):
+    return {"simple": g.SCAN_SIMPLE, "fused": g.SCAN_FUSED, "pruned": g.SCAN_PRUNED}[name]
+
+
+def check_query(g, oracle, ix, cb, codes, Q, k, frm, until, impl, boot_rows=4096):
     g.set_option("scan_impl", impl)
-    try:
+    g.set_option("boot_rows", boot_rows)       # small boot so that test-sized ranges reach the
+    try:                                       # pruned kernel proper
         got = ix.batch_query(k, Q, frm, until)
     finally:
         g.set_option("scan_impl", g.SCAN_AUTO)
+        g.set_option("boot_rows", 65536)
     ids, ds, sz = oracle.pq_query(Q, cb, codes, k, frm, until, topk_mode=oracle.TOPK_CANONICAL)
     assert np.array_equal(got.size, sz)
     for q in range(Q.shape[0]):
@@ -261,7 +270,7 @@ def check_query(g, oracle, ix, cb, codes, Q, k, frm, until, impl):
         assert np.all(got.keys[q, n:] == -1) and np.all(np.isinf(got.values[q, n:]))
 
 
-@pytest.mark.parametrize("impl", ["simple", "fused"])
+@pytest.mark.parametrize("impl", IMPLS)
 @pytest.mark.parametrize("n,D,M,nq,k,frm,until", [
     (100000, 100, 10, 9, 10, 0, None),      # c1 shape, reduced N
     (60000, 128, 16, 4, 10, 5, 59990),      # c4 shape; ragged range
@@ -277,10 +286,10 @@ def test_query_matches_oracle(g, oracle, impl, n, D, M, nq, k, frm, until):
     pq, cb, codes, ix = build_index(g, rng, n, D, M)
     Q = clustered(rng, nq, D)
     until = n if until is None else until
-    check_query(g, oracle, ix, cb, codes, Q, k, frm, until, g.SCAN_SIMPLE if impl == "simple" else g.SCAN_FUSED)
+    check_query(g, oracle, ix, cb, codes, Q, k, frm, until, impl_id(g, impl))
 
 
-@pytest.mark.parametrize("impl", ["simple", "fused"])
+@pytest.mark.parametrize("impl", IMPLS)
 def test_query_heavy_ties(g, oracle, impl):
     # few distinct codes => many equal distances => (distance, id) order decides
     rng = np.random.default_rng(2)
@@ -288,10 +297,33 @@ def test_query_heavy_ties(g, oracle, impl):
     codes = rng.integers(0, 3, (M, n)).astype(np.uint8)
     pq, cb, codes, ix = build_index(g, rng, n, D, M, codes=codes)
     Q = clustered(rng, 5, D)
-    check_query(g, oracle, ix, cb, codes, Q, 25, 3, n - 1, g.SCAN_SIMPLE if impl == "simple" else g.SCAN_FUSED)
+    check_query(g, oracle, ix, cb, codes, Q, 25, 3, n - 1, impl_id(g, impl))
 
 
-def test_query_descending_distances_overflow_path(g, oracle):
+@pytest.mark.parametrize("impl", ["pruned"])
+@pytest.mark.parametrize("n,D,M,nq,k,boot", [
+    (300000, 100, 10, 21, 10, 65536),     # default boot, several tiles
+    (200000, 300, 30, 8, 10, 8192),       # c2 shape
+    (150000, 128, 16, 3, 100, 4096),      # c4 shape, large k
+    (120000, 1000, 100, 5, 10, 4096),     # c5 shape: M = 100 sub-quantizers
+    (100000, 16, 2, 9, 1, 16),            # boot shorter than one vector load
+])
+def test_query_pruned_matches_oracle_clustered_codes(g, oracle, impl, n, D, M, nq, k, boot):
+    """Codes produced by encoding clustered data (realistic distance distribution: the lower bound
+    prunes almost everything) instead of uniform random codes."""
+    rng = np.random.default_rng(n + M)
+    X = clustered(rng, n, D, centres=40)
+    cb = random_codebook(rng, X, M, 256)
+    pq = g.ProductQuantizer.from_codebook(cb, D)
+    enc = pq.encode(X)
+    ix = g.PQIndex(pq, enc)
+    Q = clustered(rng, nq, D, centres=40)
+    Q[0] = X[n // 2]                       # a query that coincides with a database row
+    check_query(g, oracle, ix, cb, enc.codes, Q, k, 0, n, impl_id(g, impl), boot_rows=boot)
+
+
+@pytest.mark.parametrize("impl", ["fused", "pruned"])
+def test_query_descending_distances_overflow_path(g, oracle, impl):
     # rows ordered by DEcreasing distance: every row beats the running k-th best, the worst case
     # for the fused kernel's candidate buffer
     rng = np.random.default_rng(4)
@@ -302,7 +334,7 @@ def test_query_descending_distances_overflow_path(g, oracle):
     order = np.argsort(-lut, kind="stable").astype(np.uint8)     # codes by decreasing distance
     codes = order[(np.arange(n) * 256 // n)].reshape(1, n)
     ix = g.PQIndex(pq, g.EncodedMatrix(g.Coder8(n), codes))
-    check_query(g, oracle, ix, cb, codes, Q, 10, 0, n, g.SCAN_FUSED)
+    check_query(g, oracle, ix, cb, codes, Q, 10, 0, n, impl_id(g, impl))
 
 
 def test_query_cosine_normalises_queries(g, oracle):
