@@ -311,7 +311,8 @@ def main():
     if k_launches > 0:
         # algorithmic bytes: one pass over the scanned code planes per tile of Qt
         # queries whose tables share shared memory (Qt = 8 pruned kernel, 4 exact kernel)
-        QT = 8 if use_p else 4
+        fb = 8 if 127 // M >= 3 else 16          # the library's automatic field width
+        QT = (128 // fb) if use_p else 4
         rows_scanned = (pstats["pairs"] / (a.steps * Q)) if use_p else n_local
         alg_bytes = a.steps * -(-Q // QT) * rows_scanned * M / k_launches
         sec = k_ns * 1e-9 / k_launches
@@ -326,10 +327,10 @@ def main():
                 "launches": k_launches, "query_tile": QT,
                 "kernel_share_of_step": k_ns * 1e-6 / ms,
                 "other_scan_kernel_share_of_step": (scan_ns if use_p else pscan_ns) * 1e-6 / ms,
-                "smem_gather": {"bytes_per_entry": 2 if use_p else 4,
-                                "achieved_GBps": gathers * (2 if use_p else 4) / 1e9,
+                "smem_gather": {"bytes_per_entry": (fb // 8) if use_p else 4,
+                                "achieved_GBps": gathers * ((fb // 8) if use_p else 4) / 1e9,
                                 "peak_GBps": smem_peak_bytes / 1e9,
-                                "frac": gathers * (2 if use_p else 4) / smem_peak_bytes,
+                                "frac": gathers * ((fb // 8) if use_p else 4) / smem_peak_bytes,
                                 "note": "table reads from shared memory: the binding resource "
                                         "(128 B/clk/SM crossbar)"}}
         if use_p and pstats["pairs"]:

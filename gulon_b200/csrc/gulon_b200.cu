@@ -73,6 +73,7 @@ std::atomic<long long> g_encode_chunk{1 << 20};  // rows per H2D chunk in gulon_
 std::atomic<long long> g_fused_min_rows{16384};
 std::atomic<long long> g_boot_rows{65536};       // rows scanned exactly to seed the pruned scan
 std::atomic<long long> g_pruned_min_rows{1 << 20};
+std::atomic<long long> g_pruned_bits{0};         // 0 = auto, 8 or 16: width of the lower-bound fields
 std::atomic<unsigned long long> g_pstats[3];     // survivors, list candidates, slow-path items
 std::atomic<unsigned long long> g_ppairs{0};     // (row, query) pairs offered to the pruned kernel
 
@@ -677,8 +678,12 @@ int scan_batch(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 fr
     else
       impl = GULON_SCAN_SIMPLE;
   }
-  // query groups of 4 (float4 tables); the pruned scan works on tiles of 8 = two groups
-  const int G = impl == GULON_SCAN_PRUNED ? 2 * (int)ceil_div(nq, 8) : (int)ceil_div(nq, 4);
+  // query groups of 4 (float4 tables); the pruned scan works on tiles of QT = 16 queries
+  // (8-bit lower-bound fields, used while they keep >= 3 levels per quantizer) or 8 (16-bit fields)
+  int FB = (int)g_pruned_bits.load();
+  if (FB == 0) FB = (127 / M >= 3) ? 8 : 16;
+  const int QT = 128 / FB;
+  const int G = impl == GULON_SCAN_PRUNED ? (QT / 4) * (int)ceil_div(nq, QT) : (int)ceil_div(nq, 4);
   const int Q4 = G * 4;
   GCHECK(ix->lutI.ensure((size_t)G * M * 256 * sizeof(float4)));
   dim3 lg((unsigned)G, (unsigned)M);
@@ -697,12 +702,15 @@ int scan_batch(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 fr
   if (impl == GULON_SCAN_PRUNED) {
     GREQUIRE(k <= pscan::KMAX, "pruned scan supports k <= %d (k=%d)", pscan::KMAX, k);
     GREQUIRE(M <= 1024, "pruned scan supports M <= 1024 (M=%d)", M);
+    GREQUIRE(FB == 16 || 127 / M >= 1, "8-bit pruned scan needs M <= 127 (M=%d)", M);
     static std::once_flag once;
     std::call_once(once, [] {
-      cudaFuncSetAttribute(pscan::pruned_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           pscan::SMEM_BYTES);
+      cudaFuncSetAttribute(pscan::pruned_scan_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           pscan::Cfg<8>::SMEM_BYTES);
+      cudaFuncSetAttribute(pscan::pruned_scan_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           pscan::Cfg<16>::SMEM_BYTES);
     });
-    const int T = G / 2;
+    const int T = G / (QT / 4);
     // 1. exact scan of the boot rows -> one sorted list per query (its tail is tau0)
     const i64 boot = std::min<i64>(range, std::max<i64>(g_boot_rows.load(), k));
     int Sb = 1;
@@ -718,10 +726,16 @@ int scan_batch(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 fr
     GCHECK(ix->qlut.ensure((size_t)T * M * 256 * sizeof(uint4)));
     GCHECK(ix->pstats.ensure(3 * sizeof(unsigned long long)));
     GLAUNCH(pscan::qparams_kernel, (unsigned)G, 256, 0, st, ix->lutI.as<float4>(), M, K, nq, bkeys,
-            bstride, k, ix->mins.as<float>(), ix->qp.as<pscan::QParam>(), ix->boot_tail.as<u64>());
+            bstride, k, pscan::t0_units(FB, M), ix->mins.as<float>(), ix->qp.as<pscan::QParam>(),
+            ix->boot_tail.as<u64>());
     dim3 qg((unsigned)T, (unsigned)M);
-    GLAUNCH(pscan::qlut_build_kernel, qg, 256, 0, st, ix->lutI.as<float4>(), ix->mins.as<float>(),
-            ix->qp.as<pscan::QParam>(), M, K, ix->qlut.as<uint4>());
+    if (FB == 8) {
+      GLAUNCH(pscan::qlut_build_kernel<8>, qg, 256, 0, st, ix->lutI.as<float4>(),
+              ix->mins.as<float>(), ix->qp.as<pscan::QParam>(), M, K, ix->qlut.as<uint4>());
+    } else {
+      GLAUNCH(pscan::qlut_build_kernel<16>, qg, 256, 0, st, ix->lutI.as<float4>(),
+              ix->mins.as<float>(), ix->qp.as<pscan::QParam>(), M, K, ix->qlut.as<uint4>());
+    }
     // 3. pruned scan of the remaining rows
     const i64 pfrom = from + boot, prange = until - pfrom;
     const int nsm = sm_count();
@@ -754,7 +768,13 @@ int scan_batch(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 fr
     prm.S = S;
     prm.Bs = Bs;
     cudaEvent_t ev = g_t_pscan.begin(st);
-    GLAUNCH(pscan::pruned_scan_kernel, (unsigned)(S * Bs), pscan::NT, pscan::SMEM_BYTES, st, prm);
+    if (FB == 8) {
+      GLAUNCH(pscan::pruned_scan_kernel<8>, (unsigned)(S * Bs), pscan::NT,
+              pscan::Cfg<8>::SMEM_BYTES, st, prm);
+    } else {
+      GLAUNCH(pscan::pruned_scan_kernel<16>, (unsigned)(S * Bs), pscan::NT,
+              pscan::Cfg<16>::SMEM_BYTES, st, prm);
+    }
     g_t_pscan.end(ev, st);
     if (want_stats) {
       unsigned long long h[3];
@@ -815,7 +835,7 @@ int query_dev(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 fro
   const int D = ix->cb->D;
   i64 qb = g_query_batch.load();
   if (qb <= 0) qb = (i64)sm_count() * 16;
-  qb = std::min<i64>(round_up(qb, 8), 32768);
+  qb = std::min<i64>(round_up(qb, 16), 32768);
   for (i64 q0 = 0; q0 < nq; q0 += qb) {
     const i64 nb = std::min<i64>(qb, nq - q0);
     const float *q = dQ + q0 * ldq;
@@ -894,6 +914,9 @@ int gulon_set_option(const char *name, int64_t value) {
   } else if (s == "boot_rows") {
     GREQUIRE(value >= 1, "boot_rows must be >= 1");
     g_boot_rows = value;
+  } else if (s == "pruned_bits") {
+    GREQUIRE(value == 0 || value == 8 || value == 16, "pruned_bits must be 0 (auto), 8 or 16");
+    g_pruned_bits = value;
   } else if (s == "pruned_min_rows") {
     GREQUIRE(value >= 0, "pruned_min_rows must be >= 0");
     g_pruned_min_rows = value;

@@ -1,4 +1,4 @@
-// pscan.cuh -- pruned scan: a 16-bit lower-bound pass over all rows, exact fp32 re-evaluation of
+// pscan.cuh -- pruned scan: an integer lower-bound pass over all rows, exact fp32 re-evaluation of
 // the survivors only.  Results are identical to fscan::fused_scan_kernel (and to the reference:
 // PQIndex.distances + batchQuery, G/Index.scala:393-440) because every distance that can enter a
 // top-k list is still computed as (((0 + LUT[0][c0]) + LUT[1][c1]) + ...) in fp32, round-to-nearest.
@@ -7,15 +7,19 @@
 // quantizer).  A row can be discarded without computing its distance if a LOWER BOUND of it already
 // exceeds the query's current k-th best distance tau.  The bound used here is
 //     LB = base + delta * sum_m q[m][code_m],   q = min(qmax, floor((LUT[m][c] - min_c LUT[m][c]) / delta)),
-// base = sum_m min_c LUT[m][c]: 2 bytes per table entry, 8 queries per 128-bit shared-memory read,
-// plain 32-bit integer adds on packed pairs (fields cannot carry: bias + M * qmax <= 65535).  With
-// bias = 32767 - T, T = floor((tau * (1 + 2^-11) - base) / delta), bit 15 of a field is set iff
-// sum q > T, which implies fp32-sum > tau (the 2^-11 covers the fp32 summation error for M <= 2048
-// and the double rounding of the quantiser).  Rows whose 8 fields are all flagged are dropped; the
-// others ("survivors", ~1e-4 of the pairs once tau is warm) are re-evaluated exactly by one warp each
-// from the fp32 tables in global memory and offered to the top-k lists.  tau comes from an exact
-// scan of the first rows of the range (the "boot" rows, done by the fused kernel) and tightens as a
-// CTA's own list fills.
+// base = sum_m min_c LUT[m][c].  The quantised entries are FB = 8 or 16 bits wide, so one 128-bit
+// shared-memory read serves QT = 16 (FB = 8) or 8 (FB = 16) queries, accumulated with plain 32-bit
+// integer adds on packed fields (fields cannot carry: bias + M * qmax <= 2^FB - 1).  With
+// bias = FLAG - 1 - T, FLAG = 2^(FB-1), T = floor((tau * (1 + 2^-11) - base) / delta), the top bit of
+// a field is set iff sum q > T, which implies fp32-sum > tau (the 2^-11 covers the fp32 summation
+// error for M <= 2048 and the double rounding of the quantiser).  Rows whose QT fields are all
+// flagged are dropped; the others ("survivors", 1e-5 .. 1e-3 of the pairs once tau is warm) are
+// re-evaluated exactly by one warp each from the fp32 tables in global memory and offered to the
+// top-k lists.  tau comes from an exact scan of the first rows of the range (the "boot" rows, done
+// by the fused kernel) and tightens as a CTA's own list fills.
+//
+// FB = 8 halves the shared-memory bytes per (row, query, quantizer) again but is coarse
+// (qmax = 127 / M levels per quantizer); the host uses it while qmax >= 3 and falls back to FB = 16.
 #pragma once
 #include "common.cuh"
 #include "scan.cuh"
@@ -27,15 +31,27 @@ namespace pscan {
 constexpr int NT = 512;
 constexpr int RPT = 16;
 constexpr int R = NT * RPT;     // 8192 rows per item
-constexpr int QT = 8;           // queries per tile (two groups of 4)
 constexpr int KMAX = 128;
 constexpr int SORTN = 256;      // per-query sort area: k list entries + up to CAPQ candidates
 constexpr int CAPQ = SORTN - KMAX;
-constexpr int QCAP = NT * QT;   // survivor queue entries (one row per thread in the slow path)
 constexpr int SLICE_U4 = 256 * 8;  // uint4 per replicated slice (32 KB)
-constexpr int T0 = 2048;        // quantisation units between base and the boot threshold
-constexpr int FLAG = 32768;
-constexpr int SMEM_BYTES = 2 * SLICE_U4 * 16 + QT * SORTN * 8 + QCAP * 4;
+
+template <int FB>
+struct Cfg {
+  static constexpr int QT = 128 / FB;            // queries per tile
+  static constexpr int FPW = 32 / FB;            // fields per 32-bit word
+  static constexpr int FLAG = 1 << (FB - 1);
+  static constexpr uint32_t FLAGMASK = FB == 8 ? 0x80808080u : 0x80008000u;
+  static constexpr int QCAP = NT * QT;           // survivor queue (one row per thread in the slow path)
+  static constexpr int SMEM_BYTES = 2 * SLICE_U4 * 16 + QT * SORTN * 8 + QCAP * 4;
+};
+
+// quantisation units between base and the boot threshold
+inline int t0_units(int FB, int M) {
+  if (FB == 16) return 2048;
+  const int qmax = 127 / M;
+  return std::max(1, M * qmax / 2);
+}
 
 struct QParam {
   double base;       // sum_m min_c LUT[m][c]
@@ -47,21 +63,21 @@ struct Params {
   i64 ps;
   i64 from, until;  // rows scanned by this kernel (after the boot rows)
   i64 split_len;
-  const uint4 *qlut;      // [T][M][256] 8 x u16
-  const float4 *lutI;     // [2T][M][256] exact tables (scan.cuh layout)
-  const QParam *qp;       // [T*8]
-  const u64 *boot_tail;   // [T*8] key of the boot list tail (KEY_SENT: none)
-  u64 *lists;             // [S][T*8][k]
+  const uint4 *qlut;      // [T][M][256] QT packed fields
+  const float4 *lutI;     // [T*QT/4][M][256] exact tables (scan.cuh layout)
+  const QParam *qp;       // [T*QT]
+  const u64 *boot_tail;   // [T*QT] key of the boot list tail (KEY_SENT: none)
+  u64 *lists;             // [S][T*QT][k]
   unsigned long long *stats;  // [0] survivors, [1] list candidates, [2] slow-path items
   i64 nq;
   int M, T, k, S, Bs;
 };
 
 // ---- per-query quantisation parameters ---------------------------------------------------------
-// grid (G = 2T groups), block 256.  mins[(g*4+j)*M + m] = min_c LUT; qp / boot_tail per query.
+// grid (G groups of 4 queries), block 256.  mins[(g*4+j)*M + m] = min_c LUT; qp / boot_tail per query.
 __global__ void __launch_bounds__(256) qparams_kernel(const float4 *__restrict__ lutI, int M, int K,
                                                       i64 nq, const u64 *__restrict__ boot_keys,
-                                                      i64 boot_stride, int k,
+                                                      i64 boot_stride, int k, int t0,
                                                       float *__restrict__ mins,
                                                       QParam *__restrict__ qp,
                                                       u64 *__restrict__ boot_tail) {
@@ -101,7 +117,7 @@ __global__ void __launch_bounds__(256) qparams_kernel(const float4 *__restrict__
       if (tk != KEY_SENT) {
         const double tau0 = (double)ord2f((uint32_t)(tk >> 32));
         if (tau0 == tau0 && tau0 < 3.0e38 && base == base && base < 3.0e38) {
-          double delta = (tau0 - base) / (double)T0;
+          double delta = (tau0 - base) / (double)t0;
           const double floor1 = tau0 * (1.0 / 1048576.0);
           if (!(delta > floor1)) delta = floor1;
           if (!(delta > 1e-30)) delta = 1e-30;
@@ -114,17 +130,19 @@ __global__ void __launch_bounds__(256) qparams_kernel(const float4 *__restrict__
   }
 }
 
-// grid (T, M), block 256 (thread = code): the 8 x u16 quantised entries of a tile.
+// grid (T, M), block 256 (thread = code): the QT quantised entries of a tile, field f = query f.
+template <int FB>
 __global__ void __launch_bounds__(256) qlut_build_kernel(const float4 *__restrict__ lutI,
                                                          const float *__restrict__ mins,
                                                          const QParam *__restrict__ qp, int M, int K,
                                                          uint4 *__restrict__ qlut) {
+  using C = Cfg<FB>;
   const int t = blockIdx.x, m = blockIdx.y, c = threadIdx.x;
-  const int qmax = (FLAG - 1) / M;
-  uint32_t f[QT];
+  const int qmax = (C::FLAG - 1) / M;
+  uint32_t w[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-  for (int h = 0; h < 2; h++) {
-    const int g = 2 * t + h;
+  for (int h = 0; h < C::QT / 4; h++) {
+    const int g = (C::QT / 4) * t + h;
     const float4 v = lutI[((i64)g * M + m) * 256 + c];
     const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
@@ -133,11 +151,11 @@ __global__ void __launch_bounds__(256) qlut_build_kernel(const float4 *__restric
       const double d = ((double)vv[j] - (double)mins[q * M + m]) * qp[q].inv_delta;
       int qi = 0;
       if (c < K && d > 0.0) qi = d >= (double)qmax ? qmax : (int)floor(d);
-      f[h * 4 + j] = (uint32_t)qi;
+      const int f = h * 4 + j;
+      w[f / C::FPW] |= (uint32_t)qi << (FB * (f % C::FPW));
     }
   }
-  qlut[((i64)t * M + m) * 256 + c] =
-      make_uint4(f[0] | (f[1] << 16), f[2] | (f[3] << 16), f[4] | (f[5] << 16), f[6] | (f[7] << 16));
+  qlut[((i64)t * M + m) * 256 + c] = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
 // boot list [rows][boot_stride] + split lists [S][rows][k] -> keys [rows][stride]
@@ -166,14 +184,18 @@ __device__ __forceinline__ uint4 ldg_stream_u4(const void *p) {
   return r;
 }
 
+template <int FB>
 __global__ void __launch_bounds__(NT, 1) pruned_scan_kernel(const Params p) {
+  using C = Cfg<FB>;
+  constexpr int QT = C::QT;
+  constexpr int QSH = FB == 8 ? 4 : 3;  // log2(QT)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint4 *lutbuf = reinterpret_cast<uint4 *>(smem_raw);
   u64 *sortbuf = reinterpret_cast<u64 *>(smem_raw + 2 * SLICE_U4 * 16);
   uint32_t *surv = reinterpret_cast<uint32_t *>(smem_raw + 2 * SLICE_U4 * 16 + QT * SORTN * 8);
   __shared__ int s_cnt[QT];
   __shared__ u64 s_thr[QT];
-  __shared__ uint32_t s_bias[QT];
+  __shared__ uint32_t s_bias[4];
   __shared__ int s_nsurv;
   __shared__ unsigned long long s_stat[3];
 
@@ -197,6 +219,7 @@ __global__ void __launch_bounds__(NT, 1) pruned_scan_kernel(const Params p) {
   const int rep = lane & 7;
 
   if (tid < QT) s_cnt[tid] = 0;
+  if (tid < 4) s_bias[tid] = 0;
   if (tid == 0) s_nsurv = 0;
   if (tid < 3) s_stat[tid] = 0;
 
@@ -223,7 +246,7 @@ __global__ void __launch_bounds__(NT, 1) pruned_scan_kernel(const Params p) {
     const bool warp_live = chunk0 + (i64)(warp * 32) * RPT < hi;  // any row of this warp in range
 
     u64 *L0 = p.lists + ((i64)s * p.T * QT + (i64)t * QT) * k;
-    // thresholds of the tile's 8 queries (published by the barriers of the quantizer loop)
+    // thresholds of the tile's queries (published by the barriers of the quantizer loop)
     if (tid < QT) {
       const i64 q = (i64)t * QT + tid;
       const u64 tl = fscan::ldcg_u64(L0 + (i64)tid * k + (k - 1));
@@ -234,14 +257,18 @@ __global__ void __launch_bounds__(NT, 1) pruned_scan_kernel(const Params p) {
       if (q < p.nq) {
         const QParam qp = p.qp[q];
         if (thr == KEY_SENT || qp.inv_delta == 0.0) {
-          T = FLAG - 1;
+          T = C::FLAG - 1;
         } else {
           const double tau = (double)ord2f((uint32_t)(thr >> 32));
           const double x = (tau * (1.0 + 1.0 / 2048.0) - qp.base) * qp.inv_delta;
-          T = x < 0.0 ? -1 : (x >= (double)(FLAG - 1) ? FLAG - 1 : (int)floor(x));
+          T = x < 0.0 ? -1 : (x >= (double)(C::FLAG - 1) ? C::FLAG - 1 : (int)floor(x));
         }
       }
-      s_bias[tid] = (uint32_t)(FLAG - 1 - T);
+      // fields of one word are owned by consecutive threads of the first warp: combine by shuffle
+      uint32_t b = (uint32_t)(C::FLAG - 1 - T) << (FB * (tid % C::FPW));
+#pragma unroll
+      for (int o = 1; o < C::FPW; o <<= 1) b |= __shfl_xor_sync((1u << QT) - 1u, b, o);
+      if (tid % C::FPW == 0) s_bias[tid / C::FPW] = b;
     }
 
     uint32_t acc[RPT][4];
@@ -287,8 +314,7 @@ __global__ void __launch_bounds__(NT, 1) pruned_scan_kernel(const Params p) {
     // ---- flag test -------------------------------------------------------------------------
     const int vlo = lo > row0 ? (int)(lo - row0 > RPT ? RPT : lo - row0) : 0;
     const int vhi = hi - row0 >= RPT ? RPT : (hi > row0 ? (int)(hi - row0) : 0);
-    const uint32_t b0 = s_bias[0] | (s_bias[1] << 16), b1 = s_bias[2] | (s_bias[3] << 16);
-    const uint32_t b2 = s_bias[4] | (s_bias[5] << 16), b3 = s_bias[6] | (s_bias[7] << 16);
+    const uint32_t b0 = s_bias[0], b1 = s_bias[1], b2 = s_bias[2], b3 = s_bias[3];
     uint32_t all = 0xffffffffu;
 #pragma unroll
     for (int i = 0; i < RPT; i++) {
@@ -300,7 +326,7 @@ __global__ void __launch_bounds__(NT, 1) pruned_scan_kernel(const Params p) {
       if (i < vlo || i >= vhi) x = 0xffffffffu;
       all &= x;
     }
-    const bool any = (all & 0x80008000u) != 0x80008000u;
+    const bool any = (all & C::FLAGMASK) != C::FLAGMASK;
 
     // survivors of the rows selected by `rowmask` -> queue
     auto push = [&](uint32_t rowmask) {
@@ -309,14 +335,13 @@ __global__ void __launch_bounds__(NT, 1) pruned_scan_kernel(const Params p) {
         if (((rowmask >> i) & 1u) && i >= vlo && i < vhi) {
 #pragma unroll
           for (int w = 0; w < 4; w++) {
-            const uint32_t a = acc[i][w];
-            if (!(a & 0x8000u)) {
+            uint32_t live = ~acc[i][w] & C::FLAGMASK;  // unflagged fields of this word
+            while (live) {
+              const int bit = __ffs(live) - 1;
+              live &= live - 1;
+              const int f = w * C::FPW + bit / FB;
               const int pos = atomicAdd(&s_nsurv, 1);
-              if (pos < QCAP) surv[pos] = ((uint32_t)(tid * RPT + i) << 3) | (uint32_t)(2 * w);
-            }
-            if (!(a & 0x80000000u)) {
-              const int pos = atomicAdd(&s_nsurv, 1);
-              if (pos < QCAP) surv[pos] = ((uint32_t)(tid * RPT + i) << 3) | (uint32_t)(2 * w + 1);
+              if (pos < C::QCAP) surv[pos] = ((uint32_t)(tid * RPT + i) << QSH) | (uint32_t)f;
             }
           }
         }
@@ -328,9 +353,9 @@ __global__ void __launch_bounds__(NT, 1) pruned_scan_kernel(const Params p) {
         const int nb = n - b0s < CAPQ ? n - b0s : CAPQ;
         for (int si = b0s + warp; si < b0s + nb; si += NT / 32) {
           const uint32_t code = surv[si];
-          const int q = (int)(code & 7u);
-          const i64 row = chunk0 + (i64)(code >> 3);
-          const float4 *lut = p.lutI + (i64)(2 * t + (q >> 2)) * M * 256;
+          const int q = (int)(code & (uint32_t)(QT - 1));
+          const i64 row = chunk0 + (i64)(code >> QSH);
+          const float4 *lut = p.lutI + ((i64)t * (QT / 4) + (q >> 2)) * M * 256;
           const int jq = q & 3;
           float d = 0.0f;
           for (int m0 = 0; m0 < M; m0 += 32) {
@@ -374,7 +399,7 @@ __global__ void __launch_bounds__(NT, 1) pruned_scan_kernel(const Params p) {
     __syncthreads();
     const int ns = s_nsurv;
     if (ns > 0) {
-      if (ns <= QCAP) {
+      if (ns <= C::QCAP) {
         drain(ns);
         if (tid == 0) s_stat[0] += (unsigned long long)ns;
       } else {

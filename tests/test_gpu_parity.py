@@ -246,20 +246,26 @@ def build_index(g, rng, n, D, M, K=256, codes=None):
     return pq, cb, codes, g.PQIndex(pq, g.EncodedMatrix(g.Coder8(n), codes))
 
 
-IMPLS = ["simple", "fused", "pruned"]
+IMPLS = ["simple", "fused", "pruned8", "pruned16"]
 
 
 def impl_id(g, name):
-    return {"simple": g.SCAN_SIMPLE, "fused": g.SCAN_FUSED, "pruned": g.SCAN_PRUNED}[name]
+    return {"simple": (g.SCAN_SIMPLE, 0), "fused": (g.SCAN_FUSED, 0), "pruned": (g.SCAN_PRUNED, 0),
+            "pruned8": (g.SCAN_PRUNED, 8), "pruned16": (g.SCAN_PRUNED, 16)}[name]
 
 
 def check_query(g, oracle, ix, cb, codes, Q, k, frm, until, impl, boot_rows=4096):
+    impl, bits = impl
+    if bits == 8 and codes.shape[0] > 127:
+        pytest.skip("8-bit lower-bound fields need M <= 127")
     g.set_option("scan_impl", impl)
+    g.set_option("pruned_bits", bits)
     g.set_option("boot_rows", boot_rows)       # small boot so that test-sized ranges reach the
     try:                                       # pruned kernel proper
         got = ix.batch_query(k, Q, frm, until)
     finally:
         g.set_option("scan_impl", g.SCAN_AUTO)
+        g.set_option("pruned_bits", 0)
         g.set_option("boot_rows", 65536)
     ids, ds, sz = oracle.pq_query(Q, cb, codes, k, frm, until, topk_mode=oracle.TOPK_CANONICAL)
     assert np.array_equal(got.size, sz)
@@ -300,7 +306,7 @@ def test_query_heavy_ties(g, oracle, impl):
     check_query(g, oracle, ix, cb, codes, Q, 25, 3, n - 1, impl_id(g, impl))
 
 
-@pytest.mark.parametrize("impl", ["pruned"])
+@pytest.mark.parametrize("impl", ["pruned8", "pruned16", "pruned"])
 @pytest.mark.parametrize("n,D,M,nq,k,boot", [
     (300000, 100, 10, 21, 10, 65536),     # default boot, several tiles
     (200000, 300, 30, 8, 10, 8192),       # c2 shape
@@ -322,7 +328,7 @@ def test_query_pruned_matches_oracle_clustered_codes(g, oracle, impl, n, D, M, n
     check_query(g, oracle, ix, cb, enc.codes, Q, k, 0, n, impl_id(g, impl), boot_rows=boot)
 
 
-@pytest.mark.parametrize("impl", ["fused", "pruned"])
+@pytest.mark.parametrize("impl", ["fused", "pruned8", "pruned16"])
 def test_query_descending_distances_overflow_path(g, oracle, impl):
     # rows ordered by DEcreasing distance: every row beats the running k-th best, the worst case
     # for the fused kernel's candidate buffer
