@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--cpu-queries", type=int, default=0, help="0 = 2 x host threads")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-recall", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="library option name=value")
     return ap.parse_args()
 
 
@@ -185,6 +186,9 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    for kv in a.opt:
+        name, val = kv.split("=")
+        g.set_option(name, int(val))
     D, M, K, k, Q = a.dim, a.m, 256, a.k, a.queries
     mix = Mixture(D, device=dev)
 

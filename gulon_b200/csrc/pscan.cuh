@@ -34,7 +34,9 @@ constexpr int R = NT * RPT;     // 8192 rows per item
 constexpr int KMAX = 128;
 constexpr int SORTN = 256;      // per-query sort area: k list entries + up to CAPQ candidates
 constexpr int CAPQ = SORTN - KMAX;
-constexpr int SLICE_U4 = 256 * 8;  // uint4 per replicated slice (32 KB)
+constexpr int REGION_BYTES = 65536;  // both replicated slice buffers, interleaved (see the kernel)
+constexpr int SLOTS = 256;           // items whose survivors may wait in the queue
+constexpr int DRAIN_AT = 768;        // queue length that triggers an exact re-evaluation pass
 
 template <int FB>
 struct Cfg {
@@ -43,7 +45,8 @@ struct Cfg {
   static constexpr int FLAG = 1 << (FB - 1);
   static constexpr uint32_t FLAGMASK = FB == 8 ? 0x80808080u : 0x80008000u;
   static constexpr int QCAP = NT * QT;           // survivor queue (one row per thread in the slow path)
-  static constexpr int SMEM_BYTES = 2 * SLICE_U4 * 16 + QT * SORTN * 8 + QCAP * 4;
+  // up to 64 KB of alignment slack in front of the 64 KB-aligned slice region
+  static constexpr int SMEM_BYTES = 65536 + REGION_BYTES + QT * SORTN * 8 + QCAP * 4;
 };
 
 // quantisation units between base and the boot threshold
@@ -184,20 +187,41 @@ __device__ __forceinline__ uint4 ldg_stream_u4(const void *p) {
   return r;
 }
 
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "r"(addr)
+               : "memory");
+  return r;
+}
+
+// Shared-memory layout (dynamic): a 64 KB-ALIGNED 64 KB region holds both slice buffers interleaved:
+//   byte address = region | code << 8 | buffer << 7 | replica << 4
+// so that the address of a row's table entry is ONE byte-permute of (code word, per-lane base):
+// PRMT puts the row's code byte into address bits 8..15.  After the region: per-query sort areas,
+// then the survivor queue.
 template <int FB>
 __global__ void __launch_bounds__(NT, 1) pruned_scan_kernel(const Params p) {
   using C = Cfg<FB>;
   constexpr int QT = C::QT;
   constexpr int QSH = FB == 8 ? 4 : 3;  // log2(QT)
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  uint4 *lutbuf = reinterpret_cast<uint4 *>(smem_raw);
-  u64 *sortbuf = reinterpret_cast<u64 *>(smem_raw + 2 * SLICE_U4 * 16);
-  uint32_t *surv = reinterpret_cast<uint32_t *>(smem_raw + 2 * SLICE_U4 * 16 + QT * SORTN * 8);
+  const uint32_t dyn0 = smem_u32(smem_raw);
+  const uint32_t region = (dyn0 + 0xffffu) & ~0xffffu;
+  unsigned char *region_g = smem_raw + (region - dyn0);
+  u64 *sortbuf = reinterpret_cast<u64 *>(region_g + REGION_BYTES);
+  uint32_t *surv = reinterpret_cast<uint32_t *>(region_g + REGION_BYTES + QT * SORTN * 8);
   __shared__ int s_cnt[QT];
   __shared__ u64 s_thr[QT];
   __shared__ uint32_t s_bias[4];
-  __shared__ int s_nsurv;
+  __shared__ int s_nsurv, s_nbefore;
   __shared__ unsigned long long s_stat[3];
+  __shared__ i64 s_slot_chunk[SLOTS];
+  __shared__ int s_slot_tile[SLOTS];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int s = blockIdx.x / p.Bs, j = blockIdx.x % p.Bs;
@@ -211,12 +235,15 @@ __global__ void __launch_bounds__(NT, 1) pruned_scan_kernel(const Params p) {
   const int n_my = (p.T - j + p.Bs - 1) / p.Bs;
   const i64 n_items = n_chunks * n_my;
   const int M = p.M, k = p.k;
+  // survivors may wait in the queue across items only while the CTA stays on one tile (the sort
+  // areas are per query of the current tile)
+  const bool defer = n_my == 1;
 
   const int code_id = tid & 255, half = tid >> 8;
-  int fill_off[4];
+  int fill_off[4];  // byte offsets inside the region (buffer 0)
 #pragma unroll
-  for (int t = 0; t < 4; t++) fill_off[t] = code_id * 8 + ((lane + 4 * half + t) & 7);
-  const int rep = lane & 7;
+  for (int t = 0; t < 4; t++) fill_off[t] = code_id * 256 + ((lane + 4 * half + t) & 7) * 16;
+  uint32_t lane_base = region | ((uint32_t)(lane & 7) << 4);  // buffer bit toggles per quantizer
 
   if (tid < QT) s_cnt[tid] = 0;
   if (tid < 4) s_bias[tid] = 0;
@@ -227,7 +254,7 @@ __global__ void __launch_bounds__(NT, 1) pruned_scan_kernel(const Params p) {
   {
     const uint4 v = ldg_stream_u4(p.qlut + ((i64)j * M) * 256 + code_id);
 #pragma unroll
-    for (int t = 0; t < 4; t++) lutbuf[fill_off[t]] = v;
+    for (int t = 0; t < 4; t++) *reinterpret_cast<uint4 *>(region_g + fill_off[t]) = v;
   }
   uint4 ccur = make_uint4(0, 0, 0, 0);
   {
@@ -235,6 +262,8 @@ __global__ void __launch_bounds__(NT, 1) pruned_scan_kernel(const Params p) {
     if (row0 < hi) ccur = ldg_stream_u4(p.codes + row0);
   }
   __syncthreads();
+
+  int slot = 0;  // items queued since the last drain
 
   for (i64 it = 0; it < n_items; ++it) {
     const int t = j + (int)(it % n_my) * p.Bs;
@@ -270,6 +299,11 @@ __global__ void __launch_bounds__(NT, 1) pruned_scan_kernel(const Params p) {
       for (int o = 1; o < C::FPW; o <<= 1) b |= __shfl_xor_sync((1u << QT) - 1u, b, o);
       if (tid % C::FPW == 0) s_bias[tid / C::FPW] = b;
     }
+    if (tid == 0) {
+      s_slot_chunk[slot] = chunk0;
+      s_slot_tile[slot] = t;
+      s_nbefore = s_nsurv;  // entries queued by earlier items (no pushes happen during the loop)
+    }
 
     uint32_t acc[RPT][4];
 #pragma unroll
@@ -289,12 +323,12 @@ __global__ void __launch_bounds__(NT, 1) pruned_scan_kernel(const Params p) {
         do_fill = true;
       }
       if (warp_live) {
-        const uint4 *buf = lutbuf + parity * SLICE_U4 + rep;
         const uint32_t w[4] = {ccur.x, ccur.y, ccur.z, ccur.w};
 #pragma unroll
         for (int i = 0; i < RPT; i++) {
-          const uint32_t c = (w[i >> 2] >> (8 * (i & 3))) & 0xffu;
-          const uint4 v = buf[c * 8];
+          // address = lane_base with the row's code byte in bits 8..15
+          const uint32_t a = __byte_perm(w[i >> 2], lane_base, 0x7604u | ((uint32_t)(i & 3) << 4));
+          const uint4 v = lds_u4(a);
           acc[i][0] += v.x;
           acc[i][1] += v.y;
           acc[i][2] += v.z;
@@ -302,16 +336,18 @@ __global__ void __launch_bounds__(NT, 1) pruned_scan_kernel(const Params p) {
         }
       }
       if (do_fill) {
-        uint4 *dst = lutbuf + (parity ^ 1) * SLICE_U4;
+        unsigned char *dst = region_g + ((parity ^ 1) << 7);
 #pragma unroll
-        for (int t4 = 0; t4 < 4; t4++) dst[fill_off[t4]] = lnext;
+        for (int t4 = 0; t4 < 4; t4++) *reinterpret_cast<uint4 *>(dst + fill_off[t4]) = lnext;
       }
       __syncthreads();
       parity ^= 1;
+      lane_base ^= 0x80u;
       ccur = cnext;
     }
 
     // ---- flag test -------------------------------------------------------------------------
+    const int n_before = s_nbefore;  // published by the barriers of the quantizer loop
     const int vlo = lo > row0 ? (int)(lo - row0 > RPT ? RPT : lo - row0) : 0;
     const int vhi = hi - row0 >= RPT ? RPT : (hi > row0 ? (int)(hi - row0) : 0);
     const uint32_t b0 = s_bias[0], b1 = s_bias[1], b2 = s_bias[2], b3 = s_bias[3];
@@ -328,8 +364,8 @@ __global__ void __launch_bounds__(NT, 1) pruned_scan_kernel(const Params p) {
     }
     const bool any = (all & C::FLAGMASK) != C::FLAGMASK;
 
-    // survivors of the rows selected by `rowmask` -> queue
-    auto push = [&](uint32_t rowmask) {
+    // survivors of the rows selected by `rowmask` -> queue; entry = slot | local row | field
+    auto push = [&](uint32_t rowmask, int slot_) {
 #pragma unroll
       for (int i = 0; i < RPT; i++) {
         if (((rowmask >> i) & 1u) && i >= vlo && i < vhi) {
@@ -341,21 +377,26 @@ __global__ void __launch_bounds__(NT, 1) pruned_scan_kernel(const Params p) {
               live &= live - 1;
               const int f = w * C::FPW + bit / FB;
               const int pos = atomicAdd(&s_nsurv, 1);
-              if (pos < C::QCAP) surv[pos] = ((uint32_t)(tid * RPT + i) << QSH) | (uint32_t)f;
+              if (pos < C::QCAP)
+                surv[pos] = ((uint32_t)slot_ << (13 + QSH)) | ((uint32_t)(tid * RPT + i) << QSH) |
+                            (uint32_t)f;
             }
           }
         }
       }
     };
-    // exact re-evaluation of the queued survivors, CAPQ at a time, merge into the lists
+    // exact re-evaluation of queue entries [0, n), CAPQ at a time, merged into the lists of the
+    // (single) tile they belong to
     auto drain = [&](int n) {
       for (int b0s = 0; b0s < n; b0s += CAPQ) {
         const int nb = n - b0s < CAPQ ? n - b0s : CAPQ;
         for (int si = b0s + warp; si < b0s + nb; si += NT / 32) {
           const uint32_t code = surv[si];
           const int q = (int)(code & (uint32_t)(QT - 1));
-          const i64 row = chunk0 + (i64)(code >> QSH);
-          const float4 *lut = p.lutI + ((i64)t * (QT / 4) + (q >> 2)) * M * 256;
+          const int sl = (int)(code >> (13 + QSH));
+          const i64 row = s_slot_chunk[sl] + (i64)((code >> QSH) & 8191u);
+          const int ts = s_slot_tile[sl];
+          const float4 *lut = p.lutI + ((i64)ts * (QT / 4) + (q >> 2)) * M * 256;
           const int jq = q & 3;
           float d = 0.0f;
           for (int m0 = 0; m0 < M; m0 += 32) {
@@ -393,33 +434,40 @@ __global__ void __launch_bounds__(NT, 1) pruned_scan_kernel(const Params p) {
         }
         __syncthreads();
       }
+      if (tid == 0) s_stat[0] += (unsigned long long)n;
     };
 
-    if (any) push(0xffffu);
+    if (any) push(0xffffu, slot);
     __syncthreads();
     const int ns = s_nsurv;
-    if (ns > 0) {
-      if (ns <= C::QCAP) {
-        drain(ns);
-        if (tid == 0) s_stat[0] += (unsigned long long)ns;
-      } else {
-        // slow path: one row index per round, so that a round never exceeds the queue
-        for (int r = 0; r < RPT; r++) {
-          __syncthreads();
-          if (tid == 0) s_nsurv = 0;
-          __syncthreads();
-          if (any) push(1u << r);
-          __syncthreads();
-          const int nr = s_nsurv;
-          drain(nr);
-          if (tid == 0) s_stat[0] += (unsigned long long)nr;
-        }
-        if (tid == 0) s_stat[2] += 1;
+    if (ns > C::QCAP) {
+      // queue overflow (adversarial orders only): finish the entries of earlier items, then redo
+      // this item one row index per round so that a round never exceeds the queue
+      drain(n_before);
+      for (int r = 0; r < RPT; r++) {
+        __syncthreads();
+        if (tid == 0) s_nsurv = 0;
+        __syncthreads();
+        if (any) push(1u << r, slot);
+        __syncthreads();
+        drain(s_nsurv);
       }
       __syncthreads();
+      if (tid == 0) {
+        s_nsurv = 0;
+        s_stat[2] += 1;
+        s_slot_chunk[0] = chunk0;
+        s_slot_tile[0] = t;
+      }
+      slot = 0;
+    } else if (ns > 0 && (!defer || !has_next || ns >= DRAIN_AT || slot == SLOTS - 1)) {
+      drain(ns);
       if (tid == 0) s_nsurv = 0;
+      slot = 0;
+    } else if (ns > 0) {
+      slot++;
     }
-    // the quantizer loop of the next item has >= 1 barrier before the next push
+    // the quantizer loop of the next item has >= 1 barrier before its n_before read and pushes
   }
   __syncthreads();
   if (tid < 3 && p.stats && s_stat[tid]) atomicAdd(p.stats + tid, s_stat[tid]);
