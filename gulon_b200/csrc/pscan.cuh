@@ -263,7 +263,8 @@ __global__ void __launch_bounds__(NT, 1) pruned_scan_kernel(const Params p) {
   }
   __syncthreads();
 
-  int slot = 0;  // items queued since the last drain
+  int slot = 0;        // items queued since the last drain
+  bool need_thr = true;  // thresholds change only with the tile or after a drain
 
   for (i64 it = 0; it < n_items; ++it) {
     const int t = j + (int)(it % n_my) * p.Bs;
@@ -276,7 +277,7 @@ __global__ void __launch_bounds__(NT, 1) pruned_scan_kernel(const Params p) {
 
     u64 *L0 = p.lists + ((i64)s * p.T * QT + (i64)t * QT) * k;
     // thresholds of the tile's queries (published by the barriers of the quantizer loop)
-    if (tid < QT) {
+    if (need_thr && tid < QT) {
       const i64 q = (i64)t * QT + tid;
       const u64 tl = fscan::ldcg_u64(L0 + (i64)tid * k + (k - 1));
       const u64 bt = p.boot_tail[q];
@@ -299,6 +300,7 @@ __global__ void __launch_bounds__(NT, 1) pruned_scan_kernel(const Params p) {
       for (int o = 1; o < C::FPW; o <<= 1) b |= __shfl_xor_sync((1u << QT) - 1u, b, o);
       if (tid % C::FPW == 0) s_bias[tid / C::FPW] = b;
     }
+    need_thr = !defer;
     if (tid == 0) {
       s_slot_chunk[slot] = chunk0;
       s_slot_tile[slot] = t;
@@ -351,24 +353,24 @@ __global__ void __launch_bounds__(NT, 1) pruned_scan_kernel(const Params p) {
     const int vlo = lo > row0 ? (int)(lo - row0 > RPT ? RPT : lo - row0) : 0;
     const int vhi = hi - row0 >= RPT ? RPT : (hi > row0 ? (int)(hi - row0) : 0);
     const uint32_t b0 = s_bias[0], b1 = s_bias[1], b2 = s_bias[2], b3 = s_bias[3];
-    uint32_t all = 0xffffffffu;
+    uint32_t rm = 0;  // rows of this thread with at least one unflagged field
 #pragma unroll
     for (int i = 0; i < RPT; i++) {
       acc[i][0] += b0;
       acc[i][1] += b1;
       acc[i][2] += b2;
       acc[i][3] += b3;
-      uint32_t x = acc[i][0] & acc[i][1] & acc[i][2] & acc[i][3];
-      if (i < vlo || i >= vhi) x = 0xffffffffu;
-      all &= x;
+      const uint32_t x = acc[i][0] & acc[i][1] & acc[i][2] & acc[i][3];
+      if ((x & C::FLAGMASK) != C::FLAGMASK && i >= vlo && i < vhi) rm |= 1u << i;
     }
-    const bool any = (all & C::FLAGMASK) != C::FLAGMASK;
 
     // survivors of the rows selected by `rowmask` -> queue; entry = slot | local row | field
     auto push = [&](uint32_t rowmask, int slot_) {
+      const uint32_t todo = rm & rowmask;
+      if (todo == 0) return;
 #pragma unroll
       for (int i = 0; i < RPT; i++) {
-        if (((rowmask >> i) & 1u) && i >= vlo && i < vhi) {
+        if ((todo >> i) & 1u) {
 #pragma unroll
           for (int w = 0; w < 4; w++) {
             uint32_t live = ~acc[i][w] & C::FLAGMASK;  // unflagged fields of this word
@@ -437,7 +439,7 @@ __global__ void __launch_bounds__(NT, 1) pruned_scan_kernel(const Params p) {
       if (tid == 0) s_stat[0] += (unsigned long long)n;
     };
 
-    if (any) push(0xffffu, slot);
+    push(0xffffu, slot);
     __syncthreads();
     const int ns = s_nsurv;
     if (ns > C::QCAP) {
@@ -448,7 +450,7 @@ __global__ void __launch_bounds__(NT, 1) pruned_scan_kernel(const Params p) {
         __syncthreads();
         if (tid == 0) s_nsurv = 0;
         __syncthreads();
-        if (any) push(1u << r, slot);
+        push(1u << r, slot);
         __syncthreads();
         drain(s_nsurv);
       }
@@ -460,10 +462,12 @@ __global__ void __launch_bounds__(NT, 1) pruned_scan_kernel(const Params p) {
         s_slot_tile[0] = t;
       }
       slot = 0;
+      need_thr = true;
     } else if (ns > 0 && (!defer || !has_next || ns >= DRAIN_AT || slot == SLOTS - 1)) {
       drain(ns);
       if (tid == 0) s_nsurv = 0;
       slot = 0;
+      need_thr = true;
     } else if (ns > 0) {
       slot++;
     }
