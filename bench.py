@@ -316,7 +316,7 @@ def main():
         # algorithmic bytes: one pass over the scanned code planes per tile of Qt
         # queries whose tables share shared memory (Qt = 8 pruned kernel, 4 exact kernel)
         fb = 8 if 127 // M >= 3 else 16          # the library's automatic field width
-        QT = (128 // fb) if use_p else 4
+        QT = (N.counter("pscan_qt") or 128 // fb) if use_p else 4
         rows_scanned = (pstats["pairs"] / (a.steps * Q)) if use_p else n_local
         alg_bytes = a.steps * -(-Q // QT) * rows_scanned * M / k_launches
         sec = k_ns * 1e-9 / k_launches

@@ -50,6 +50,8 @@ struct gulon_index_s {
   i64 N = 0, ps = 0;
   bool owned = false;
   std::mutex mu;  // guards the scratch below: one query batch in flight per index handle
+  std::mutex mu_host;  // guards the host-call staging buffers
+  DevBuf h_q, h_ids, h_dists, h_sizes;
   DevBuf lutI, keys, lists, qbuf, ids, dists, sizes, merged;
   DevBuf qlut, mins, qp, boot_tail, plists, pstats, boot_keys;
   Selector sel, sel_boot;
@@ -59,6 +61,7 @@ struct gulon_index_s {
     ids.release(); dists.release(); sizes.release(); merged.release();
     qlut.release(); mins.release(); qp.release(); boot_tail.release(); plists.release();
     pstats.release(); boot_keys.release();
+    h_q.release(); h_ids.release(); h_dists.release(); h_sizes.release();
     sel.release(); sel_boot.release();
   }
 };
@@ -74,6 +77,8 @@ std::atomic<long long> g_fused_min_rows{16384};
 std::atomic<long long> g_boot_rows{65536};       // rows scanned exactly to seed the pruned scan
 std::atomic<long long> g_pruned_min_rows{1 << 20};
 std::atomic<long long> g_pruned_bits{0};         // 0 = auto, 8 or 16: width of the lower-bound fields
+std::atomic<long long> g_pruned_words{0};        // 0 = auto, 1/2/4: 32-bit words per table entry
+std::atomic<long long> g_last_qt{0};             // queries per tile of the last pruned launch
 std::atomic<unsigned long long> g_pstats[3];     // survivors, list candidates, slow-path items
 std::atomic<unsigned long long> g_ppairs{0};     // (row, query) pairs offered to the pruned kernel
 
@@ -682,7 +687,11 @@ int scan_batch(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 fr
   // (8-bit lower-bound fields, used while they keep >= 3 levels per quantizer) or 8 (16-bit fields)
   int FB = (int)g_pruned_bits.load();
   if (FB == 0) FB = (127 / M >= 3) ? 8 : 16;
-  const int QT = 128 / FB;
+  // words per table entry: 4 (most queries per pass) unless the batch is too small to fill a tile
+  int W = (int)g_pruned_words.load();
+  if (W == 0) W = nq * FB > 64 ? 4 : (nq * FB > 32 ? 2 : 1);
+  if (FB == 16 && W == 1) W = 2;  // a tile is made of whole query groups of 4
+  const int QT = W * 32 / FB;
   const int G = impl == GULON_SCAN_PRUNED ? (QT / 4) * (int)ceil_div(nq, QT) : (int)ceil_div(nq, 4);
   const int Q4 = G * 4;
   GCHECK(ix->lutI.ensure((size_t)G * M * 256 * sizeof(float4)));
@@ -703,14 +712,21 @@ int scan_batch(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 fr
     GREQUIRE(k <= pscan::KMAX, "pruned scan supports k <= %d (k=%d)", pscan::KMAX, k);
     GREQUIRE(M <= 1024, "pruned scan supports M <= 1024 (M=%d)", M);
     GREQUIRE(FB == 16 || 127 / M >= 1, "8-bit pruned scan needs M <= 127 (M=%d)", M);
+#define GULON_PSCAN_VARIANTS(X) X(8, 4) X(8, 2) X(8, 1) X(16, 4) X(16, 2)
     static std::once_flag once;
     std::call_once(once, [] {
-      cudaFuncSetAttribute(pscan::pruned_scan_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           pscan::Cfg<8>::SMEM_BYTES);
-      cudaFuncSetAttribute(pscan::pruned_scan_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           pscan::Cfg<16>::SMEM_BYTES);
+#define GULON_X(FB_, W_)                                                                        \
+  {                                                                                             \
+    auto kern = pscan::pruned_scan_kernel<FB_, W_>;                                             \
+    using CfgT = pscan::Cfg<FB_, W_>;                                                           \
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgT::SMEM_BYTES);  \
+  }
+      GULON_PSCAN_VARIANTS(GULON_X)
+#undef GULON_X
     });
     const int T = G / (QT / 4);
+    const int RI = pscan::NT * (64 / W);  // rows per work item
+    g_last_qt = QT;
     // 1. exact scan of the boot rows -> one sorted list per query (its tail is tau0)
     const i64 boot = std::min<i64>(range, std::max<i64>(g_boot_rows.load(), k));
     int Sb = 1;
@@ -723,25 +739,29 @@ int scan_batch(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 fr
     GCHECK(ix->mins.ensure((size_t)Q4 * M * sizeof(float)));
     GCHECK(ix->qp.ensure((size_t)Q4 * sizeof(pscan::QParam)));
     GCHECK(ix->boot_tail.ensure((size_t)Q4 * sizeof(u64)));
-    GCHECK(ix->qlut.ensure((size_t)T * M * 256 * sizeof(uint4)));
+    GCHECK(ix->qlut.ensure((size_t)T * M * 256 * W * sizeof(uint32_t)));
     GCHECK(ix->pstats.ensure(3 * sizeof(unsigned long long)));
     GLAUNCH(pscan::qparams_kernel, (unsigned)G, 256, 0, st, ix->lutI.as<float4>(), M, K, nq, bkeys,
             bstride, k, pscan::t0_units(FB, M), ix->mins.as<float>(), ix->qp.as<pscan::QParam>(),
             ix->boot_tail.as<u64>());
     dim3 qg((unsigned)T, (unsigned)M);
-    if (FB == 8) {
-      GLAUNCH(pscan::qlut_build_kernel<8>, qg, 256, 0, st, ix->lutI.as<float4>(),
-              ix->mins.as<float>(), ix->qp.as<pscan::QParam>(), M, K, ix->qlut.as<uint4>());
-    } else {
-      GLAUNCH(pscan::qlut_build_kernel<16>, qg, 256, 0, st, ix->lutI.as<float4>(),
-              ix->mins.as<float>(), ix->qp.as<pscan::QParam>(), M, K, ix->qlut.as<uint4>());
-    }
+    bool built = false;
+#define GULON_X(FB_, W_)                                                                        \
+  if (FB == FB_ && W == W_) {                                                                   \
+    auto kern = pscan::qlut_build_kernel<FB_, W_>;                                              \
+    GLAUNCH(kern, qg, 256, 0, st, ix->lutI.as<float4>(), ix->mins.as<float>(),                  \
+            ix->qp.as<pscan::QParam>(), M, K, ix->qlut.as<uint32_t>());                         \
+    built = true;                                                                               \
+  }
+    GULON_PSCAN_VARIANTS(GULON_X)
+#undef GULON_X
+    GREQUIRE(built, "unsupported pruned-scan variant: %d-bit fields, %d words", FB, W);
     // 3. pruned scan of the remaining rows
     const i64 pfrom = from + boot, prange = until - pfrom;
     const int nsm = sm_count();
     int Bs = std::min(T, nsm);
     int S = std::max(1, nsm / Bs);
-    S = (int)std::max<i64>(1, std::min<i64>(S, prange / (2 * pscan::R)));
+    S = (int)std::max<i64>(1, std::min<i64>(S, prange / (2 * (i64)RI)));
     const i64 split_len = round_up(ceil_div(prange, S), 16);
     S = (int)ceil_div(prange, split_len);
     const size_t nl = (size_t)S * Q4 * k;
@@ -755,7 +775,7 @@ int scan_batch(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 fr
     prm.from = pfrom;
     prm.until = until;
     prm.split_len = split_len;
-    prm.qlut = ix->qlut.as<uint4>();
+    prm.qlut = ix->qlut.as<uint32_t>();
     prm.lutI = ix->lutI.as<float4>();
     prm.qp = ix->qp.as<pscan::QParam>();
     prm.boot_tail = ix->boot_tail.as<u64>();
@@ -768,13 +788,15 @@ int scan_batch(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 fr
     prm.S = S;
     prm.Bs = Bs;
     cudaEvent_t ev = g_t_pscan.begin(st);
-    if (FB == 8) {
-      GLAUNCH(pscan::pruned_scan_kernel<8>, (unsigned)(S * Bs), pscan::NT,
-              pscan::Cfg<8>::SMEM_BYTES, st, prm);
-    } else {
-      GLAUNCH(pscan::pruned_scan_kernel<16>, (unsigned)(S * Bs), pscan::NT,
-              pscan::Cfg<16>::SMEM_BYTES, st, prm);
-    }
+#define GULON_X(FB_, W_)                                                                        \
+  if (FB == FB_ && W == W_) {                                                                   \
+    auto kern = pscan::pruned_scan_kernel<FB_, W_>;                                             \
+    using CfgT = pscan::Cfg<FB_, W_>;                                                           \
+    GLAUNCH(kern, (unsigned)(S * Bs), pscan::NT, CfgT::SMEM_BYTES, st, prm);                    \
+  }
+    GULON_PSCAN_VARIANTS(GULON_X)
+#undef GULON_X
+#undef GULON_PSCAN_VARIANTS
     g_t_pscan.end(ev, st);
     if (want_stats) {
       unsigned long long h[3];
@@ -917,6 +939,10 @@ int gulon_set_option(const char *name, int64_t value) {
   } else if (s == "pruned_bits") {
     GREQUIRE(value == 0 || value == 8 || value == 16, "pruned_bits must be 0 (auto), 8 or 16");
     g_pruned_bits = value;
+  } else if (s == "pruned_words") {
+    GREQUIRE(value == 0 || value == 1 || value == 2 || value == 4,
+             "pruned_words must be 0 (auto), 1, 2 or 4");
+    g_pruned_words = value;
   } else if (s == "pruned_min_rows") {
     GREQUIRE(value >= 0, "pruned_min_rows must be >= 0");
     g_pruned_min_rows = value;
@@ -948,6 +974,10 @@ int gulon_get_counter(const char *name, int64_t *value) {
   }
   if (s == "pscan_survivors" || s == "pscan_candidates" || s == "pscan_slow_items") {
     *value = (int64_t)g_pstats[s == "pscan_survivors" ? 0 : s == "pscan_candidates" ? 1 : 2].load();
+    return GULON_OK;
+  }
+  if (s == "pscan_qt") {
+    *value = (int64_t)g_last_qt.load();
     return GULON_OK;
   }
   if (s == "pscan_pairs") {
@@ -1441,32 +1471,27 @@ int gulon_pq_query(gulon_index_t ix, const float *queries, int64_t nq, int64_t l
   GCHECK(need_device());
   if (nq == 0) return GULON_OK;
   const int D = ix->cb->D;
-  float *dq = nullptr;
-  int32_t *di = nullptr, *dz = nullptr;
-  float *dd = nullptr;
   const size_t nk = (size_t)nq * std::max(k, 1);
-  int rc = [&]() -> int {
-    GCU(cudaMalloc(&dq, (size_t)nq * D * sizeof(float)));
-    GCU(cudaMalloc(&di, nk * sizeof(int32_t)));
-    GCU(cudaMalloc(&dd, nk * sizeof(float)));
-    GCU(cudaMalloc(&dz, (size_t)nq * sizeof(int32_t)));
-    GCU(cudaMemcpy2DAsync(dq, (size_t)D * 4, queries, (size_t)ldq * 4, (size_t)D * 4, (size_t)nq,
-                          cudaMemcpyHostToDevice, 0));
-    GCHECK(query_dev(ix, dq, nq, D, k, from, until, normalize, id_offset, di, dd, dz, 0));
-    if (k > 0) {
-      GCU(cudaMemcpyAsync(out_ids, di, (size_t)nq * k * sizeof(int32_t), cudaMemcpyDeviceToHost, 0));
-      GCU(cudaMemcpyAsync(out_dists, dd, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, 0));
-    }
-    if (out_sizes)
-      GCU(cudaMemcpyAsync(out_sizes, dz, (size_t)nq * sizeof(int32_t), cudaMemcpyDeviceToHost, 0));
-    GCU(cudaStreamSynchronize(0));
-    return GULON_OK;
-  }();
-  if (dq) cudaFree(dq);
-  if (di) cudaFree(di);
-  if (dd) cudaFree(dd);
-  if (dz) cudaFree(dz);
-  return rc;
+  // staging buffers live in the handle (grow-only): no cudaMalloc / cudaFree per call
+  std::unique_lock<std::mutex> lock(ix->mu_host);
+  GCHECK(ix->h_q.ensure((size_t)nq * D * sizeof(float)));
+  GCHECK(ix->h_ids.ensure(nk * sizeof(int32_t)));
+  GCHECK(ix->h_dists.ensure(nk * sizeof(float)));
+  GCHECK(ix->h_sizes.ensure((size_t)nq * sizeof(int32_t)));
+  float *dq = ix->h_q.as<float>();
+  int32_t *di = ix->h_ids.as<int32_t>(), *dz = ix->h_sizes.as<int32_t>();
+  float *dd = ix->h_dists.as<float>();
+  GCU(cudaMemcpy2DAsync(dq, (size_t)D * 4, queries, (size_t)ldq * 4, (size_t)D * 4, (size_t)nq,
+                        cudaMemcpyHostToDevice, 0));
+  GCHECK(query_dev(ix, dq, nq, D, k, from, until, normalize, id_offset, di, dd, dz, 0));
+  if (k > 0) {
+    GCU(cudaMemcpyAsync(out_ids, di, (size_t)nq * k * sizeof(int32_t), cudaMemcpyDeviceToHost, 0));
+    GCU(cudaMemcpyAsync(out_dists, dd, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, 0));
+  }
+  if (out_sizes)
+    GCU(cudaMemcpyAsync(out_sizes, dz, (size_t)nq * sizeof(int32_t), cudaMemcpyDeviceToHost, 0));
+  GCU(cudaStreamSynchronize(0));
+  return GULON_OK;
 }
 
 int gulon_topk_merge_dev(const int32_t *d_ids, const float *d_dists, int32_t S, int64_t nq,

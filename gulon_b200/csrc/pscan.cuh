@@ -29,8 +29,6 @@ namespace gulon {
 namespace pscan {
 
 constexpr int NT = 512;
-constexpr int RPT = 16;
-constexpr int R = NT * RPT;     // 8192 rows per item
 constexpr int KMAX = 128;
 constexpr int SORTN = 256;      // per-query sort area: k list entries + up to CAPQ candidates
 constexpr int CAPQ = SORTN - KMAX;
@@ -38,16 +36,29 @@ constexpr int REGION_BYTES = 65536;  // both replicated slice buffers, interleav
 constexpr int SLOTS = 256;           // items whose survivors may wait in the queue
 constexpr int DRAIN_AT = 768;        // queue length that triggers an exact re-evaluation pass
 
-template <int FB>
+// FB = bits per lower-bound field, W = 32-bit words per table entry (one LDS.32/64/128 per row).
+//   queries per tile QT = W * 32 / FB; replicas of an entry = 128 B / (4 W) so that every lane of a
+//   wavefront reads its own bank group; rows per thread RPT = 64 / W (64 accumulator registers).
+// W = 4 serves the most queries per pass (best when many queries wait); W = 1 makes a pass 4x
+// shorter: the code planes then stream from HBM at a large fraction of its bandwidth, the
+// low-latency shape for small query batches.
+template <int FB, int W>
 struct Cfg {
-  static constexpr int QT = 128 / FB;            // queries per tile
+  static constexpr int QT = W * 32 / FB;         // queries per tile
   static constexpr int FPW = 32 / FB;            // fields per 32-bit word
+  static constexpr int RPT = 64 / W;             // rows per thread
+  static constexpr int R = NT * RPT;             // rows per item
+  static constexpr int NREP = 32 / W;            // replicas of a table entry in a slice
   static constexpr int FLAG = 1 << (FB - 1);
   static constexpr uint32_t FLAGMASK = FB == 8 ? 0x80808080u : 0x80008000u;
+  static constexpr int QSH = QT == 16 ? 4 : QT == 8 ? 3 : 2;       // log2(QT)
+  static constexpr int RSH = RPT == 16 ? 13 : RPT == 32 ? 14 : 15;  // log2(R)
   static constexpr int QCAP = NT * QT;           // survivor queue (one row per thread in the slow path)
   // up to 64 KB of alignment slack in front of the 64 KB-aligned slice region
   static constexpr int SMEM_BYTES = 65536 + REGION_BYTES + QT * SORTN * 8 + QCAP * 4;
+  static_assert(QT >= 4 && QT % 4 == 0, "tiles are made of query groups of 4");
 };
+constexpr int R_MAX = NT * 64;
 
 // quantisation units between base and the boot threshold
 inline int t0_units(int FB, int M) {
@@ -66,7 +77,7 @@ struct Params {
   i64 ps;
   i64 from, until;  // rows scanned by this kernel (after the boot rows)
   i64 split_len;
-  const uint4 *qlut;      // [T][M][256] QT packed fields
+  const uint32_t *qlut;   // [T][M][256][W] QT packed fields
   const float4 *lutI;     // [T*QT/4][M][256] exact tables (scan.cuh layout)
   const QParam *qp;       // [T*QT]
   const u64 *boot_tail;   // [T*QT] key of the boot list tail (KEY_SENT: none)
@@ -134,15 +145,17 @@ __global__ void __launch_bounds__(256) qparams_kernel(const float4 *__restrict__
 }
 
 // grid (T, M), block 256 (thread = code): the QT quantised entries of a tile, field f = query f.
-template <int FB>
+template <int FB, int W>
 __global__ void __launch_bounds__(256) qlut_build_kernel(const float4 *__restrict__ lutI,
                                                          const float *__restrict__ mins,
                                                          const QParam *__restrict__ qp, int M, int K,
-                                                         uint4 *__restrict__ qlut) {
-  using C = Cfg<FB>;
+                                                         uint32_t *__restrict__ qlut) {
+  using C = Cfg<FB, W>;
   const int t = blockIdx.x, m = blockIdx.y, c = threadIdx.x;
   const int qmax = (C::FLAG - 1) / M;
-  uint32_t w[4] = {0u, 0u, 0u, 0u};
+  uint32_t w[W];
+#pragma unroll
+  for (int i = 0; i < W; i++) w[i] = 0u;
 #pragma unroll
   for (int h = 0; h < C::QT / 4; h++) {
     const int g = (C::QT / 4) * t + h;
@@ -158,7 +171,8 @@ __global__ void __launch_bounds__(256) qlut_build_kernel(const float4 *__restric
       w[f / C::FPW] |= (uint32_t)qi << (FB * (f % C::FPW));
     }
   }
-  qlut[((i64)t * M + m) * 256 + c] = make_uint4(w[0], w[1], w[2], w[3]);
+#pragma unroll
+  for (int i = 0; i < W; i++) qlut[(((i64)t * M + m) * 256 + c) * W + i] = w[i];
 }
 
 // boot list [rows][boot_stride] + split lists [S][rows][k] -> keys [rows][stride]
@@ -190,25 +204,43 @@ __device__ __forceinline__ uint4 ldg_stream_u4(const void *p) {
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
   return (uint32_t)__cvta_generic_to_shared(p);
 }
-__device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
-  uint4 r;
-  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-               : "r"(addr)
-               : "memory");
-  return r;
+template <int W>
+__device__ __forceinline__ void lds_words(uint32_t addr, uint32_t (&v)[W]) {
+  if constexpr (W == 4) {
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
+                 : "r"(addr)
+                 : "memory");
+  } else if constexpr (W == 2) {
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v[0]), "=r"(v[1]) : "r"(addr) : "memory");
+  } else {
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v[0]) : "r"(addr) : "memory");
+  }
+}
+// table entry of (tile, quantizer, code) replicated into one 16-byte store value
+template <int W>
+__device__ __forceinline__ uint4 ldg_entry(const uint32_t *p) {
+  if constexpr (W == 4) {
+    return ldg_stream_u4(p);
+  } else if constexpr (W == 2) {
+    const uint2 e = __ldg(reinterpret_cast<const uint2 *>(p));
+    return make_uint4(e.x, e.y, e.x, e.y);
+  } else {
+    const uint32_t e = __ldg(p);
+    return make_uint4(e, e, e, e);
+  }
 }
 
 // Shared-memory layout (dynamic): a 64 KB-ALIGNED 64 KB region holds both slice buffers interleaved:
-//   byte address = region | code << 8 | buffer << 7 | replica << 4
+//   byte address = region | code << 8 | buffer << 7 | replica * 4W
 // so that the address of a row's table entry is ONE byte-permute of (code word, per-lane base):
 // PRMT puts the row's code byte into address bits 8..15.  After the region: per-query sort areas,
 // then the survivor queue.
-template <int FB>
+template <int FB, int W>
 __global__ void __launch_bounds__(NT, 1) pruned_scan_kernel(const Params p) {
-  using C = Cfg<FB>;
-  constexpr int QT = C::QT;
-  constexpr int QSH = FB == 8 ? 4 : 3;  // log2(QT)
+  using C = Cfg<FB, W>;
+  constexpr int QT = C::QT, RPT = C::RPT, R = C::R, QSH = C::QSH, RSH = C::RSH;
+  constexpr int NV = RPT / 16;  // 16-byte code vectors per thread and quantizer
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const uint32_t dyn0 = smem_u32(smem_raw);
   const uint32_t region = (dyn0 + 0xffffu) & ~0xffffu;
@@ -217,7 +249,7 @@ __global__ void __launch_bounds__(NT, 1) pruned_scan_kernel(const Params p) {
   uint32_t *surv = reinterpret_cast<uint32_t *>(region_g + REGION_BYTES + QT * SORTN * 8);
   __shared__ int s_cnt[QT];
   __shared__ u64 s_thr[QT];
-  __shared__ uint32_t s_bias[4];
+  __shared__ uint32_t s_bias[W];
   __shared__ int s_nsurv, s_nbefore;
   __shared__ unsigned long long s_stat[3];
   __shared__ i64 s_slot_chunk[SLOTS];
@@ -243,27 +275,30 @@ __global__ void __launch_bounds__(NT, 1) pruned_scan_kernel(const Params p) {
   int fill_off[4];  // byte offsets inside the region (buffer 0)
 #pragma unroll
   for (int t = 0; t < 4; t++) fill_off[t] = code_id * 256 + ((lane + 4 * half + t) & 7) * 16;
-  uint32_t lane_base = region | ((uint32_t)(lane & 7) << 4);  // buffer bit toggles per quantizer
+  // buffer bit (0x80) toggles per quantizer
+  uint32_t lane_base = region | ((uint32_t)(lane & (C::NREP - 1)) * (4u * W));
 
   if (tid < QT) s_cnt[tid] = 0;
-  if (tid < 4) s_bias[tid] = 0;
+  if (tid < W) s_bias[tid] = 0;
   if (tid == 0) s_nsurv = 0;
   if (tid < 3) s_stat[tid] = 0;
 
   int parity = 0;
   {
-    const uint4 v = ldg_stream_u4(p.qlut + ((i64)j * M) * 256 + code_id);
+    const uint4 v = ldg_entry<W>(p.qlut + (((i64)j * M) * 256 + code_id) * W);
 #pragma unroll
     for (int t = 0; t < 4; t++) *reinterpret_cast<uint4 *>(region_g + fill_off[t]) = v;
   }
-  uint4 ccur = make_uint4(0, 0, 0, 0);
-  {
-    const i64 row0 = origin + (i64)tid * RPT;
-    if (row0 < hi) ccur = ldg_stream_u4(p.codes + row0);
+  uint4 ccur[NV];
+#pragma unroll
+  for (int v = 0; v < NV; v++) {
+    ccur[v] = make_uint4(0, 0, 0, 0);
+    const i64 r = origin + (i64)tid * RPT + 16 * v;
+    if (r < hi) ccur[v] = ldg_stream_u4(p.codes + r);
   }
   __syncthreads();
 
-  int slot = 0;        // items queued since the last drain
+  int slot = 0;          // items queued since the last drain
   bool need_thr = true;  // thresholds change only with the tile or after a drain
 
   for (i64 it = 0; it < n_items; ++it) {
@@ -307,34 +342,44 @@ __global__ void __launch_bounds__(NT, 1) pruned_scan_kernel(const Params p) {
       s_nbefore = s_nsurv;  // entries queued by earlier items (no pushes happen during the loop)
     }
 
-    uint32_t acc[RPT][4];
+    uint32_t acc[RPT][W];
 #pragma unroll
-    for (int i = 0; i < RPT; i++) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0u;
+    for (int i = 0; i < RPT; i++)
+#pragma unroll
+      for (int w = 0; w < W; w++) acc[i][w] = 0u;
 
     for (int m = 0; m < M; ++m) {
-      uint4 cnext = make_uint4(0, 0, 0, 0);
+      uint4 cnext[NV];
+#pragma unroll
+      for (int v = 0; v < NV; v++) cnext[v] = make_uint4(0, 0, 0, 0);
       uint4 lnext = make_uint4(0, 0, 0, 0);
       bool do_fill = false;
       if (m + 1 < M) {
-        if (row0 < hi) cnext = ldg_stream_u4(p.codes + (i64)(m + 1) * p.ps + row0);
-        lnext = ldg_stream_u4(p.qlut + ((i64)t * M + m + 1) * 256 + code_id);
+#pragma unroll
+        for (int v = 0; v < NV; v++)
+          if (row0 + 16 * v < hi)
+            cnext[v] = ldg_stream_u4(p.codes + (i64)(m + 1) * p.ps + row0 + 16 * v);
+        lnext = ldg_entry<W>(p.qlut + (((i64)t * M + m + 1) * 256 + code_id) * W);
         do_fill = true;
       } else if (has_next) {
-        if (row0n < hi) cnext = ldg_stream_u4(p.codes + row0n);
-        lnext = ldg_stream_u4(p.qlut + ((i64)tn * M) * 256 + code_id);
+#pragma unroll
+        for (int v = 0; v < NV; v++)
+          if (row0n + 16 * v < hi) cnext[v] = ldg_stream_u4(p.codes + row0n + 16 * v);
+        lnext = ldg_entry<W>(p.qlut + (((i64)tn * M) * 256 + code_id) * W);
         do_fill = true;
       }
       if (warp_live) {
-        const uint32_t w[4] = {ccur.x, ccur.y, ccur.z, ccur.w};
 #pragma unroll
         for (int i = 0; i < RPT; i++) {
+          const uint4 &cv = ccur[i >> 4];
+          const uint32_t cw = ((i >> 2) & 3) == 0 ? cv.x : ((i >> 2) & 3) == 1 ? cv.y
+                              : ((i >> 2) & 3) == 2 ? cv.z : cv.w;
           // address = lane_base with the row's code byte in bits 8..15
-          const uint32_t a = __byte_perm(w[i >> 2], lane_base, 0x7604u | ((uint32_t)(i & 3) << 4));
-          const uint4 v = lds_u4(a);
-          acc[i][0] += v.x;
-          acc[i][1] += v.y;
-          acc[i][2] += v.z;
-          acc[i][3] += v.w;
+          const uint32_t a = __byte_perm(cw, lane_base, 0x7604u | ((uint32_t)(i & 3) << 4));
+          uint32_t v[W];
+          lds_words<W>(a, v);
+#pragma unroll
+          for (int w = 0; w < W; w++) acc[i][w] += v[w];
         }
       }
       if (do_fill) {
@@ -345,34 +390,38 @@ __global__ void __launch_bounds__(NT, 1) pruned_scan_kernel(const Params p) {
       __syncthreads();
       parity ^= 1;
       lane_base ^= 0x80u;
-      ccur = cnext;
+#pragma unroll
+      for (int v = 0; v < NV; v++) ccur[v] = cnext[v];
     }
 
     // ---- flag test -------------------------------------------------------------------------
     const int n_before = s_nbefore;  // published by the barriers of the quantizer loop
     const int vlo = lo > row0 ? (int)(lo - row0 > RPT ? RPT : lo - row0) : 0;
     const int vhi = hi - row0 >= RPT ? RPT : (hi > row0 ? (int)(hi - row0) : 0);
-    const uint32_t b0 = s_bias[0], b1 = s_bias[1], b2 = s_bias[2], b3 = s_bias[3];
-    uint32_t rm = 0;  // rows of this thread with at least one unflagged field
+    uint32_t bias[W];
+#pragma unroll
+    for (int w = 0; w < W; w++) bias[w] = s_bias[w];
+    unsigned long long rm = 0;  // rows of this thread with at least one unflagged field
 #pragma unroll
     for (int i = 0; i < RPT; i++) {
-      acc[i][0] += b0;
-      acc[i][1] += b1;
-      acc[i][2] += b2;
-      acc[i][3] += b3;
-      const uint32_t x = acc[i][0] & acc[i][1] & acc[i][2] & acc[i][3];
-      if ((x & C::FLAGMASK) != C::FLAGMASK && i >= vlo && i < vhi) rm |= 1u << i;
+      uint32_t x = 0xffffffffu;
+#pragma unroll
+      for (int w = 0; w < W; w++) {
+        acc[i][w] += bias[w];
+        x &= acc[i][w];
+      }
+      if ((x & C::FLAGMASK) != C::FLAGMASK && i >= vlo && i < vhi) rm |= 1ull << i;
     }
 
     // survivors of the rows selected by `rowmask` -> queue; entry = slot | local row | field
-    auto push = [&](uint32_t rowmask, int slot_) {
-      const uint32_t todo = rm & rowmask;
+    auto push = [&](unsigned long long rowmask, int slot_) {
+      const unsigned long long todo = rm & rowmask;
       if (todo == 0) return;
 #pragma unroll
       for (int i = 0; i < RPT; i++) {
-        if ((todo >> i) & 1u) {
+        if ((todo >> i) & 1ull) {
 #pragma unroll
-          for (int w = 0; w < 4; w++) {
+          for (int w = 0; w < W; w++) {
             uint32_t live = ~acc[i][w] & C::FLAGMASK;  // unflagged fields of this word
             while (live) {
               const int bit = __ffs(live) - 1;
@@ -380,7 +429,7 @@ __global__ void __launch_bounds__(NT, 1) pruned_scan_kernel(const Params p) {
               const int f = w * C::FPW + bit / FB;
               const int pos = atomicAdd(&s_nsurv, 1);
               if (pos < C::QCAP)
-                surv[pos] = ((uint32_t)slot_ << (13 + QSH)) | ((uint32_t)(tid * RPT + i) << QSH) |
+                surv[pos] = ((uint32_t)slot_ << (RSH + QSH)) | ((uint32_t)(tid * RPT + i) << QSH) |
                             (uint32_t)f;
             }
           }
@@ -395,8 +444,8 @@ __global__ void __launch_bounds__(NT, 1) pruned_scan_kernel(const Params p) {
         for (int si = b0s + warp; si < b0s + nb; si += NT / 32) {
           const uint32_t code = surv[si];
           const int q = (int)(code & (uint32_t)(QT - 1));
-          const int sl = (int)(code >> (13 + QSH));
-          const i64 row = s_slot_chunk[sl] + (i64)((code >> QSH) & 8191u);
+          const int sl = (int)(code >> (RSH + QSH));
+          const i64 row = s_slot_chunk[sl] + (i64)((code >> QSH) & (uint32_t)(R - 1));
           const int ts = s_slot_tile[sl];
           const float4 *lut = p.lutI + ((i64)ts * (QT / 4) + (q >> 2)) * M * 256;
           const int jq = q & 3;
@@ -439,7 +488,7 @@ __global__ void __launch_bounds__(NT, 1) pruned_scan_kernel(const Params p) {
       if (tid == 0) s_stat[0] += (unsigned long long)n;
     };
 
-    push(0xffffu, slot);
+    push(~0ull, slot);
     __syncthreads();
     const int ns = s_nsurv;
     if (ns > C::QCAP) {
@@ -450,7 +499,7 @@ __global__ void __launch_bounds__(NT, 1) pruned_scan_kernel(const Params p) {
         __syncthreads();
         if (tid == 0) s_nsurv = 0;
         __syncthreads();
-        push(1u << r, slot);
+        push(1ull << r, slot);
         __syncthreads();
         drain(s_nsurv);
       }

@@ -246,26 +246,31 @@ def build_index(g, rng, n, D, M, K=256, codes=None):
     return pq, cb, codes, g.PQIndex(pq, g.EncodedMatrix(g.Coder8(n), codes))
 
 
-IMPLS = ["simple", "fused", "pruned8", "pruned16"]
+IMPLS = ["simple", "fused", "pruned8", "pruned16", "pruned8w1", "pruned8w2", "pruned16w2"]
 
 
 def impl_id(g, name):
-    return {"simple": (g.SCAN_SIMPLE, 0), "fused": (g.SCAN_FUSED, 0), "pruned": (g.SCAN_PRUNED, 0),
-            "pruned8": (g.SCAN_PRUNED, 8), "pruned16": (g.SCAN_PRUNED, 16)}[name]
+    return {"simple": (g.SCAN_SIMPLE, 0, 0), "fused": (g.SCAN_FUSED, 0, 0),
+            "pruned": (g.SCAN_PRUNED, 0, 0),
+            "pruned8": (g.SCAN_PRUNED, 8, 4), "pruned16": (g.SCAN_PRUNED, 16, 4),
+            "pruned8w1": (g.SCAN_PRUNED, 8, 1), "pruned8w2": (g.SCAN_PRUNED, 8, 2),
+            "pruned16w2": (g.SCAN_PRUNED, 16, 2)}[name]
 
 
 def check_query(g, oracle, ix, cb, codes, Q, k, frm, until, impl, boot_rows=4096):
-    impl, bits = impl
+    impl, bits, words = impl
     if bits == 8 and codes.shape[0] > 127:
         pytest.skip("8-bit lower-bound fields need M <= 127")
     g.set_option("scan_impl", impl)
     g.set_option("pruned_bits", bits)
+    g.set_option("pruned_words", words)
     g.set_option("boot_rows", boot_rows)       # small boot so that test-sized ranges reach the
     try:                                       # pruned kernel proper
         got = ix.batch_query(k, Q, frm, until)
     finally:
         g.set_option("scan_impl", g.SCAN_AUTO)
         g.set_option("pruned_bits", 0)
+        g.set_option("pruned_words", 0)
         g.set_option("boot_rows", 65536)
     ids, ds, sz = oracle.pq_query(Q, cb, codes, k, frm, until, topk_mode=oracle.TOPK_CANONICAL)
     assert np.array_equal(got.size, sz)
@@ -306,7 +311,8 @@ def test_query_heavy_ties(g, oracle, impl):
     check_query(g, oracle, ix, cb, codes, Q, 25, 3, n - 1, impl_id(g, impl))
 
 
-@pytest.mark.parametrize("impl", ["pruned8", "pruned16", "pruned"])
+@pytest.mark.parametrize("impl", ["pruned8", "pruned16", "pruned", "pruned8w1", "pruned8w2",
+                                  "pruned16w2"])
 @pytest.mark.parametrize("n,D,M,nq,k,boot", [
     (300000, 100, 10, 21, 10, 65536),     # default boot, several tiles
     (200000, 300, 30, 8, 10, 8192),       # c2 shape
@@ -328,7 +334,7 @@ def test_query_pruned_matches_oracle_clustered_codes(g, oracle, impl, n, D, M, n
     check_query(g, oracle, ix, cb, enc.codes, Q, k, 0, n, impl_id(g, impl), boot_rows=boot)
 
 
-@pytest.mark.parametrize("impl", ["fused", "pruned8", "pruned16"])
+@pytest.mark.parametrize("impl", ["fused", "pruned8", "pruned16", "pruned8w1", "pruned8w2"])
 def test_query_descending_distances_overflow_path(g, oracle, impl):
     # rows ordered by DEcreasing distance: every row beats the running k-th best, the worst case
     # for the fused kernel's candidate buffer
@@ -483,3 +489,88 @@ def test_self_query_finds_own_code(g):
     for i, row in enumerate(rows):
         assert np.array_equal(enc.codes[:, r.keys[i, 0]], enc.codes[:, row])
         assert r.keys[i, 0] <= row  # lowest id among identical codes
+
+
+# ---- sharded k-means: two ranks emulated by two host threads on one GPU ------------------------------
+def test_sharded_kmeans_two_ranks_one_gpu(g, oracle):
+    """gulon_kmeans_train with gulon_comm_t hooks: rows sharded over 2 ranks, one all-reduce of
+    sums/counts (+ one of the changed-assignment count) per Lloyd iteration.  The ranks are two host
+    threads sharing the GPU; their hooks exchange through a host barrier (no kernel ever waits on
+    another rank)."""
+    import ctypes as C
+    import threading
+    import torch
+    from gulon_b200 import _native as N
+    from gulon_b200.sharded import _view
+
+    rng = np.random.default_rng(17)
+    n, D, K = 20000, 12, 16
+    X = clustered(rng, n, D, centres=16, scale=4.0, noise=0.3)
+    world = 2
+    bounds = [(0, 9984), (9984, n)]
+    bar = threading.Barrier(world)
+    slots = [None] * world
+    dev = torch.device("cuda", 0)
+    calls = [0] * world
+
+    def make_comm(rank):
+        def allreduce(buf, cnt, typestr):
+            try:
+                t = _view(buf, cnt, typestr, dev)
+                torch.cuda.synchronize()
+                slots[rank] = t
+                bar.wait()
+                total = slots[0].clone()
+                for r in range(1, world):
+                    total += slots[r]
+                torch.cuda.synchronize()
+                bar.wait()
+                t.copy_(total)
+                torch.cuda.synchronize()
+                bar.wait()
+                calls[rank] += 1
+                return 0
+            except Exception:
+                bar.abort()
+                return 1
+        f32 = N.Comm.ALLREDUCE_F32(lambda u, b, c, s: allreduce(b, c, "<f4"))
+        i32 = N.Comm.ALLREDUCE_I32(lambda u, b, c, s: allreduce(b, c, "<i4"))
+        ag = N.Comm.ALLGATHER(lambda u, a, b, c, s: 1)
+        return N.Comm(rank, world, f32, i32, ag, None), (f32, i32, ag)
+
+    out = [None] * world
+    errs = []
+
+    def run(rank):
+        try:
+            lo, hi = bounds[rank]
+            comm, keep = make_comm(rank)
+            km, info = g.KMeans.compute_clusters(
+                g.Vectors(g.Matrix(X[lo:hi])), g.KMeansConfig(K, 40, seed=5, update_mode=g.UPDATE_SUM),
+                comm=comm, n_total=n, row_offset=lo, return_info=True)
+            out[rank] = (km.centroids.copy(), info)
+        except Exception as e:  # pragma: no cover
+            errs.append(e)
+            bar.abort()
+
+    ths = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join(120)
+    assert not errs, errs
+    (c0, i0), (c1, i1) = out
+    assert np.array_equal(c0.view(np.uint32), c1.view(np.uint32))     # every rank ends identical
+    assert i0 == i1 and calls[0] == calls[1] > 0
+    # same problem on one rank, same update rule
+    km, info = g.KMeans.compute_clusters(g.Vectors(g.Matrix(X)),
+                                         g.KMeansConfig(K, 40, seed=5, update_mode=g.UPDATE_SUM),
+                                         return_info=True)
+    a_sh = oracle.assign(X, 0, D, c0, tie_mode=oracle.TIE_LOWEST)
+    a_1 = oracle.assign(X, 0, D, km.centroids, tie_mode=oracle.TIE_LOWEST)
+    o_sh = oracle.objective(X, 0, D, c0, a_sh)
+    o_1 = oracle.objective(X, 0, D, km.centroids, a_1)
+    assert o_sh == pytest.approx(o_1, rel=1e-4)
+    assert info["converged"] == i0["converged"]
+    if np.array_equal(a_sh, a_1):
+        assert np.allclose(c0, km.centroids, rtol=1e-5, atol=1e-5)
