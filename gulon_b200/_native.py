@@ -14,12 +14,13 @@ _ROOT = os.path.dirname(_HERE)
 SO_PATH = os.path.join(_HERE, "libgulon_b200.so")
 _SRC_DIR = os.path.join(_HERE, "csrc")
 _SOURCES = ["gulon_b200.cu"]
-_HEADERS = ["common.cuh", "kmeans.cuh", "scan.cuh", "select.cuh", "pscan.cuh"]
+_HEADERS = ["common.cuh", "kmeans.cuh", "scan.cuh", "select.cuh", "pscan.cuh", "tcassign.cuh"]
 
 OK, EINVAL, ECUDA, ENOMEM, ENODEVICE, ECOMM, EUNSUPPORTED, ESTATE = 0, -1, -2, -3, -4, -5, -6, -7
 TIE_LOWEST = 1
 UPDATE_RUNNING_MEAN, UPDATE_SUM = 0, 1
 SCAN_AUTO, SCAN_SIMPLE, SCAN_FUSED, SCAN_PRUNED = 0, 1, 2, 3
+ASSIGN_AUTO, ASSIGN_EXACT, ASSIGN_TENSOR = 0, 1, 2
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -16,6 +16,7 @@
 #include "pscan.cuh"
 #include "scan.cuh"
 #include "select.cuh"
+#include "tcassign.cuh"
 
 using namespace gulon;
 
@@ -37,7 +38,9 @@ struct gulon_codebook_s {
   std::map<int, DevBuf> d_by_dim;
   std::mutex mu;
   DevBuf scratch_q, scratch_lut;  // gulon_prepare_query staging
+  DevBuf tc;                      // tensor-core assignment operands (tcassign.cuh)
   ~gulon_codebook_s() {
+    tc.release();
     cb.release(); off.release(); dfrom.release(); ddim.release();
     for (auto &kv : d_by_dim) kv.second.release();
     scratch_q.release(); scratch_lut.release();
@@ -78,6 +81,9 @@ std::atomic<long long> g_boot_rows{65536};       // rows scanned exactly to seed
 std::atomic<long long> g_pruned_min_rows{1 << 20};
 std::atomic<long long> g_pruned_bits{0};         // 0 = auto, 8 or 16: width of the lower-bound fields
 std::atomic<long long> g_pruned_words{0};        // 0 = auto, 1/2/4: 32-bit words per table entry
+std::atomic<long long> g_assign_impl{GULON_ASSIGN_AUTO};  // exact CUDA-core kernel or tcgen05 filter + exact recheck
+std::atomic<long long> g_assign_tc_min_rows{4096};
+std::atomic<unsigned long long> g_tc_stats[3];   // candidate (row, chunk) pairs, overflow tiles, (row, window) pairs
 std::atomic<long long> g_last_qt{0};             // queries per tile of the last pruned launch
 std::atomic<unsigned long long> g_pstats[3];     // survivors, list candidates, slow-path items
 std::atomic<unsigned long long> g_ppairs{0};     // (row, query) pairs offered to the pruned kernel
@@ -221,13 +227,91 @@ int launch_assign_dim(const float *dX, i64 N, i64 ld, const float *cb, const flo
   return GULON_OK;
 }
 
+// Tensor-core assignment (tcassign.cuh): approximate scores on tcgen05, exact recheck of the
+// candidate chunks.  `scratch` holds a 256-byte header (statistics) and one operand blob per window.
+template <int DIM, typename OutT>
+int launch_assign_tc_dim(const float *dX, i64 N, i64 ld, const float *cb, const float *off, int K,
+                         int dmax, const int32_t *dsubs, int nsub, const int32_t *dfrom,
+                         const int32_t *ddim, int n_windows, DevBuf &scratch, bool prep, OutT *out,
+                         i64 out_stride, cudaStream_t st) {
+  if (prep) GCHECK(scratch.ensure(256 + (size_t)n_windows * tca::BLOB_BYTES));
+  unsigned char *blobs = scratch.as<unsigned char>() + 256;
+  unsigned long long *stats = nullptr;
+  const bool prof = g_profile.load() != 0;
+  DevBuf stats_buf;
+  struct Guard {
+    DevBuf &b;
+    ~Guard() { b.release(); }
+  } guard{stats_buf};
+  if (prof) {
+    GCHECK(stats_buf.ensure(16));
+    stats = stats_buf.as<unsigned long long>();
+    GCU(cudaMemsetAsync(stats, 0, 16, st));
+  }
+  if (prep)
+    GLAUNCH(tca::tc_prep_kernel, (unsigned)nsub, 256, 0, st, cb, off, dsubs, ddim, K, dmax, blobs);
+  auto kern = tca::tc_assign_kernel<DIM, OutT>;
+  static std::once_flag once;  // one per instantiation
+  std::call_once(once, [&] {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tca::SMEM_BYTES);
+  });
+  tca::Params p;
+  p.X = dX;
+  p.N = N;
+  p.ld = ld;
+  p.blobs = blobs;
+  p.subs = dsubs;
+  p.from = dfrom;
+  p.nsub = nsub;
+  p.K = K;
+  p.out = out;
+  p.out_stride = out_stride;
+  p.stats = stats;
+  const i64 units = ceil_div(N, tca::UNIT_ROWS) * ceil_div(nsub, tca::GRP);
+  const unsigned grid = (unsigned)std::min<i64>(units, sm_count());
+  cudaEvent_t ev = g_t_assign.begin(st);
+  GLAUNCH(kern, grid, tca::NT, tca::SMEM_BYTES, st, p);
+  g_t_assign.end(ev, st);
+  if (prof) {
+    unsigned long long h[2] = {0, 0};
+    GCU(cudaMemcpyAsync(h, stats, 16, cudaMemcpyDeviceToHost, st));
+    GCU(cudaStreamSynchronize(st));
+    g_tc_stats[0] += h[0];
+    g_tc_stats[1] += h[1];
+    g_tc_stats[2] += (unsigned long long)N * (unsigned long long)nsub;
+  }
+  return GULON_OK;
+}
+
 // One launch for `nsub` sub-quantizers that share the window width `dim`.
 template <typename OutT>
 int launch_assign(const float *dX, i64 N, i64 ld, const float *cb, const float *off, int K,
                   int dmax, const int32_t *dsubs, int nsub, const int32_t *dfrom,
-                  const int32_t *ddim, int dim, OutT *out, i64 out_stride, cudaStream_t st) {
+                  const int32_t *ddim, int dim, int n_windows, DevBuf *tc_scratch, bool tc_prep,
+                  OutT *out, i64 out_stride, cudaStream_t st) {
   if (N <= 0 || nsub <= 0) return GULON_OK;
   GREQUIRE(nsub <= 65535, "too many sub-quantizers in one launch (%d)", nsub);
+  const long long impl = g_assign_impl.load();
+  const bool tc_ok = tc_scratch && K <= tca::TN && 3 * dim + 3 <= tca::KP &&
+                     (tc_prep || tc_scratch->p);
+  GREQUIRE(impl != GULON_ASSIGN_TENSOR || tc_ok,
+           "assign_impl=tensor needs K <= %d and window width <= %d (K=%d, width=%d)", tca::TN,
+           (tca::KP - 3) / 3, K, dim);
+  if (tc_ok && (impl == GULON_ASSIGN_TENSOR ||
+                (impl == GULON_ASSIGN_AUTO && N >= g_assign_tc_min_rows.load()))) {
+    switch (dim) {
+#define GULON_CASE(DD)                                                                           \
+  case DD:                                                                                       \
+    return launch_assign_tc_dim<DD, OutT>(dX, N, ld, cb, off, K, dmax, dsubs, nsub, dfrom, ddim, \
+                                          n_windows, *tc_scratch, tc_prep, out, out_stride, st);
+      GULON_CASE(1) GULON_CASE(2) GULON_CASE(3) GULON_CASE(4) GULON_CASE(5) GULON_CASE(6)
+      GULON_CASE(7) GULON_CASE(8) GULON_CASE(9) GULON_CASE(10) GULON_CASE(11) GULON_CASE(12)
+      GULON_CASE(13) GULON_CASE(14) GULON_CASE(15)
+#undef GULON_CASE
+      default:
+        break;
+    }
+  }
   switch (dim) {
 #define GULON_CASE(DD)                                                                           \
   case DD:                                                                                       \
@@ -259,8 +343,9 @@ struct Problems {
   int n = 0, K = 0, dmax = 0;
   std::vector<int32_t> from, dim;
   DevBuf cb, off, dfrom, ddim, dsubs, diff, sums, counts, part_sum, part_cnt, tile_hist, base,
-      order, rows;
+      order, rows, tc;
   ~Problems() {
+    tc.release();
     cb.release(); off.release(); dfrom.release(); ddim.release(); dsubs.release(); diff.release();
     sums.release(); counts.release(); part_sum.release(); part_cnt.release();
     tile_hist.release(); base.release(); order.release(); rows.release();
@@ -310,7 +395,8 @@ struct Problems {
              i64 out_stride, cudaStream_t st) {
     return for_each_width(subs, st, [&](int w, const int32_t *ds, int ns) {
       return launch_assign<int32_t>(dX, N, ld, cb.as<float>(), off.as<float>(), K, dmax, ds, ns,
-                                    dfrom.as<int32_t>(), ddim.as<int32_t>(), w, out, out_stride, st);
+                                    dfrom.as<int32_t>(), ddim.as<int32_t>(), w, n, &tc, true, out,
+                                    out_stride, st);
     });
   }
   // local per-cluster sums / counts (GULON_UPDATE_SUM); the caller all-reduces and finalises
@@ -573,6 +659,18 @@ int codebook_offsets(gulon_codebook_t cb, cudaStream_t st) {
   const i64 t = (i64)cb->M * cb->K;
   GLAUNCH(offsets_kernel, (unsigned)ceil_div(t, 256), 256, 0, st, cb->cb.as<float>(),
           cb->ddim.as<int32_t>(), cb->M, cb->K, cb->dmax, cb->off.as<float>());
+  // operands of the tensor-core assignment (tcassign.cuh), prepared once per codebook
+  bool any = false;
+  for (auto &kv : cb->by_dim) any = any || 3 * kv.first + 3 <= tca::KP;
+  if (cb->K <= tca::TN && any) {
+    GCHECK(cb->tc.ensure(256 + (size_t)cb->M * tca::BLOB_BYTES));
+    for (auto &kv : cb->by_dim) {
+      if (3 * kv.first + 3 > tca::KP) continue;
+      GLAUNCH(tca::tc_prep_kernel, (unsigned)kv.second.size(), 256, 0, st, cb->cb.as<float>(),
+              cb->off.as<float>(), cb->d_by_dim[kv.first].as<int32_t>(), cb->ddim.as<int32_t>(),
+              cb->K, cb->dmax, cb->tc.as<unsigned char>() + 256);
+    }
+  }
   return GULON_OK;
 }
 
@@ -582,7 +680,8 @@ int encode_dev(gulon_codebook_t cb, const float *dX, i64 N, i64 ld, uint8_t *dco
     GCHECK(launch_assign<uint8_t>(dX, N, ld, cb->cb.as<float>(), cb->off.as<float>(), cb->K,
                                   cb->dmax, cb->d_by_dim[kv.first].as<int32_t>(),
                                   (int)kv.second.size(), cb->dfrom.as<int32_t>(),
-                                  cb->ddim.as<int32_t>(), kv.first, dcodes, ps, st));
+                                  cb->ddim.as<int32_t>(), kv.first, cb->M, &cb->tc, false, dcodes,
+                                  ps, st));
   }
   return GULON_OK;
 }
@@ -926,8 +1025,15 @@ int gulon_set_option(const char *name, int64_t value) {
   } else if (s == "encode_chunk_rows") {
     GREQUIRE(value >= 1, "encode_chunk_rows must be >= 1");
     g_encode_chunk = value;
+  } else if (s == "assign_impl") {
+    GREQUIRE(value >= GULON_ASSIGN_AUTO && value <= GULON_ASSIGN_TENSOR, "assign_impl must be 0..2");
+    g_assign_impl = value;
+  } else if (s == "assign_tc_min_rows") {
+    GREQUIRE(value >= 0, "assign_tc_min_rows must be >= 0");
+    g_assign_tc_min_rows = value;
   } else if (s == "profile") {
     g_profile = value ? 1 : 0;
+    for (int i = 0; i < 3; i++) g_tc_stats[i] = 0;
     g_t_scan.reset();
     g_t_assign.reset();
     g_t_pscan.reset();
@@ -982,6 +1088,10 @@ int gulon_get_counter(const char *name, int64_t *value) {
   }
   if (s == "pscan_pairs") {
     *value = (int64_t)g_ppairs.load();
+    return GULON_OK;
+  }
+  if (s == "assign_tc_pairs" || s == "assign_tc_overflow_tiles" || s == "assign_tc_rows") {
+    *value = (int64_t)g_tc_stats[s == "assign_tc_pairs" ? 0 : s == "assign_tc_overflow_tiles" ? 1 : 2].load();
     return GULON_OK;
   }
   if (s == "assign_kernel_ns" || s == "assign_kernel_launches") {

@@ -62,6 +62,12 @@ extern "C" {
 #define GULON_SCAN_FUSED  2 /* replicated-LUT gather kernel with in-kernel top-k (k <= 128)        */
 #define GULON_SCAN_PRUNED 3 /* 16-bit lower-bound pass + exact fp32 re-evaluation of survivors      */
 
+/* assignment / encode implementation selector for gulon_set_option("assign_impl", ...).
+ * Both produce the same bits: the tensor path only discards centroids that provably cannot win. */
+#define GULON_ASSIGN_AUTO   0
+#define GULON_ASSIGN_EXACT  1 /* CUDA-core kernel: all K scores in the reference's arithmetic          */
+#define GULON_ASSIGN_TENSOR 2 /* tcgen05 approximate scores + exact recheck of near-minimum centroids  */
+
 typedef struct gulon_points_s   *gulon_points_t;   /* device-resident float32 matrix (Matrix)      */
 typedef struct gulon_codebook_s *gulon_codebook_t; /* device-resident ProductQuantizer codebooks   */
 typedef struct gulon_index_s    *gulon_index_t;    /* device-resident Index.PQIndex                */
