@@ -6,6 +6,7 @@
 // in the kernels of kmeans.cuh / scan.cuh / select.cuh; there is NO CPU fallback -- without a CUDA
 // device every compute entry point returns GULON_ENODEVICE.
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <map>
@@ -39,8 +40,11 @@ struct gulon_codebook_s {
   std::mutex mu;
   DevBuf scratch_q, scratch_lut;  // gulon_prepare_query staging
   DevBuf tc;                      // tensor-core assignment operands (tcassign.cuh)
+  std::map<int, DevBuf> tc_groups;  // per window width: groups of adjacent windows
+  std::map<int, int> tc_ngroups;
   ~gulon_codebook_s() {
     tc.release();
+    for (auto &kv : tc_groups) kv.second.release();
     cb.release(); off.release(); dfrom.release(); ddim.release();
     for (auto &kv : d_by_dim) kv.second.release();
     scratch_q.release(); scratch_lut.release();
@@ -227,15 +231,95 @@ int launch_assign_dim(const float *dX, i64 N, i64 ld, const float *cb, const flo
   return GULON_OK;
 }
 
-// Tensor-core assignment (tcassign.cuh): approximate scores on tcgen05, exact recheck of the
-// candidate chunks.  `scratch` holds a 256-byte header (statistics) and one operand blob per window.
+// ---- tensor-core assignment (tcassign.cuh) ---------------------------------------------------
+// What the tensor path needs besides the exact path's arguments.
+struct TcCtx {
+  DevBuf *blobs = nullptr;        // 256-byte header + one operand blob per window
+  int n_windows = 0;
+  bool prep = false;              // run tc_prep_kernel for the launch's windows first (centroids changed)
+  const int32_t *hsubs = nullptr; // host copy of the launch's window list
+  const int32_t *hfrom = nullptr; // host copy of the from[] table
+  DevBuf *groups = nullptr;       // scratch for the group table when d_groups is null
+  const int32_t *d_groups = nullptr;  // prepared group table (codebooks)
+  int n_groups = 0;
+};
+
+// Groups of up to GRP_MAX windows that are adjacent in the row, so that one TMA box (32 floats from
+// the 16-byte boundary below the first window) serves them all.
+std::vector<int32_t> build_tc_groups(const int32_t *subs, int n, const int32_t *from, int dim) {
+  std::vector<int32_t> g;
+  int i = 0;
+  while (i < n) {
+    const int m0 = from[subs[i]] & 3;
+    int cnt = 1;
+    while (cnt < tca::GRP_MAX && i + cnt < n && from[subs[i + cnt]] == from[subs[i + cnt - 1]] + dim &&
+           m0 + (cnt + 1) * dim <= tca::BOX_COLS)
+      cnt++;
+    for (int j = 0; j < tca::GRP_MAX; j++) g.push_back(j < cnt ? subs[i + j] : -1);
+    i += cnt;
+  }
+  return g;
+}
+
+typedef CUresult (*tensor_map_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+                                         const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                         const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                         CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+tensor_map_encode_fn tensor_map_encoder() {
+  static tensor_map_encode_fn fn = [] {
+    void *f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess) {
+      cudaGetLastError();
+      f = nullptr;
+    }
+    return reinterpret_cast<tensor_map_encode_fn>(f);
+  }();
+  return fn;
+}
+
+// the row-major matrix as a TMA tensor: boxes of [TM rows][32 floats], 128-byte swizzle, zero fill
+int make_row_map(const float *dX, i64 N, i64 ld, int ncols, CUtensorMap *map) {
+  tensor_map_encode_fn enc = tensor_map_encoder();
+  GREQUIRE(enc, "cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t gdim[2] = {(cuuint64_t)ncols, (cuuint64_t)N};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)tca::BOX_COLS, (cuuint32_t)tca::TM};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(dX), gdim, gstride, box,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(GULON_ECUDA, "cuTensorMapEncodeTiled failed (%d) for N=%lld ld=%lld cols=%d", (int)r,
+                (long long)N, (long long)ld, ncols);
+  return GULON_OK;
+}
+
+bool tc_eligible(const float *dX, i64 N, i64 ld, int K, int dim) {
+  return K <= tca::TN && 3 * dim + 3 <= tca::KP && (ld % 4) == 0 && ld * 4 < (1LL << 40) &&
+         (reinterpret_cast<uintptr_t>(dX) & 15) == 0 && N < (1LL << 31) && tensor_map_encoder() != nullptr;
+}
+
+// Approximate scores on tcgen05, exact recheck of the candidate chunks.
 template <int DIM, typename OutT>
 int launch_assign_tc_dim(const float *dX, i64 N, i64 ld, const float *cb, const float *off, int K,
                          int dmax, const int32_t *dsubs, int nsub, const int32_t *dfrom,
-                         const int32_t *ddim, int n_windows, DevBuf &scratch, bool prep, OutT *out,
-                         i64 out_stride, cudaStream_t st) {
-  if (prep) GCHECK(scratch.ensure(256 + (size_t)n_windows * tca::BLOB_BYTES));
+                         const int32_t *ddim, TcCtx &tc, OutT *out, i64 out_stride,
+                         cudaStream_t st) {
+  DevBuf &scratch = *tc.blobs;
+  if (tc.prep) GCHECK(scratch.ensure(256 + (size_t)tc.n_windows * tca::BLOB_BYTES));
   unsigned char *blobs = scratch.as<unsigned char>() + 256;
+  int ncols = 0;
+  for (int i = 0; i < nsub; i++) ncols = std::max(ncols, tc.hfrom[tc.hsubs[i]] + DIM);
+  const int32_t *d_groups = tc.d_groups;
+  int n_groups = tc.n_groups;
+  if (!d_groups) {
+    std::vector<int32_t> g = build_tc_groups(tc.hsubs, nsub, tc.hfrom, DIM);
+    n_groups = (int)(g.size() / tca::GRP_MAX);
+    GCHECK(upload(*tc.groups, g, st));
+    d_groups = tc.groups->as<int32_t>();
+  }
   unsigned long long *stats = nullptr;
   const bool prof = g_profile.load() != 0;
   DevBuf stats_buf;
@@ -248,36 +332,67 @@ int launch_assign_tc_dim(const float *dX, i64 N, i64 ld, const float *cb, const 
     stats = stats_buf.as<unsigned long long>();
     GCU(cudaMemsetAsync(stats, 0, 16, st));
   }
-  if (prep)
+  if (tc.prep)
     GLAUNCH(tca::tc_prep_kernel, (unsigned)nsub, 256, 0, st, cb, off, dsubs, ddim, K, dmax, blobs);
   auto kern = tca::tc_assign_kernel<DIM, OutT>;
   static std::once_flag once;  // one per instantiation
   std::call_once(once, [&] {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tca::SMEM_BYTES);
   });
+  CUtensorMap map;
+  GCHECK(make_row_map(dX, N, ld, ncols, &map));
   tca::Params p;
-  p.X = dX;
   p.N = N;
-  p.ld = ld;
+  // rows per work unit: at least ~16 units per CTA, at most 8192 rows
+  const int sms = sm_count();
+  i64 ur = 8192;
+  while (ur > 1024 && ceil_div(N, ur) * n_groups < 16LL * sms) ur >>= 1;
+  p.unit_rows = (int)ur;
   p.blobs = blobs;
-  p.subs = dsubs;
+  p.groups = d_groups;
   p.from = dfrom;
-  p.nsub = nsub;
+  p.n_groups = n_groups;
   p.K = K;
   p.out = out;
   p.out_stride = out_stride;
   p.stats = stats;
-  const i64 units = ceil_div(N, tca::UNIT_ROWS) * ceil_div(nsub, tca::GRP);
-  const unsigned grid = (unsigned)std::min<i64>(units, sm_count());
+  // GULON_TC_DEBUG=1: breadcrumbs of CTA 0 in host-mapped memory, printed when the launch fails
+  static int *dbg_host = [] {
+    int *h = nullptr;
+    const char *e = getenv("GULON_TC_DEBUG");
+    if (e && *e == '1' && cudaHostAlloc(&h, 14 * 8 * sizeof(int), cudaHostAllocMapped) != cudaSuccess) h = nullptr;
+    return h;
+  }();
+  p.dbg = nullptr;
+  if (dbg_host) {
+    memset(dbg_host, 0, 14 * 8 * sizeof(int));
+    int *d = nullptr;
+    if (cudaHostGetDevicePointer(&d, dbg_host, 0) == cudaSuccess) p.dbg = d;
+  }
+  const i64 units = ceil_div(N, ur) * n_groups;
+  const unsigned grid = (unsigned)std::min<i64>(units, sms);
   cudaEvent_t ev = g_t_assign.begin(st);
-  GLAUNCH(kern, grid, tca::NT, tca::SMEM_BYTES, st, p);
+  GLAUNCH(kern, grid, tca::NT, tca::SMEM_BYTES, st, map, p);
   g_t_assign.end(ev, st);
+  if (dbg_host) {
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+      std::string m;
+      for (int w = 0; w < 14; w++) {
+        char b[160];
+        snprintf(b, sizeof(b), " w%d[%d %d %d %d %d]", w, dbg_host[w * 8], dbg_host[w * 8 + 1],
+                 dbg_host[w * 8 + 2], dbg_host[w * 8 + 3], dbg_host[w * 8 + 4]);
+        m += b;
+      }
+      return fail(GULON_ECUDA, "tc_assign_kernel<%d>: %s; N=%lld groups=%d unit_rows=%d grid=%u;%s", DIM,
+                  cudaGetErrorString(e), (long long)N, n_groups, p.unit_rows, grid, m.c_str());
+    }
+  }
   if (prof) {
     unsigned long long h[2] = {0, 0};
     GCU(cudaMemcpyAsync(h, stats, 16, cudaMemcpyDeviceToHost, st));
     GCU(cudaStreamSynchronize(st));
     g_tc_stats[0] += h[0];
-    g_tc_stats[1] += h[1];
     g_tc_stats[2] += (unsigned long long)N * (unsigned long long)nsub;
   }
   return GULON_OK;
@@ -287,23 +402,24 @@ int launch_assign_tc_dim(const float *dX, i64 N, i64 ld, const float *cb, const 
 template <typename OutT>
 int launch_assign(const float *dX, i64 N, i64 ld, const float *cb, const float *off, int K,
                   int dmax, const int32_t *dsubs, int nsub, const int32_t *dfrom,
-                  const int32_t *ddim, int dim, int n_windows, DevBuf *tc_scratch, bool tc_prep,
-                  OutT *out, i64 out_stride, cudaStream_t st) {
+                  const int32_t *ddim, int dim, TcCtx *tc, OutT *out, i64 out_stride,
+                  cudaStream_t st) {
   if (N <= 0 || nsub <= 0) return GULON_OK;
   GREQUIRE(nsub <= 65535, "too many sub-quantizers in one launch (%d)", nsub);
   const long long impl = g_assign_impl.load();
-  const bool tc_ok = tc_scratch && K <= tca::TN && 3 * dim + 3 <= tca::KP &&
-                     (tc_prep || tc_scratch->p);
+  const bool tc_ok = tc && tc->blobs && tc->hsubs && tc->hfrom && (tc->prep || tc->blobs->p) &&
+                     tc_eligible(dX, N, ld, K, dim);
   GREQUIRE(impl != GULON_ASSIGN_TENSOR || tc_ok,
-           "assign_impl=tensor needs K <= %d and window width <= %d (K=%d, width=%d)", tca::TN,
-           (tca::KP - 3) / 3, K, dim);
+           "assign_impl=tensor needs K <= %d, window width <= %d, a 16-byte aligned matrix and a row "
+           "stride that is a multiple of 4 floats (K=%d, width=%d, ld=%lld)", tca::TN,
+           (tca::KP - 3) / 3, K, dim, (long long)ld);
   if (tc_ok && (impl == GULON_ASSIGN_TENSOR ||
                 (impl == GULON_ASSIGN_AUTO && N >= g_assign_tc_min_rows.load()))) {
     switch (dim) {
 #define GULON_CASE(DD)                                                                           \
   case DD:                                                                                       \
     return launch_assign_tc_dim<DD, OutT>(dX, N, ld, cb, off, K, dmax, dsubs, nsub, dfrom, ddim, \
-                                          n_windows, *tc_scratch, tc_prep, out, out_stride, st);
+                                          *tc, out, out_stride, st);
       GULON_CASE(1) GULON_CASE(2) GULON_CASE(3) GULON_CASE(4) GULON_CASE(5) GULON_CASE(6)
       GULON_CASE(7) GULON_CASE(8) GULON_CASE(9) GULON_CASE(10) GULON_CASE(11) GULON_CASE(12)
       GULON_CASE(13) GULON_CASE(14) GULON_CASE(15)
@@ -343,9 +459,11 @@ struct Problems {
   int n = 0, K = 0, dmax = 0;
   std::vector<int32_t> from, dim;
   DevBuf cb, off, dfrom, ddim, dsubs, diff, sums, counts, part_sum, part_cnt, tile_hist, base,
-      order, rows, tc;
+      order, rows, tc, tc_groups;
+  const int32_t *h_cur = nullptr;  // host copy of the window list for_each_width is handing out
   ~Problems() {
     tc.release();
+    tc_groups.release();
     cb.release(); off.release(); dfrom.release(); ddim.release(); dsubs.release(); diff.release();
     sums.release(); counts.release(); part_sum.release(); part_cnt.release();
     tile_hist.release(); base.release(); order.release(); rows.release();
@@ -386,16 +504,25 @@ struct Problems {
                         cudaMemcpyHostToDevice, st));
     GCU(cudaStreamSynchronize(st));
     for (auto &kv : groups) {
+      h_cur = kv.second.data();
       GCHECK(f(kv.first, dsubs.as<int32_t>() + at, (int)kv.second.size()));
       at += kv.second.size();
     }
+    h_cur = nullptr;
     return GULON_OK;
   }
   int assign(const float *dX, i64 N, i64 ld, const std::vector<int32_t> &subs, int32_t *out,
              i64 out_stride, cudaStream_t st) {
     return for_each_width(subs, st, [&](int w, const int32_t *ds, int ns) {
+      TcCtx ctx;
+      ctx.blobs = &tc;
+      ctx.n_windows = n;
+      ctx.prep = true;
+      ctx.hsubs = h_cur;
+      ctx.hfrom = from.data();
+      ctx.groups = &tc_groups;
       return launch_assign<int32_t>(dX, N, ld, cb.as<float>(), off.as<float>(), K, dmax, ds, ns,
-                                    dfrom.as<int32_t>(), ddim.as<int32_t>(), w, n, &tc, true, out,
+                                    dfrom.as<int32_t>(), ddim.as<int32_t>(), w, &ctx, out,
                                     out_stride, st);
     });
   }
@@ -669,6 +796,10 @@ int codebook_offsets(gulon_codebook_t cb, cudaStream_t st) {
       GLAUNCH(tca::tc_prep_kernel, (unsigned)kv.second.size(), 256, 0, st, cb->cb.as<float>(),
               cb->off.as<float>(), cb->d_by_dim[kv.first].as<int32_t>(), cb->ddim.as<int32_t>(),
               cb->K, cb->dmax, cb->tc.as<unsigned char>() + 256);
+      std::vector<int32_t> g =
+          build_tc_groups(kv.second.data(), (int)kv.second.size(), cb->from.data(), kv.first);
+      cb->tc_ngroups[kv.first] = (int)(g.size() / tca::GRP_MAX);
+      GCHECK(upload(cb->tc_groups[kv.first], g, st));
     }
   }
   return GULON_OK;
@@ -677,11 +808,21 @@ int codebook_offsets(gulon_codebook_t cb, cudaStream_t st) {
 int encode_dev(gulon_codebook_t cb, const float *dX, i64 N, i64 ld, uint8_t *dcodes, i64 ps,
                cudaStream_t st) {
   for (auto &kv : cb->by_dim) {
+    TcCtx ctx;
+    ctx.blobs = &cb->tc;
+    ctx.n_windows = cb->M;
+    ctx.hsubs = kv.second.data();
+    ctx.hfrom = cb->from.data();
+    auto it = cb->tc_groups.find(kv.first);
+    if (it != cb->tc_groups.end()) {
+      ctx.d_groups = it->second.as<int32_t>();
+      ctx.n_groups = cb->tc_ngroups[kv.first];
+    }
     GCHECK(launch_assign<uint8_t>(dX, N, ld, cb->cb.as<float>(), cb->off.as<float>(), cb->K,
                                   cb->dmax, cb->d_by_dim[kv.first].as<int32_t>(),
                                   (int)kv.second.size(), cb->dfrom.as<int32_t>(),
-                                  cb->ddim.as<int32_t>(), kv.first, cb->M, &cb->tc, false, dcodes,
-                                  ps, st));
+                                  cb->ddim.as<int32_t>(), kv.first,
+                                  ctx.d_groups ? &ctx : nullptr, dcodes, ps, st));
   }
   return GULON_OK;
 }
@@ -1090,8 +1231,8 @@ int gulon_get_counter(const char *name, int64_t *value) {
     *value = (int64_t)g_ppairs.load();
     return GULON_OK;
   }
-  if (s == "assign_tc_pairs" || s == "assign_tc_overflow_tiles" || s == "assign_tc_rows") {
-    *value = (int64_t)g_tc_stats[s == "assign_tc_pairs" ? 0 : s == "assign_tc_overflow_tiles" ? 1 : 2].load();
+  if (s == "assign_tc_pairs" || s == "assign_tc_rows") {
+    *value = (int64_t)g_tc_stats[s == "assign_tc_pairs" ? 0 : 2].load();
     return GULON_OK;
   }
   if (s == "assign_kernel_ns" || s == "assign_kernel_launches") {
@@ -1118,16 +1259,17 @@ int gulon_points_create(const float *X, int64_t N, int32_t D, int64_t ld, gulon_
   std::unique_ptr<gulon_points_s> p(new gulon_points_s);
   p->N = N;
   p->D = D;
-  p->ld = D;
+  p->ld = round_up(D, 4);  // 16-byte row pitch: the TMA path of the tensor-core assignment needs it
   p->owned = true;
   if (N > 0) {
-    cudaError_t e = cudaMalloc(&p->d, (size_t)N * D * sizeof(float));
+    const size_t bytes = (size_t)N * p->ld * sizeof(float);
+    cudaError_t e = cudaMalloc(&p->d, bytes);
     if (e != cudaSuccess) {
       cudaGetLastError();
-      return fail(GULON_ENOMEM, "cudaMalloc(%zu bytes) failed: %s", (size_t)N * D * sizeof(float),
-                  cudaGetErrorString(e));
+      return fail(GULON_ENOMEM, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
     }
-    e = cudaMemcpy2D(p->d, (size_t)D * 4, X, (size_t)ld * 4, (size_t)D * 4, (size_t)N,
+    if (p->ld != D) cudaMemset(p->d, 0, bytes);
+    e = cudaMemcpy2D(p->d, (size_t)p->ld * 4, X, (size_t)ld * 4, (size_t)D * 4, (size_t)N,
                      cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
       cudaFree(p->d);
@@ -1395,6 +1537,7 @@ int gulon_pq_encode(gulon_codebook_t cb, const float *X, int64_t N, int64_t ld, 
   if (N == 0) return GULON_OK;
   // Double-buffered row chunks: copy chunk c+1 to HBM while chunk c is encoded.
   const int D = cb->D, M = cb->M;
+  const int Dp = (int)round_up(D, 4);  // 16-byte row pitch of the staged chunks (TMA)
   const i64 chunk = std::min<i64>(N, g_encode_chunk.load());
   const i64 cps = round_up(chunk, 16);
   struct Res {
@@ -1411,15 +1554,16 @@ int gulon_pq_encode(gulon_codebook_t cb, const float *X, int64_t N, int64_t ld, 
   } r;
   for (int i = 0; i < 2; i++) {
     GCU(cudaStreamCreateWithFlags(&r.st[i], cudaStreamNonBlocking));
-    GCU(cudaMalloc(&r.dx[i], (size_t)chunk * D * sizeof(float)));
+    GCU(cudaMalloc(&r.dx[i], (size_t)chunk * Dp * sizeof(float)));
+    if (Dp != D) GCU(cudaMemset(r.dx[i], 0, (size_t)chunk * Dp * sizeof(float)));
     GCU(cudaMalloc(&r.dc[i], (size_t)M * cps));
   }
   int b = 0;
   for (i64 r0 = 0; r0 < N; r0 += chunk, b ^= 1) {
     const i64 n = std::min<i64>(chunk, N - r0);
-    GCU(cudaMemcpy2DAsync(r.dx[b], (size_t)D * 4, X + r0 * ld, (size_t)ld * 4, (size_t)D * 4,
+    GCU(cudaMemcpy2DAsync(r.dx[b], (size_t)Dp * 4, X + r0 * ld, (size_t)ld * 4, (size_t)D * 4,
                           (size_t)n, cudaMemcpyHostToDevice, r.st[b]));
-    GCHECK(encode_dev(cb, r.dx[b], n, D, r.dc[b], cps, r.st[b]));
+    GCHECK(encode_dev(cb, r.dx[b], n, Dp, r.dc[b], cps, r.st[b]));
     GCU(cudaMemcpy2DAsync(codes + r0, (size_t)N, r.dc[b], (size_t)cps, (size_t)n, (size_t)M,
                           cudaMemcpyDeviceToHost, r.st[b]));
     // buffer pair b is reused two chunks later on the same stream, so reuse is stream-ordered

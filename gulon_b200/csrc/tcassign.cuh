@@ -8,27 +8,30 @@
 // argmin, and re-evaluates the few remaining candidates with the reference's literal arithmetic:
 //
 //   A[row][.]  = [ xh | xh | xl | 1 1 1 | 0.. ]            (bf16, K-major, 48 slots)
-//   B[k][.]    = [ bh | bl | bh | o1 o2 o3 | 0.. ]          b = -2 c_k = bh + bl (+2^-16), O_k = o1+o2+o3
-//   D = A B^T  = off_k - 2 x.c_k  up to  E <= 2^-13 |x| |c_k| + 2^-16 |off_k|   (fp32 accumulate in TMEM)
+//   B[k][.]    = [ bh | bl | bh | o1 o2 o3 | 0.. ]          b = -2 c_k ~ bh + bl, off_k = o1 + o2 + o3
+//   D = A B^T  = off_k - 2 x.c_k  up to  E <= 2^-13.4 |x| |c_k| + 2^-17 |off_k|   (fp32 accumulate in TMEM)
 //
-// Epilogue ("sweep"): thread = row = TMEM lane; the 256 columns are reduced to 32 chunk minima of
-// 8 columns with FMNMX; every chunk whose minimum is within 2E of the row minimum is a candidate
-// (this always includes the chunk of the true argmin and of every exact tie).  Candidate (row,
-// chunk) pairs go through a shared-memory queue to the "exact" warps, which evaluate the 8
-// centroids of the chunk with __fmul_rn/__fadd_rn in the reference's order and keep the
-// (score, index)-lexicographic minimum per row.  On clustered data ~1.05 chunks per row survive,
-// i.e. ~8.4 exact evaluations per row instead of 256.
+// (xh = x truncated to bf16, xl = bf16(x - xh); the dropped terms are xl'.bl, the rounding of xl and
+// the third piece of b: 4.5 * 2^-16 |x||c| in total, plus the accumulation error of the tensor core.)
 //
-// Warp roles (416 threads, 1 CTA/SM, persistent over work units):
-//   warps 0-3   producers: load the rows' windows (fp32), split to bf16, write the A tile in the
-//               canonical no-swizzle K-major UMMA layout, the fp32 rows and the 2E windows
-//   warps 4-7   sweep: tcgen05.ld the accumulator (warp w owns TMEM lanes 32*(w%4)..), queue pairs
-//   warps 8-11  exact evaluation of queued pairs, output
-//   warp 12     TMEM allocation, TMA bulk loads of the per-window operand blobs, tcgen05.mma issue
-// Pipelines: A tiles x2 (a_full/a_empty), TMEM accumulators x2 (t_full/t_empty), tile slots x3
-// (s_ready/q_full/slot_free), all mbarriers.  A work unit = (group of <= 3 windows, 8192 rows): the
-// windows of a group are adjacent in the row, so a CTA reads up to 120 contiguous bytes per row.
+// Data path, per CTA (persistent over work units; unit = (group of <= 3 adjacent windows, row range)):
+//   TMA     X[128 rows][32 floats] boxes (128-byte swizzle) straight from the row-major matrix into a
+//           ring of raw tiles; one box serves all windows of the group.  The per-window operand
+//           blobs (B tile, fp32 centroids, offsets) arrive by bulk copies once per unit.
+//   warps 0-3   "split": thread = row; read the row's window from the raw tile, split to bf16, write
+//               the A tile in the canonical no-swizzle K-major UMMA layout.
+//   warp 12     one thread issues tcgen05.mma (M=128, N=256, 3 x K16) into one of two TMEM accumulators.
+//   warps 4-11  two groups of 4 warps, one per accumulator; thread = row = TMEM lane.  "Sweep": the
+//               256 scores are reduced with FMNMX3 to 32 minima of 8-centroid chunks; a chunk is a
+//               candidate if its minimum is within 2E of the row minimum (this always includes the
+//               chunk of the true argmin and of every exact tie).  "Exact": the same thread evaluates
+//               the 8 centroids of every candidate chunk with __fmul_rn/__fadd_rn in the reference's
+//               order (ascending k, strict '<') and writes the index.  On clustered data ~1.01 chunks
+//               per row survive, i.e. ~8 exact evaluations per row instead of 256.
+//   warp 13     one thread issues the TMA loads.
+// All hand-offs are mbarriers; nothing but the setup / teardown __syncthreads is CTA-wide.
 #pragma once
+#include <cuda.h>
 #include <cuda_bf16.h>
 #include <float.h>
 
@@ -37,38 +40,43 @@
 namespace gulon {
 namespace tca {
 
-constexpr int NT = 416;
+constexpr int NT = 448;
 constexpr int TM = 128;          // rows per tile (UMMA M)
 constexpr int TN = 256;          // centroids per tile (UMMA N)
 constexpr int KP = 48;           // padded contraction depth (3 x K16)
-constexpr int GRP = 3;           // windows per work unit
-constexpr int UNIT_ROWS = 8192;  // rows per work unit
-constexpr int NS = 3;            // tile slots in flight (fp32 rows, queue, results)
-constexpr int QCAP = 1024;       // queued (row, chunk) pairs per tile before the overflow path
-constexpr int A_BYTES = TM * KP * 2;         // 12288
-constexpr int B_BYTES = TN * KP * 2;         // 24576
-constexpr int CB_LD = 17;                    // floats per centroid row in shared memory (odd: no bank conflicts)
-constexpr int CB_BYTES = TN * CB_LD * 4;     // 17408
-constexpr int OFF_BYTES = TN * 4;            // 1024
-constexpr int META_BYTES = 16;               // cmax, omax, flags, pad
-constexpr int BLOB_BYTES = B_BYTES + CB_BYTES + OFF_BYTES + META_BYTES;  // per window, 16 B multiple
-constexpr int XS_LD = 17;                    // floats per fp32 row in a slot
-constexpr int SLOT_BYTES = TM * XS_LD * 4 + TM * 4 + QCAP * 2 + TM * 8 + 16;  // 8-byte multiple
-constexpr int SMEM_BYTES = GRP * BLOB_BYTES + 2 * A_BYTES + NS * SLOT_BYTES + 256 + 1024;
-constexpr u64 RES_INIT = ((u64)0xFF7FFFFFu << 32);  // (ord(FLT_MAX), k = 0): "nothing accepted yet"
+constexpr int GRP_MAX = 3;       // windows per work unit (stride of the group table)
+constexpr int BOX_COLS = 32;     // floats per row of a raw tile = the 128-byte swizzle span
+constexpr int NRAW = 3;          // raw tiles in flight
+constexpr int RAW_BYTES = TM * BOX_COLS * 4;  // 16384
+constexpr int A_BYTES = TM * KP * 2;          // 12288
+constexpr int B_BYTES = TN * KP * 2;          // 24576
+constexpr int CH = 8;                         // centroids per chunk
+constexpr int NCH = TN / CH;                  // 32 chunks = one mask word
+constexpr int CB_LD = 20;                     // floats per centroid (odd number of 16-byte units)
+constexpr int CHUNK_FLOATS = CH * CB_LD + 4;  // + 16 bytes: chunks start in different bank groups
+constexpr int CB_BYTES = NCH * CHUNK_FLOATS * 4;  // 20992
+constexpr int OFF_BYTES = TN * 4;                 // 1024
+constexpr int META_BYTES = 16;                    // max |c|, max |off|, flags, pad
+constexpr int BLOB_BYTES = B_BYTES + CB_BYTES + OFF_BYTES + META_BYTES;  // per window
+constexpr int BAR_BYTES = 256;
+constexpr int SMEM_BYTES = NRAW * RAW_BYTES + 2 * A_BYTES + GRP_MAX * BLOB_BYTES + BAR_BYTES;
 
 static_assert(BLOB_BYTES % 16 == 0, "bulk copies move multiples of 16 bytes");
+static_assert(NCH == 32, "the candidate mask is one 32-bit word");
+
 
 struct Params {
-  const float *X;
-  i64 N, ld;
+  i64 N;
+  int unit_rows;                // rows per work unit, a multiple of TM
   const unsigned char *blobs;   // [M][BLOB_BYTES] prepared operands (tc_prep_kernel)
-  const int32_t *subs;          // windows to process (device list), nsub entries
+  const int32_t *groups;        // [n_groups][GRP_MAX] window ids, -1 padded; the windows of a group are adjacent
+                                // and (first column % 4) + nw * DIM <= BOX_COLS
   const int32_t *from;          // [M] first column of every window
-  int nsub, K;
+  int n_groups, K;
   void *out;                    // [M][out_stride] uint8 or int32
   i64 out_stride;
-  unsigned long long *stats;    // [0] exact evaluations (pairs), [1] overflow tiles
+  unsigned long long *stats;    // [0] candidate (row, chunk) pairs
+  volatile int *dbg;            // host-mapped breadcrumbs [warp][8] of CTA 0 (diagnostics), or null
 };
 
 // ---- PTX helpers ---------------------------------------------------------------------------------
@@ -101,6 +109,14 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sa(dst)),
                "l"(src), "r"(bytes), "r"(sa(bar))
                : "memory");
+}
+// one [TM rows][BOX_COLS floats] box of the matrix; rows / columns outside the matrix arrive as zeros
+__device__ __forceinline__ void tma_box(void *dst, const CUtensorMap *map, int col, int row, uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          sa(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(sa(bar)), "r"(col), "r"(row)
+      : "memory");
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -164,6 +180,12 @@ constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >
 
 __device__ __forceinline__ uint16_t bf16_bits(float f) { return __bfloat16_as_ushort(__float2bfloat16_rn(f)); }
 __device__ __forceinline__ float bf16_val(uint16_t b) { return __uint_as_float((uint32_t)b << 16); }
+// two floats -> packed bf16x2 (lo in the low half), round to nearest
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
 
 // ---- operand preparation: one blob per window ------------------------------------------------------
 // grid (nsub), block 256 (thread = centroid).  cb [M][K][dmax] fp32, off [M][K]; blob of window m at m * BLOB_BYTES.
@@ -173,7 +195,7 @@ __global__ void __launch_bounds__(256) tc_prep_kernel(const float *__restrict__ 
                                                       unsigned char *__restrict__ blobs) {
   const int m = subs[blockIdx.x], k = threadIdx.x, dim = dims[m];
   unsigned char *blob = blobs + (size_t)m * BLOB_BYTES;
-  float *cbs = reinterpret_cast<float *>(blob + B_BYTES);
+  float *cbs = reinterpret_cast<float *>(blob + B_BYTES) + (k / CH) * CHUNK_FLOATS + (k % CH) * CB_LD;
   float *offs = reinterpret_cast<float *>(blob + B_BYTES + CB_BYTES);
   float *meta = reinterpret_cast<float *>(blob + B_BYTES + CB_BYTES + OFF_BYTES);
   __shared__ float s_c[256], s_o[256];
@@ -185,6 +207,9 @@ __global__ void __launch_bounds__(256) tc_prep_kernel(const float *__restrict__ 
   for (int i = 0; i < KP; i++) slots[i] = 0;
   float nrm2 = 0.0f, o = 0.0f;
   bool bad = false;
+  for (int j = 0; j < CB_LD; j++) cbs[j] = 0.0f;
+  if ((k % CH) == 0)
+    for (int j = 0; j < 4; j++) cbs[CH * CB_LD + j] = 0.0f;
   if (k < K && 3 * dim + 3 <= KP) {
     const float *c = cb + ((size_t)m * K + k) * dmax;
     o = off[(size_t)m * K + k];
@@ -197,10 +222,9 @@ __global__ void __launch_bounds__(256) tc_prep_kernel(const float *__restrict__ 
       slots[dim + j] = bl;
       slots[2 * dim + j] = bh;
       nrm2 += cj * cj;
-      cbs[k * CB_LD + j] = cj;
+      cbs[j] = cj;
       if (!(fabsf(cj) < 1e18f)) bad = true;
     }
-    for (int j = dim; j < CB_LD; j++) cbs[k * CB_LD + j] = 0.0f;
     const uint16_t o1 = bf16_bits(o);
     const float r1 = o - bf16_val(o1);
     const uint16_t o2 = bf16_bits(r1);
@@ -209,13 +233,13 @@ __global__ void __launch_bounds__(256) tc_prep_kernel(const float *__restrict__ 
     slots[3 * dim + 1] = o2;
     slots[3 * dim + 2] = o3;
     if (!(fabsf(o) < 1e36f)) bad = true;
+    offs[k] = o;
   } else {
-    // padding centroid: approximate score 3e38, never within 2E of a real minimum
-    for (int j = 0; j < CB_LD; j++) cbs[k * CB_LD + j] = 0.0f;
-    if (3 * dim < KP) slots[3 * dim] = bf16_bits(3.0e38f);  // times the row's 1.0 slot
+    // padding centroid: approximate score 3e38 (times the row's 1.0 slot), exact score +inf: never accepted
+    if (3 * dim < KP) slots[3 * dim] = bf16_bits(3.0e38f);
+    offs[k] = __int_as_float(0x7f800000);
     o = 0.0f;
   }
-  offs[k] = o;
   // canonical layout: element (k, slot) at (k/8)*SBO + (slot/8)*128 + (k%8)*16 + (slot%8)*2
 #pragma unroll
   for (int kc = 0; kc < KP / 8; kc++) {
@@ -245,59 +269,87 @@ __global__ void __launch_bounds__(256) tc_prep_kernel(const float *__restrict__ 
   }
 }
 
+// ---- reading a row's window out of a 128-byte-swizzled raw tile ---------------------------------------
+// Row r of the tile starts at r * 128 bytes; its 16-byte unit u is stored at unit (u ^ (r & 7)).
+template <int DIM, int OFF>
+__device__ __forceinline__ void load_window(const unsigned char *row_base, int sw, float (&x)[DIM]) {
+  constexpr int U0 = OFF / 4, U1 = (OFF + DIM - 1) / 4;
+  float v[(U1 - U0 + 1) * 4];
+#pragma unroll
+  for (int u = U0; u <= U1; u++) {
+    const float4 q = *reinterpret_cast<const float4 *>(row_base + ((u ^ sw) << 4));
+    v[(u - U0) * 4 + 0] = q.x;
+    v[(u - U0) * 4 + 1] = q.y;
+    v[(u - U0) * 4 + 2] = q.z;
+    v[(u - U0) * 4 + 3] = q.w;
+  }
+#pragma unroll
+  for (int j = 0; j < DIM; j++) x[j] = v[OFF + j - 4 * U0];
+}
+// runtime offset (first float of the window inside the box, 0 .. BOX_COLS - DIM): one compile-time
+// variant per offset, so that the window lands in fixed registers without dynamic indexing
+template <int DIM, int OFF>
+struct WindowAt {
+  static __device__ __forceinline__ void load(const unsigned char *row_base, int sw, int off, float (&x)[DIM]) {
+    if (off == OFF) load_window<DIM, OFF>(row_base, sw, x);
+    else WindowAt<DIM, OFF + 1>::load(row_base, sw, off, x);
+  }
+};
+template <int DIM>
+struct WindowAt<DIM, BOX_COLS - DIM> {
+  static __device__ __forceinline__ void load(const unsigned char *row_base, int sw, int, float (&x)[DIM]) {
+    load_window<DIM, BOX_COLS - DIM>(row_base, sw, x);
+  }
+};
+
 // ---- the kernel ----------------------------------------------------------------------------------
 template <int DIM, typename OutT>
-__global__ void __launch_bounds__(NT, 1) tc_assign_kernel(const Params p) {
+__global__ void __launch_bounds__(NT, 1) tc_assign_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
   static_assert(3 * DIM + 3 <= KP, "window too wide for the 48-slot contraction");
-  extern __shared__ __align__(1024) unsigned char smem[];
-  unsigned char *blob_s = smem;                              // GRP blobs
-  unsigned char *a_s = smem + GRP * BLOB_BYTES;              // 2 A tiles
-  unsigned char *slot_s = a_s + 2 * A_BYTES;                 // NS slots
-  uint64_t *bars = reinterpret_cast<uint64_t *>(slot_s + NS * SLOT_BYTES);
-  uint64_t *b_full = bars;            // 1
-  uint64_t *a_full = bars + 1;        // 2
-  uint64_t *a_empty = bars + 3;       // 2
-  uint64_t *t_full = bars + 5;        // 2
-  uint64_t *t_empty = bars + 7;       // 2
-  uint64_t *s_ready = bars + 9;       // NS
-  uint64_t *q_full = bars + 12;       // NS
-  uint64_t *slot_free = bars + 15;    // NS
-  uint32_t *tmem_base_s = reinterpret_cast<uint32_t *>(bars + 20);
+  static_assert(DIM <= BOX_COLS - 3, "a window at any alignment must fit one box");
+  constexpr int DP = (DIM + 3) & ~3;
+  extern __shared__ __align__(1024) unsigned char smem[];  // the 128-byte swizzle needs 1024-byte aligned tiles
+  unsigned char *raw_s = smem;                                // NRAW raw tiles, 1024-byte aligned
+  unsigned char *a_s = raw_s + NRAW * RAW_BYTES;              // 2 A tiles
+  unsigned char *blob_s = a_s + 2 * A_BYTES;                  // GRP_MAX blobs
+  uint64_t *bars = reinterpret_cast<uint64_t *>(blob_s + GRP_MAX * BLOB_BYTES);
+  uint64_t *blob_full = bars;         // 1
+  uint64_t *blob_empty = bars + 1;    // 1
+  uint64_t *raw_full = bars + 2;      // NRAW
+  uint64_t *raw_empty = bars + 5;     // NRAW
+  uint64_t *a_full = bars + 8;        // 2
+  uint64_t *a_empty = bars + 10;      // 2
+  uint64_t *t_full = bars + 12;       // 2
+  uint64_t *t_empty = bars + 14;      // 2
+  uint32_t *tmem_base_s = reinterpret_cast<uint32_t *>(bars + 16);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n_groups = (p.nsub + GRP - 1) / GRP;
-  const i64 n_ranges = (p.N + UNIT_ROWS - 1) / UNIT_ROWS;
-  const i64 n_units = n_ranges * n_groups;
-
-  auto slot_xs = [&](int s) { return reinterpret_cast<float *>(slot_s + s * SLOT_BYTES); };
-  auto slot_win = [&](int s) { return reinterpret_cast<float *>(slot_s + s * SLOT_BYTES + TM * XS_LD * 4); };
-  auto slot_q = [&](int s) { return reinterpret_cast<uint16_t *>(slot_s + s * SLOT_BYTES + TM * XS_LD * 4 + TM * 4); };
-  auto slot_res = [&](int s) {
-    return reinterpret_cast<u64 *>(slot_s + s * SLOT_BYTES + TM * XS_LD * 4 + TM * 4 + QCAP * 2);
-  };
-  auto slot_cnt = [&](int s) {
-    return reinterpret_cast<int *>(slot_s + s * SLOT_BYTES + TM * XS_LD * 4 + TM * 4 + QCAP * 2 + TM * 8);
-  };
+#define TC_DBG(slot, val)                                      \
+  do {                                                         \
+    if (p.dbg && blockIdx.x == 0 && lane == 0) {               \
+      p.dbg[warp * 8 + (slot)] = (int)(val);                   \
+      __threadfence_system();                                  \
+    }                                                          \
+  } while (0)
+  const i64 n_ranges = (p.N + p.unit_rows - 1) / p.unit_rows;
+  const i64 n_units = n_ranges * p.n_groups;
 
   if (tid == 0) {
-    mb_init(b_full, 1);
+    mb_init(blob_full, 1);
+    mb_init(blob_empty, 9);          // 8 sweep warps + the MMA commit
+    for (int i = 0; i < NRAW; i++) {
+      mb_init(raw_full + i, 1);
+      mb_init(raw_empty + i, 12);    // 4 split warps + 8 sweep warps
+    }
     for (int i = 0; i < 2; i++) {
       mb_init(a_full + i, 4);
       mb_init(a_empty + i, 1);
       mb_init(t_full + i, 1);
       mb_init(t_empty + i, 4);
     }
-    for (int i = 0; i < NS; i++) {
-      mb_init(s_ready + i, 4);
-      mb_init(q_full + i, 4);
-      mb_init(slot_free + i, 4);
-    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int s = 0; s < NS; s++) {
-    if (tid < TM) slot_res(s)[tid] = RES_INIT;
-    if (tid < 2) slot_cnt(s)[tid] = 0;
-  }
+  TC_DBG(0, 1);
   if (warp == 12) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sa(tmem_base_s)), "r"(512)
                  : "memory");
@@ -307,107 +359,150 @@ __global__ void __launch_bounds__(NT, 1) tc_assign_kernel(const Params p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_s;
+  TC_DBG(0, 2);
+  TC_DBG(1, tmem_base);
 
-  i64 tile = 0;        // tiles processed by this CTA so far (drives every ring index / phase)
-  uint32_t b_phase = 0;
+  i64 tile = 0;     // tiles of earlier units (drives the A / accumulator ring indices and phases)
+  i64 blk = 0;      // row blocks of earlier units (drives the raw ring)
+  uint32_t ui = 0;  // units done (blob phase)
 
-  for (i64 unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-    const int g = (int)(unit % n_groups);
-    const i64 r_begin = (unit / n_groups) * UNIT_ROWS;
-    const i64 r_end = r_begin + UNIT_ROWS < p.N ? r_begin + UNIT_ROWS : p.N;
-    const int nw = p.nsub - g * GRP < GRP ? p.nsub - g * GRP : GRP;   // windows in this group
+  for (i64 unit = blockIdx.x; unit < n_units; unit += gridDim.x, ui++) {
+    const int g = (int)(unit % p.n_groups);
+    const i64 r_begin = (unit / p.n_groups) * p.unit_rows;
+    const i64 r_end = r_begin + p.unit_rows < p.N ? r_begin + p.unit_rows : p.N;
+    const int32_t *gw = p.groups + g * GRP_MAX;
+    const int nw = 1 + (gw[1] >= 0 ? 1 : 0) + (gw[2] >= 0 ? 1 : 0);
+    // TMA needs a 16-byte aligned box start: the box begins at the 4-float boundary below the
+    // group's first column, the windows sit at m0 + w * DIM inside it
+    const int from0 = p.from[gw[0]];
+    const int col0 = from0 & ~3, m0 = from0 & 3;
     const int n_blocks = (int)((r_end - r_begin + TM - 1) / TM);
     const int n_tiles = n_blocks * nw;
 
-    // operands of the group's windows -> shared memory (TMA bulk copies, one mbarrier)
-    if (warp == 12 && lane == 0) {
-      mb_expect_tx(b_full, (uint32_t)nw * BLOB_BYTES);
-      for (int w = 0; w < nw; w++)
-        bulk_g2s(blob_s + w * BLOB_BYTES, p.blobs + (size_t)p.subs[g * GRP + w] * BLOB_BYTES, BLOB_BYTES, b_full);
-    }
-    mb_wait(b_full, b_phase);
-    b_phase ^= 1u;
-
-    if (warp < 4) {
-      // ================= producers: thread = row of the tile =================
-      const int r = tid;
-      float xn[DIM];
-      auto load_row = [&](int t) {
-        const int w = t % nw;
-        const i64 row = r_begin + (i64)(t / nw) * TM + r;
-        const int fr = p.from[p.subs[g * GRP + w]];
-        if (row < r_end) {
-          const float *src = p.X + row * p.ld + fr;
-#pragma unroll
-          for (int j = 0; j < DIM; j++) xn[j] = __ldg(src + j);
-        } else {
-#pragma unroll
-          for (int j = 0; j < DIM; j++) xn[j] = 0.0f;
-        }
-      };
-      if (n_tiles > 0) load_row(0);
-      for (int t = 0; t < n_tiles; t++) {
-        const i64 ti = tile + t;
-        const int ab = (int)(ti & 1), sl = (int)(ti % NS);
-        float x[DIM];
-#pragma unroll
-        for (int j = 0; j < DIM; j++) x[j] = xn[j];
-        if (t + 1 < n_tiles) load_row(t + 1);
-        const float *meta = reinterpret_cast<const float *>(blob_s + (t % nw) * BLOB_BYTES + B_BYTES + CB_BYTES + OFF_BYTES);
-        // split and pack
-        uint16_t slots[KP];
-#pragma unroll
-        for (int i = 0; i < KP; i++) slots[i] = 0;
-        float n2 = 0.0f;
-        bool bad = meta[2] != 0.0f;
-#pragma unroll
-        for (int j = 0; j < DIM; j++) {
-          const uint16_t xh = bf16_bits(x[j]);
-          const uint16_t xl = bf16_bits(x[j] - bf16_val(xh));
-          slots[j] = xh;
-          slots[DIM + j] = xh;
-          slots[2 * DIM + j] = xl;
-          n2 += x[j] * x[j];
-          if (!(fabsf(x[j]) < 1e18f)) bad = true;
-        }
-        slots[3 * DIM] = slots[3 * DIM + 1] = slots[3 * DIM + 2] = 0x3F80;  // bf16 1.0
-        // 2E window: E = 2^-12 |x| max|c| + 2^-15 max|off| (twice the derived bound, see header)
-        const float xnorm = sqrtf(n2) * 1.001f;
-        float win = 2.0f * (xnorm * meta[0] * (1.0f / 4096.0f) + meta[1] * (1.0f / 32768.0f)) + 1e-30f;
-        if (bad) win = __int_as_float(0x7f800000);  // +inf: every chunk is a candidate
-        mb_wait(slot_free + sl, (uint32_t)(((ti / NS) & 1) ^ 1));
-        mb_wait(a_empty + ab, (uint32_t)(((ti >> 1) & 1) ^ 1));
-        unsigned char *A = a_s + ab * A_BYTES + (r >> 3) * (KP / 8) * 128 + (r & 7) * 16;
-#pragma unroll
-        for (int kc = 0; kc < KP / 8; kc++) {
-          uint4 v;
-          v.x = slots[kc * 8 + 0] | ((uint32_t)slots[kc * 8 + 1] << 16);
-          v.y = slots[kc * 8 + 2] | ((uint32_t)slots[kc * 8 + 3] << 16);
-          v.z = slots[kc * 8 + 4] | ((uint32_t)slots[kc * 8 + 5] << 16);
-          v.w = slots[kc * 8 + 6] | ((uint32_t)slots[kc * 8 + 7] << 16);
-          *reinterpret_cast<uint4 *>(A + kc * 128) = v;
-        }
-        float *xs = slot_xs(sl) + r * XS_LD;
-#pragma unroll
-        for (int j = 0; j < DIM; j++) xs[j] = x[j];
-        slot_win(sl)[r] = win;
-        fence_async_smem();  // A is read by the tensor core through the async proxy
-        __syncwarp();
-        if (lane == 0) {
-          mb_arrive(a_full + ab);
-          mb_arrive(s_ready + sl);
-        }
+    if (warp == 13) {
+      // ================= TMA issue (one thread) =================
+      if (lane == 0) {
+        auto issue_raw = [&](int b) {
+          const i64 bi = blk + b;
+          const int rb = (int)(bi % NRAW);
+          mb_wait(raw_empty + rb, (uint32_t)(((bi / NRAW) & 1) ^ 1));
+          TC_DBG(2, 100 + b);
+          mb_expect_tx(raw_full + rb, RAW_BYTES);
+          tma_box(raw_s + rb * RAW_BYTES, &tmap, col0, (int)(r_begin + (i64)b * TM), raw_full + rb);
+          TC_DBG(2, 200 + b);
+        };
+        // the first raw tiles only need ring slots of the previous unit, not its operands
+        int b = 0;
+        for (; b < n_blocks && b < NRAW - 1; b++) issue_raw(b);
+        mb_wait(blob_empty, (ui & 1u) ^ 1u);
+        TC_DBG(3, 1 + ui);
+        mb_expect_tx(blob_full, (uint32_t)nw * BLOB_BYTES);
+        for (int w = 0; w < nw; w++)
+          bulk_g2s(blob_s + w * BLOB_BYTES, p.blobs + (size_t)gw[w] * BLOB_BYTES, BLOB_BYTES, blob_full);
+        for (; b < n_blocks; b++) issue_raw(b);
       }
-    } else if (warp < 8) {
-      // ================= sweep: thread = row = TMEM lane =================
-      const int q4 = warp & 3, r = q4 * 32 + lane;
-      for (int t = 0; t < n_tiles; t++) {
+      __syncwarp();
+    } else if (warp == 12) {
+      // ================= MMA issue (one thread) =================
+      if (lane == 0) {
+        mb_wait(blob_full, ui & 1u);
+        int w = 0;
+        for (int t = 0; t < n_tiles; t++) {
+          const i64 ti = tile + t;
+          const int ab = (int)(ti & 1);
+          mb_wait(a_full + ab, (uint32_t)((ti >> 1) & 1));
+          mb_wait(t_empty + ab, (uint32_t)(((ti >> 1) & 1) ^ 1));
+          tc_fence_after();
+          TC_DBG(2, 100 + t);
+          const uint32_t a_addr = sa(a_s + ab * A_BYTES), b_addr = sa(blob_s + w * BLOB_BYTES);
+#pragma unroll
+          for (int ks = 0; ks < KP / 16; ks++) {
+            const u64 ad = smem_desc(a_addr + ks * 256, 128, (KP / 8) * 128);
+            const u64 bd = smem_desc(b_addr + ks * 256, 128, (KP / 8) * 128);
+            tc_mma_bf16(tmem_base + (uint32_t)(ab * TN), ad, bd, IDESC, ks > 0 ? 1u : 0u);
+          }
+          tc_commit(a_empty + ab);   // A tile consumed
+          tc_commit(t_full + ab);    // accumulator ready
+          TC_DBG(2, 200 + t);
+          if (++w == nw) w = 0;
+        }
+        tc_commit(blob_empty);       // the unit's B operands are no longer read
+      }
+      __syncwarp();
+    } else if (warp < 4) {
+      // ================= split: thread = row of the tile =================
+      const int r = tid;
+      const unsigned char *row_off = raw_s + r * 128;
+      const int sw = r & 7;
+      unsigned char *a_row = a_s + (r >> 3) * (KP / 8) * 128 + (r & 7) * 16;
+      i64 ti = tile;
+      for (int b = 0; b < n_blocks; b++) {
+        const i64 bi = blk + b;
+        const int rb = (int)(bi % NRAW);
+        mb_wait(raw_full + rb, (uint32_t)((bi / NRAW) & 1));
+        TC_DBG(2, 100 + b);
+        for (int w = 0; w < nw; w++, ti++) {
+          float x[DIM];
+          WindowAt<DIM, 0>::load(row_off + rb * RAW_BYTES, sw, m0 + w * DIM, x);
+          // xh = x truncated to bf16 (exactly representable), xl = bf16(x - xh)
+          float xh[DIM], xl[DIM];
+#pragma unroll
+          for (int j = 0; j < DIM; j++) {
+            xh[j] = __uint_as_float(__float_as_uint(x[j]) & 0xFFFF0000u);
+            xl[j] = x[j] - xh[j];
+          }
+          auto slot = [&](int s) -> float {
+            return s < DIM ? xh[s]
+                           : s < 2 * DIM ? xh[s - DIM] : s < 3 * DIM ? xl[s - 2 * DIM] : s < 3 * DIM + 3 ? 1.0f : 0.0f;
+          };
+          uint4 v[KP / 8];
+#pragma unroll
+          for (int kc = 0; kc < KP / 8; kc++) {
+            v[kc].x = pack_bf16x2(slot(kc * 8 + 0), slot(kc * 8 + 1));
+            v[kc].y = pack_bf16x2(slot(kc * 8 + 2), slot(kc * 8 + 3));
+            v[kc].z = pack_bf16x2(slot(kc * 8 + 4), slot(kc * 8 + 5));
+            v[kc].w = pack_bf16x2(slot(kc * 8 + 6), slot(kc * 8 + 7));
+          }
+          const int ab = (int)(ti & 1);
+          mb_wait(a_empty + ab, (uint32_t)(((ti >> 1) & 1) ^ 1));
+#pragma unroll
+          for (int kc = 0; kc < KP / 8; kc++) *reinterpret_cast<uint4 *>(a_row + ab * A_BYTES + kc * 128) = v[kc];
+          fence_async_smem();  // A is read by the tensor core through the async proxy
+          __syncwarp();
+          if (lane == 0) mb_arrive(a_full + ab);
+          TC_DBG(3, 100 + (int)(ti - tile));
+        }
+        __syncwarp();
+        if (lane == 0) mb_arrive(raw_empty + rb);
+      }
+    } else {
+      // ============ sweep + exact: thread = row = TMEM lane; group wg owns accumulator wg ============
+      const int wg = (warp - 4) >> 2, q4 = warp & 3, r = q4 * 32 + lane;
+      const unsigned char *row_off = raw_s + r * 128;
+      const int sw = r & 7;
+      mb_wait(blob_full, ui & 1u);
+      unsigned n_pairs = 0;
+      int rel = 0;  // next row block this warp has not released yet
+      int t = (int)((wg - tile) & 1), b = 0, w = t;
+      while (w >= nw) {
+        w -= nw;
+        b++;
+      }
+      for (; t < n_tiles; t += 2) {
         const i64 ti = tile + t;
-        const int acc = (int)(ti & 1), sl = (int)(ti % NS);
-        mb_wait(t_full + acc, (uint32_t)((ti >> 1) & 1));
+        if (rel < b) {
+          __syncwarp();
+          if (lane == 0)
+            for (int j = rel; j < b; j++) mb_arrive(raw_empty + (int)((blk + j) % NRAW));
+          rel = b;
+        }
+        // ---- sweep ----
+        __syncwarp();  // the exact loop of the previous tile diverges; tcgen05.ld is warp-collective
+        mb_wait(t_full + wg, (uint32_t)((ti >> 1) & 1));
         tc_fence_after();
-        float cmin[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(acc * TN);
+        TC_DBG(2, 100 + t);
+        float cmin[NCH];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(wg * TN);
         {
           // two register buffers: the next 32 columns are in flight while the previous are reduced
           uint32_t v0[32], v1[32];
@@ -425,128 +520,102 @@ __global__ void __launch_bounds__(NT, 1) tc_assign_kernel(const Params p) {
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mb_arrive(t_empty + acc);  // accumulator drained
+        if (lane == 0) mb_arrive(t_empty + wg);  // accumulator drained
+        TC_DBG(3, 100 + t);
         float rmin = cmin[0];
 #pragma unroll
-        for (int c = 1; c < 32; c++) rmin = fminf(rmin, cmin[c]);
-        mb_wait(s_ready + sl, (uint32_t)((ti / NS) & 1));
-        const float thr = rmin + slot_win(sl)[r];
-        const bool all = !(thr < __int_as_float(0x7f800000));  // +inf or NaN: take everything
-        const i64 row = r_begin + (i64)(t / nw) * TM + r;
-        if (row < r_end) {
-          int *cnt = slot_cnt(sl);
-          uint16_t *q = slot_q(sl);
+        for (int c = 1; c < NCH; c++) rmin = fminf(rmin, cmin[c]);
+        // ---- the row, its 2E window, the candidate mask ----
+        const i64 bi = blk + b;
+        const int rb = (int)(bi % NRAW);
+        mb_wait(raw_full + rb, (uint32_t)((bi / NRAW) & 1));
+        float x[DIM];
+        WindowAt<DIM, 0>::load(row_off + rb * RAW_BYTES, sw, m0 + w * DIM, x);
+        const unsigned char *blob = blob_s + w * BLOB_BYTES;
+        const float *meta = reinterpret_cast<const float *>(blob + B_BYTES + CB_BYTES + OFF_BYTES);
+        float n2 = 0.0f;
 #pragma unroll
-          for (int c = 0; c < 32; c++) {
-            if (all || cmin[c] <= thr) {
-              const int pos = atomicAdd(cnt, 1);
-              if (pos < QCAP) q[pos] = (uint16_t)((r << 5) | c);
-              else cnt[1] = 1;  // overflow: the exact warps take every (row, chunk) of the tile
+        for (int j = 0; j < DIM; j++) n2 = fmaf(x[j], x[j], n2);
+        // E = 2^-12 |x| max|c| + 2^-15 max|off| (more than twice the derived bound, see header); window = 2E
+        const float win =
+            2.0f * (sqrtf(n2) * 1.001f * meta[0] * (1.0f / 4096.0f) + meta[1] * (1.0f / 32768.0f)) + 1e-30f;
+        const float thr = rmin + win;
+        // non-finite / huge rows or operands, +inf or NaN thresholds: every chunk is a candidate
+        const bool all = !(n2 < 1e36f) || meta[2] != 0.0f || !(thr < __int_as_float(0x7f800000));
+        uint32_t mask = 0;
+#pragma unroll
+        for (int c = 0; c < NCH; c++) mask |= (cmin[c] <= thr) ? (1u << c) : 0u;
+        if (all) mask = 0xffffffffu;
+        const i64 row = r_begin + (i64)b * TM + r;
+        if (row >= r_end) mask = 0;
+        n_pairs += __popc(mask);
+        // ---- exact evaluation of the candidate chunks: ascending k, strict '<' from Float.MaxValue ----
+        const float *cbs = reinterpret_cast<const float *>(blob + B_BYTES);
+        const float *offs = reinterpret_cast<const float *>(blob + B_BYTES + CB_BYTES);
+        float best = FLT_MAX;
+        int idx = 0;
+        while (mask) {
+          const int c = __ffs(mask) - 1;
+          mask &= mask - 1;
+          const float *cc = cbs + c * CHUNK_FLOATS;
+          float o[CH];
+          {
+            const float4 o0 = *reinterpret_cast<const float4 *>(offs + c * CH);
+            const float4 o1 = *reinterpret_cast<const float4 *>(offs + c * CH + 4);
+            o[0] = o0.x; o[1] = o0.y; o[2] = o0.z; o[3] = o0.w;
+            o[4] = o1.x; o[5] = o1.y; o[6] = o1.z; o[7] = o1.w;
+          }
+#pragma unroll
+          for (int i = 0; i < CH; i++) {
+            float cv[DP];
+#pragma unroll
+            for (int j4 = 0; j4 < DP / 4; j4++) {
+              const float4 q = *reinterpret_cast<const float4 *>(cc + i * CB_LD + 4 * j4);
+              cv[4 * j4 + 0] = q.x; cv[4 * j4 + 1] = q.y; cv[4 * j4 + 2] = q.z; cv[4 * j4 + 3] = q.w;
+            }
+            float d = 0.0f;
+#pragma unroll
+            for (int j = 0; j < DIM; j++) d = __fadd_rn(d, __fmul_rn(x[j], cv[j]));
+            const float s = __fsub_rn(o[i], __fmul_rn(2.0f, d));
+            if (s < best) {
+              best = s;
+              idx = c * CH + i;
             }
           }
         }
-        __syncwarp();
-        if (lane == 0) mb_arrive(q_full + sl);
-      }
-    } else if (warp < 12) {
-      // ================= exact evaluation of candidate chunks =================
-      const int xt = tid - 256;        // 0..127
-      const int pj = xt & 7, pp = xt >> 3;  // centroid inside the chunk, pair lane (16 pairs at a time)
-      unsigned long long n_eval = 0, n_over = 0;
-      for (int t = 0; t < n_tiles; t++) {
-        const i64 ti = tile + t;
-        const int sl = (int)(ti % NS), w = t % nw;
-        mb_wait(q_full + sl, (uint32_t)((ti / NS) & 1));
-        const float *cbs = reinterpret_cast<const float *>(blob_s + w * BLOB_BYTES + B_BYTES);
-        const float *offs = reinterpret_cast<const float *>(blob_s + w * BLOB_BYTES + B_BYTES + CB_BYTES);
-        const float *xs = slot_xs(sl);
-        const uint16_t *q = slot_q(sl);
-        u64 *res = slot_res(sl);
-        int *cnt = slot_cnt(sl);
-        const bool over = cnt[1] != 0;
-        const int n = over ? TM * 32 : cnt[0];
-        for (int p0 = 0; p0 < n; p0 += 16) {
-          const int pi = p0 + pp;
-          u64 key = ~0ull;
-          int rr = 0;
-          if (pi < n) {
-            const int code = over ? pi : (int)q[pi];
-            rr = code >> 5;
-            const int k = ((code & 31) << 3) + pj;
-            if (k < p.K) {
-              const float *xr = xs + rr * XS_LD;
-              const float *c = cbs + k * CB_LD;
-              float d = 0.0f;
-#pragma unroll
-              for (int j = 0; j < DIM; j++) d = __fadd_rn(d, __fmul_rn(xr[j], c[j]));
-              float s = __fsub_rn(offs[k], __fmul_rn(2.0f, d));
-              if (s < FLT_MAX) {            // NaN and >= Float.MaxValue are never accepted
-                s = s + 0.0f;               // -0.0 == +0.0 for the reference's '<'
-                key = ((u64)f2ord(s) << 32) | (u64)k;
-              }
-            }
-          }
-          // minimum over the 8 centroids of the chunk (8 consecutive lanes)
-#pragma unroll
-          for (int o = 1; o < 8; o <<= 1) {
-            const u64 other = __shfl_xor_sync(0xffffffffu, key, o);
-            key = other < key ? other : key;
-          }
-          if (pj == 0 && pi < n && key != ~0ull) atomicMin(res + rr, key);
-        }
-        n_eval += (unsigned long long)n;
-        n_over += over ? 1 : 0;
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // all pairs of the tile are folded into res
-        const i64 row = r_begin + (i64)(t / nw) * TM + xt;
-        const u64 rk = res[xt];
-        res[xt] = RES_INIT;
-        if (row < r_end) {
-          OutT *out = reinterpret_cast<OutT *>(p.out) + (i64)p.subs[g * GRP + w] * p.out_stride + row;
-          *out = (OutT)(uint32_t)(rk & 0xffffffffu);
-        }
-        if (xt == 0) {
-          cnt[0] = 0;
-          cnt[1] = 0;
-        }
-        __syncwarp();
-        if (lane == 0) mb_arrive(slot_free + sl);
-      }
-      if (p.stats && xt == 0) {
-        atomicAdd(p.stats, n_eval);
-        if (n_over) atomicAdd(p.stats + 1, n_over);
-      }
-    } else {
-      // ================= MMA issue (one thread) =================
-      if (lane == 0) {
-        for (int t = 0; t < n_tiles; t++) {
-          const i64 ti = tile + t;
-          const int ab = (int)(ti & 1), acc = (int)(ti & 1), w = t % nw;
-          mb_wait(a_full + ab, (uint32_t)((ti >> 1) & 1));
-          mb_wait(t_empty + acc, (uint32_t)(((ti >> 1) & 1) ^ 1));
-          tc_fence_after();
-          const uint32_t a_addr = sa(a_s + ab * A_BYTES), b_addr = sa(blob_s + w * BLOB_BYTES);
-#pragma unroll
-          for (int ks = 0; ks < KP / 16; ks++) {
-            const u64 ad = smem_desc(a_addr + ks * 256, 128, (KP / 8) * 128);
-            const u64 bd = smem_desc(b_addr + ks * 256, 128, (KP / 8) * 128);
-            tc_mma_bf16(tmem_base + (uint32_t)(acc * TN), ad, bd, IDESC, ks > 0 ? 1u : 0u);
-          }
-          tc_commit(a_empty + ab);   // A tile consumed
-          tc_commit(t_full + acc);   // accumulator ready
+        if (row < r_end) reinterpret_cast<OutT *>(p.out)[(i64)gw[w] * p.out_stride + row] = (OutT)idx;
+        TC_DBG(4, 100 + t);
+        // next tile of this group
+        w += 2;
+        while (w >= nw) {
+          w -= nw;
+          b++;
         }
       }
+      // release the remaining row blocks and the unit's operands
       __syncwarp();
+      if (lane == 0) {
+        for (int j = rel; j < n_blocks; j++) mb_arrive(raw_empty + (int)((blk + j) % NRAW));
+        mb_arrive(blob_empty);
+      }
+      if (p.stats) {
+        n_pairs = __reduce_add_sync(0xffffffffu, n_pairs);
+        if (lane == 0) atomicAdd(p.stats, (unsigned long long)n_pairs);
+      }
     }
     tile += n_tiles;
-    // every role is done with the group's operands before the next unit overwrites them
-    __syncthreads();
+    blk += n_blocks;
   }
 
+  TC_DBG(0, 3);
   tc_fence_before();
   __syncthreads();
+  TC_DBG(0, 4);
   if (warp == 12) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
+  TC_DBG(0, 5);
+#undef TC_DBG
 }
 
 }  // namespace tca

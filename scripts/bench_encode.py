@@ -60,7 +60,6 @@ def main():
                                                 codes.data_ptr(), stride, st))
             torch.cuda.synchronize()
             line["chunks_per_row_window"] = N.counter("assign_tc_pairs") / max(1, N.counter("assign_tc_rows"))
-            line["overflow_tiles"] = N.counter("assign_tc_overflow_tiles")
             g.set_option("profile", 0)
         out[name] = codes
         print(json.dumps(line), flush=True)
