@@ -360,12 +360,12 @@ int launch_assign_tc_dim(const float *dX, i64 N, i64 ld, const float *cb, const 
   static int *dbg_host = [] {
     int *h = nullptr;
     const char *e = getenv("GULON_TC_DEBUG");
-    if (e && *e == '1' && cudaHostAlloc(&h, 14 * 8 * sizeof(int), cudaHostAllocMapped) != cudaSuccess) h = nullptr;
+    if (e && *e == '1' && cudaHostAlloc(&h, 32 * 8 * sizeof(int), cudaHostAllocMapped) != cudaSuccess) h = nullptr;
     return h;
   }();
   p.dbg = nullptr;
   if (dbg_host) {
-    memset(dbg_host, 0, 14 * 8 * sizeof(int));
+    memset(dbg_host, 0, 32 * 8 * sizeof(int));
     int *d = nullptr;
     if (cudaHostGetDevicePointer(&d, dbg_host, 0) == cudaSuccess) p.dbg = d;
   }
@@ -378,7 +378,7 @@ int launch_assign_tc_dim(const float *dX, i64 N, i64 ld, const float *cb, const 
     cudaError_t e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) {
       std::string m;
-      for (int w = 0; w < 14; w++) {
+      for (int w = 0; w < tca::NT / 32; w++) {
         char b[160];
         snprintf(b, sizeof(b), " w%d[%d %d %d %d %d]", w, dbg_host[w * 8], dbg_host[w * 8 + 1],
                  dbg_host[w * 8 + 2], dbg_host[w * 8 + 3], dbg_host[w * 8 + 4]);

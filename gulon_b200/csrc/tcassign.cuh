@@ -40,7 +40,8 @@
 namespace gulon {
 namespace tca {
 
-constexpr int NT = 448;
+constexpr int NWG = 4;            // sweep/exact warp groups (4 warps each); tile t belongs to group t % NWG
+constexpr int NT = 32 * (4 + 4 * NWG + 2);
 constexpr int TM = 128;          // rows per tile (UMMA M)
 constexpr int TN = 256;          // centroids per tile (UMMA N)
 constexpr int KP = 48;           // padded contraction depth (3 x K16)
@@ -92,18 +93,24 @@ __device__ __forceinline__ void mb_expect_tx(uint64_t *b, uint32_t bytes) {
                "r"(bytes)
                : "memory");
 }
-__device__ __forceinline__ void mb_wait(uint64_t *b, uint32_t parity) {
+__device__ __forceinline__ bool mb_try(uint64_t *b, uint32_t parity) {
+  uint32_t ok;
   asm volatile(
       "{\n\t"
       ".reg .pred P1;\n\t"
-      "LAB_WAIT:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-      "@P1 bra DONE;\n\t"
-      "bra LAB_WAIT;\n\t"
-      "DONE:\n\t"
-      "}" ::"r"(sa(b)),
-      "r"(parity)
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(sa(b)), "r"(parity)
       : "memory");
+  return ok != 0;
+}
+// A hand-off that never arrives is a bug in the pipeline: trap (the launch fails with an error and
+// the breadcrumbs) instead of hanging the device.  Legitimate waits are microseconds long.
+__device__ __forceinline__ void mb_wait(uint64_t *b, uint32_t parity) {
+  for (uint32_t spins = 0; !mb_try(b, parity); spins++)
+    if (spins > (1u << 24)) __trap();
 }
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sa(dst)),
@@ -157,6 +164,34 @@ __device__ __forceinline__ void tc_ld_wait(uint32_t (&r)[32]) {
                  "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
                :
                : "memory");
+}
+// 32 lanes x 16 consecutive columns (two chunks of 8)
+__device__ __forceinline__ void tc_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld_wait16(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
+__device__ __forceinline__ float min3(float a, float b, float c) { return fminf(fminf(a, b), c); }
+// minima of the 2 chunks of 8 columns held in r[16]: four FMNMX3 / FMNMX per chunk
+__device__ __forceinline__ void chunk_mins16(const uint32_t (&r)[16], float *cm) {
+#pragma unroll
+  for (int c = 0; c < 2; c++) {
+    const float t1 = min3(__uint_as_float(r[c * 8 + 0]), __uint_as_float(r[c * 8 + 1]), __uint_as_float(r[c * 8 + 2]));
+    const float t2 = min3(__uint_as_float(r[c * 8 + 3]), __uint_as_float(r[c * 8 + 4]), __uint_as_float(r[c * 8 + 5]));
+    const float t3 = min3(__uint_as_float(r[c * 8 + 6]), __uint_as_float(r[c * 8 + 7]), t1);
+    cm[c] = fminf(t2, t3);
+  }
 }
 // minima of the 4 chunks of 8 columns held in r[32]
 __device__ __forceinline__ void chunk_mins(const uint32_t (&r)[32], float *cm) {
@@ -271,36 +306,33 @@ __global__ void __launch_bounds__(256) tc_prep_kernel(const float *__restrict__ 
 
 // ---- reading a row's window out of a 128-byte-swizzled raw tile ---------------------------------------
 // Row r of the tile starts at r * 128 bytes; its 16-byte unit u is stored at unit (u ^ (r & 7)).
-template <int DIM, int OFF>
-__device__ __forceinline__ void load_window(const unsigned char *row_base, int sw, float (&x)[DIM]) {
-  constexpr int U0 = OFF / 4, U1 = (OFF + DIM - 1) / 4;
-  float v[(U1 - U0 + 1) * 4];
+// `off` = first float of the window inside the box.  The units holding the window are read with
+// runtime addresses; the sub-unit shift (off & 3) selects one of four register renamings.
+template <int DIM, int SH>
+__device__ __forceinline__ void load_window_sh(const unsigned char *row_base, int sw, int u0, float (&x)[DIM]) {
+  constexpr int NU = (SH + DIM + 3) / 4;
+  float v[NU * 4];
 #pragma unroll
-  for (int u = U0; u <= U1; u++) {
-    const float4 q = *reinterpret_cast<const float4 *>(row_base + ((u ^ sw) << 4));
-    v[(u - U0) * 4 + 0] = q.x;
-    v[(u - U0) * 4 + 1] = q.y;
-    v[(u - U0) * 4 + 2] = q.z;
-    v[(u - U0) * 4 + 3] = q.w;
+  for (int u = 0; u < NU; u++) {
+    const float4 q = *reinterpret_cast<const float4 *>(row_base + (((u0 + u) ^ sw) << 4));
+    v[u * 4 + 0] = q.x;
+    v[u * 4 + 1] = q.y;
+    v[u * 4 + 2] = q.z;
+    v[u * 4 + 3] = q.w;
   }
 #pragma unroll
-  for (int j = 0; j < DIM; j++) x[j] = v[OFF + j - 4 * U0];
+  for (int j = 0; j < DIM; j++) x[j] = v[SH + j];
 }
-// runtime offset (first float of the window inside the box, 0 .. BOX_COLS - DIM): one compile-time
-// variant per offset, so that the window lands in fixed registers without dynamic indexing
-template <int DIM, int OFF>
-struct WindowAt {
-  static __device__ __forceinline__ void load(const unsigned char *row_base, int sw, int off, float (&x)[DIM]) {
-    if (off == OFF) load_window<DIM, OFF>(row_base, sw, x);
-    else WindowAt<DIM, OFF + 1>::load(row_base, sw, off, x);
-  }
-};
 template <int DIM>
-struct WindowAt<DIM, BOX_COLS - DIM> {
-  static __device__ __forceinline__ void load(const unsigned char *row_base, int sw, int, float (&x)[DIM]) {
-    load_window<DIM, BOX_COLS - DIM>(row_base, sw, x);
+__device__ __forceinline__ void load_window(const unsigned char *row_base, int sw, int off, float (&x)[DIM]) {
+  const int u0 = off >> 2;
+  switch (off & 3) {
+    case 0: load_window_sh<DIM, 0>(row_base, sw, u0, x); break;
+    case 1: load_window_sh<DIM, 1>(row_base, sw, u0, x); break;
+    case 2: load_window_sh<DIM, 2>(row_base, sw, u0, x); break;
+    default: load_window_sh<DIM, 3>(row_base, sw, u0, x); break;
   }
-};
+}
 
 // ---- the kernel ----------------------------------------------------------------------------------
 template <int DIM, typename OutT>
@@ -308,6 +340,7 @@ __global__ void __launch_bounds__(NT, 1) tc_assign_kernel(const __grid_constant_
   static_assert(3 * DIM + 3 <= KP, "window too wide for the 48-slot contraction");
   static_assert(DIM <= BOX_COLS - 3, "a window at any alignment must fit one box");
   constexpr int DP = (DIM + 3) & ~3;
+  constexpr int W_MMA = 4 + 4 * NWG, W_TMA = W_MMA + 1;
   extern __shared__ __align__(1024) unsigned char smem[];  // the 128-byte swizzle needs 1024-byte aligned tiles
   unsigned char *raw_s = smem;                                // NRAW raw tiles, 1024-byte aligned
   unsigned char *a_s = raw_s + NRAW * RAW_BYTES;              // 2 A tiles
@@ -319,9 +352,12 @@ __global__ void __launch_bounds__(NT, 1) tc_assign_kernel(const __grid_constant_
   uint64_t *raw_empty = bars + 5;     // NRAW
   uint64_t *a_full = bars + 8;        // 2
   uint64_t *a_empty = bars + 10;      // 2
-  uint64_t *t_full = bars + 12;       // 2
-  uint64_t *t_empty = bars + 14;      // 2
-  uint32_t *tmem_base_s = reinterpret_cast<uint32_t *>(bars + 16);
+  uint64_t *t_empty = bars + 12;      // 2: accumulator (tile & 1) swept
+  // accumulator of tile t ready, one barrier per sweep group (t % NWG): a barrier with a single
+  // waiting group can never be polled two phases ahead
+  uint64_t *t_full = bars + 14;       // NWG
+  uint32_t *tmem_base_s = reinterpret_cast<uint32_t *>(bars + 14 + NWG);
+  static_assert((14 + NWG) * 8 + 4 <= BAR_BYTES, "barrier area too small");
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 #define TC_DBG(slot, val)                                      \
@@ -336,21 +372,21 @@ __global__ void __launch_bounds__(NT, 1) tc_assign_kernel(const __grid_constant_
 
   if (tid == 0) {
     mb_init(blob_full, 1);
-    mb_init(blob_empty, 9);          // 8 sweep warps + the MMA commit
+    mb_init(blob_empty, 4 * NWG + 1);   // the sweep warps + the MMA commit
     for (int i = 0; i < NRAW; i++) {
       mb_init(raw_full + i, 1);
-      mb_init(raw_empty + i, 12);    // 4 split warps + 8 sweep warps
+      mb_init(raw_empty + i, 4 + 4 * NWG);  // 4 split warps + the sweep warps
     }
     for (int i = 0; i < 2; i++) {
       mb_init(a_full + i, 4);
       mb_init(a_empty + i, 1);
-      mb_init(t_full + i, 1);
       mb_init(t_empty + i, 4);
     }
+    for (int i = 0; i < NWG; i++) mb_init(t_full + i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   TC_DBG(0, 1);
-  if (warp == 12) {
+  if (warp == W_MMA) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sa(tmem_base_s)), "r"(512)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -379,7 +415,7 @@ __global__ void __launch_bounds__(NT, 1) tc_assign_kernel(const __grid_constant_
     const int n_blocks = (int)((r_end - r_begin + TM - 1) / TM);
     const int n_tiles = n_blocks * nw;
 
-    if (warp == 13) {
+    if (warp == W_TMA) {
       // ================= TMA issue (one thread) =================
       if (lane == 0) {
         auto issue_raw = [&](int b) {
@@ -402,7 +438,7 @@ __global__ void __launch_bounds__(NT, 1) tc_assign_kernel(const __grid_constant_
         for (; b < n_blocks; b++) issue_raw(b);
       }
       __syncwarp();
-    } else if (warp == 12) {
+    } else if (warp == W_MMA) {
       // ================= MMA issue (one thread) =================
       if (lane == 0) {
         mb_wait(blob_full, ui & 1u);
@@ -422,7 +458,7 @@ __global__ void __launch_bounds__(NT, 1) tc_assign_kernel(const __grid_constant_
             tc_mma_bf16(tmem_base + (uint32_t)(ab * TN), ad, bd, IDESC, ks > 0 ? 1u : 0u);
           }
           tc_commit(a_empty + ab);   // A tile consumed
-          tc_commit(t_full + ab);    // accumulator ready
+          tc_commit(t_full + (int)(ti % NWG));  // accumulator ready
           TC_DBG(2, 200 + t);
           if (++w == nw) w = 0;
         }
@@ -443,7 +479,7 @@ __global__ void __launch_bounds__(NT, 1) tc_assign_kernel(const __grid_constant_
         TC_DBG(2, 100 + b);
         for (int w = 0; w < nw; w++, ti++) {
           float x[DIM];
-          WindowAt<DIM, 0>::load(row_off + rb * RAW_BYTES, sw, m0 + w * DIM, x);
+          load_window<DIM>(row_off + rb * RAW_BYTES, sw, m0 + w * DIM, x);
           // xh = x truncated to bf16 (exactly representable), xl = bf16(x - xh)
           float xh[DIM], xl[DIM];
 #pragma unroll
@@ -476,20 +512,18 @@ __global__ void __launch_bounds__(NT, 1) tc_assign_kernel(const __grid_constant_
         if (lane == 0) mb_arrive(raw_empty + rb);
       }
     } else {
-      // ============ sweep + exact: thread = row = TMEM lane; group wg owns accumulator wg ============
+      // ===== sweep + exact: thread = row = TMEM lane; group wg takes the tiles with index % NWG == wg =====
       const int wg = (warp - 4) >> 2, q4 = warp & 3, r = q4 * 32 + lane;
       const unsigned char *row_off = raw_s + r * 128;
       const int sw = r & 7;
       mb_wait(blob_full, ui & 1u);
       unsigned n_pairs = 0;
       int rel = 0;  // next row block this warp has not released yet
-      int t = (int)((wg - tile) & 1), b = 0, w = t;
-      while (w >= nw) {
-        w -= nw;
-        b++;
-      }
-      for (; t < n_tiles; t += 2) {
+      int t = (int)(((wg - tile) % NWG + NWG) % NWG);
+      int b = t / nw, w = t - b * nw;
+      for (; t < n_tiles; t += NWG) {
         const i64 ti = tile + t;
+        const int acc = (int)(ti & 1);
         if (rel < b) {
           __syncwarp();
           if (lane == 0)
@@ -498,39 +532,43 @@ __global__ void __launch_bounds__(NT, 1) tc_assign_kernel(const __grid_constant_
         }
         // ---- sweep ----
         __syncwarp();  // the exact loop of the previous tile diverges; tcgen05.ld is warp-collective
-        mb_wait(t_full + wg, (uint32_t)((ti >> 1) & 1));
+        mb_wait(t_full + wg, (uint32_t)((ti / NWG) & 1));
         tc_fence_after();
-        TC_DBG(2, 100 + t);
         float cmin[NCH];
-        const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(wg * TN);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(acc * TN);
         {
-          // two register buffers: the next 32 columns are in flight while the previous are reduced
-          uint32_t v0[32], v1[32];
-          tc_ld32_issue(taddr, v0);
-          tc_ld_wait(v0);
+          // two register buffers: the next 16 columns are in flight while the previous are reduced
+          uint32_t v0[16], v1[16];
+          tc_ld16_issue(taddr, v0);
+          tc_ld_wait16(v0);
 #pragma unroll
-          for (int cb = 0; cb < 8; cb += 2) {
-            tc_ld32_issue(taddr + (cb + 1) * 32, v1);
-            chunk_mins(v0, cmin + cb * 4);
-            tc_ld_wait(v1);
-            if (cb + 2 < 8) tc_ld32_issue(taddr + (cb + 2) * 32, v0);
-            chunk_mins(v1, cmin + (cb + 1) * 4);
-            if (cb + 2 < 8) tc_ld_wait(v0);
+          for (int cb = 0; cb < 16; cb += 2) {
+            tc_ld16_issue(taddr + (cb + 1) * 16, v1);
+            chunk_mins16(v0, cmin + cb * 2);
+            tc_ld_wait16(v1);
+            if (cb + 2 < 16) tc_ld16_issue(taddr + (cb + 2) * 16, v0);
+            chunk_mins16(v1, cmin + (cb + 1) * 2);
+            if (cb + 2 < 16) tc_ld_wait16(v0);
           }
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mb_arrive(t_empty + wg);  // accumulator drained
-        TC_DBG(3, 100 + t);
-        float rmin = cmin[0];
+        if (lane == 0) mb_arrive(t_empty + acc);  // accumulator drained
+        // row minimum: four independent FMNMX3 chains
+        float rm[4];
 #pragma unroll
-        for (int c = 1; c < NCH; c++) rmin = fminf(rmin, cmin[c]);
+        for (int q = 0; q < 4; q++) {
+          const float a = min3(cmin[q * 8 + 0], cmin[q * 8 + 1], cmin[q * 8 + 2]);
+          const float bq = min3(cmin[q * 8 + 3], cmin[q * 8 + 4], cmin[q * 8 + 5]);
+          rm[q] = fminf(min3(cmin[q * 8 + 6], cmin[q * 8 + 7], a), bq);
+        }
+        const float rmin = fminf(fminf(rm[0], rm[1]), fminf(rm[2], rm[3]));
         // ---- the row, its 2E window, the candidate mask ----
         const i64 bi = blk + b;
         const int rb = (int)(bi % NRAW);
         mb_wait(raw_full + rb, (uint32_t)((bi / NRAW) & 1));
         float x[DIM];
-        WindowAt<DIM, 0>::load(row_off + rb * RAW_BYTES, sw, m0 + w * DIM, x);
+        load_window<DIM>(row_off + rb * RAW_BYTES, sw, m0 + w * DIM, x);
         const unsigned char *blob = blob_s + w * BLOB_BYTES;
         const float *meta = reinterpret_cast<const float *>(blob + B_BYTES + CB_BYTES + OFF_BYTES);
         float n2 = 0.0f;
@@ -542,9 +580,11 @@ __global__ void __launch_bounds__(NT, 1) tc_assign_kernel(const __grid_constant_
         const float thr = rmin + win;
         // non-finite / huge rows or operands, +inf or NaN thresholds: every chunk is a candidate
         const bool all = !(n2 < 1e36f) || meta[2] != 0.0f || !(thr < __int_as_float(0x7f800000));
+        // bit c = sign of (cmin[c] - thrU), thrU just above thr so that cmin == thr counts as well
+        const float thr_u = thr + (fabsf(thr) * 2.4e-7f + 1e-37f);
         uint32_t mask = 0;
 #pragma unroll
-        for (int c = 0; c < NCH; c++) mask |= (cmin[c] <= thr) ? (1u << c) : 0u;
+        for (int c = NCH - 1; c >= 0; c--) mask = __funnelshift_l(__float_as_uint(cmin[c] - thr_u), mask, 1);
         if (all) mask = 0xffffffffu;
         const i64 row = r_begin + (i64)b * TM + r;
         if (row >= r_end) mask = 0;
@@ -586,7 +626,7 @@ __global__ void __launch_bounds__(NT, 1) tc_assign_kernel(const __grid_constant_
         if (row < r_end) reinterpret_cast<OutT *>(p.out)[(i64)gw[w] * p.out_stride + row] = (OutT)idx;
         TC_DBG(4, 100 + t);
         // next tile of this group
-        w += 2;
+        w += NWG;
         while (w >= nw) {
           w -= nw;
           b++;
@@ -611,7 +651,7 @@ __global__ void __launch_bounds__(NT, 1) tc_assign_kernel(const __grid_constant_
   tc_fence_before();
   __syncthreads();
   TC_DBG(0, 4);
-  if (warp == 12) {
+  if (warp == W_MMA) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
   TC_DBG(0, 5);
