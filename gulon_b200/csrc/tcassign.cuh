@@ -56,9 +56,12 @@ constexpr int NCH = TN / CH;                  // 32 chunks = one mask word
 constexpr int CB_LD = 20;                     // floats per centroid (odd number of 16-byte units)
 constexpr int CHUNK_FLOATS = CH * CB_LD + 4;  // + 16 bytes: chunks start in different bank groups
 constexpr int CB_BYTES = NCH * CHUNK_FLOATS * 4;  // 20992
-constexpr int OFF_BYTES = TN * 4;                 // 1024
 constexpr int META_BYTES = 16;                    // max |c|, max |off|, flags, pad
-constexpr int BLOB_BYTES = B_BYTES + CB_BYTES + OFF_BYTES + META_BYTES;  // per window
+constexpr int BLOB_BYTES = B_BYTES + CB_BYTES + META_BYTES;  // per window
+// a centroid row holds its dim coordinates and, in the last float of the 16-byte unit after them,
+// its offset |c|^2 (+inf for padding centroids), so that one run of LDS.128 fetches both
+__host__ __device__ constexpr int off_slot(int dim) { return ((dim + 1 + 3) & ~3) - 1; }
+static_assert(off_slot(15) < CB_LD, "offset slot outside the centroid row");
 constexpr int BAR_BYTES = 256;
 constexpr int SMEM_BYTES = NRAW * RAW_BYTES + 2 * A_BYTES + GRP_MAX * BLOB_BYTES + BAR_BYTES;
 
@@ -231,8 +234,7 @@ __global__ void __launch_bounds__(256) tc_prep_kernel(const float *__restrict__ 
   const int m = subs[blockIdx.x], k = threadIdx.x, dim = dims[m];
   unsigned char *blob = blobs + (size_t)m * BLOB_BYTES;
   float *cbs = reinterpret_cast<float *>(blob + B_BYTES) + (k / CH) * CHUNK_FLOATS + (k % CH) * CB_LD;
-  float *offs = reinterpret_cast<float *>(blob + B_BYTES + CB_BYTES);
-  float *meta = reinterpret_cast<float *>(blob + B_BYTES + CB_BYTES + OFF_BYTES);
+  float *meta = reinterpret_cast<float *>(blob + B_BYTES + CB_BYTES);
   __shared__ float s_c[256], s_o[256];
   __shared__ int s_bad;
   if (k == 0) s_bad = 0;
@@ -268,11 +270,11 @@ __global__ void __launch_bounds__(256) tc_prep_kernel(const float *__restrict__ 
     slots[3 * dim + 1] = o2;
     slots[3 * dim + 2] = o3;
     if (!(fabsf(o) < 1e36f)) bad = true;
-    offs[k] = o;
+    cbs[off_slot(dim)] = o;
   } else {
     // padding centroid: approximate score 3e38 (times the row's 1.0 slot), exact score +inf: never accepted
     if (3 * dim < KP) slots[3 * dim] = bf16_bits(3.0e38f);
-    offs[k] = __int_as_float(0x7f800000);
+    cbs[off_slot(dim < CB_LD - 1 ? dim : 0)] = __int_as_float(0x7f800000);
     o = 0.0f;
   }
   // canonical layout: element (k, slot) at (k/8)*SBO + (slot/8)*128 + (k%8)*16 + (slot%8)*2
@@ -339,7 +341,7 @@ template <int DIM, typename OutT>
 __global__ void __launch_bounds__(NT, 1) tc_assign_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
   static_assert(3 * DIM + 3 <= KP, "window too wide for the 48-slot contraction");
   static_assert(DIM <= BOX_COLS - 3, "a window at any alignment must fit one box");
-  constexpr int DP = (DIM + 3) & ~3;
+  constexpr int DO = off_slot(DIM) + 1;  // floats of a centroid row the exact loop reads
   constexpr int W_MMA = 4 + 4 * NWG, W_TMA = W_MMA + 1;
   extern __shared__ __align__(1024) unsigned char smem[];  // the 128-byte swizzle needs 1024-byte aligned tiles
   unsigned char *raw_s = smem;                                // NRAW raw tiles, 1024-byte aligned
@@ -570,7 +572,7 @@ __global__ void __launch_bounds__(NT, 1) tc_assign_kernel(const __grid_constant_
         float x[DIM];
         load_window<DIM>(row_off + rb * RAW_BYTES, sw, m0 + w * DIM, x);
         const unsigned char *blob = blob_s + w * BLOB_BYTES;
-        const float *meta = reinterpret_cast<const float *>(blob + B_BYTES + CB_BYTES + OFF_BYTES);
+        const float *meta = reinterpret_cast<const float *>(blob + B_BYTES + CB_BYTES);
         float n2 = 0.0f;
 #pragma unroll
         for (int j = 0; j < DIM; j++) n2 = fmaf(x[j], x[j], n2);
@@ -589,37 +591,37 @@ __global__ void __launch_bounds__(NT, 1) tc_assign_kernel(const __grid_constant_
         const i64 row = r_begin + (i64)b * TM + r;
         if (row >= r_end) mask = 0;
         n_pairs += __popc(mask);
-        // ---- exact evaluation of the candidate chunks: ascending k, strict '<' from Float.MaxValue ----
+        // ---- exact evaluation of the candidate chunks ----
+        // Reference rule: ascending k, strict '<' from Float.MaxValue = the (score, k)-lexicographic
+        // minimum over accepted scores.  The 8 centroids of a chunk are visited in a per-lane rotated
+        // order, i = (step + rot) & 7 with rot = 5 (lane - c) mod 8, which puts the 16-byte units the 8
+        // lanes of a quarter warp read at one step into 8 different bank groups whatever their chunks
+        // are (unit index = 41 c + 5 i + j4 = lane + 5 step + j4 mod 8): conflict-free LDS.128.
         const float *cbs = reinterpret_cast<const float *>(blob + B_BYTES);
-        const float *offs = reinterpret_cast<const float *>(blob + B_BYTES + CB_BYTES);
         float best = FLT_MAX;
         int idx = 0;
         while (mask) {
           const int c = __ffs(mask) - 1;
           mask &= mask - 1;
           const float *cc = cbs + c * CHUNK_FLOATS;
-          float o[CH];
-          {
-            const float4 o0 = *reinterpret_cast<const float4 *>(offs + c * CH);
-            const float4 o1 = *reinterpret_cast<const float4 *>(offs + c * CH + 4);
-            o[0] = o0.x; o[1] = o0.y; o[2] = o0.z; o[3] = o0.w;
-            o[4] = o1.x; o[5] = o1.y; o[6] = o1.z; o[7] = o1.w;
-          }
+          const int rot = (5 * (lane - c)) & 7;
 #pragma unroll
-          for (int i = 0; i < CH; i++) {
-            float cv[DP];
+          for (int step = 0; step < CH; step++) {
+            const int i = (step + rot) & 7;
+            float cv[DO];
 #pragma unroll
-            for (int j4 = 0; j4 < DP / 4; j4++) {
+            for (int j4 = 0; j4 < DO / 4; j4++) {
               const float4 q = *reinterpret_cast<const float4 *>(cc + i * CB_LD + 4 * j4);
               cv[4 * j4 + 0] = q.x; cv[4 * j4 + 1] = q.y; cv[4 * j4 + 2] = q.z; cv[4 * j4 + 3] = q.w;
             }
             float d = 0.0f;
 #pragma unroll
             for (int j = 0; j < DIM; j++) d = __fadd_rn(d, __fmul_rn(x[j], cv[j]));
-            const float s = __fsub_rn(o[i], __fmul_rn(2.0f, d));
-            if (s < best) {
+            const float s = __fsub_rn(cv[DO - 1], __fmul_rn(2.0f, d));
+            const int k = c * CH + i;
+            if (s < best || (s == best && k < idx)) {
               best = s;
-              idx = c * CH + i;
+              idx = k;
             }
           }
         }
