@@ -101,11 +101,11 @@ __device__ __forceinline__ bool mb_try(uint64_t *b, uint32_t parity) {
   asm volatile(
       "{\n\t"
       ".reg .pred P1;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, P1;\n\t"
       "}"
       : "=r"(ok)
-      : "r"(sa(b)), "r"(parity)
+      : "r"(sa(b)), "r"(parity), "r"(0x989680u)  // suspend-time hint: sleep in hardware, do not spin
       : "memory");
   return ok != 0;
 }
@@ -113,7 +113,7 @@ __device__ __forceinline__ bool mb_try(uint64_t *b, uint32_t parity) {
 // the breadcrumbs) instead of hanging the device.  Legitimate waits are microseconds long.
 __device__ __forceinline__ void mb_wait(uint64_t *b, uint32_t parity) {
   for (uint32_t spins = 0; !mb_try(b, parity); spins++)
-    if (spins > (1u << 24)) __trap();
+    if (spins > (1u << 22)) __trap();
 }
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sa(dst)),
@@ -186,6 +186,27 @@ __device__ __forceinline__ void tc_ld_wait16(uint32_t (&r)[16]) {
                : "memory");
 }
 __device__ __forceinline__ float min3(float a, float b, float c) { return fminf(fminf(a, b), c); }
+// Two IEEE products / sums per instruction (FMUL2 / FADD2).  Each lane is rounded to nearest like
+// __fmul_rn / __fadd_rn.  ptxas contracts a packed mul feeding a packed add into FFMA2, so the
+// exact path may only pair a packed mul with SCALAR adds (and packed adds with no mul at all).  (A
+// packed mul in the exact loop was tried: the operand pairs cost two MOVs each at 80 registers.)
+__device__ __forceinline__ u64 mul2_rn(u64 a, u64 b) {  // operands / result: (lo float, hi float) in one b64
+  u64 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ u64 pack2(float lo, float hi) {
+  return (u64)__float_as_uint(lo) | ((u64)__float_as_uint(hi) << 32);
+}
+__device__ __forceinline__ float lo_of(u64 v) { return __uint_as_float((uint32_t)v); }
+__device__ __forceinline__ float hi_of(u64 v) { return __uint_as_float((uint32_t)(v >> 32)); }
+__device__ __forceinline__ float2 add2_rn(float2 a, float2 b) {
+  unsigned long long r;
+  asm("add.rn.f32x2 %0, %1, %2;"
+      : "=l"(r)
+      : "l"(*reinterpret_cast<unsigned long long *>(&a)), "l"(*reinterpret_cast<unsigned long long *>(&b)));
+  return *reinterpret_cast<float2 *>(&r);
+}
 // minima of the 2 chunks of 8 columns held in r[16]: four FMNMX3 / FMNMX per chunk
 __device__ __forceinline__ void chunk_mins16(const uint32_t (&r)[16], float *cm) {
 #pragma unroll
@@ -585,8 +606,13 @@ __global__ void __launch_bounds__(NT, 1) tc_assign_kernel(const __grid_constant_
         // bit c = sign of (cmin[c] - thrU), thrU just above thr so that cmin == thr counts as well
         const float thr_u = thr + (fabsf(thr) * 2.4e-7f + 1e-37f);
         uint32_t mask = 0;
+        const float2 nthr = make_float2(-thr_u, -thr_u);
 #pragma unroll
-        for (int c = NCH - 1; c >= 0; c--) mask = __funnelshift_l(__float_as_uint(cmin[c] - thr_u), mask, 1);
+        for (int c = NCH - 2; c >= 0; c -= 2) {
+          const float2 dlt = add2_rn(make_float2(cmin[c], cmin[c + 1]), nthr);
+          mask = __funnelshift_l(__float_as_uint(dlt.y), mask, 1);
+          mask = __funnelshift_l(__float_as_uint(dlt.x), mask, 1);
+        }
         if (all) mask = 0xffffffffu;
         const i64 row = r_begin + (i64)b * TM + r;
         if (row >= r_end) mask = 0;
@@ -605,6 +631,8 @@ __global__ void __launch_bounds__(NT, 1) tc_assign_kernel(const __grid_constant_
           mask &= mask - 1;
           const float *cc = cbs + c * CHUNK_FLOATS;
           const int rot = (5 * (lane - c)) & 7;
+          float sc[CH];
+          int kk[CH];
 #pragma unroll
           for (int step = 0; step < CH; step++) {
             const int i = (step + rot) & 7;
@@ -617,12 +645,22 @@ __global__ void __launch_bounds__(NT, 1) tc_assign_kernel(const __grid_constant_
             float d = 0.0f;
 #pragma unroll
             for (int j = 0; j < DIM; j++) d = __fadd_rn(d, __fmul_rn(x[j], cv[j]));
-            const float s = __fsub_rn(cv[DO - 1], __fmul_rn(2.0f, d));
-            const int k = c * CH + i;
-            if (s < best || (s == best && k < idx)) {
-              best = s;
-              idx = k;
-            }
+            sc[step] = __fsub_rn(cv[DO - 1], __fmul_rn(2.0f, d));
+            kk[step] = c * CH + i;
+          }
+          // the chunk's (score, k)-lexicographic minimum; NaN scores never win (fminf drops them)
+          float m = min3(sc[0], sc[1], sc[2]);
+          m = min3(m, sc[3], sc[4]);
+          m = min3(m, sc[5], sc[6]);
+          m = fminf(m, sc[7]);
+          int km = 0x7fffffff;
+#pragma unroll
+          for (int step = 0; step < CH; step++) km = min(km, sc[step] == m ? kk[step] : 0x7fffffff);
+          // accepted only below Float.MaxValue (the reference's initial minimum); chunks ascend, so on
+          // equal scores the earlier chunk (lower k) stays
+          if (m < best) {
+            best = m;
+            idx = km;
           }
         }
         if (row < r_end) reinterpret_cast<OutT *>(p.out)[(i64)gw[w] * p.out_stride + row] = (OutT)idx;
