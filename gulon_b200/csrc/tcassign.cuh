@@ -540,6 +540,15 @@ __global__ void __launch_bounds__(NT, 1) tc_assign_kernel(const __grid_constant_
       const unsigned char *row_off = raw_s + r * 128;
       const int sw = r & 7;
       mb_wait(blob_full, ui & 1u);
+      // "This warp is done with row block bi."  The arrival must land in the ring slot's phase OF THAT
+      // BLOCK: a warp that skips blocks (tiles of other groups) could otherwise arrive while the slot
+      // still holds an earlier block and complete that block's phase early.  Waiting for the block's
+      // load first pins the phase (and keeps this warp at most one phase ahead of the barrier).
+      auto release_block = [&](i64 bi) {
+        const int rb = (int)(bi % NRAW);
+        mb_wait(raw_full + rb, (uint32_t)((bi / NRAW) & 1));
+        mb_arrive(raw_empty + rb);
+      };
       unsigned n_pairs = 0;
       int rel = 0;  // next row block this warp has not released yet
       int t = (int)(((wg - tile) % NWG + NWG) % NWG);
@@ -550,7 +559,7 @@ __global__ void __launch_bounds__(NT, 1) tc_assign_kernel(const __grid_constant_
         if (rel < b) {
           __syncwarp();
           if (lane == 0)
-            for (int j = rel; j < b; j++) mb_arrive(raw_empty + (int)((blk + j) % NRAW));
+            for (int j = rel; j < b; j++) release_block(blk + j);
           rel = b;
         }
         // ---- sweep ----
@@ -675,7 +684,7 @@ __global__ void __launch_bounds__(NT, 1) tc_assign_kernel(const __grid_constant_
       // release the remaining row blocks and the unit's operands
       __syncwarp();
       if (lane == 0) {
-        for (int j = rel; j < n_blocks; j++) mb_arrive(raw_empty + (int)((blk + j) % NRAW));
+        for (int j = rel; j < n_blocks; j++) release_block(blk + j);
         mb_arrive(blob_empty);
       }
       if (p.stats) {

@@ -66,6 +66,19 @@ def test_tensor_assign_matches_oracle(g, oracle, tensor, n, D, frm, dim, K):
     assert tensor.counter("assign_tc_rows") >= n  # the tensor kernel really ran
 
 
+@pytest.mark.parametrize("n,D,frm,dim", [(300_000, 12, 1, 10), (150_001, 40, 8, 8), (200_000, 33, 3, 15)])
+def test_tensor_assign_single_window_many_blocks(g, oracle, tensor, n, D, frm, dim):
+    # one window per group: every sweep group skips row blocks, the raw-tile ring is recycled fastest
+    rng = np.random.default_rng(n)
+    X = clustered(rng, n, D, centres=200)
+    Cm = X[rng.integers(0, n, 256), frm:frm + dim].copy()
+    t, e = assign_both(g, X, frm, dim, Cm)
+    assert np.array_equal(t, e)
+    sl = slice(n // 2, n // 2 + 5000)
+    want = oracle.assign(np.ascontiguousarray(X[sl]), frm, dim, Cm, batch=0, tie_mode=oracle.TIE_LOWEST)
+    assert np.array_equal(t[sl], want)
+
+
 def test_tensor_assign_centroids_from_data(g, oracle, tensor):
     # centroids sampled from the rows (KMeans.init): a row equals its own centroid, near ties abound
     rng = np.random.default_rng(11)
