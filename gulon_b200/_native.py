@@ -14,7 +14,7 @@ _ROOT = os.path.dirname(_HERE)
 SO_PATH = os.path.join(_HERE, "libgulon_b200.so")
 _SRC_DIR = os.path.join(_HERE, "csrc")
 _SOURCES = ["gulon_b200.cu"]
-_HEADERS = ["common.cuh", "kmeans.cuh", "scan.cuh", "select.cuh", "pscan.cuh", "tcassign.cuh"]
+_HEADERS = ["common.cuh", "kmeans.cuh", "scan.cuh", "select.cuh", "pscan.cuh", "tcassign.cuh", "kupdate.cuh"]
 
 OK, EINVAL, ECUDA, ENOMEM, ENODEVICE, ECOMM, EUNSUPPORTED, ESTATE = 0, -1, -2, -3, -4, -5, -6, -7
 TIE_LOWEST = 1
@@ -71,11 +71,15 @@ class Comm(C.Structure):
     ALLREDUCE_F32 = C.CFUNCTYPE(C.c_int, vp, vp, i64, vp)
     ALLREDUCE_I32 = C.CFUNCTYPE(C.c_int, vp, vp, i64, vp)
     ALLGATHER = C.CFUNCTYPE(C.c_int, vp, vp, vp, i64, vp)
+    ALLREDUCE_I64 = C.CFUNCTYPE(C.c_int, vp, vp, i64, vp)
+    ALLREDUCE_MAX_F32 = C.CFUNCTYPE(C.c_int, vp, vp, i64, vp)
     _fields_ = [("rank", i32), ("world", i32),
                 ("allreduce_sum_f32", ALLREDUCE_F32),
                 ("allreduce_sum_i32", ALLREDUCE_I32),
                 ("allgather", ALLGATHER),
-                ("user", vp)]
+                ("user", vp),
+                ("allreduce_sum_i64", ALLREDUCE_I64),
+                ("allreduce_max_f32", ALLREDUCE_MAX_F32)]
 
 
 class Progress(C.Structure):

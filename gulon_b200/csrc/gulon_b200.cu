@@ -18,6 +18,7 @@
 #include "scan.cuh"
 #include "select.cuh"
 #include "tcassign.cuh"
+#include "kupdate.cuh"
 
 using namespace gulon;
 
@@ -87,6 +88,7 @@ std::atomic<long long> g_pruned_bits{0};         // 0 = auto, 8 or 16: width of 
 std::atomic<long long> g_pruned_words{0};        // 0 = auto, 1/2/4: 32-bit words per table entry
 std::atomic<long long> g_assign_impl{GULON_ASSIGN_AUTO};  // exact CUDA-core kernel or tcgen05 filter + exact recheck
 std::atomic<long long> g_assign_tc_min_rows{4096};
+std::atomic<long long> g_update_fixed{1};        // GULON_UPDATE_SUM as the exact fixed-point sum when possible
 std::atomic<unsigned long long> g_tc_stats[3];   // candidate (row, chunk) pairs, overflow tiles, (row, window) pairs
 std::atomic<long long> g_last_qt{0};             // queries per tile of the last pruned launch
 std::atomic<unsigned long long> g_pstats[3];     // survivors, list candidates, slow-path items
@@ -279,13 +281,13 @@ tensor_map_encode_fn tensor_map_encoder() {
   return fn;
 }
 
-// the row-major matrix as a TMA tensor: boxes of [TM rows][32 floats], 128-byte swizzle, zero fill
-int make_row_map(const float *dX, i64 N, i64 ld, int ncols, CUtensorMap *map) {
+// the row-major matrix as a TMA tensor: boxes of [box_rows][32 floats], 128-byte swizzle, zero fill
+int make_row_map(const float *dX, i64 N, i64 ld, int ncols, int box_rows, CUtensorMap *map) {
   tensor_map_encode_fn enc = tensor_map_encoder();
   GREQUIRE(enc, "cuTensorMapEncodeTiled is not available from this driver");
   cuuint64_t gdim[2] = {(cuuint64_t)ncols, (cuuint64_t)N};
   cuuint64_t gstride[1] = {(cuuint64_t)ld * 4};
-  cuuint32_t box[2] = {(cuuint32_t)tca::BOX_COLS, (cuuint32_t)tca::TM};
+  cuuint32_t box[2] = {(cuuint32_t)tca::BOX_COLS, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(dX), gdim, gstride, box,
                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -340,7 +342,7 @@ int launch_assign_tc_dim(const float *dX, i64 N, i64 ld, const float *cb, const 
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tca::SMEM_BYTES);
   });
   CUtensorMap map;
-  GCHECK(make_row_map(dX, N, ld, ncols, &map));
+  GCHECK(make_row_map(dX, N, ld, ncols, tca::TM, &map));
   tca::Params p;
   p.N = N;
   // rows per work unit: at least ~16 units per CTA, at most 8192 rows
@@ -459,11 +461,13 @@ struct Problems {
   int n = 0, K = 0, dmax = 0;
   std::vector<int32_t> from, dim;
   DevBuf cb, off, dfrom, ddim, dsubs, diff, sums, counts, part_sum, part_cnt, tile_hist, base,
-      order, rows, tc, tc_groups;
+      order, rows, tc, tc_groups, sums64, bad, absmax, scale, col2win;
+  bool fixed = false;              // GULON_UPDATE_SUM runs as the exact fixed-point sum (kupdate.cuh)
   const int32_t *h_cur = nullptr;  // host copy of the window list for_each_width is handing out
   ~Problems() {
     tc.release();
     tc_groups.release();
+    sums64.release(); bad.release(); absmax.release(); scale.release(); col2win.release();
     cb.release(); off.release(); dfrom.release(); ddim.release(); dsubs.release(); diff.release();
     sums.release(); counts.release(); part_sum.release(); part_cnt.release();
     tile_hist.release(); base.release(); order.release(); rows.release();
@@ -526,9 +530,103 @@ struct Problems {
                                     out_stride, st);
     });
   }
+  // GULON_UPDATE_SUM as an exact fixed-point sum (kupdate.cuh): finds the per-window scale with one
+  // pass over the matrix.  Sets `fixed` when the shapes allow it (K <= 256, widths <= 16, TMA-able
+  // matrix, and -- sharded -- a host that provides the int64 / max hooks); otherwise the fp32 path
+  // below stays in charge.
+  int prepare_fixed(const float *dX, i64 N, i64 ld, const gulon_comm_t *comm, cudaStream_t st) {
+    fixed = false;
+    const bool sharded = comm && comm->world > 1;
+    if (sharded && (!comm->allreduce_sum_i64 || !comm->allreduce_max_f32)) return GULON_OK;
+    if (K > upd::KMAX || N < 1) return GULON_OK;
+    int ncols = 0;
+    for (int s = 0; s < n; s++) {
+      if (dim[s] > 16) return GULON_OK;
+      ncols = std::max(ncols, from[s] + dim[s]);
+    }
+    if ((ld % 4) != 0 || (reinterpret_cast<uintptr_t>(dX) & 15) != 0 || N >= (1LL << 31) ||
+        !tensor_map_encoder() || (size_t)ncols * 4 > 64 * 1024)
+      return GULON_OK;
+    std::vector<int32_t> c2w((size_t)ncols, -1);
+    for (int s = 0; s < n; s++)
+      for (int j = 0; j < dim[s]; j++) c2w[from[s] + j] = s;
+    GCHECK(upload(col2win, c2w, st));
+    GCHECK(absmax.ensure((size_t)n * sizeof(float)));
+    GCHECK(scale.ensure((size_t)n * sizeof(float)));
+    GCHECK(sums64.ensure((size_t)n * K * dmax * sizeof(unsigned long long)));
+    GCHECK(bad.ensure((size_t)n * K * sizeof(int32_t)));
+    GCU(cudaMemsetAsync(absmax.p, 0, (size_t)n * sizeof(float), st));
+    const unsigned grid = (unsigned)std::max<i64>(1, std::min<i64>(4LL * sm_count(), ceil_div(N, 8)));
+    GLAUNCH(upd::absmax_kernel, grid, 256, (size_t)ncols * 4, st, dX, N, ncols, ld, col2win.as<int32_t>(), n,
+            absmax.as<unsigned int>());
+    if (sharded)
+      GREQUIRE(comm->allreduce_max_f32(comm->user, absmax.as<float>(), (i64)n, st) == 0,
+               "allreduce_max_f32 hook failed");
+    GLAUNCH(upd::scale_kernel, (unsigned)ceil_div(n, 128), 128, 0, st, absmax.as<unsigned int>(), n,
+            scale.as<float>());
+    fixed = true;
+    return GULON_OK;
+  }
+  template <int DIM>
+  int launch_fixed(const float *dX, i64 N, i64 ld, const int32_t *assign, i64 astride, int ns,
+                   cudaStream_t st) {
+    std::vector<int32_t> g = build_tc_groups(h_cur, ns, from.data(), DIM);
+    const int n_groups = (int)(g.size() / tca::GRP_MAX);
+    GCHECK(upload(tc_groups, g, st));
+    int ncols = 0;
+    for (int i = 0; i < ns; i++) ncols = std::max(ncols, from[h_cur[i]] + DIM);
+    CUtensorMap map;
+    GCHECK(make_row_map(dX, N, ld, ncols, upd::ROWS, &map));
+    auto kern = upd::update_fixed_kernel<DIM>;
+    static std::once_flag once;
+    std::call_once(once, [&] {
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, upd::smem_bytes(DIM));
+    });
+    upd::Params p;
+    p.N = N;
+    const int sms = sm_count();
+    i64 ur = 65536;
+    while (ur > 2048 && ceil_div(N, ur) * n_groups < 8LL * sms) ur >>= 1;
+    p.unit_rows = (int)ur;
+    p.groups = tc_groups.as<int32_t>();
+    p.from = dfrom.as<int32_t>();
+    p.n_groups = n_groups;
+    p.K = K;
+    p.dmax = dmax;
+    p.assign = assign;
+    p.astride = astride;
+    p.scale = scale.as<float>();
+    p.sums = sums64.as<unsigned long long>();
+    p.counts = counts.as<int32_t>();
+    p.bad = bad.as<int32_t>();
+    const i64 units = ceil_div(N, ur) * n_groups;
+    GLAUNCH(kern, (unsigned)std::min<i64>(units, sms), upd::NT, upd::smem_bytes(DIM), st, map, p);
+    return GULON_OK;
+  }
+  int partial_sums_fixed(const float *dX, i64 N, i64 ld, const int32_t *assign, i64 astride,
+                         const std::vector<int32_t> &subs, cudaStream_t st) {
+    GCU(cudaMemsetAsync(sums64.p, 0, (size_t)n * K * dmax * sizeof(unsigned long long), st));
+    GCU(cudaMemsetAsync(counts.p, 0, (size_t)n * K * sizeof(int32_t), st));
+    GCU(cudaMemsetAsync(bad.p, 0, (size_t)n * K * sizeof(int32_t), st));
+    if (N <= 0) return GULON_OK;
+    return for_each_width(subs, st, [&](int w, const int32_t *, int ns) -> int {
+      switch (w) {
+#define GULON_CASE(DD) \
+  case DD:             \
+    return launch_fixed<DD>(dX, N, ld, assign, astride, ns, st);
+        GULON_CASE(1) GULON_CASE(2) GULON_CASE(3) GULON_CASE(4) GULON_CASE(5) GULON_CASE(6)
+        GULON_CASE(7) GULON_CASE(8) GULON_CASE(9) GULON_CASE(10) GULON_CASE(11) GULON_CASE(12)
+        GULON_CASE(13) GULON_CASE(14) GULON_CASE(15) GULON_CASE(16)
+#undef GULON_CASE
+        default:
+          return fail(GULON_EINVAL, "window width %d not supported by the fixed-point update", w);
+      }
+    });
+  }
   // local per-cluster sums / counts (GULON_UPDATE_SUM); the caller all-reduces and finalises
   int partial_sums(const float *dX, i64 N, i64 ld, const int32_t *assign, i64 astride,
                    const std::vector<int32_t> &subs, cudaStream_t st) {
+    if (fixed) return partial_sums_fixed(dX, N, ld, assign, astride, subs, st);
     GCHECK(sums.ensure((size_t)n * K * dmax * sizeof(float)));
     return for_each_width(subs, st, [&](int w, const int32_t *ds, int ns) -> int {
       int W = 8;
@@ -557,8 +655,28 @@ struct Problems {
       return GULON_OK;
     });
   }
+  int allreduce_sums(const gulon_comm_t *comm, cudaStream_t st) {
+    if (fixed) {
+      GREQUIRE(comm->allreduce_sum_i64(comm->user, sums64.as<int64_t>(), (i64)n * K * dmax, st) == 0,
+               "allreduce_sum_i64 hook failed");
+      GREQUIRE(comm->allreduce_sum_i32(comm->user, bad.as<int32_t>(), (i64)n * K, st) == 0,
+               "allreduce_sum_i32 hook failed");
+    } else {
+      GREQUIRE(comm->allreduce_sum_f32(comm->user, sums.as<float>(), (i64)n * K * dmax, st) == 0,
+               "allreduce_sum_f32 hook failed");
+    }
+    GREQUIRE(comm->allreduce_sum_i32(comm->user, counts.as<int32_t>(), (i64)n * K, st) == 0,
+             "allreduce_sum_i32 hook failed");
+    return GULON_OK;
+  }
   int finalize(const int32_t *d_active, cudaStream_t st) {
     const i64 t = (i64)n * K * dmax;
+    if (fixed) {
+      GLAUNCH(upd::finalize_fixed_kernel, (unsigned)ceil_div(t, 256), 256, 0, st,
+              sums64.as<unsigned long long>(), counts.as<int32_t>(), bad.as<int32_t>(), scale.as<float>(),
+              ddim.as<int32_t>(), d_active, n, K, dmax, cb.as<float>());
+      return GULON_OK;
+    }
     GLAUNCH(update_finalize_kernel, (unsigned)ceil_div(t, 256), 256, 0, st, sums.as<float>(),
             counts.as<int32_t>(), d_active, n, K, dmax, cb.as<float>());
     return GULON_OK;
@@ -676,6 +794,7 @@ int train_problems(Problems &pr, gulon_points_t p, const int32_t *seeds, int max
 
   std::vector<int32_t> active(n);
   for (int s = 0; s < n; s++) active[s] = s;
+  if (update_mode == GULON_UPDATE_SUM && g_update_fixed.load()) GCHECK(pr.prepare_fixed(p->d, N, p->ld, comm, st));
   GCHECK(pr.assign(p->d, N, p->ld, active, a_prev.as<int32_t>(), astride, st));
 
   std::vector<float> h_prev, h_next;
@@ -702,12 +821,7 @@ int train_problems(Problems &pr, gulon_points_t p, const int32_t *seeds, int max
       GCHECK(pr.running_mean(p->d, N, p->ld, a_prev.as<int32_t>(), astride, active, st));
     } else {
       GCHECK(pr.partial_sums(p->d, N, p->ld, a_prev.as<int32_t>(), astride, active, st));
-      if (sharded) {
-        GREQUIRE(comm->allreduce_sum_f32(comm->user, pr.sums.as<float>(), (i64)n * K * dmax, st) == 0,
-                 "allreduce_sum_f32 hook failed");
-        GREQUIRE(comm->allreduce_sum_i32(comm->user, pr.counts.as<int32_t>(), (i64)n * K, st) == 0,
-                 "allreduce_sum_i32 hook failed");
-      }
+      if (sharded) GCHECK(pr.allreduce_sums(comm, st));
       GCHECK(pr.finalize(d_active.as<int32_t>(), st));
     }
     GCHECK(pr.offsets(st));
@@ -1169,6 +1283,8 @@ int gulon_set_option(const char *name, int64_t value) {
   } else if (s == "assign_impl") {
     GREQUIRE(value >= GULON_ASSIGN_AUTO && value <= GULON_ASSIGN_TENSOR, "assign_impl must be 0..2");
     g_assign_impl = value;
+  } else if (s == "update_fixed") {
+    g_update_fixed = value ? 1 : 0;
   } else if (s == "assign_tc_min_rows") {
     GREQUIRE(value >= 0, "assign_tc_min_rows must be >= 0");
     g_assign_tc_min_rows = value;
@@ -1390,7 +1506,9 @@ int gulon_kmeans_update(gulon_points_t p, int32_t from, int32_t dim, const int32
     if (update_mode == GULON_UPDATE_RUNNING_MEAN) {
       rc = pr.running_mean(p->d, p->N, p->ld, a.as<int32_t>(), std::max<i64>(p->N, 1), {0}, 0);
     } else {
-      rc = pr.partial_sums(p->d, p->N, p->ld, a.as<int32_t>(), std::max<i64>(p->N, 1), {0}, 0);
+      if (g_update_fixed.load()) rc = pr.prepare_fixed(p->d, p->N, p->ld, nullptr, 0);
+      if (rc == GULON_OK)
+        rc = pr.partial_sums(p->d, p->N, p->ld, a.as<int32_t>(), std::max<i64>(p->N, 1), {0}, 0);
       if (rc == GULON_OK) rc = pr.finalize(nullptr, 0);
     }
   }

@@ -78,14 +78,25 @@ class TorchComm:
             except Exception:  # surfaced by the library as GULON_EINVAL "hook failed"
                 return 1
 
-        self._cbs = (N.Comm.ALLREDUCE_F32(ar_f32), N.Comm.ALLREDUCE_I32(ar_i32), N.Comm.ALLGATHER(ag))
-        self.struct = N.Comm(self.rank, self.world, self._cbs[0], self._cbs[1], self._cbs[2], None)
+        def ar_i64(_u, buf, n, _stream):
+            return self._allreduce(buf, n, "<i8", "allreduce_i64")
 
-    def _allreduce(self, buf, n, typestr, name):
+        def ar_max(_u, buf, n, _stream):
+            return self._allreduce(buf, n, "<f4", "allreduce_max_f32", op=dist.ReduceOp.MAX)
+
+        self.calls["allreduce_i64"] = 0
+        self.calls["allreduce_max_f32"] = 0
+        self._cbs = (N.Comm.ALLREDUCE_F32(ar_f32), N.Comm.ALLREDUCE_I32(ar_i32), N.Comm.ALLGATHER(ag),
+                     N.Comm.ALLREDUCE_I64(ar_i64), N.Comm.ALLREDUCE_MAX_F32(ar_max))
+        self.struct = N.Comm(self.rank, self.world, self._cbs[0], self._cbs[1], self._cbs[2], None,
+                             self._cbs[3], self._cbs[4])
+
+    def _allreduce(self, buf, n, typestr, name, op=None):
         try:
             if n > 0:
                 t = _view(buf, n, typestr, self.device)
-                self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+                self.dist.all_reduce(t, op=op if op is not None else self.dist.ReduceOp.SUM,
+                                     group=self.group)
             self.calls[name] += 1
             return 0
         except Exception:

@@ -85,6 +85,11 @@ typedef struct gulon_comm {
   int (*allgather)(void *user, const void *dev_send, void *dev_recv, int64_t bytes_per_rank,
                    void *stream);
   void *user;
+  /* Optional (may be NULL).  With both present, GULON_UPDATE_SUM accumulates in fixed point and
+   * all-reduces the sums as int64: the trained centroids are then bit-identical for ANY number of
+   * ranks.  Without them the sums are all-reduced in fp32 (rank-count dependent in the last bits). */
+  int (*allreduce_sum_i64)(void *user, int64_t *dev_buf, int64_t n, void *stream);
+  int (*allreduce_max_f32)(void *user, float *dev_buf, int64_t n, void *stream);
 } gulon_comm_t;
 
 /* KMeans.ProgressReport (G/KMeans.scala:119-127), delivered synchronously on the calling thread.
