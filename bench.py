@@ -224,6 +224,23 @@ def main():
             enc_ns += e0.elapsed_time(e1) * 1e6
             enc_rows += n
         del x
+    # candidate statistics of the tensor-core encode (one untimed chunk, profile counters on)
+    enc_stats = None
+    if n_local > 0:
+        n = min(CH, n_local)
+        x = X[:n] if keep_x else mix.rows(lo, lo + n)
+        g.set_option("profile", 1)
+        N.check(N.lib().gulon_pq_encode_dev(pq.handle, x.data_ptr(), n, D, N.TIE_LOWEST,
+                                            codes.data_ptr(), stride, st))
+        torch.cuda.synchronize()
+        tc_rows = N.counter("assign_tc_rows")
+        if tc_rows:
+            enc_stats = {"kernel": "tca::tc_assign_kernel (tcgen05 filter + exact fp32 recheck)",
+                         "candidate_chunks_per_row_window": N.counter("assign_tc_pairs") / tc_rows}
+        else:
+            enc_stats = {"kernel": "assign_exact_kernel (CUDA cores)"}
+        g.set_option("profile", 0)
+        del x
     ix = g.PQIndex.from_device_codes(pq, codes, n_local)
     sh = ShardedPQIndex(ix, lo)
     queries = mix.rows(0, Q, stream_seed=1)
@@ -371,9 +388,13 @@ def main():
                     "d2h_bytes_per_step": Q * k * 8 + (Q * 4 if world == 1 else 0),
                     "ms_per_step": e2e_ms / a.steps, "ids_equal_device_path": same},
             "gpu_launches": launches,
-            "encode": {"value": enc_rows / (enc_ns * 1e-9) if enc_ns else None, "unit": "vectors/s",
-                       "rows": enc_rows, "resident": True,
-                       "hbm_gbs": enc_rows * (D * 4 + M) / enc_ns if enc_ns else None},
+            "encode": dict({"value": enc_rows / (enc_ns * 1e-9) if enc_ns else None, "unit": "vectors/s",
+                            "rows": enc_rows, "resident": True,
+                            "roofline": {"bound": "hbm", "unit": "GB/s", "peak": peak,
+                                         "achieved": enc_rows * (D * 4 + M) / enc_ns if enc_ns else None,
+                                         "frac": enc_rows * (D * 4 + M) / enc_ns / peak if enc_ns else None,
+                                         "algorithmic_bytes_per_vector": D * 4 + M}},
+                           **(enc_stats or {})),
             "train": {"rows": min(a.train_rows, a.rows), "iters": a.train_iters, "seconds": train_s},
         }
         line.update(extra)

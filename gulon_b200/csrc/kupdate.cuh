@@ -169,18 +169,21 @@ __global__ void __launch_bounds__(NT, 1) update_fixed_kernel(const __grid_consta
             load_window<DIM>(row_off + rb * RAW_BYTES, sw, m0 + w * DIM, x);
             unsigned int *lo = acc + w * WSTRIDE + a[w] * DIM;
             unsigned int *hi = lo + KMAX * DIM;
+            // all low-word atomics first (back to back, their returns in flight together), carries after
             bool bad = false;
+            unsigned int v[DIM], old[DIM];
 #pragma unroll
             for (int j = 0; j < DIM; j++) {
               const float sx = x[j] * scl[w];            // exact: a power of two
-              if (fabsf(sx) <= 268435456.0f) {           // finite and within 2^28 (always, for finite x)
-                const unsigned int v = (unsigned int)(__float2int_rn(sx) + (1 << FIX_BITS));
-                const unsigned int old = atomicAdd(lo + j, v);
-                if (old + v < old) atomicAdd(hi + j, 1u);  // carry out of the low word
-              } else {
-                bad = true;
-              }
+              const bool ok = fabsf(sx) <= 268435456.0f;  // finite and within 2^28 (always, for finite x)
+              bad = bad || !ok;
+              v[j] = ok ? (unsigned int)(__float2int_rn(sx) + (1 << FIX_BITS)) : 0u;
             }
+#pragma unroll
+            for (int j = 0; j < DIM; j++) old[j] = atomicAdd(lo + j, v[j]);
+#pragma unroll
+            for (int j = 0; j < DIM; j++)
+              if (old[j] + v[j] < old[j]) atomicAdd(hi + j, 1u);  // carry out of the low word
             atomicAdd(acc + w * WSTRIDE + 2 * KMAX * DIM + a[w], 1u);
             if (bad) atomicOr(acc + w * WSTRIDE + 2 * KMAX * DIM + KMAX + a[w], 1u);
           }

@@ -1,0 +1,44 @@
+"""Key rows of an .ncu-rep (ncu --page raw --csv) as kernel,metric,value,unit -- the committed summary
+format of profiles/.  usage: python scripts/summarize_ncu.py report.ncu-rep out.csv"""
+import csv
+import subprocess
+import sys
+
+KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "dram__throughput.avg.pct_of_peak_sustained_elapsed", "launch__grid_size", "launch__block_size",
+        "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic",
+        "sm__cycles_elapsed.avg", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_tensor_op_hmma.avg.pct_of_peak_sustained_active",
+        "sm__pipe_tensor_op_hmma_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_tc.sum", "sm__inst_executed_pipe_uniform.sum",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_ld.sum",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_atom.sum",
+        "lts__t_sectors_srcunit_tex_op_read.sum", "lts__t_sector_hit_rate.pct",
+        "sm__warps_active.avg.per_cycle_active", "smsp__warps_eligible.avg.per_cycle_active"]
+
+
+def main():
+    rep, out = sys.argv[1], sys.argv[2]
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    ki = hdr.index("Kernel Name")
+    with open(out, "w", newline="") as f:
+        w = csv.writer(f)
+        w.writerow(["kernel", "metric", "value", "unit"])
+        for r in rows[2:]:
+            for h, u, v in zip(hdr, units, r):
+                if h in KEYS or ("issue_stalled" in h and h.endswith("per_issue_active.ratio")) or \
+                        ("tensor" in h and h.endswith("pct_of_peak_sustained_active")):
+                    w.writerow([r[ki][:80], h, v, u])
+
+
+if __name__ == "__main__":
+    main()
