@@ -7,6 +7,7 @@ from . import _native
 from ._native import (GulonError, NoDeviceError, SCAN_AUTO, SCAN_FUSED, SCAN_PRUNED, SCAN_SIMPLE, TIE_LOWEST,
                       UPDATE_RUNNING_MEAN, UPDATE_SUM, build, device_count, kernel_launches,
                       set_option)
+from .grouped import GroupedIndex, GroupedVectors, LimitGroups, LimitVectors
 from .index import PQIndex, TopK, exact_nearest_neighbours, prepare_query
 from .kmeans import Config as KMeansConfig
 from .kmeans import KMeans
@@ -18,7 +19,7 @@ from .vectors import DevicePoints, Matrix, Vectors, normalize, subvector_windows
 __all__ = [
     "GulonError", "NoDeviceError", "SCAN_AUTO", "SCAN_FUSED", "SCAN_PRUNED", "SCAN_SIMPLE", "TIE_LOWEST",
     "UPDATE_RUNNING_MEAN", "UPDATE_SUM", "build", "device_count", "kernel_launches", "set_option",
-    "PQIndex", "TopK", "exact_nearest_neighbours", "prepare_query", "KMeans", "KMeansConfig",
+    "GroupedIndex", "GroupedVectors", "LimitGroups", "LimitVectors", "PQIndex", "TopK", "exact_nearest_neighbours", "prepare_query", "KMeans", "KMeansConfig",
     "KMeansProgressReport", "Coder8", "EncodedMatrix", "ProductQuantizer", "Quantizer",
     "coder_width", "ProductQuantizerConfig", "DevicePoints", "Matrix", "Vectors", "normalize",
     "subvector_windows",

@@ -108,6 +108,7 @@ SIGNATURES = {
     "gulon_points_destroy": (C.c_int, [vp]),
     "gulon_points_normalize": (C.c_int, [vp]),
     "gulon_normalize": (C.c_int, [vp, i64, i32, i64, vp, i64]),
+    "gulon_subtract_rows_dev": (C.c_int, [vp, i64, vp, vp, i64, vp, i64, i32, vp, i64, vp]),
     "gulon_kmeans_assign": (C.c_int, [vp, i32, i32, vp, i32, i64, i32, vp]),
     "gulon_kmeans_update": (C.c_int, [vp, i32, i32, vp, i32, i32, vp, vp]),
     "gulon_kmeans_init": (C.c_int, [vp, i32, i32, i32, i32, vp, vp]),

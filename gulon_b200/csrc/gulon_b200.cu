@@ -1866,6 +1866,19 @@ int gulon_pq_query(gulon_index_t ix, const float *queries, int64_t nq, int64_t l
   return GULON_OK;
 }
 
+int gulon_subtract_rows_dev(const float *dX, int64_t ldx, const int64_t *d_src, const float *dC,
+                            int64_t ldc, const int32_t *d_group, int64_t n, int32_t D, float *d_out,
+                            int64_t ldo, void *stream) {
+  GREQUIRE(n >= 0 && D >= 1 && ldx >= D && ldo >= D, "bad shapes n=%lld D=%d", (long long)n, D);
+  GREQUIRE((dX && d_out) || n == 0, "null argument");
+  GREQUIRE(!d_group || (dC && ldc >= D), "centroids missing");
+  GCHECK(need_device());
+  if (n == 0) return GULON_OK;
+  GLAUNCH(subtract_rows_kernel, (unsigned)ceil_div(n, 8), 256, 0, (cudaStream_t)stream, dX, (i64)ldx,
+          (const i64 *)d_src, dC, (i64)ldc, d_group, (i64)n, D, d_out, (i64)ldo);
+  return GULON_OK;
+}
+
 int gulon_topk_merge_dev(const int32_t *d_ids, const float *d_dists, int32_t S, int64_t nq,
                          int32_t k, int32_t *d_out_ids, float *d_out_dists, int32_t *d_out_sizes,
                          void *stream) {

@@ -30,6 +30,21 @@ __global__ void normalize_rows_kernel(const float *__restrict__ X, i64 N, int D,
   for (int j = 0; j < D; j++) out[i * ldo + j] = __fdiv_rn(x[j], d);
 }
 
+// ---- MathUtils.subtract per row (residuals) ------------------------------------------------------
+// out[i] = X[src ? src[i] : i] - C[group[i]]  (fp32, G/MathUtils.scala subtract; WordVectors.Grouped#residuals
+// G/WordVectors.scala:118-138 and the residual query of GroupedIndex#query G/Index.scala:277);
+// group == nullptr gathers only.  One warp per row, lanes over columns.
+__global__ void subtract_rows_kernel(const float *__restrict__ X, i64 ldx, const i64 *__restrict__ src,
+                                     const float *__restrict__ Cm, i64 ldc,
+                                     const int32_t *__restrict__ group, i64 n, int D,
+                                     float *__restrict__ out, i64 ldo) {
+  const i64 i = (i64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= n) return;
+  const float *x = X + (src ? src[i] : i) * ldx;
+  const float *c = group ? Cm + (i64)group[i] * ldc : nullptr;
+  for (int j = threadIdx.x & 31; j < D; j += 32) out[i * ldo + j] = c ? __fsub_rn(x[j], c[j]) : x[j];
+}
+
 // ---- Index.prepareQuery ------------------------------------------------------------------------
 // Interleaved layout used by both scan kernels: lutI[(g*M + m)*256 + code] is a float4 holding
 // the table entries of queries 4g..4g+3 (zero for queries past nq and for codes >= K).

@@ -129,6 +129,17 @@ int gulon_points_normalize(gulon_points_t p);
 /* Host convenience: out[i] = normalize(X[i]). */
 int gulon_normalize(const float *X, int64_t N, int32_t D, int64_t ld, float *out, int64_t ldo);
 
+/*
+ * MathUtils.subtract per row on device buffers: out[i] = X[src ? src[i] : i] - C[group[i]] (fp32).
+ * This is WordVectors.Grouped#residuals (G/WordVectors.scala:118-138: rows minus the centroid of
+ * their group) and the residual query of GroupedIndex#query (G/Index.scala:277).  d_src (int64 row
+ * ids) may be NULL (identity); d_group NULL gathers rows without subtracting (the grouped matrix of
+ * WordVectors#grouped, G/WordVectors.scala:24-58).
+ */
+int gulon_subtract_rows_dev(const float *dX, int64_t ldx, const int64_t *d_src, const float *dC,
+                            int64_t ldc, const int32_t *d_group, int64_t n, int32_t D, float *d_out,
+                            int64_t ldo, void *stream);
+
 /* ---- KMeans (G/KMeans.scala) -------------------------------------------------------------- */
 /*
  * KMeans#assign (batch = 0, G/KMeans.scala:18-22,70-98) and #parAssign (batch = 25000, :57-68)

@@ -304,3 +304,87 @@ class Heap:
             lib().go_heap_free(self._h)
         except Exception:
             pass
+
+
+# ---- WordVectors.Grouped / Index.GroupedIndex (host restatement over the C primitives) ----------
+def grouped_build(X, assignments, coarse_centroids, keys=None):
+    """WordVectors#grouped, G/WordVectors.scala:24-58, literally: two stable sorts (by word, then by
+    assignment) and the run detection seeded with assignments(0) (:39) -- not with the first sorted
+    row's assignment -- which yields an empty leading group unless row 0 lies in the lowest cluster.
+    Returns (order, centroids [P][D], offsets [P-1])."""
+    X = _f32(X)
+    a = np.asarray(assignments)
+    n = X.shape[0]
+    idx = list(range(n))
+    if keys is not None:
+        idx.sort(key=lambda j: keys[j])
+    idx.sort(key=lambda j: a[j])
+    cents, offsets = [], []
+    if n > 0:
+        prev = a[0]
+        cents.append(coarse_centroids[prev])
+        for i, j in enumerate(idx):
+            if prev != a[j]:
+                offsets.append(i)
+                prev = a[j]
+                cents.append(coarse_centroids[prev])
+    return (np.asarray(idx, np.int64), np.asarray(cents, np.float32).reshape(len(cents), X.shape[1]),
+            np.asarray(offsets, np.int32))
+
+
+def grouped_residuals(X, order, cents, offsets):
+    """Grouped#residuals, G/WordVectors.scala:118-138."""
+    G = _f32(X)[order]
+    out = np.empty_like(G)
+    k, nxt = -1, 0
+    for i in range(G.shape[0]):
+        while i >= nxt:
+            k += 1
+            nxt = offsets[k] if k < len(offsets) else G.shape[0]
+        out[i] = G[i] - cents[k]
+    return out
+
+
+def grouped_query(queries, cents, offsets, n, cb, codes, k, strategy, normalized=False):
+    """GroupedIndex#query, G/Index.scala:266-299 with the canonical (distance, id) heap order.
+    strategy = ("groups", m) | ("vectors", n)."""
+    Q = _f32(queries)
+    if normalized:
+        Q = normalize(Q)
+    P = cents.shape[0]
+
+    def bounds(i):
+        return (0 if i == 0 else int(offsets[i - 1])), (n if i == len(offsets) else int(offsets[i]))
+
+    ids = np.full((Q.shape[0], k), -1, np.int32)
+    ds = np.full((Q.shape[0], k), np.inf, np.float32)
+    sz = np.zeros(Q.shape[0], np.int32)
+    for qi in range(Q.shape[0]):
+        q = Q[qi:qi + 1]
+        if strategy[0] == "groups":
+            o, _, s = exact_nn(cents, q, min(strategy[1], P))
+            nn = o[0, :s[0]]
+        else:
+            o, _, s = exact_nn(cents, q, P)
+            order = o[0, :s[0]]
+            i = cnt = 0
+            while i < len(order) and cnt < strategy[1]:
+                f, u = bounds(order[i])
+                cnt += u - f
+                i += 1
+            nn = order[:i]
+        cand = []
+        for c in nn:
+            f, u = bounds(int(c))
+            if u <= f:
+                continue
+            r = q - cents[c]                                  # MathUtils.subtract, fp32
+            ci, cd, cs = pq_query(r, cb, codes, k, f, u)
+            cand += [(float(cd[0, j]), int(ci[0, j])) for j in range(cs[0])]
+        cand.sort()
+        cand = cand[:k]
+        sz[qi] = len(cand)
+        for j, (d, i) in enumerate(cand):
+            ids[qi, j] = i
+            ds[qi, j] = np.float32(d)
+    return ids, ds, sz
