@@ -14,6 +14,7 @@ from .kmeans import KMeans
 from .kmeans import ProgressReport as KMeansProgressReport
 from .quantizer import Coder8, EncodedMatrix, ProductQuantizer, Quantizer, coder_width
 from .quantizer import Config as ProductQuantizerConfig
+from .storage import SortedIndex
 from .vectors import DevicePoints, Matrix, Vectors, normalize, subvector_windows
 
 __all__ = [
@@ -22,5 +23,5 @@ __all__ = [
     "GroupedIndex", "GroupedVectors", "LimitGroups", "LimitVectors", "PQIndex", "TopK", "exact_nearest_neighbours", "prepare_query", "KMeans", "KMeansConfig",
     "KMeansProgressReport", "Coder8", "EncodedMatrix", "ProductQuantizer", "Quantizer",
     "coder_width", "ProductQuantizerConfig", "DevicePoints", "Matrix", "Vectors", "normalize",
-    "subvector_windows",
+    "subvector_windows", "SortedIndex",
 ]

@@ -181,7 +181,10 @@ class GroupedIndex:
     def lookup(self, position):
         part = self.grouped.cluster_of(position)
         base = self.grouped.centroids[part]
-        codes = self.vector_index._keepalive[:, position].cpu().numpy()
+        if self.vector_index.data is not None:
+            codes = self.vector_index.data(position)
+        else:
+            codes = self.vector_index._keepalive[:, position].cpu().numpy()
         residual = self.vector_index.product_quantizer.decode(codes)
         return (base + residual).astype(np.float32)      # MathUtils.add, fp32
 
@@ -228,7 +231,12 @@ class GroupedIndex:
         ids = np.full((Q, k), -1, np.int32)
         ds = np.full((Q, k), np.inf, np.float32)
         sz = np.zeros(Q, np.int32)
-        dev = self.grouped.matrix_dev.device
+        if self.grouped.matrix_dev is not None:
+            dev = self.grouped.matrix_dev.device
+        elif self.vector_index._keepalive is not None:
+            dev = self.vector_index._keepalive.device      # an index loaded from disk has no raw rows
+        else:
+            dev = torch.device("cuda", torch.cuda.current_device())
         cent_dev = torch.from_numpy(self.grouped.centroids).to(dev)
         for q0 in range(0, Q, batch):
             qb = q[q0:q0 + batch]
