@@ -271,6 +271,7 @@ def main():
     pscan_ns = N.counter("pscan_kernel_ns")
     pscan_launches = N.counter("pscan_kernel_launches")
     pstats = {nm: N.counter("pscan_" + nm) for nm in ("survivors", "candidates", "slow_items", "pairs")}
+    lb_quantizers = N.counter("pscan_lb_quantizers")
     g.set_option("profile", 0)
     value = Q * a.steps / (ms * 1e-3)
 
@@ -332,13 +333,15 @@ def main():
     if k_launches > 0:
         # algorithmic bytes: one pass over the scanned code planes per tile of Qt
         # queries whose tables share shared memory (Qt = 8 pruned kernel, 4 exact kernel)
-        fb = 8 if 127 // M >= 3 else 16          # the library's automatic field width
+        ml = lb_quantizers or M                  # quantizers summed by the lower bound (main stage)
+        fb = 8 if 127 // ml >= 3 else 16         # the library's automatic field width
         QT = (N.counter("pscan_qt") or 128 // fb) if use_p else 4
         rows_scanned = (pstats["pairs"] / (a.steps * Q)) if use_p else n_local
         alg_bytes = a.steps * -(-Q // QT) * rows_scanned * M / k_launches
         sec = k_ns * 1e-9 / k_launches
         ach = alg_bytes / sec / 1e9
-        gathers = a.steps * Q * rows_scanned * M / (k_ns * 1e-9)
+        # table reads actually issued: the bound pass reads ml of the M quantizers
+        gathers = a.steps * Q * rows_scanned * (ml if use_p else M) / (k_ns * 1e-9)
         clk_mhz = (clk or {}).get("sm_mhz") or 1965.0
         smem_peak_bytes = 148 * 128 * clk_mhz * 1e6
         roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
@@ -346,6 +349,10 @@ def main():
                 "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
                 "algorithmic_bytes_per_launch": alg_bytes, "launch_seconds": sec,
                 "launches": k_launches, "query_tile": QT,
+                "lower_bound_quantizers": ml if use_p else None,
+                "note": "algorithmic bytes count all M code planes per pass (SURVEY 8d); the pruned kernel "
+                        "streams only the planes its lower bound sums, so `achieved` is work done per "
+                        "second, not bytes moved" if use_p else None,
                 "kernel_share_of_step": k_ns * 1e-6 / ms,
                 "other_scan_kernel_share_of_step": (scan_ns if use_p else pscan_ns) * 1e-6 / ms,
                 "smem_gather": {"bytes_per_entry": (fb // 8) if use_p else 4,

@@ -61,14 +61,26 @@ struct gulon_index_s {
   std::mutex mu_host;  // guards the host-call staging buffers
   DevBuf h_q, h_ids, h_dists, h_sizes;
   DevBuf lutI, keys, lists, qbuf, ids, dists, sizes, merged;
-  DevBuf qlut, mins, qp, boot_tail, plists, pstats, boot_keys;
-  Selector sel, sel_boot;
+  DevBuf qlut, mins, qp, boot_tail, plists, pstats, boot_keys, spread, msel, merged2, sufmin;
+  DevBuf rowcodes;            // row-major copy of the planes, built by the first pruned scan
+  i64 rcs = 0;
+  int rowcodes_state = 0;     // 0 not tried, 1 ready, -1 unavailable (no memory): planes are used
+  Selector sel, sel_boot, sel2;
+  // lower-bound subset size learned from the survivor rate of earlier launches (0: none yet)
+  int ml_hint = 0, ml_hint_M = 0;
+  unsigned long long *h_stats = nullptr;  // pinned: [0..2] stats of the last main stage, [3] its pairs / 1024
+  cudaEvent_t stats_ev = nullptr;
+  bool stats_pending = false;
+  int stats_ml = 0;
   ~gulon_index_s() {
     if (owned && codes) cudaFree((void *)codes);
     lutI.release(); keys.release(); lists.release(); qbuf.release();
     ids.release(); dists.release(); sizes.release(); merged.release();
     qlut.release(); mins.release(); qp.release(); boot_tail.release(); plists.release();
-    pstats.release(); boot_keys.release();
+    pstats.release(); boot_keys.release(); spread.release(); msel.release(); merged2.release();
+    sel2.release(); sufmin.release(); rowcodes.release();
+    if (h_stats) cudaFreeHost(h_stats);
+    if (stats_ev) cudaEventDestroy(stats_ev);
     h_q.release(); h_ids.release(); h_dists.release(); h_sizes.release();
     sel.release(); sel_boot.release();
   }
@@ -86,6 +98,10 @@ std::atomic<long long> g_boot_rows{65536};       // rows scanned exactly to seed
 std::atomic<long long> g_pruned_min_rows{1 << 20};
 std::atomic<long long> g_pruned_bits{0};         // 0 = auto, 8 or 16: width of the lower-bound fields
 std::atomic<long long> g_pruned_words{0};        // 0 = auto, 1/2/4: 32-bit words per table entry
+std::atomic<long long> g_pruned_lb{0};           // 0 = auto (feedback), else quantizers in the lower bound
+std::atomic<long long> g_pruned_stage_div{32};   // first stage = range / div rows with the full bound; 0 = one stage
+std::atomic<long long> g_pruned_rowcodes{1};     // keep a row-major copy of the codes for the survivor evaluation
+std::atomic<long long> g_last_ml{0};             // quantizers in the lower bound of the last main stage
 std::atomic<long long> g_assign_impl{GULON_ASSIGN_AUTO};  // exact CUDA-core kernel or tcgen05 filter + exact recheck
 std::atomic<long long> g_assign_tc_min_rows{4096};
 std::atomic<long long> g_update_fixed{1};        // GULON_UPDATE_SUM as the exact fixed-point sum when possible
@@ -1038,9 +1054,38 @@ int scan_batch(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 fr
       impl = GULON_SCAN_SIMPLE;
   }
   // query groups of 4 (float4 tables); the pruned scan works on tiles of QT = 16 queries
-  // (8-bit lower-bound fields, used while they keep >= 3 levels per quantizer) or 8 (16-bit fields)
+  // (8-bit lower-bound fields, used while they keep >= 3 levels per quantizer) or 8 (16-bit fields).
+  // The lower bound of the main stage sums ML <= M quantizers (see pscan::qselect_kernel).
+  int ML = M;
+  if (impl == GULON_SCAN_PRUNED) {
+    const long long want = g_pruned_lb.load();
+    if (want > 0) {
+      ML = (int)std::min<long long>(want, M);
+    } else {
+      // feedback: fold in the survivor rate of the previous launch on this index, if it is known
+      if (ix->stats_pending && cudaEventQuery(ix->stats_ev) == cudaSuccess) {
+        ix->stats_pending = false;
+        const double pairs = (double)ix->h_stats[3] * 1024.0;
+        if (pairs > 0 && ix->ml_hint_M == M && ix->stats_ml == ix->ml_hint) {
+          const double rate = (double)ix->h_stats[0] / pairs;
+          int h = ix->ml_hint;
+          // measured on the c2 shape (profiles/README.md, round 1d): the launch is fastest where
+          // about 2e-4 of the pairs survive; fewer quantizers cost more in survivor evaluation
+          // than they save in the bound pass, more quantizers the other way round
+          if (rate > 3.5e-4) h = std::min(M, h + std::max(1, h / 8));
+          else if (rate < 1.2e-4) h = std::max(std::min(M, 4), h - std::max(1, h / 6));
+          ix->ml_hint = h;
+        }
+      }
+      if (ix->ml_hint_M != M || ix->ml_hint <= 0) {
+        ix->ml_hint = M;  // a cold index starts with the full bound and sheds quantizers launch by launch
+        ix->ml_hint_M = M;
+      }
+      ML = ix->ml_hint;
+    }
+  }
   int FB = (int)g_pruned_bits.load();
-  if (FB == 0) FB = (127 / M >= 3) ? 8 : 16;
+  if (FB == 0) FB = (127 / ML >= 3) ? 8 : 16;
   // words per table entry: 4 (most queries per pass) unless the batch is too small to fill a tile
   int W = (int)g_pruned_words.load();
   if (W == 0) W = nq * FB > 64 ? 4 : (nq * FB > 32 ? 2 : 1);
@@ -1064,8 +1109,8 @@ int scan_batch(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 fr
 
   if (impl == GULON_SCAN_PRUNED) {
     GREQUIRE(k <= pscan::KMAX, "pruned scan supports k <= %d (k=%d)", pscan::KMAX, k);
-    GREQUIRE(M <= 1024, "pruned scan supports M <= 1024 (M=%d)", M);
-    GREQUIRE(FB == 16 || 127 / M >= 1, "8-bit pruned scan needs M <= 127 (M=%d)", M);
+    GREQUIRE(M <= pscan::MSEL_MAX, "pruned scan supports M <= %d (M=%d)", pscan::MSEL_MAX, M);
+    GREQUIRE(FB == 16 || 127 / ML >= 1, "8-bit pruned scan needs <= 127 quantizers in the bound (%d)", ML);
 #define GULON_PSCAN_VARIANTS(X) X(8, 4) X(8, 2) X(8, 1) X(16, 4) X(16, 2)
     static std::once_flag once;
     std::call_once(once, [] {
@@ -1089,86 +1134,145 @@ int scan_batch(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 fr
     i64 bstride;
     GCHECK(collapse_lists(ix->lists, Sb, Q4, k, ix->boot_keys, ix->sel_boot, &bkeys, &bstride, st));
     if (boot == range) return unpack(bkeys, bstride, nq, k, id_offset, d_ids, d_dists, d_sizes, st);
-    // 2. quantised lower-bound tables
     GCHECK(ix->mins.ensure((size_t)Q4 * M * sizeof(float)));
+    GCHECK(ix->spread.ensure((size_t)Q4 * M * sizeof(float)));
+    GCHECK(ix->sufmin.ensure((size_t)Q4 * (M + 1) * sizeof(float)));
+    if (ix->rowcodes_state == 0 && g_pruned_rowcodes.load() != 0) {
+      // the codes of a row side by side: what the survivor evaluation gathers (built once; the code
+      // planes of an index must not change after its first query)
+      ix->rcs = round_up(M, 16);
+      if (ix->rowcodes.ensure((size_t)ix->N * (size_t)ix->rcs) == GULON_OK) {
+        GLAUNCH(pscan::rowcodes_kernel, (unsigned)ceil_div(ix->N, 256), 256, 0, st, ix->codes, ix->ps,
+                ix->N, M, ix->rcs, ix->rowcodes.as<uint8_t>());
+        ix->rowcodes_state = 1;
+      } else {
+        cudaGetLastError();
+        ix->rowcodes_state = -1;
+      }
+    }
     GCHECK(ix->qp.ensure((size_t)Q4 * sizeof(pscan::QParam)));
     GCHECK(ix->boot_tail.ensure((size_t)Q4 * sizeof(u64)));
-    GCHECK(ix->qlut.ensure((size_t)T * M * 256 * W * sizeof(uint32_t)));
-    GCHECK(ix->pstats.ensure(3 * sizeof(unsigned long long)));
-    GLAUNCH(pscan::qparams_kernel, (unsigned)G, 256, 0, st, ix->lutI.as<float4>(), M, K, nq, bkeys,
-            bstride, k, pscan::t0_units(FB, M), ix->mins.as<float>(), ix->qp.as<pscan::QParam>(),
-            ix->boot_tail.as<u64>());
-    dim3 qg((unsigned)T, (unsigned)M);
-    bool built = false;
+    GCHECK(ix->pstats.ensure(8 * sizeof(unsigned long long)));
+    if (!ix->h_stats) {
+      GCU(cudaMallocHost((void **)&ix->h_stats, 8 * sizeof(unsigned long long)));
+      GCU(cudaEventCreateWithFlags(&ix->stats_ev, cudaEventDisableTiming));
+    }
+    // 2. stages over the remaining rows.  A stage quantises the tables against the best lists known
+    //    so far (boot, then boot + earlier stages), scans its rows, and merges its lists into them.
+    //    The first, short stage uses every quantizer; its result gives the main stage thresholds
+    //    tight enough for a lower bound over a SUBSET of the quantizers.
+    const i64 pfrom = from + boot, prange = until - pfrom;
+    const long long sdiv = g_pruned_stage_div.load();
+    i64 stageA = 0;
+    if (ML < M && sdiv > 0) {
+      stageA = round_up(prange / sdiv, RI);
+      if (stageA < 8 * (i64)RI || stageA >= prange) stageA = 0;
+    }
+    const int nsm = sm_count();
+    const bool want_stats = g_profile.load() != 0;
+    u64 *cur = bkeys;
+    i64 cur_stride = bstride;
+    for (int stage = stageA > 0 ? 0 : 1; stage < 2; ++stage) {
+      const i64 sfrom = stage == 0 ? pfrom : pfrom + stageA;
+      const i64 suntil = stage == 0 ? pfrom + stageA : until;
+      const i64 srange = suntil - sfrom;
+      // the first stage sums every quantizer, or as many as 8-bit fields hold with >= 3 levels each
+      const int sML = stage == 1 ? ML : (FB == 8 ? std::min(M, std::max(ML, 42)) : M);
+      GCHECK(ix->qlut.ensure((size_t)T * sML * 256 * W * sizeof(uint32_t)));
+      GCHECK(ix->msel.ensure((size_t)T * sML * sizeof(int32_t)));
+      GLAUNCH(pscan::qparams_kernel, (unsigned)G, 256, 0, st, ix->lutI.as<float4>(), M, K, nq, cur,
+              cur_stride, k, pscan::t0_units(FB, sML), ix->mins.as<float>(), ix->spread.as<float>(),
+              ix->sufmin.as<float>(), ix->qp.as<pscan::QParam>(), ix->boot_tail.as<u64>());
+      GLAUNCH(pscan::qselect_kernel, (unsigned)T, 256, 0, st, ix->spread.as<float>(),
+              ix->qp.as<pscan::QParam>(), M, sML, QT, ix->msel.as<int32_t>());
+      dim3 qg((unsigned)T, (unsigned)sML);
+      bool built = false;
 #define GULON_X(FB_, W_)                                                                        \
   if (FB == FB_ && W == W_) {                                                                   \
     auto kern = pscan::qlut_build_kernel<FB_, W_>;                                              \
     GLAUNCH(kern, qg, 256, 0, st, ix->lutI.as<float4>(), ix->mins.as<float>(),                  \
-            ix->qp.as<pscan::QParam>(), M, K, ix->qlut.as<uint32_t>());                         \
+            ix->qp.as<pscan::QParam>(), ix->msel.as<int32_t>(), M, sML, K,                      \
+            ix->qlut.as<uint32_t>());                                                           \
     built = true;                                                                               \
   }
-    GULON_PSCAN_VARIANTS(GULON_X)
+      GULON_PSCAN_VARIANTS(GULON_X)
 #undef GULON_X
-    GREQUIRE(built, "unsupported pruned-scan variant: %d-bit fields, %d words", FB, W);
-    // 3. pruned scan of the remaining rows
-    const i64 pfrom = from + boot, prange = until - pfrom;
-    const int nsm = sm_count();
-    int Bs = std::min(T, nsm);
-    int S = std::max(1, nsm / Bs);
-    S = (int)std::max<i64>(1, std::min<i64>(S, prange / (2 * (i64)RI)));
-    const i64 split_len = round_up(ceil_div(prange, S), 16);
-    S = (int)ceil_div(prange, split_len);
-    const size_t nl = (size_t)S * Q4 * k;
-    GCHECK(ix->plists.ensure(nl * sizeof(u64)));
-    GCU(cudaMemsetAsync(ix->plists.p, 0xFF, nl * sizeof(u64), st));
-    const bool want_stats = g_profile.load() != 0;
-    if (want_stats) GCU(cudaMemsetAsync(ix->pstats.p, 0, 3 * sizeof(unsigned long long), st));
-    pscan::Params prm;
-    prm.codes = ix->codes;
-    prm.ps = ix->ps;
-    prm.from = pfrom;
-    prm.until = until;
-    prm.split_len = split_len;
-    prm.qlut = ix->qlut.as<uint32_t>();
-    prm.lutI = ix->lutI.as<float4>();
-    prm.qp = ix->qp.as<pscan::QParam>();
-    prm.boot_tail = ix->boot_tail.as<u64>();
-    prm.lists = ix->plists.as<u64>();
-    prm.stats = want_stats ? ix->pstats.as<unsigned long long>() : nullptr;
-    prm.nq = nq;
-    prm.M = M;
-    prm.T = T;
-    prm.k = k;
-    prm.S = S;
-    prm.Bs = Bs;
-    cudaEvent_t ev = g_t_pscan.begin(st);
+      GREQUIRE(built, "unsupported pruned-scan variant: %d-bit fields, %d words", FB, W);
+      int Bs = std::min(T, nsm);
+      int S = std::max(1, nsm / Bs);
+      S = (int)std::max<i64>(1, std::min<i64>(S, srange / (2 * (i64)RI)));
+      const i64 split_len = round_up(ceil_div(srange, S), 16);
+      S = (int)ceil_div(srange, split_len);
+      const size_t nl = (size_t)S * Q4 * k;
+      GCHECK(ix->plists.ensure(nl * sizeof(u64)));
+      GCU(cudaMemsetAsync(ix->plists.p, 0xFF, nl * sizeof(u64), st));
+      unsigned long long *dstats = ix->pstats.as<unsigned long long>() + 4 * stage;
+      GCU(cudaMemsetAsync(dstats, 0, 3 * sizeof(unsigned long long), st));
+      pscan::Params prm;
+      prm.codes = ix->codes;
+      prm.ps = ix->ps;
+      const bool use_rows = ix->rowcodes_state == 1 && g_pruned_rowcodes.load() != 0;
+      prm.rowcodes = use_rows ? ix->rowcodes.as<uint8_t>() : nullptr;
+      prm.rcs = ix->rcs;
+      prm.sufmin = ix->sufmin.as<float>();
+      prm.from = sfrom;
+      prm.until = suntil;
+      prm.split_len = split_len;
+      prm.qlut = ix->qlut.as<uint32_t>();
+      prm.msel = ix->msel.as<int32_t>();
+      prm.lutI = ix->lutI.as<float4>();
+      prm.qp = ix->qp.as<pscan::QParam>();
+      prm.boot_tail = ix->boot_tail.as<u64>();
+      prm.lists = ix->plists.as<u64>();
+      prm.stats = dstats;
+      prm.nq = nq;
+      prm.M = M;
+      prm.ML = sML;
+      prm.T = T;
+      prm.k = k;
+      prm.S = S;
+      prm.Bs = Bs;
+      cudaEvent_t ev = g_t_pscan.begin(st);
 #define GULON_X(FB_, W_)                                                                        \
   if (FB == FB_ && W == W_) {                                                                   \
     auto kern = pscan::pruned_scan_kernel<FB_, W_>;                                             \
     using CfgT = pscan::Cfg<FB_, W_>;                                                           \
     GLAUNCH(kern, (unsigned)(S * Bs), pscan::NT, CfgT::SMEM_BYTES, st, prm);                    \
   }
-    GULON_PSCAN_VARIANTS(GULON_X)
+      GULON_PSCAN_VARIANTS(GULON_X)
 #undef GULON_X
-#undef GULON_PSCAN_VARIANTS
-    g_t_pscan.end(ev, st);
-    if (want_stats) {
-      unsigned long long h[3];
-      GCU(cudaMemcpyAsync(h, ix->pstats.p, sizeof(h), cudaMemcpyDeviceToHost, st));
-      GCU(cudaStreamSynchronize(st));
-      for (int i = 0; i < 3; i++) g_pstats[i] += h[i];
-      g_ppairs += (unsigned long long)prange * (unsigned long long)nq;
+      g_t_pscan.end(ev, st);
+      if (want_stats) {
+        unsigned long long h[3];
+        GCU(cudaMemcpyAsync(h, dstats, sizeof(h), cudaMemcpyDeviceToHost, st));
+        GCU(cudaStreamSynchronize(st));
+        for (int i = 0; i < 3; i++) g_pstats[i] += h[i];
+        g_ppairs += (unsigned long long)srange * (unsigned long long)nq;
+      }
+      if (stage == 1) {
+        g_last_ml = sML;
+        if (g_pruned_lb.load() == 0 && !ix->stats_pending) {
+          // survivor rate of this launch -> subset size of the next one (read when it has landed)
+          ix->h_stats[3] = (unsigned long long)(((double)srange * (double)nq) / 1024.0);
+          ix->stats_ml = sML;
+          GCU(cudaMemcpyAsync(ix->h_stats, dstats, 3 * sizeof(unsigned long long),
+                              cudaMemcpyDeviceToHost, st));
+          GCU(cudaEventRecord(ix->stats_ev, st));
+          ix->stats_pending = true;
+        }
+      }
+      // best lists so far + this stage's split lists -> best lists so far
+      DevBuf &mb = stage == 0 ? ix->merged2 : ix->merged;
+      Selector &sl = stage == 0 ? ix->sel2 : ix->sel;
+      const i64 ms = round_up((i64)(S + 1) * k, SEL_CHUNK);
+      GCHECK(mb.ensure((size_t)Q4 * ms * sizeof(u64)));
+      dim3 gg((unsigned)ceil_div(ms, 256), (unsigned)Q4);
+      GLAUNCH(pscan::gather_lists2_kernel, gg, 256, 0, st, ix->plists.as<u64>(), S, (i64)Q4, k, cur,
+              cur_stride, mb.as<u64>(), ms);
+      GCHECK(sl.run(mb.as<u64>(), ms, Q4, k, st, &cur, &cur_stride));
     }
-    // 4. boot list + split lists -> answer
-    const i64 ms = round_up((i64)(S + 1) * k, SEL_CHUNK);
-    GCHECK(ix->merged.ensure((size_t)Q4 * ms * sizeof(u64)));
-    dim3 gg((unsigned)ceil_div(ms, 256), (unsigned)Q4);
-    GLAUNCH(pscan::gather_lists2_kernel, gg, 256, 0, st, ix->plists.as<u64>(), S, (i64)Q4, k, bkeys,
-            bstride, ix->merged.as<u64>(), ms);
-    u64 *res;
-    i64 rs;
-    GCHECK(ix->sel.run(ix->merged.as<u64>(), ms, Q4, k, st, &res, &rs));
-    return unpack(res, rs, nq, k, id_offset, d_ids, d_dists, d_sizes, st);
+#undef GULON_PSCAN_VARIANTS
+    return unpack(cur, cur_stride, nq, k, id_offset, d_ids, d_dists, d_sizes, st);
   }
 
   // simple path: materialise keys for a few query groups at a time, select
@@ -1306,6 +1410,14 @@ int gulon_set_option(const char *name, int64_t value) {
     GREQUIRE(value == 0 || value == 1 || value == 2 || value == 4,
              "pruned_words must be 0 (auto), 1, 2 or 4");
     g_pruned_words = value;
+  } else if (s == "pruned_lb_quantizers") {
+    GREQUIRE(value >= 0, "pruned_lb_quantizers must be >= 0 (0 = auto)");
+    g_pruned_lb = value;
+  } else if (s == "pruned_rowcodes") {
+    g_pruned_rowcodes = value != 0;
+  } else if (s == "pruned_stage_div") {
+    GREQUIRE(value >= 0, "pruned_stage_div must be >= 0 (0 = one stage)");
+    g_pruned_stage_div = value;
   } else if (s == "pruned_min_rows") {
     GREQUIRE(value >= 0, "pruned_min_rows must be >= 0");
     g_pruned_min_rows = value;
@@ -1337,6 +1449,10 @@ int gulon_get_counter(const char *name, int64_t *value) {
   }
   if (s == "pscan_survivors" || s == "pscan_candidates" || s == "pscan_slow_items") {
     *value = (int64_t)g_pstats[s == "pscan_survivors" ? 0 : s == "pscan_candidates" ? 1 : 2].load();
+    return GULON_OK;
+  }
+  if (s == "pscan_lb_quantizers") {
+    *value = g_last_ml.load();
     return GULON_OK;
   }
   if (s == "pscan_qt") {

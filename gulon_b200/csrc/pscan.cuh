@@ -34,7 +34,6 @@ constexpr int SORTN = 256;      // per-query sort area: k list entries + up to C
 constexpr int CAPQ = SORTN - KMAX;
 constexpr int REGION_BYTES = 65536;  // both replicated slice buffers, interleaved (see the kernel)
 constexpr int SLOTS = 256;           // items whose survivors may wait in the queue
-constexpr int DRAIN_AT = 768;        // queue length that triggers an exact re-evaluation pass
 
 // FB = bits per lower-bound field, W = 32-bit words per table entry (one LDS.32/64/128 per row).
 //   queries per tile QT = W * 32 / FB; replicas of an entry = 128 B / (4 W) so that every lane of a
@@ -54,6 +53,8 @@ struct Cfg {
   static constexpr int QSH = QT == 16 ? 4 : QT == 8 ? 3 : 2;       // log2(QT)
   static constexpr int RSH = RPT == 16 ? 13 : RPT == 32 ? 14 : 15;  // log2(R)
   static constexpr int QCAP = NT * QT;           // survivor queue (one row per thread in the slow path)
+  // queue length that triggers an exact re-evaluation pass (>= NT: a pass evaluates one per thread)
+  static constexpr int DRAIN_AT = QCAP / 4 < 2048 ? QCAP / 4 : 2048;
   // up to 64 KB of alignment slack in front of the 64 KB-aligned slice region
   static constexpr int SMEM_BYTES = 65536 + REGION_BYTES + QT * SORTN * 8 + QCAP * 4;
   static_assert(QT >= 4 && QT % 4 == 0, "tiles are made of query groups of 4");
@@ -61,10 +62,10 @@ struct Cfg {
 constexpr int R_MAX = NT * 64;
 
 // quantisation units between base and the boot threshold
-inline int t0_units(int FB, int M) {
+inline int t0_units(int FB, int ML) {
   if (FB == 16) return 2048;
-  const int qmax = 127 / M;
-  return std::max(1, M * qmax / 2);
+  const int qmax = 127 / ML;
+  return std::max(1, ML * qmax / 2);
 }
 
 struct QParam {
@@ -75,16 +76,20 @@ struct QParam {
 struct Params {
   const uint8_t *codes;
   i64 ps;
+  const uint8_t *rowcodes;  // row-major copy [N][rcs] of the planes (survivor evaluation), or null
+  i64 rcs;
+  const float *sufmin;      // [T*QT][M+1]: sum_{i >= m} min_c LUT[i][c], rounded down
   i64 from, until;  // rows scanned by this kernel (after the boot rows)
   i64 split_len;
-  const uint32_t *qlut;   // [T][M][256][W] QT packed fields
+  const uint32_t *qlut;   // [T][ML][256][W] QT packed fields
+  const int32_t *msel;    // [T][ML] quantizers of the lower bound, ascending
   const float4 *lutI;     // [T*QT/4][M][256] exact tables (scan.cuh layout)
   const QParam *qp;       // [T*QT]
   const u64 *boot_tail;   // [T*QT] key of the boot list tail (KEY_SENT: none)
   u64 *lists;             // [S][T*QT][k]
   unsigned long long *stats;  // [0] survivors, [1] list candidates, [2] slow-path items
   i64 nq;
-  int M, T, k, S, Bs;
+  int M, ML, T, k, S, Bs;
 };
 
 // ---- per-query quantisation parameters ---------------------------------------------------------
@@ -93,35 +98,60 @@ __global__ void __launch_bounds__(256) qparams_kernel(const float4 *__restrict__
                                                       i64 nq, const u64 *__restrict__ boot_keys,
                                                       i64 boot_stride, int k, int t0,
                                                       float *__restrict__ mins,
+                                                      float *__restrict__ spread,
+                                                      float *__restrict__ sufmin,
                                                       QParam *__restrict__ qp,
                                                       u64 *__restrict__ boot_tail) {
   __shared__ float red[8][4];
+  __shared__ float reds[8][4];
   const int g = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float INF = __int_as_float(0x7f800000);
   double base = 0.0;
   for (int m = 0; m < M; m++) {
     float4 v = make_float4(INF, INF, INF, INF);
-    if (tid < K) v = lutI[((i64)g * M + m) * 256 + tid];
+    float4 sm = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tid < K) {
+      v = lutI[((i64)g * M + m) * 256 + tid];
+      sm = v;
+    }
     for (int o = 16; o > 0; o >>= 1) {
       v.x = fminf(v.x, __shfl_xor_sync(0xffffffffu, v.x, o));
       v.y = fminf(v.y, __shfl_xor_sync(0xffffffffu, v.y, o));
       v.z = fminf(v.z, __shfl_xor_sync(0xffffffffu, v.z, o));
       v.w = fminf(v.w, __shfl_xor_sync(0xffffffffu, v.w, o));
+      sm.x += __shfl_xor_sync(0xffffffffu, sm.x, o);
+      sm.y += __shfl_xor_sync(0xffffffffu, sm.y, o);
+      sm.z += __shfl_xor_sync(0xffffffffu, sm.z, o);
+      sm.w += __shfl_xor_sync(0xffffffffu, sm.w, o);
     }
     __syncthreads();
     if (lane == 0) {
       red[warp][0] = v.x; red[warp][1] = v.y; red[warp][2] = v.z; red[warp][3] = v.w;
+      reds[warp][0] = sm.x; reds[warp][1] = sm.y; reds[warp][2] = sm.z; reds[warp][3] = sm.w;
     }
     __syncthreads();
     if (tid < 4) {
-      float mn = red[0][tid];
-      for (int w = 1; w < 8; w++) mn = fminf(mn, red[w][tid]);
+      float mn = red[0][tid], su = reds[0][tid];
+      for (int w = 1; w < 8; w++) {
+        mn = fminf(mn, red[w][tid]);
+        su += reds[w][tid];
+      }
       mins[((i64)g * 4 + tid) * M + m] = mn;
+      // mean_c LUT - min_c LUT: what a random row adds to the lower bound through this quantizer
+      // (only ranks the quantizers for the subset choice; never enters a distance)
+      spread[((i64)g * 4 + tid) * M + m] = su / (float)(K > 0 ? K : 1) - mn;
       base += (double)mn;
     }
   }
   if (tid < 4) {
     const i64 q = (i64)g * 4 + tid;
+    // suffix sums of the minima (what the quantizers not yet summed add at least), rounded down
+    double suf = 0.0;
+    sufmin[q * (M + 1) + M] = 0.0f;
+    for (int m = M - 1; m >= 0; m--) {
+      suf += (double)mins[q * M + m];
+      sufmin[q * (M + 1) + m] = __double2float_rd(suf);
+    }
     QParam p;
     p.base = base;
     p.inv_delta = 0.0;
@@ -144,15 +174,62 @@ __global__ void __launch_bounds__(256) qparams_kernel(const float4 *__restrict__
   }
 }
 
-// grid (T, M), block 256 (thread = code): the QT quantised entries of a tile, field f = query f.
+// The lower bound may leave quantizers out (they then contribute their minimum, which `base` already
+// holds): LB = base + delta * sum_{m in SEL} q[m][code_m] is still a lower bound of the distance, and
+// the pass reads ML = |SEL| <= M code planes and table slices instead of M.  Each tile keeps the ML
+// quantizers that add most, on average, to the bound of its queries, measured in units of each
+// query's slack tau - base.  grid T, block 256; msel[t][ML] ascending.
+constexpr int MSEL_MAX = 1024;
+__global__ void __launch_bounds__(256) qselect_kernel(const float *__restrict__ spread,
+                                                      const QParam *__restrict__ qp, int M, int ML,
+                                                      int QT, int32_t *__restrict__ msel) {
+  __shared__ float score[MSEL_MAX];
+  __shared__ unsigned char pick[MSEL_MAX];
+  const int t = blockIdx.x, tid = threadIdx.x;
+  for (int m = tid; m < M; m += 256) {
+    float sc = 0.f;
+    for (int f = 0; f < QT; f++) {
+      const i64 q = (i64)t * QT + f;
+      const double w = qp[q].inv_delta;
+      float a = spread[q * M + m] * (w > 0.0 ? (float)w : 0.f);
+      if (!(a > 0.f)) a = 0.f;            // NaN / negative: no contribution
+      if (a > 1e30f) a = 1e30f;
+      sc += a;
+    }
+    score[m] = sc;
+  }
+  __syncthreads();
+  for (int m = tid; m < M; m += 256) {
+    const float sc = score[m];
+    int rank = 0;
+    for (int o = 0; o < M; o++) {
+      const float so = score[o];
+      rank += (so > sc || (so == sc && o < m)) ? 1 : 0;
+    }
+    pick[m] = rank < ML ? 1 : 0;
+  }
+  __syncthreads();
+  for (int m = tid; m < M; m += 256) {
+    if (pick[m]) {
+      int pos = 0;
+      for (int o = 0; o < m; o++) pos += pick[o];
+      msel[(i64)t * ML + pos] = m;
+    }
+  }
+}
+
+// grid (T, ML), block 256 (thread = code): the QT quantised entries of a tile, field f = query f.
 template <int FB, int W>
 __global__ void __launch_bounds__(256) qlut_build_kernel(const float4 *__restrict__ lutI,
                                                          const float *__restrict__ mins,
-                                                         const QParam *__restrict__ qp, int M, int K,
+                                                         const QParam *__restrict__ qp,
+                                                         const int32_t *__restrict__ msel, int M,
+                                                         int ML, int K,
                                                          uint32_t *__restrict__ qlut) {
   using C = Cfg<FB, W>;
-  const int t = blockIdx.x, m = blockIdx.y, c = threadIdx.x;
-  const int qmax = (C::FLAG - 1) / M;
+  const int t = blockIdx.x, c = threadIdx.x;
+  const int m = msel[(i64)t * ML + blockIdx.y];
+  const int qmax = (C::FLAG - 1) / ML;
   uint32_t w[W];
 #pragma unroll
   for (int i = 0; i < W; i++) w[i] = 0u;
@@ -172,7 +249,7 @@ __global__ void __launch_bounds__(256) qlut_build_kernel(const float4 *__restric
     }
   }
 #pragma unroll
-  for (int i = 0; i < W; i++) qlut[(((i64)t * M + m) * 256 + c) * W + i] = w[i];
+  for (int i = 0; i < W; i++) qlut[(((i64)t * ML + blockIdx.y) * 256 + c) * W + i] = w[i];
 }
 
 // boot list [rows][boot_stride] + split lists [S][rows][k] -> keys [rows][stride]
@@ -193,11 +270,51 @@ __global__ void gather_lists2_kernel(const u64 *__restrict__ lists, int S, i64 r
   }
 }
 
+// planes [M][ps] -> rows [N][rcs] (rcs = M rounded up to 16): a survivor's M codes are one or two
+// 32-byte sectors instead of M sectors in M planes.  grid over rows, thread = row.
+__global__ void __launch_bounds__(256) rowcodes_kernel(const uint8_t *__restrict__ codes, i64 ps,
+                                                       i64 N, int M, i64 rcs,
+                                                       uint8_t *__restrict__ rows) {
+  const i64 r = (i64)blockIdx.x * 256 + threadIdx.x;
+  if (r >= N) return;
+  for (int m0 = 0; m0 < M; m0 += 16) {
+    uint32_t w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int u = 0; u < 16; u++)
+      if (m0 + u < M) w[u >> 2] |= (uint32_t)codes[(i64)(m0 + u) * ps + r] << (8 * (u & 3));
+    *reinterpret_cast<uint4 *>(rows + r * rcs + m0) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+// The code planes stream through L2 once per pass: evict-first keeps them from displacing the exact
+// tables (tens of MB, re-read at random by the survivor evaluation), which are loaded evict-last.
+__device__ __forceinline__ u64 l2_policy_evict_first() {
+  u64 pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ u64 l2_policy_evict_last() {
+  u64 pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint4 ldg_stream_u4(const void *p, u64 pol) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p), "l"(pol));
+  return r;
+}
 __device__ __forceinline__ uint4 ldg_stream_u4(const void *p) {
   uint4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
                : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float ldg_keep_f32(const float *p, u64 pol) {
+  float r;
+  asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(r) : "l"(p), "l"(pol));
   return r;
 }
 
@@ -258,6 +375,7 @@ __global__ void __launch_bounds__(NT, 1) pruned_scan_kernel(const Params p) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int s = blockIdx.x / p.Bs, j = blockIdx.x % p.Bs;
   if (s >= p.S) return;
+  const u64 pol_stream = l2_policy_evict_first();
   const i64 lo = p.from + (i64)s * p.split_len;
   i64 hi = lo + p.split_len;
   if (hi > p.until) hi = p.until;
@@ -266,7 +384,7 @@ __global__ void __launch_bounds__(NT, 1) pruned_scan_kernel(const Params p) {
   const i64 n_chunks = (hi - origin + R - 1) / R;
   const int n_my = (p.T - j + p.Bs - 1) / p.Bs;
   const i64 n_items = n_chunks * n_my;
-  const int M = p.M, k = p.k;
+  const int M = p.M, ML = p.ML, k = p.k;
   // survivors may wait in the queue across items only while the CTA stays on one tile (the sort
   // areas are per query of the current tile)
   const bool defer = n_my == 1;
@@ -285,7 +403,7 @@ __global__ void __launch_bounds__(NT, 1) pruned_scan_kernel(const Params p) {
 
   int parity = 0;
   {
-    const uint4 v = ldg_entry<W>(p.qlut + (((i64)j * M) * 256 + code_id) * W);
+    const uint4 v = ldg_entry<W>(p.qlut + (((i64)j * ML) * 256 + code_id) * W);
 #pragma unroll
     for (int t = 0; t < 4; t++) *reinterpret_cast<uint4 *>(region_g + fill_off[t]) = v;
   }
@@ -294,7 +412,7 @@ __global__ void __launch_bounds__(NT, 1) pruned_scan_kernel(const Params p) {
   for (int v = 0; v < NV; v++) {
     ccur[v] = make_uint4(0, 0, 0, 0);
     const i64 r = origin + (i64)tid * RPT + 16 * v;
-    if (r < hi) ccur[v] = ldg_stream_u4(p.codes + r);
+    if (r < hi) ccur[v] = ldg_stream_u4(p.codes + (i64)__ldg(p.msel + (i64)j * ML) * p.ps + r, pol_stream);
   }
   __syncthreads();
 
@@ -348,24 +466,25 @@ __global__ void __launch_bounds__(NT, 1) pruned_scan_kernel(const Params p) {
 #pragma unroll
       for (int w = 0; w < W; w++) acc[i][w] = 0u;
 
-    for (int m = 0; m < M; ++m) {
+    for (int m = 0; m < ML; ++m) {
       uint4 cnext[NV];
 #pragma unroll
       for (int v = 0; v < NV; v++) cnext[v] = make_uint4(0, 0, 0, 0);
       uint4 lnext = make_uint4(0, 0, 0, 0);
       bool do_fill = false;
-      if (m + 1 < M) {
+      if (m + 1 < ML) {
+        const uint8_t *plane = p.codes + (i64)__ldg(p.msel + (i64)t * ML + m + 1) * p.ps;
 #pragma unroll
         for (int v = 0; v < NV; v++)
-          if (row0 + 16 * v < hi)
-            cnext[v] = ldg_stream_u4(p.codes + (i64)(m + 1) * p.ps + row0 + 16 * v);
-        lnext = ldg_entry<W>(p.qlut + (((i64)t * M + m + 1) * 256 + code_id) * W);
+          if (row0 + 16 * v < hi) cnext[v] = ldg_stream_u4(plane + row0 + 16 * v, pol_stream);
+        lnext = ldg_entry<W>(p.qlut + (((i64)t * ML + m + 1) * 256 + code_id) * W);
         do_fill = true;
       } else if (has_next) {
+        const uint8_t *plane = p.codes + (i64)__ldg(p.msel + (i64)tn * ML) * p.ps;
 #pragma unroll
         for (int v = 0; v < NV; v++)
-          if (row0n + 16 * v < hi) cnext[v] = ldg_stream_u4(p.codes + row0n + 16 * v);
-        lnext = ldg_entry<W>(p.qlut + (((i64)tn * M) * 256 + code_id) * W);
+          if (row0n + 16 * v < hi) cnext[v] = ldg_stream_u4(plane + row0n + 16 * v, pol_stream);
+        lnext = ldg_entry<W>(p.qlut + (((i64)tn * ML) * 256 + code_id) * W);
         do_fill = true;
       }
       if (warp_live) {
@@ -436,54 +555,105 @@ __global__ void __launch_bounds__(NT, 1) pruned_scan_kernel(const Params p) {
         }
       }
     };
-    // exact re-evaluation of queue entries [0, n), CAPQ at a time, merged into the lists of the
-    // (single) tile they belong to
+    // exact re-evaluation of queue entries [0, n): one THREAD per survivor, NT survivors per round.
+    // The distance is summed exactly as the reference does -- (((0 + t_0) + t_1) + ...) in fp32, m
+    // ascending -- eight table reads in flight at a time, and the walk stops as soon as the exact
+    // prefix plus the minima of the quantizers still to come exceeds the query's threshold (with
+    // the same 2^-11 margin as the integer bound: the finished sum would compare greater).  Most
+    // survivors of a subset bound stop after a third of the quantizers.  Codes come from the
+    // row-major copy (one or two sectors per survivor) when the index has one.  Keys that beat
+    // their query's threshold go to the query's sort area; a key that finds the area full (CAPQ)
+    // waits in its register for the next merge round and is re-tested against the new threshold.
     auto drain = [&](int n) {
-      for (int b0s = 0; b0s < n; b0s += CAPQ) {
-        const int nb = n - b0s < CAPQ ? n - b0s : CAPQ;
-        for (int si = b0s + warp; si < b0s + nb; si += NT / 32) {
-          const uint32_t code = surv[si];
-          const int q = (int)(code & (uint32_t)(QT - 1));
+      for (int b0s = 0; b0s < n; b0s += NT) {
+        bool pending = false;
+        u64 key = KEY_SENT;
+        int q = 0;
+        if (b0s + tid < n) {
+          const uint32_t code = surv[b0s + tid];
+          q = (int)(code & (uint32_t)(QT - 1));
           const int sl = (int)(code >> (RSH + QSH));
           const i64 row = s_slot_chunk[sl] + (i64)((code >> QSH) & (uint32_t)(R - 1));
           const int ts = s_slot_tile[sl];
-          const float4 *lut = p.lutI + ((i64)ts * (QT / 4) + (q >> 2)) * M * 256;
-          const int jq = q & 3;
-          float d = 0.0f;
-          for (int m0 = 0; m0 < M; m0 += 32) {
-            const int m = m0 + lane;
-            float v = 0.0f;
-            if (m < M) {
-              const int c = p.codes[(i64)m * p.ps + row];
-              v = f4comp(__ldg(lut + m * 256 + c), jq);
-            }
-            const int nn = M - m0 < 32 ? M - m0 : 32;
-            for (int u = 0; u < nn; u++) d = __fadd_rn(d, __shfl_sync(0xffffffffu, v, u));
+          const float *lut = reinterpret_cast<const float *>(
+                                 p.lutI + ((i64)ts * (QT / 4) + (q >> 2)) * M * 256) + (q & 3);
+          const float *suf = p.sufmin + ((i64)ts * QT + q) * (M + 1);
+          const u64 pol_keep = l2_policy_evict_last();
+          const u64 thr = s_thr[q];
+          double tau_hi = 1.0e300;   // no early exit without a finite threshold
+          if (thr != KEY_SENT) {
+            const float tau = ord2f((uint32_t)(thr >> 32));
+            if (tau == tau && tau < 3.0e38f) tau_hi = (double)tau * (1.0 + 1.0 / 2048.0);
           }
-          if (lane == 0) {
-            const u64 key = make_key(d, (uint32_t)row);
+          float d = 0.0f;
+          bool out = false;
+          for (int m0 = 0; m0 < M && !out; m0 += 16) {
+            uint32_t cw[4];
+            if (p.rowcodes) {
+              const uint4 c4 = *reinterpret_cast<const uint4 *>(p.rowcodes + row * p.rcs + m0);
+              cw[0] = c4.x; cw[1] = c4.y; cw[2] = c4.z; cw[3] = c4.w;
+            } else {
+#pragma unroll
+              for (int u = 0; u < 4; u++) cw[u] = 0u;
+#pragma unroll
+              for (int u = 0; u < 16; u++)
+                if (m0 + u < M)
+                  cw[u >> 2] |= (uint32_t)p.codes[(i64)(m0 + u) * p.ps + row] << (8 * (u & 3));
+            }
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+              const int mb = m0 + 8 * h;
+              if (mb < M && !out) {
+                float v[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                  const int c = (int)((cw[2 * h + (u >> 2)] >> (8 * (u & 3))) & 0xffu);
+                  v[u] = mb + u < M ? ldg_keep_f32(lut + ((mb + u) * 256 + c) * 4, pol_keep) : 0.0f;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; u++)
+                  if (mb + u < M) d = __fadd_rn(d, v[u]);
+                const int done = mb + 8 < M ? mb + 8 : M;
+                if ((double)d + (double)suf[done] > tau_hi) out = true;
+              }
+            }
+          }
+          if (!out) {
+            key = make_key(d, (uint32_t)row);
+            pending = true;
+          }
+        }
+        for (;;) {
+          if (pending) {
             if (key < s_thr[q]) {
               const int pos = atomicAdd(&s_cnt[q], 1);
-              sortbuf[q * SORTN + k + pos] = key;
+              if (pos < CAPQ) {
+                sortbuf[q * SORTN + k + pos] = key;
+                pending = false;
+              }
+            } else {
+              pending = false;
             }
           }
-        }
-        __syncthreads();
-        if (warp < QT) {
-          const int nc = s_cnt[warp];
-          if (nc > 0) {
-            u64 *L = L0 + (i64)warp * k;
-            fscan::warp_merge(sortbuf + warp * SORTN, L, k, nc, lane);
-            if (lane == 0) {
-              const u64 tl = L[k - 1];
-              const u64 bt = p.boot_tail[(i64)t * QT + warp];
-              s_thr[warp] = tl < bt ? tl : bt;
-              s_cnt[warp] = 0;
-              atomicAdd(&s_stat[1], (unsigned long long)nc);
+          const int more = __syncthreads_or(pending ? 1 : 0);
+          if (warp < QT) {
+            const int nc = s_cnt[warp] < CAPQ ? s_cnt[warp] : CAPQ;
+            if (nc > 0) {
+              u64 *L = L0 + (i64)warp * k;
+              fscan::warp_merge(sortbuf + warp * SORTN, L, k, nc, lane);
+              if (lane == 0) {
+                const u64 tl = L[k - 1];
+                const u64 bt = p.boot_tail[(i64)t * QT + warp];
+                s_thr[warp] = tl < bt ? tl : bt;
+                atomicAdd(&s_stat[1], (unsigned long long)nc);
+              }
             }
+            __syncwarp();
+            if (lane == 0) s_cnt[warp] = 0;
           }
+          __syncthreads();
+          if (!more) break;
         }
-        __syncthreads();
       }
       if (tid == 0) s_stat[0] += (unsigned long long)n;
     };
@@ -512,7 +682,7 @@ __global__ void __launch_bounds__(NT, 1) pruned_scan_kernel(const Params p) {
       }
       slot = 0;
       need_thr = true;
-    } else if (ns > 0 && (!defer || !has_next || ns >= DRAIN_AT || slot == SLOTS - 1)) {
+    } else if (ns > 0 && (!defer || !has_next || ns >= C::DRAIN_AT || slot == SLOTS - 1)) {
       drain(ns);
       if (tid == 0) s_nsurv = 0;
       slot = 0;

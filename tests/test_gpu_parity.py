@@ -257,7 +257,7 @@ def impl_id(g, name):
             "pruned16w2": (g.SCAN_PRUNED, 16, 2)}[name]
 
 
-def check_query(g, oracle, ix, cb, codes, Q, k, frm, until, impl, boot_rows=4096):
+def check_query(g, oracle, ix, cb, codes, Q, k, frm, until, impl, boot_rows=4096, lb=0, stage_div=32):
     impl, bits, words = impl
     if bits == 8 and codes.shape[0] > 127:
         pytest.skip("8-bit lower-bound fields need M <= 127")
@@ -265,6 +265,8 @@ def check_query(g, oracle, ix, cb, codes, Q, k, frm, until, impl, boot_rows=4096
     g.set_option("pruned_bits", bits)
     g.set_option("pruned_words", words)
     g.set_option("boot_rows", boot_rows)       # small boot so that test-sized ranges reach the
+    g.set_option("pruned_lb_quantizers", lb)
+    g.set_option("pruned_stage_div", stage_div)
     try:                                       # pruned kernel proper
         got = ix.batch_query(k, Q, frm, until)
     finally:
@@ -272,6 +274,8 @@ def check_query(g, oracle, ix, cb, codes, Q, k, frm, until, impl, boot_rows=4096
         g.set_option("pruned_bits", 0)
         g.set_option("pruned_words", 0)
         g.set_option("boot_rows", 65536)
+        g.set_option("pruned_lb_quantizers", 0)
+        g.set_option("pruned_stage_div", 32)
     ids, ds, sz = oracle.pq_query(Q, cb, codes, k, frm, until, topk_mode=oracle.TOPK_CANONICAL)
     assert np.array_equal(got.size, sz)
     for q in range(Q.shape[0]):
@@ -332,6 +336,51 @@ def test_query_pruned_matches_oracle_clustered_codes(g, oracle, impl, n, D, M, n
     Q = clustered(rng, nq, D, centres=40)
     Q[0] = X[n // 2]                       # a query that coincides with a database row
     check_query(g, oracle, ix, cb, enc.codes, Q, k, 0, n, impl_id(g, impl), boot_rows=boot)
+
+
+@pytest.mark.parametrize("impl", ["pruned", "pruned8", "pruned16", "pruned8w1"])
+@pytest.mark.parametrize("lb,stage_div", [(1, 0), (1, 2), (3, 2), (7, 3), (1000, 2), (0, 2)])
+@pytest.mark.parametrize("n,D,M,nq,k,boot", [
+    (200000, 300, 30, 19, 10, 8192),      # c2 shape
+    (170000, 1000, 100, 5, 10, 4096),     # c5 shape: 8-bit fields only through the subset
+    (150000, 37, 5, 40, 100, 4096),       # ragged windows, large k, several tiles
+])
+def test_query_pruned_subset_bound_and_stages(g, oracle, impl, lb, stage_div, n, D, M, nq, k, boot):
+    """The lower bound over a SUBSET of the quantizers (pruned_lb_quantizers) and the two-stage scan
+    (first range / stage_div rows with the full bound, tables re-quantised against the merged lists)
+    change only how much is pruned, never the result."""
+    if impl in ("pruned8", "pruned8w1") and min(lb, M) > 127:
+        pytest.skip("8-bit lower-bound fields hold at most 127 quantizers")
+    rng = np.random.default_rng(n + M + lb)
+    X = clustered(rng, n, D, centres=40)
+    cb = random_codebook(rng, X, M, 256)
+    pq = g.ProductQuantizer.from_codebook(cb, D)
+    enc = pq.encode(X)
+    ix = g.PQIndex(pq, enc)
+    Q = clustered(rng, nq, D, centres=40)
+    Q[0] = X[n // 3]
+    check_query(g, oracle, ix, cb, enc.codes, Q, k, 0, n, impl_id(g, impl), boot_rows=boot, lb=lb,
+                stage_div=stage_div)
+    if lb:
+        assert g._native.counter("pscan_lb_quantizers") == min(lb, M)
+
+
+def test_query_pruned_feedback_keeps_results(g, oracle):
+    """Auto mode adapts the subset size from the survivor rate of earlier launches on the same index;
+    every launch still returns the oracle's answer."""
+    rng = np.random.default_rng(77)
+    n, D, M = 160000, 120, 12
+    X = clustered(rng, n, D, centres=40)
+    cb = random_codebook(rng, X, M, 256)
+    pq = g.ProductQuantizer.from_codebook(cb, D)
+    enc = pq.encode(X)
+    ix = g.PQIndex(pq, enc)
+    seen = set()
+    for it in range(6):
+        Q = clustered(rng, 33, D, centres=40)
+        check_query(g, oracle, ix, cb, enc.codes, Q, 10, 0, n, impl_id(g, "pruned"), boot_rows=4096)
+        seen.add(g._native.counter("pscan_lb_quantizers"))
+    assert all(1 <= v <= M for v in seen)
 
 
 @pytest.mark.parametrize("impl", ["fused", "pruned8", "pruned16", "pruned8w1", "pruned8w2"])
