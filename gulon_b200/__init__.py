@@ -12,6 +12,9 @@ from .index import PQIndex, TopK, exact_nearest_neighbours, prepare_query
 from .kmeans import Config as KMeansConfig
 from .kmeans import KMeans
 from .kmeans import ProgressReport as KMeansProgressReport
+from .coder import BytePlus, Coder0, Coder2, Coder4, factory_for
+from .coder import coder as make_coder
+from . import coder
 from .quantizer import Coder8, EncodedMatrix, ProductQuantizer, Quantizer, coder_width
 from .quantizer import Config as ProductQuantizerConfig
 from .storage import SortedIndex
@@ -23,5 +26,5 @@ __all__ = [
     "GroupedIndex", "GroupedVectors", "LimitGroups", "LimitVectors", "PQIndex", "TopK", "exact_nearest_neighbours", "prepare_query", "KMeans", "KMeansConfig",
     "KMeansProgressReport", "Coder8", "EncodedMatrix", "ProductQuantizer", "Quantizer",
     "coder_width", "ProductQuantizerConfig", "DevicePoints", "Matrix", "Vectors", "normalize",
-    "subvector_windows", "SortedIndex",
+    "subvector_windows", "SortedIndex", "BytePlus", "Coder0", "Coder2", "Coder4", "make_coder", "factory_for",
 ]

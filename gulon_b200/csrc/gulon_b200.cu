@@ -1264,12 +1264,20 @@ int scan_batch(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 fr
       // best lists so far + this stage's split lists -> best lists so far
       DevBuf &mb = stage == 0 ? ix->merged2 : ix->merged;
       Selector &sl = stage == 0 ? ix->sel2 : ix->sel;
-      const i64 ms = round_up((i64)(S + 1) * k, SEL_CHUNK);
-      GCHECK(mb.ensure((size_t)Q4 * ms * sizeof(u64)));
-      dim3 gg((unsigned)ceil_div(ms, 256), (unsigned)Q4);
-      GLAUNCH(pscan::gather_lists2_kernel, gg, 256, 0, st, ix->plists.as<u64>(), S, (i64)Q4, k, cur,
-              cur_stride, mb.as<u64>(), ms);
-      GCHECK(sl.run(mb.as<u64>(), ms, Q4, k, st, &cur, &cur_stride));
+      if ((i64)(S + 1) * k <= pscan::MERGE_SMALL_MAX) {
+        GCHECK(mb.ensure((size_t)Q4 * k * sizeof(u64)));
+        GLAUNCH(pscan::merge_small_kernel, (unsigned)ceil_div(Q4, 4), 128, 0, st, ix->plists.as<u64>(), S,
+                (i64)Q4, k, cur, cur_stride, mb.as<u64>());
+        cur = mb.as<u64>();
+        cur_stride = k;
+      } else {
+        const i64 ms = round_up((i64)(S + 1) * k, SEL_CHUNK);
+        GCHECK(mb.ensure((size_t)Q4 * ms * sizeof(u64)));
+        dim3 gg((unsigned)ceil_div(ms, 256), (unsigned)Q4);
+        GLAUNCH(pscan::gather_lists2_kernel, gg, 256, 0, st, ix->plists.as<u64>(), S, (i64)Q4, k, cur,
+                cur_stride, mb.as<u64>(), ms);
+        GCHECK(sl.run(mb.as<u64>(), ms, Q4, k, st, &cur, &cur_stride));
+      }
     }
 #undef GULON_PSCAN_VARIANTS
     return unpack(cur, cur_stride, nq, k, id_offset, d_ids, d_dists, d_sizes, st);

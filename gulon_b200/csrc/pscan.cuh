@@ -298,6 +298,35 @@ __device__ __forceinline__ u64 l2_policy_evict_last() {
   asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
   return pol;
 }
+// Same inputs as gather_lists2_kernel, but sorted on the spot: when the (S + 1) * k keys of a query
+// fit MERGE_SMALL_MAX, one warp sorts them in shared memory and writes the k smallest -- no 4096-key
+// selection pass for a handful of keys.  grid ceil(rows / 4), block 128 (warp = query).
+constexpr int MERGE_SMALL_MAX = 1024;
+__global__ void __launch_bounds__(128) merge_small_kernel(const u64 *__restrict__ lists, int S, i64 rows,
+                                                          int k, const u64 *__restrict__ boot,
+                                                          i64 boot_stride, u64 *__restrict__ out) {
+  __shared__ u64 sb[4][MERGE_SMALL_MAX];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const i64 q = (i64)blockIdx.x * 4 + warp;
+  if (q >= rows) return;
+  const int total = (S + 1) * k;
+  int P = 2;
+  while (P < total) P <<= 1;
+  for (int t = lane; t < P; t += 32) {
+    u64 v = KEY_SENT;
+    if (t < S * k) {
+      const int s = t / k, i = t % k;
+      v = lists[((i64)s * rows + q) * k + i];
+    } else if (t < total) {
+      v = boot[q * boot_stride + (t - S * k)];
+    }
+    sb[warp][t] = v;
+  }
+  __syncwarp();
+  warp_bitonic_sort(sb[warp], P, lane);
+  for (int i = lane; i < k; i += 32) out[q * k + i] = sb[warp][i];
+}
+
 __device__ __forceinline__ uint4 ldg_stream_u4(const void *p, u64 pol) {
   uint4 r;
   asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"

@@ -1,5 +1,6 @@
 """ProductQuantizer / Coder / EncodedMatrix: host-side mirror of G/ProductQuantizer.scala,
-G/Coder.scala (Coder8 only: 256 centroids => width 8) and G/EncodedMatrix.scala over the C ABI.
+G/Coder.scala (coder.py; K <= 256, i.e. widths 0/2/4/8, on the device) and G/EncodedMatrix.scala
+over the C ABI.
 
 Codes are plane-major: one uint8 array of length N per quantizer (EncodedMatrix.encodings,
 G/EncodedMatrix.scala:11-23), held here as one uint8 [M][N] array.
@@ -12,48 +13,64 @@ import numpy as np
 
 from . import _native as N
 from .kmeans import KMeans, ProgressReport as KMeansProgressReport, _progress_cb
+from .coder import Coder0, Coder2, Coder4, Coder8, BytePlus, coder, factory_for, max_width
 from .vectors import Matrix, subvector_windows
 
 
 def coder_width(num_clusters):
-    """ProductQuantizer.coderFactory, G/ProductQuantizer.scala:11-16: 32 - nlz(K - 1)."""
-    w = max(int(num_clusters) - 1, 0).bit_length()
-    if w > 8:
-        # G/Coder.scala:35-45 also has 10/12/16-bit coders; this library ships Coder8 only.
-        raise ValueError("too many clusters: %d (this build supports Coder8: K <= 256)" % num_clusters)
-    return w
-
-
-class Coder8:
-    """G/Coder.scala:129-140: one byte per index."""
-    width = 8
-
-    def __init__(self, length):
-        self.length = int(length)
-
-    def build_code(self, indices):
-        a = np.asarray(indices)
-        if a.shape[0] != self.length:
-            raise IndexError("expected %d indices" % self.length)
-        return a.astype(np.uint8)
-
-    @staticmethod
-    def get_index(code, i):
-        return int(code[i]) & 0xFF
+    """ProductQuantizer.coderFactory, G/ProductQuantizer.scala:11-16: 32 - nlz(K - 1), rounded up to a
+    supported coder (G/Coder.scala:35-45).  The kernels of this library keep one byte per centroid id,
+    so K <= 256 (coders 0, 2, 4, 8); the 10/12/16-bit coders exist in `coder.py` for the packed format
+    only."""
+    w = max_width(num_clusters)
+    f = factory_for(w)
+    if f is None:
+        raise ValueError("too many clusters: %d" % num_clusters)
+    if f.width > 8:
+        raise ValueError("too many clusters: %d (the scan kernels of this build hold one byte per "
+                         "centroid id: K <= 256)" % num_clusters)
+    return f.width
 
 
 class EncodedMatrix:
-    """G/EncodedMatrix.scala:11-23."""
+    """G/EncodedMatrix.scala:11-51: one packed `Code` per quantizer, each holding the ids of all N rows.
+
+    `codes` is the unpacked view the kernels use -- uint8 [M][N], one byte per id -- whatever the
+    coder's packed width; `encodings` / `unwrapped_encodings` are the reference's packed planes."""
 
     def __init__(self, coder, encodings):
         self.coder = coder
-        self.codes = np.ascontiguousarray(encodings, np.uint8)
+        if isinstance(encodings, np.ndarray) and encodings.ndim == 2 and coder.width == 8:
+            self.codes = np.ascontiguousarray(encodings, np.uint8)
+        elif isinstance(encodings, np.ndarray) and encodings.ndim != 2:
+            raise ValueError("expected codes [M][N]")
+        else:
+            planes = [coder.unpack(coder.wrap_code(e) if e is not None else None) for e in encodings]
+            if coder.width > 8:
+                raise ValueError("unsupported width: %d (one byte per centroid id: width <= 8)" % coder.width)
+            self.codes = (np.stack(planes).astype(np.uint8) if planes
+                          else np.zeros((0, coder.length), np.uint8))
         if self.codes.ndim != 2:
             raise ValueError("expected codes [M][N]")
 
+    @classmethod
+    def from_planes(cls, coder, planes):
+        """uint8 [M][N] ids -> EncodedMatrix with `coder`'s packing."""
+        m = cls.__new__(cls)
+        m.coder = coder
+        m.codes = np.ascontiguousarray(planes, np.uint8)
+        if m.codes.ndim != 2:
+            raise ValueError("expected codes [M][N]")
+        return m
+
     @property
     def encodings(self):
-        return [self.codes[m] for m in range(self.codes.shape[0])]
+        """Vector[coder.Code]: the packed plane of every quantizer."""
+        return [self.coder.build_code(self.codes[m]) for m in range(self.codes.shape[0])]
+
+    @property
+    def unwrapped_encodings(self):
+        return [self.coder.unwrap_code(c) for c in self.encodings]
 
     @property
     def length(self):
@@ -62,6 +79,12 @@ class EncodedMatrix:
     def __call__(self, row):
         """EncodedVector: the M centroid ids of one row."""
         return self.codes[:, row].astype(np.int32)
+
+    def __eq__(self, other):
+        return isinstance(other, EncodedMatrix) and self.coder == other.coder and \
+            np.array_equal(self.codes, other.codes)
+
+    __hash__ = None
 
 
 @dataclass
@@ -127,6 +150,11 @@ class ProductQuantizer:
     @property
     def handle(self):
         return self._handle
+
+    @property
+    def coder_factory(self):
+        """ProductQuantizer#coderFactory, G/ProductQuantizer.scala:11-16."""
+        return factory_for(max_width(self.num_clusters))
 
     def __del__(self):
         try:
@@ -201,7 +229,7 @@ class ProductQuantizer:
         codes = np.zeros((M, x.shape[0]), np.uint8)
         N.check(N.lib().gulon_pq_encode(self._handle, x.ctypes.data, x.shape[0], x.shape[1],
                                         N.TIE_LOWEST, codes.ctypes.data))
-        return EncodedMatrix(Coder8(x.shape[0]), codes)
+        return EncodedMatrix.from_planes(self.coder_factory(x.shape[0]), codes)
 
     def encode_dev(self, x, out=None, stream=None):
         """Device-resident encode: x CUDA float32 [N][D] -> CUDA uint8 [M][stride] (torch tensors)."""

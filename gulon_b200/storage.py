@@ -5,8 +5,9 @@ G/EncodedMatrix.scala:38-51).
 
 An index file written by the reference CLI loads straight into device-resident code planes
 (`repeated bytes encodings` ARE the plane-major uint8 planes the scan kernels read), and an index built
-here can be written for the reference to read.  Only `code_width = 8` (Coder8, K <= 256) is supported,
-like the rest of this library.
+here can be written for the reference to read.  Code widths 0, 2, 4 and 8 (K <= 256) are supported:
+packed planes (Coder2 / Coder4, G/Coder.scala:99-127) are unpacked to one byte per id on load and
+packed again on write; the BytePlus widths (K > 256) are refused like everywhere else in this library.
 
 Two layers: `encode_index` / `decode_index` work on plain dicts of numpy arrays (no GPU needed; the
 CPU tests pin them against google.protobuf with the same schema), `to_protobuf` / `from_protobuf`
@@ -328,8 +329,11 @@ def _pq_index_dict(vector_index):
         planes = vector_index.data.codes
     else:
         planes = vector_index._keepalive[:, :vector_index.length].cpu().numpy()
+    # EncodedMatrix.toProtobuf, G/EncodedMatrix.scala:38-42: the coder's width and its packed planes
+    cd = pq.coder_factory(int(vector_index.length))
+    packed = [cd.unwrap_code(cd.build_code(p)) for p in planes]
     return {"product_quantizer": {"num_clusters": int(pq.num_clusters), "quantizers": quantizers},
-            "data": {"code_width": 8, "length": int(vector_index.length), "encodings": list(planes)}}
+            "data": {"code_width": int(cd.width), "length": int(vector_index.length), "encodings": packed}}
 
 
 def to_protobuf(index):
@@ -352,10 +356,12 @@ def to_protobuf(index):
 
 def _pq_index_from_dict(v):
     from .index import PQIndex
-    from .quantizer import Coder8, EncodedMatrix, ProductQuantizer
+    from .coder import coder as make_coder
+    from .quantizer import EncodedMatrix, ProductQuantizer
     pqd, data = v["product_quantizer"], v["data"]
-    if data["code_width"] != 8:
-        raise ValueError("unsupported width: %d (this build ships Coder8 only)" % data["code_width"])
+    cd = make_coder(data["code_width"], data["length"])          # "unsupported width" as the reference
+    if cd.width > 8:
+        raise ValueError("unsupported width: %d (one byte per centroid id: width <= 8)" % cd.width)
     M, K = len(pqd["quantizers"]), pqd["num_clusters"]
     D = sum(q["dimension"] for q in pqd["quantizers"])
     dmax = max([q["dimension"] for q in pqd["quantizers"]] + [1])
@@ -369,9 +375,13 @@ def _pq_index_from_dict(v):
         cb[m, :, :q["dimension"]] = q["centroids"]
         at += q["dimension"]
     pq = ProductQuantizer.from_codebook(cb, D)
-    if len(data["encodings"]) != M or any(len(p) != data["length"] for p in data["encodings"]):
-        raise ValueError("one code plane of %d bytes per quantizer expected" % data["length"])
-    codes = np.stack(data["encodings"]) if M else np.zeros((0, data["length"]), np.uint8)
+    want = getattr(cd, "bytes_per_code", 0)
+    if len(data["encodings"]) != M or any(len(p) != want for p in data["encodings"]):
+        raise ValueError("one code plane of %d bytes per quantizer expected" % want)
+    codes = (np.stack([cd.unpack(p) for p in data["encodings"]]).astype(np.uint8) if M
+             else np.zeros((0, data["length"]), np.uint8))
+    if codes.size and int(codes.max()) >= max(K, 1):
+        raise ValueError("centroid id %d out of range (numClusters = %d)" % (int(codes.max()), K))
     # the planes go straight to HBM (16-byte padded stride); the host copy stays for decode / lookup
     import torch
     dev = torch.device("cuda", torch.cuda.current_device())
@@ -380,7 +390,7 @@ def _pq_index_from_dict(v):
     if data["length"]:
         planes[:, :data["length"]] = torch.from_numpy(codes).to(dev)
     ix = PQIndex.from_device_codes(pq, planes, data["length"])
-    ix.data = EncodedMatrix(Coder8(data["length"]), codes)
+    ix.data = EncodedMatrix.from_planes(cd, codes)
     return ix
 
 

@@ -287,3 +287,80 @@ def normalize(x):
         s = f32(s + f32(v * v))
     d = f32(math.sqrt(float(s)))
     return np.array([f32(v / d) for v in x], f32)
+
+
+# ---- Coder (G/Coder.scala), literal per-index loops ------------------------------------------------
+def _to_byte(v):
+    return v & 0xFF
+
+
+def coder_bytes_per_code(width, length):
+    """BytePackedCoder.bytesPerCode, G/Coder.scala:82-83."""
+    cpb = 8 // width
+    return (length + cpb - 1) // cpb
+
+
+def _packed_build(width, code, indices, offset):
+    """Coder2/4/8#buildCodeWithOffset, G/Coder.scala:100-108,115-123,130-136."""
+    for i, v in enumerate(indices):
+        if width == 2:
+            j = offset + (i >> 2)
+            code[j] = _to_byte(code[j] | ((v & 0x3) << ((i & 0x3) * 2)))
+        elif width == 4:
+            j = offset + (i >> 1)
+            code[j] = _to_byte(code[j] | ((v & 0xF) << ((i & 0x1) * 4)))
+        else:
+            code[offset + i] = _to_byte(v)
+
+
+def _packed_get(width, code, offset, i):
+    """Coder2/4/8#getIndexWithOffset, G/Coder.scala:110-111,125-126,138-139."""
+    if width == 2:
+        return (code[offset + (i >> 2)] >> ((i & 0x3) * 2)) & 0x3
+    if width == 4:
+        return (code[offset + (i >> 1)] >> ((i & 0x1) * 4)) & 0xF
+    return code[offset + i] & 0xFF
+
+
+def coder_supported_width(width):
+    """Coder.factoryFor, G/Coder.scala:35-45 -> the width actually used, or None."""
+    if width < 0 or width > 16:
+        return None
+    for w in (0, 2, 4, 8, 10, 12, 16):
+        if width <= w:
+            return w
+    return None
+
+
+def coder_build(width, length, indices):
+    """Coder(width, length).buildCode(indices) -> list of byte values (None for width 0)."""
+    w = coder_supported_width(width)
+    if w is None:
+        raise ValueError("unsupported width: %d" % width)
+    if w == 0:
+        return None
+    if w <= 8:
+        code = [0] * coder_bytes_per_code(w, length)
+        _packed_build(w, code, indices, 0)
+        return code
+    lw = w - 8                                                 # BytePlus, G/Coder.scala:147-161
+    if len(indices) != length:
+        raise ValueError("indices.length != %d" % length)
+    code = [0] * (length + coder_bytes_per_code(lw, length))
+    for i in range(length):
+        code[i] = _to_byte((indices[i] & 0xFFFFFFFF) >> lw)
+    _packed_build(lw, code, indices, length)
+    return code
+
+
+def coder_get_index(width, length, code, i):
+    """Coder(width, length).getIndex(code, i), G/Coder.scala:68-72,93-94,163-167."""
+    w = coder_supported_width(width)
+    if w == 0:
+        if i < 0 or i >= length:
+            raise IndexError(str(i))
+        return 0
+    if w <= 8:
+        return _packed_get(w, code, 0, i)
+    lw = w - 8
+    return ((code[i] & 0xFF) << lw) | (_packed_get(lw, code, length, i) & 0xFF)

@@ -68,3 +68,34 @@ def test_grouped_index_round_trip(g, oracle, tmp_path, strategy):
     assert np.array_equal(a.values.view(np.uint32), b.values.view(np.uint32))
     assert np.array_equal(back.lookup(123).view(np.uint32), ix.lookup(123).view(np.uint32))
     assert storage.to_protobuf(back) == raw
+
+
+@pytest.mark.parametrize("K", [1, 4, 16, 100])
+def test_small_codebooks_use_the_packed_coders(g, oracle, tmp_path, K):
+    """numClusters <= 16 selects Coder0 / Coder2 / Coder4 (G/ProductQuantizer.scala:11-16,
+    G/Coder.scala:35-45): the packed planes are what the file holds; the device works on one byte per id."""
+    from gulon_b200 import storage
+    from gulon_b200.coder import factory_for, max_width
+    rng = np.random.default_rng(100 + K)
+    n, D, M = 3001, 20, 4
+    X = clustered(rng, n, D)
+    pq = g.ProductQuantizer.train(g.Matrix(X), g.ProductQuantizerConfig(K, M, 3))
+    enc = pq.encode(g.Matrix(X))
+    width = factory_for(max_width(K)).width
+    assert enc.coder.width == width == {1: 0, 4: 2, 16: 4, 100: 8}[K]
+    want_codes = oracle.pq_encode(X, pq.codebook(), tie_mode=oracle.TIE_LOWEST)
+    assert np.array_equal(enc.codes, want_codes)
+    assert all(len(p) == (n * width + 7) // 8 for p in enc.unwrapped_encodings)
+    ix = storage.SortedIndex(["w%05d" % i for i in range(n)], g.PQIndex(pq, enc), False)
+    raw = storage.to_protobuf(ix)
+    d = storage.decode_index(raw)
+    assert d["vector_index"]["data"]["code_width"] == width
+    assert all(len(p) == (n * width + 7) // 8 for p in d["vector_index"]["data"]["encodings"])
+    back = storage.from_protobuf(raw)
+    assert back.vector_index.data == enc
+    Q = clustered(rng, 9, D)
+    a, b = ix.batch_query(7, Q), back.batch_query(7, Q)
+    wi, wd, ws = oracle.pq_query(Q, pq.codebook(), enc.codes, 7)
+    for r in (a, b):
+        assert np.array_equal(r.keys, wi) and np.array_equal(r.values.view(np.uint32), wd.view(np.uint32))
+    assert storage.to_protobuf(back) == raw

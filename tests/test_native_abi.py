@@ -55,7 +55,8 @@ def test_split_rule_matches_oracle(native, oracle):
 
 def test_coder_width():
     from gulon_b200 import coder_width
-    assert [coder_width(k) for k in (1, 2, 3, 4, 16, 17, 255, 256)] == [0, 1, 2, 2, 4, 5, 8, 8]
+    # width of ProductQuantizer#coderFactory: 32 - nlz(K - 1) rounded up to a supported coder
+    assert [coder_width(k) for k in (1, 2, 3, 4, 16, 17, 255, 256)] == [0, 2, 2, 2, 4, 8, 8, 8]
     with pytest.raises(ValueError):
         coder_width(257)   # "too many clusters" for the shipped Coder8
 
