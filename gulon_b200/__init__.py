@@ -18,6 +18,7 @@ from . import coder
 from .quantizer import Coder8, EncodedMatrix, ProductQuantizer, Quantizer, coder_width
 from .quantizer import Config as ProductQuantizerConfig
 from .storage import SortedIndex
+from .recall import SummaryStats, Tests
 from .vectors import DevicePoints, Matrix, Vectors, normalize, subvector_windows
 
 __all__ = [
@@ -26,5 +27,5 @@ __all__ = [
     "GroupedIndex", "GroupedVectors", "LimitGroups", "LimitVectors", "PQIndex", "TopK", "exact_nearest_neighbours", "prepare_query", "KMeans", "KMeansConfig",
     "KMeansProgressReport", "Coder8", "EncodedMatrix", "ProductQuantizer", "Quantizer",
     "coder_width", "ProductQuantizerConfig", "DevicePoints", "Matrix", "Vectors", "normalize",
-    "subvector_windows", "SortedIndex", "BytePlus", "Coder0", "Coder2", "Coder4", "make_coder", "factory_for",
+    "subvector_windows", "SortedIndex", "BytePlus", "Coder0", "Coder2", "Coder4", "make_coder", "factory_for", "SummaryStats", "Tests",
 ]

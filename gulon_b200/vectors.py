@@ -52,6 +52,19 @@ class DevicePoints:
     def normalize(self):
         N.check(N.lib().gulon_points_normalize(self.handle))
 
+    def info(self):
+        n, d, ld = C.c_int64(0), C.c_int32(0), C.c_int64(0)
+        N.check(N.lib().gulon_points_info(self.handle, C.byref(n), C.byref(d), C.byref(ld), None))
+        return int(n.value), int(d.value), int(ld.value)
+
+    @property
+    def rows(self):
+        return self.info()[0]
+
+    @property
+    def cols(self):
+        return self.info()[1]
+
     def __del__(self):
         try:
             if self.handle:

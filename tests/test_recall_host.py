@@ -1,0 +1,51 @@
+"""Host pieces of the recall harness (G/Tests.scala, SummaryStats G/MathUtils.scala:5-60): the
+java.util.Random sampler against the JDK known answers and the oracle's generator, and the
+SummaryStats monoid properties of T/SummaryStatsSpec.scala.  CPU only."""
+import numpy as np
+from hypothesis import given, settings, strategies as st
+
+from gulon_b200.recall import JavaRandom, SummaryStats
+
+
+def test_java_random_known_answers(oracle):
+    # JDK-documented values: new Random(0).nextInt(1000000) x5, nextInt(10000) x5
+    r = JavaRandom(0)
+    assert [r.next_int(1000000) for _ in range(5)] == [741360, 505948, 548029, 116447, 843515]
+    r = JavaRandom(0)
+    assert [r.next_int(10000) for _ in range(5)] == [1360, 5948, 8029, 6447, 3515]
+    r = JavaRandom(1)
+    assert [r.next_int(1000000) for _ in range(5)] == [548985, 764588, 641847, 970313, 64254]
+    # power-of-two bounds take the multiply-shift branch
+    for seed, bound in ((0, 1024), (7, 1), (123, 1 << 20), (5, 1000003)):
+        r = JavaRandom(seed)
+        got = [r.next_int(bound) for _ in range(50)]
+        o = oracle.JRandom(seed)
+        assert got == [o.next_int(bound) for _ in range(50)]
+
+
+vals = st.lists(st.floats(-1e4, 1e4, width=32), max_size=30)
+
+
+def nearly(a, b):
+    return abs(a - b) <= 1e-3 * max(1.0, abs(a), abs(b))
+
+
+@settings(max_examples=200, deadline=None)
+@given(vals, vals, vals)
+def test_summary_stats_associative(x, y, z):
+    x, y, z = SummaryStats.of(x), SummaryStats.of(y), SummaryStats.of(z)
+    lhs, rhs = (x + y) + z, x + (y + z)
+    assert lhs.count == rhs.count and nearly(lhs.mean, rhs.mean)
+    if lhs.count > 0:
+        assert nearly(lhs.variance, rhs.variance) or abs(lhs.variance - rhs.variance) <= 1e-3 * 1e8
+
+
+@settings(max_examples=100, deadline=None)
+@given(vals)
+def test_summary_stats_identity_and_naive(x):
+    s = SummaryStats.of(x)
+    assert s + SummaryStats() == s and SummaryStats() + s == s
+    if x:
+        assert nearly(s.mean, float(np.mean(np.asarray(x, np.float64))))
+        want = float(np.mean((np.asarray(x, np.float64) - s.mean) ** 2))
+        assert abs(s.variance - want) <= 1e-3 * max(1.0, want)
