@@ -94,8 +94,8 @@ std::atomic<long long> g_query_batch{0};      // 0 = auto (multiple of 16 * #SM)
 std::atomic<long long> g_simple_scratch{1LL << 30};
 std::atomic<long long> g_encode_chunk{1 << 20};  // rows per H2D chunk in gulon_pq_encode
 std::atomic<long long> g_fused_min_rows{16384};
-std::atomic<long long> g_boot_rows{65536};       // rows scanned exactly to seed the pruned scan
-std::atomic<long long> g_pruned_min_rows{1 << 20};
+std::atomic<long long> g_boot_rows{0};           // rows scanned exactly to seed the pruned scan; 0 = range / 64 in [8192, 65536]
+std::atomic<long long> g_pruned_min_rows{1 << 18};
 std::atomic<long long> g_pruned_bits{0};         // 0 = auto, 8 or 16: width of the lower-bound fields
 std::atomic<long long> g_pruned_words{0};        // 0 = auto, 1/2/4: 32-bit words per table entry
 std::atomic<long long> g_pruned_lb{0};           // 0 = auto (feedback), else quantizers in the lower bound
@@ -1127,7 +1127,11 @@ int scan_batch(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 fr
     const int RI = pscan::NT * (64 / W);  // rows per work item
     g_last_qt = QT;
     // 1. exact scan of the boot rows -> one sorted list per query (its tail is tau0)
-    const i64 boot = std::min<i64>(range, std::max<i64>(g_boot_rows.load(), k));
+    // (measured on the 1M-row shapes c1 / c5: 16384 boot rows beat 65536 by 3-7 %, and the pruned scan
+    // beats the exact kernel 2x there; profiles/README.md round 1d)
+    i64 boot_want = g_boot_rows.load();
+    if (boot_want <= 0) boot_want = std::min<i64>(65536, std::max<i64>(8192, range / 64));
+    const i64 boot = std::min<i64>(range, std::max<i64>(boot_want, k));
     int Sb = 1;
     GCHECK(fused_lists(ix, from, from + boot, G, k, ix->lists, &Sb, st));
     u64 *bkeys;
@@ -1409,7 +1413,7 @@ int gulon_set_option(const char *name, int64_t value) {
     for (int i = 0; i < 3; i++) g_pstats[i] = 0;
     g_ppairs = 0;
   } else if (s == "boot_rows") {
-    GREQUIRE(value >= 1, "boot_rows must be >= 1");
+    GREQUIRE(value >= 0, "boot_rows must be >= 0 (0 = auto)");
     g_boot_rows = value;
   } else if (s == "pruned_bits") {
     GREQUIRE(value == 0 || value == 8 || value == 16, "pruned_bits must be 0 (auto), 8 or 16");

@@ -17,6 +17,7 @@ def main():
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--centres", type=int, default=4096)
+    ap.add_argument("--opt", action="append", default=[], help="library option name=value")
     ap.add_argument("cfgs", nargs="*")
     a = ap.parse_args()
     import torch
@@ -24,6 +25,9 @@ def main():
     from gulon_b200 import _native as N
     from gulon_b200.synth import Mixture
     dev = torch.device("cuda", 0)
+    for kv in a.opt:
+        name, val = kv.split("=")
+        g.set_option(name, int(val))
     D, M, K = a.dim, a.m, 256
     mix = Mixture(D, device=dev, centres=a.centres)
     xt = mix.rows(0, min(262144, a.rows))

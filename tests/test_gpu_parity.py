@@ -273,7 +273,7 @@ def check_query(g, oracle, ix, cb, codes, Q, k, frm, until, impl, boot_rows=4096
         g.set_option("scan_impl", g.SCAN_AUTO)
         g.set_option("pruned_bits", 0)
         g.set_option("pruned_words", 0)
-        g.set_option("boot_rows", 65536)
+        g.set_option("boot_rows", 0)
         g.set_option("pruned_lb_quantizers", 0)
         g.set_option("pruned_stage_div", 32)
     ids, ds, sz = oracle.pq_query(Q, cb, codes, k, frm, until, topk_mode=oracle.TOPK_CANONICAL)
