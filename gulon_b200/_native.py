@@ -124,6 +124,11 @@ SIGNATURES = {
     "gulon_pq_encode": (C.c_int, [vp, vp, i64, i64, i32, vp]),
     "gulon_pq_encode_dev": (C.c_int, [vp, vp, i64, i64, i32, vp, i64, vp]),
     "gulon_pq_decode": (C.c_int, [vp, vp, i64, i64, vp, i64]),
+    "gulon_pq_encode16": (C.c_int, [vp, vp, i64, i64, i32, vp]),
+    "gulon_pq_encode16_dev": (C.c_int, [vp, vp, i64, i64, i32, vp, i64, vp]),
+    "gulon_pq_decode16": (C.c_int, [vp, vp, i64, i64, vp, i64]),
+    "gulon_index_create16": (C.c_int, [vp, vp, i64, i64, C.POINTER(vp)]),
+    "gulon_index_create16_dev": (C.c_int, [vp, vp, i64, i64, C.POINTER(vp)]),
     "gulon_index_create": (C.c_int, [vp, vp, i64, i64, C.POINTER(vp)]),
     "gulon_index_create_dev": (C.c_int, [vp, vp, i64, i64, C.POINTER(vp)]),
     "gulon_index_info": (C.c_int, [vp, C.POINTER(i64), C.POINTER(i32), C.POINTER(i32),

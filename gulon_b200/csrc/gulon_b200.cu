@@ -55,8 +55,10 @@ struct gulon_codebook_s {
 struct gulon_index_s {
   gulon_codebook_t cb = nullptr;
   const uint8_t *codes = nullptr;
+  const uint16_t *codes16 = nullptr;  // wide index (256 < K <= 65536): 16-bit ids, `codes` is null
   i64 N = 0, ps = 0;
   bool owned = false;
+  DevBuf lutW;
   std::mutex mu;  // guards the scratch below: one query batch in flight per index handle
   std::mutex mu_host;  // guards the host-call staging buffers
   DevBuf h_q, h_ids, h_dists, h_sizes;
@@ -74,6 +76,8 @@ struct gulon_index_s {
   int stats_ml = 0;
   ~gulon_index_s() {
     if (owned && codes) cudaFree((void *)codes);
+    if (owned && codes16) cudaFree((void *)codes16);
+    lutW.release();
     lutI.release(); keys.release(); lists.release(); qbuf.release();
     ids.release(); dists.release(); sizes.release(); merged.release();
     qlut.release(); mins.release(); qp.release(); boot_tail.release(); plists.release();
@@ -431,6 +435,7 @@ int launch_assign(const float *dX, i64 N, i64 ld, const float *cb, const float *
            "assign_impl=tensor needs K <= %d, window width <= %d, a 16-byte aligned matrix and a row "
            "stride that is a multiple of 4 floats (K=%d, width=%d, ld=%lld)", tca::TN,
            (tca::KP - 3) / 3, K, dim, (long long)ld);
+  if constexpr (sizeof(OutT) != 2)  // 16-bit codes mean K > 256: never tensor-eligible
   if (tc_ok && (impl == GULON_ASSIGN_TENSOR ||
                 (impl == GULON_ASSIGN_AUTO && N >= g_assign_tc_min_rows.load()))) {
     switch (dim) {
@@ -935,7 +940,8 @@ int codebook_offsets(gulon_codebook_t cb, cudaStream_t st) {
   return GULON_OK;
 }
 
-int encode_dev(gulon_codebook_t cb, const float *dX, i64 N, i64 ld, uint8_t *dcodes, i64 ps,
+template <typename CodeT>
+int encode_dev(gulon_codebook_t cb, const float *dX, i64 N, i64 ld, CodeT *dcodes, i64 ps,
                cudaStream_t st) {
   for (auto &kv : cb->by_dim) {
     TcCtx ctx;
@@ -948,7 +954,7 @@ int encode_dev(gulon_codebook_t cb, const float *dX, i64 N, i64 ld, uint8_t *dco
       ctx.d_groups = it->second.as<int32_t>();
       ctx.n_groups = cb->tc_ngroups[kv.first];
     }
-    GCHECK(launch_assign<uint8_t>(dX, N, ld, cb->cb.as<float>(), cb->off.as<float>(), cb->K,
+    GCHECK(launch_assign<CodeT>(dX, N, ld, cb->cb.as<float>(), cb->off.as<float>(), cb->K,
                                   cb->dmax, cb->d_by_dim[kv.first].as<int32_t>(),
                                   (int)kv.second.size(), cb->dfrom.as<int32_t>(),
                                   cb->ddim.as<int32_t>(), kv.first,
@@ -1044,6 +1050,29 @@ int scan_batch(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 fr
   gulon_codebook_t cb = ix->cb;
   const int M = cb->M, K = cb->K;
   const i64 range = until - from;
+  if (ix->codes16) {
+    // wide index: plain tables, materialised keys, selection (any k the selector takes)
+    const i64 n_pad = round_up(range, SEL_CHUNK);
+    i64 qb = std::min<i64>(g_simple_scratch.load() / (8 * n_pad), (512LL << 20) / ((i64)M * K * 4));
+    qb = std::max<i64>(1, std::min<i64>(std::min<i64>(qb, nq), 32768));
+    GCHECK(ix->keys.ensure((size_t)qb * n_pad * sizeof(u64)));
+    GCHECK(ix->lutW.ensure((size_t)qb * M * K * sizeof(float)));
+    for (i64 q0 = 0; q0 < nq; q0 += qb) {
+      const i64 nb = std::min<i64>(qb, nq - q0);
+      dim3 lg((unsigned)ceil_div(K, 256), (unsigned)M, (unsigned)nb);
+      GLAUNCH(lut_wide_kernel, lg, 256, 0, st, dQ + q0 * ldq, ldq, cb->cb.as<float>(),
+              cb->dfrom.as<int32_t>(), cb->ddim.as<int32_t>(), M, K, cb->dmax, ix->lutW.as<float>());
+      dim3 kg((unsigned)(n_pad / 256), (unsigned)nb);
+      GLAUNCH(adc_keys_wide_kernel, kg, 256, 0, st, ix->codes16, ix->ps, from, until,
+              ix->lutW.as<float>(), M, K, ix->keys.as<u64>(), n_pad);
+      u64 *res;
+      i64 rs;
+      GCHECK(ix->sel.run(ix->keys.as<u64>(), n_pad, nb, k, st, &res, &rs));
+      GCHECK(unpack(res, rs, nb, k, id_offset, d_ids + q0 * k, d_dists + q0 * k,
+                    d_sizes ? d_sizes + q0 : nullptr, st));
+    }
+    return GULON_OK;
+  }
   long long impl = g_scan_impl.load();
   if (impl == GULON_SCAN_AUTO) {
     if (k <= pscan::KMAX && M <= 1024 && range >= g_pruned_min_rows.load())
@@ -1769,14 +1798,17 @@ int gulon_pq_encode_dev(gulon_codebook_t cb, const float *dX, int64_t N, int64_t
            (long long)N, (long long)ld, (long long)plane_stride);
   GREQUIRE((dX && dcodes) || N == 0, "null argument");
   GCHECK(need_device());
-  return encode_dev(cb, dX, N, ld, dcodes, plane_stride, (cudaStream_t)stream);
+  return encode_dev<uint8_t>(cb, dX, N, ld, dcodes, plane_stride, (cudaStream_t)stream);
 }
 
-int gulon_pq_encode(gulon_codebook_t cb, const float *X, int64_t N, int64_t ld, int32_t tie_mode,
-                    uint8_t *codes) {
+}  // extern "C"
+template <typename CodeT>
+static int pq_encode_host(gulon_codebook_t cb, const float *X, int64_t N, int64_t ld, int32_t tie_mode,
+                          CodeT *codes) {
   GREQUIRE(cb, "null handle");
   GREQUIRE(tie_mode == GULON_TIE_LOWEST, "unsupported tie_mode %d (only GULON_TIE_LOWEST)", tie_mode);
-  GREQUIRE(cb->K <= 256, "Coder8 needs K <= 256 (K=%d)", cb->K);
+  GREQUIRE(sizeof(CodeT) == 2 ? cb->K <= 65536 : cb->K <= 256,
+           "K=%d does not fit %d-byte codes", cb->K, (int)sizeof(CodeT));
   GREQUIRE(N >= 0 && ld >= cb->D, "bad shapes N=%lld ld=%lld", (long long)N, (long long)ld);
   GREQUIRE((X && codes) || N == 0, "null argument");
   GCHECK(need_device());
@@ -1789,7 +1821,7 @@ int gulon_pq_encode(gulon_codebook_t cb, const float *X, int64_t N, int64_t ld, 
   struct Res {
     cudaStream_t st[2] = {nullptr, nullptr};
     float *dx[2] = {nullptr, nullptr};
-    uint8_t *dc[2] = {nullptr, nullptr};
+    CodeT *dc[2] = {nullptr, nullptr};
     ~Res() {
       for (int i = 0; i < 2; i++) {
         if (dx[i]) cudaFree(dx[i]);
@@ -1802,7 +1834,7 @@ int gulon_pq_encode(gulon_codebook_t cb, const float *X, int64_t N, int64_t ld, 
     GCU(cudaStreamCreateWithFlags(&r.st[i], cudaStreamNonBlocking));
     GCU(cudaMalloc(&r.dx[i], (size_t)chunk * Dp * sizeof(float)));
     if (Dp != D) GCU(cudaMemset(r.dx[i], 0, (size_t)chunk * Dp * sizeof(float)));
-    GCU(cudaMalloc(&r.dc[i], (size_t)M * cps));
+    GCU(cudaMalloc(&r.dc[i], (size_t)M * cps * sizeof(CodeT)));
   }
   int b = 0;
   for (i64 r0 = 0; r0 < N; r0 += chunk, b ^= 1) {
@@ -1810,8 +1842,8 @@ int gulon_pq_encode(gulon_codebook_t cb, const float *X, int64_t N, int64_t ld, 
     GCU(cudaMemcpy2DAsync(r.dx[b], (size_t)Dp * 4, X + r0 * ld, (size_t)ld * 4, (size_t)D * 4,
                           (size_t)n, cudaMemcpyHostToDevice, r.st[b]));
     GCHECK(encode_dev(cb, r.dx[b], n, Dp, r.dc[b], cps, r.st[b]));
-    GCU(cudaMemcpy2DAsync(codes + r0, (size_t)N, r.dc[b], (size_t)cps, (size_t)n, (size_t)M,
-                          cudaMemcpyDeviceToHost, r.st[b]));
+    GCU(cudaMemcpy2DAsync(codes + r0, (size_t)N * sizeof(CodeT), r.dc[b], (size_t)cps * sizeof(CodeT),
+                          (size_t)n * sizeof(CodeT), (size_t)M, cudaMemcpyDeviceToHost, r.st[b]));
     // buffer pair b is reused two chunks later on the same stream, so reuse is stream-ordered
   }
   GCU(cudaStreamSynchronize(r.st[0]));
@@ -1819,12 +1851,38 @@ int gulon_pq_encode(gulon_codebook_t cb, const float *X, int64_t N, int64_t ld, 
   return GULON_OK;
 }
 
-int gulon_pq_decode(gulon_codebook_t cb, const uint8_t *codes, int64_t N, int64_t plane_stride,
-                    float *out, int64_t ldo) {
+extern "C" {
+int gulon_pq_encode(gulon_codebook_t cb, const float *X, int64_t N, int64_t ld, int32_t tie_mode,
+                    uint8_t *codes) {
+  return pq_encode_host<uint8_t>(cb, X, N, ld, tie_mode, codes);
+}
+
+int gulon_pq_encode16(gulon_codebook_t cb, const float *X, int64_t N, int64_t ld, int32_t tie_mode,
+                      uint16_t *codes) {
+  return pq_encode_host<uint16_t>(cb, X, N, ld, tie_mode, codes);
+}
+
+int gulon_pq_encode16_dev(gulon_codebook_t cb, const float *dX, int64_t N, int64_t ld,
+                          int32_t tie_mode, uint16_t *dcodes, int64_t plane_stride, void *stream) {
+  GREQUIRE(cb, "null handle");
+  GREQUIRE(tie_mode == GULON_TIE_LOWEST, "unsupported tie_mode %d (only GULON_TIE_LOWEST)", tie_mode);
+  GREQUIRE(cb->K <= 65536, "too many clusters: %d", cb->K);
+  GREQUIRE(N >= 0 && ld >= cb->D && plane_stride >= N, "bad shapes N=%lld ld=%lld stride=%lld",
+           (long long)N, (long long)ld, (long long)plane_stride);
+  GREQUIRE((dX && dcodes) || N == 0, "null argument");
+  GCHECK(need_device());
+  return encode_dev<uint16_t>(cb, dX, N, ld, dcodes, plane_stride, (cudaStream_t)stream);
+}
+
+}  // extern "C"
+template <typename CodeT>
+static int pq_decode_host(gulon_codebook_t cb, const CodeT *codes, int64_t N, int64_t plane_stride,
+                          float *out, int64_t ldo) {
   GREQUIRE(cb, "null handle");
   GREQUIRE(N >= 0 && plane_stride >= N && ldo >= cb->D, "bad shapes");
   GREQUIRE((codes && out) || N == 0, "null argument");
-  GREQUIRE(cb->K <= 256, "Coder8 needs K <= 256 (K=%d)", cb->K);
+  GREQUIRE(sizeof(CodeT) == 2 ? cb->K <= 65536 : cb->K <= 256,
+           "K=%d does not fit %d-byte codes", cb->K, (int)sizeof(CodeT));
   GCHECK(need_device());
   if (N == 0) return GULON_OK;
   for (int m = 0; m < cb->M; m++)
@@ -1833,12 +1891,12 @@ int gulon_pq_decode(gulon_codebook_t cb, const uint8_t *codes, int64_t N, int64_
                (int)codes[(i64)m * plane_stride + i], cb->K, m, (long long)i);
   DevBuf dc, dout;
   int rc = [&]() -> int {
-    GCHECK(dc.ensure((size_t)cb->M * N));
+    GCHECK(dc.ensure((size_t)cb->M * N * sizeof(CodeT)));
     GCHECK(dout.ensure((size_t)N * cb->D * sizeof(float)));
-    GCU(cudaMemcpy2D(dc.p, (size_t)N, codes, (size_t)plane_stride, (size_t)N, (size_t)cb->M,
-                     cudaMemcpyHostToDevice));
+    GCU(cudaMemcpy2D(dc.p, (size_t)N * sizeof(CodeT), codes, (size_t)plane_stride * sizeof(CodeT),
+                     (size_t)N * sizeof(CodeT), (size_t)cb->M, cudaMemcpyHostToDevice));
     dim3 block(32, 8);
-    GLAUNCH(decode_kernel, (unsigned)ceil_div(N, 8), block, 0, 0, dc.as<uint8_t>(), N, N,
+    GLAUNCH(decode_kernel<CodeT>, (unsigned)ceil_div(N, 8), block, 0, 0, dc.as<CodeT>(), N, N,
             cb->cb.as<float>(), cb->dfrom.as<int32_t>(), cb->ddim.as<int32_t>(), cb->M, cb->K,
             cb->dmax, dout.as<float>(), (i64)cb->D);
     GCU(cudaMemcpy2D(out, (size_t)ldo * 4, dout.p, (size_t)cb->D * 4, (size_t)cb->D * 4, (size_t)N,
@@ -1848,6 +1906,17 @@ int gulon_pq_decode(gulon_codebook_t cb, const uint8_t *codes, int64_t N, int64_
   dc.release();
   dout.release();
   return rc;
+}
+
+extern "C" {
+int gulon_pq_decode(gulon_codebook_t cb, const uint8_t *codes, int64_t N, int64_t plane_stride,
+                    float *out, int64_t ldo) {
+  return pq_decode_host<uint8_t>(cb, codes, N, plane_stride, out, ldo);
+}
+
+int gulon_pq_decode16(gulon_codebook_t cb, const uint16_t *codes, int64_t N, int64_t plane_stride,
+                      float *out, int64_t ldo) {
+  return pq_decode_host<uint16_t>(cb, codes, N, plane_stride, out, ldo);
 }
 
 // ---- Index.PQIndex ----------------------------------------------------------------------------
@@ -1902,6 +1971,61 @@ int gulon_index_create_dev(gulon_codebook_t cb, const uint8_t *dcodes, int64_t N
   return GULON_OK;
 }
 
+/* Wide index: 16-bit centroid ids (256 < K <= 65536).  plane_stride in elements. */
+int gulon_index_create16(gulon_codebook_t cb, const uint16_t *codes, int64_t N, int64_t plane_stride,
+                         gulon_index_t *out) {
+  GREQUIRE(cb && out, "null argument");
+  GREQUIRE(N >= 0 && plane_stride >= N, "bad shapes N=%lld stride=%lld", (long long)N,
+           (long long)plane_stride);
+  GREQUIRE(codes || N == 0, "null codes");
+  GREQUIRE(cb->K <= 65536, "too many clusters: %d", cb->K);
+  GREQUIRE(N < (1LL << 31), "row ids are Int in the reference: N must be < 2^31");
+  GCHECK(need_device());
+  for (int m = 0; m < cb->M; m++)
+    for (i64 i = 0; i < N; i++)
+      GREQUIRE(codes[(i64)m * plane_stride + i] < cb->K, "code %d >= K=%d (plane %d row %lld)",
+               (int)codes[(i64)m * plane_stride + i], cb->K, m, (long long)i);
+  std::unique_ptr<gulon_index_s> ix(new gulon_index_s);
+  ix->cb = cb;
+  ix->N = N;
+  ix->ps = round_up(std::max<i64>(N, 1), 16);
+  ix->owned = true;
+  uint16_t *d = nullptr;
+  const size_t bytes = (size_t)cb->M * ix->ps * sizeof(uint16_t);
+  cudaError_t e = cudaMalloc(&d, bytes);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(GULON_ENOMEM, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+  }
+  ix->codes16 = d;
+  GCU(cudaMemset(d, 0, bytes));
+  if (N > 0)
+    GCU(cudaMemcpy2D(d, (size_t)ix->ps * 2, codes, (size_t)plane_stride * 2, (size_t)N * 2,
+                     (size_t)cb->M, cudaMemcpyHostToDevice));
+  *out = ix.release();
+  return GULON_OK;
+}
+
+/* Adopts device codes (borrowed): uint16 [M][plane_stride], ids < K. */
+int gulon_index_create16_dev(gulon_codebook_t cb, const uint16_t *dcodes, int64_t N,
+                             int64_t plane_stride, gulon_index_t *out) {
+  GREQUIRE(cb && out, "null argument");
+  GREQUIRE(N >= 0 && plane_stride >= N, "bad shapes N=%lld stride=%lld", (long long)N,
+           (long long)plane_stride);
+  GREQUIRE(dcodes || N == 0, "null codes");
+  GREQUIRE(cb->K <= 65536, "too many clusters: %d", cb->K);
+  GREQUIRE(N < (1LL << 31), "row ids are Int in the reference: N must be < 2^31");
+  GCHECK(need_device());
+  gulon_index_s *ix = new gulon_index_s;
+  ix->cb = cb;
+  ix->codes16 = dcodes;
+  ix->N = N;
+  ix->ps = plane_stride;
+  ix->owned = false;
+  *out = ix;
+  return GULON_OK;
+}
+
 int gulon_index_info(gulon_index_t ix, int64_t *N, int32_t *M, int32_t *K, int32_t *D) {
   GREQUIRE(ix, "null handle");
   if (N) *N = ix->N;
@@ -1926,6 +2050,24 @@ int gulon_prepare_query(gulon_codebook_t cb, const float *queries, int64_t nq, i
   if (nq == 0) return GULON_OK;
   std::lock_guard<std::mutex> lock(cb->mu);
   const int M = cb->M, K = cb->K, D = cb->D;
+  if (K > 256) {
+    const i64 qw = std::max<i64>(1, std::min<i64>(4096, (256LL << 20) / ((i64)M * K * 4)));
+    GCHECK(cb->scratch_q.ensure((size_t)qw * D * sizeof(float) + (size_t)qw * M * K * sizeof(float)));
+    float *dq = cb->scratch_q.as<float>();
+    float *dl = dq + (size_t)qw * D;
+    for (i64 q0 = 0; q0 < nq; q0 += qw) {
+      const i64 nb = std::min<i64>(qw, nq - q0);
+      GCU(cudaMemcpy2DAsync(dq, (size_t)D * 4, queries + q0 * ldq, (size_t)ldq * 4, (size_t)D * 4,
+                            (size_t)nb, cudaMemcpyHostToDevice, 0));
+      dim3 lg((unsigned)ceil_div(K, 256), (unsigned)M, (unsigned)nb);
+      GLAUNCH(lut_wide_kernel, lg, 256, 0, 0, dq, (i64)D, cb->cb.as<float>(), cb->dfrom.as<int32_t>(),
+              cb->ddim.as<int32_t>(), M, K, cb->dmax, dl);
+      GCU(cudaMemcpyAsync(lut + q0 * M * K, dl, (size_t)nb * M * K * sizeof(float),
+                          cudaMemcpyDeviceToHost, 0));
+      GCU(cudaStreamSynchronize(0));
+    }
+    return GULON_OK;
+  }
   const i64 qb = 4096;
   GCHECK(cb->scratch_q.ensure((size_t)qb * D * sizeof(float) + (size_t)qb * M * K * sizeof(float)));
   GCHECK(cb->scratch_lut.ensure((size_t)(qb / 4) * M * 256 * sizeof(float4)));

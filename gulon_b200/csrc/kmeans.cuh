@@ -471,7 +471,8 @@ __global__ void __launch_bounds__(128) rerank_keys_kernel(const float *__restric
 }
 
 // codes [M][ps] -> out [N][ldo]: ProductQuantizer.decode, G/ProductQuantizer.scala:58-78
-__global__ void decode_kernel(const uint8_t *__restrict__ codes, i64 ps, i64 N,
+template <typename CodeT>
+__global__ void decode_kernel(const CodeT *__restrict__ codes, i64 ps, i64 N,
                               const float *__restrict__ cb, const int32_t *__restrict__ from,
                               const int32_t *__restrict__ dims, int M, int K, int dmax,
                               float *__restrict__ out, i64 ldo) {

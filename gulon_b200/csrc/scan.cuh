@@ -124,6 +124,47 @@ __global__ void __launch_bounds__(256) adc_keys_kernel(const uint8_t *__restrict
   keys[((i64)s * Q4 + q) * n_pad + t] = key;
 }
 
+// ---- wide codes: 256 < K <= 65536 (the BytePlus coders, G/Coder.scala:142-168) ------------------------
+// Plain tables lut[q][m][K] and 16-bit centroid ids; the cross-check path's structure (materialised keys +
+// selection), same arithmetic: Index.prepareQuery (G/Index.scala:352-383) and PQIndex.distances (:393-409).
+// grid (ceil(K / 256), M, nq), block 256 (thread = code)
+__global__ void __launch_bounds__(256) lut_wide_kernel(const float *__restrict__ Q, i64 ldq,
+                                                       const float *__restrict__ cb,
+                                                       const int32_t *__restrict__ from,
+                                                       const int32_t *__restrict__ dim, int M, int K,
+                                                       int dmax, float *__restrict__ lut) {
+  const int code = blockIdx.x * 256 + threadIdx.x, m = blockIdx.y;
+  const i64 q = blockIdx.z;
+  if (code >= K) return;
+  const int f = from[m], dm = dim[m];
+  const float *c = cb + ((i64)m * K + code) * dmax;
+  const float *qv = Q + q * ldq + f;
+  float s = 0.0f;
+  for (int t = 0; t < dm; t++) {
+    const float d = __fsub_rn(qv[t], c[t]);
+    s = __fadd_rn(s, __fmul_rn(d, d));
+  }
+  lut[(q * M + m) * K + code] = s;
+}
+
+// keys[q][t], t in [0, n_pad): row = from + t while row < until, else KEY_SENT.  grid (n_pad / 256, nq)
+__global__ void __launch_bounds__(256) adc_keys_wide_kernel(const uint16_t *__restrict__ codes, i64 ps,
+                                                            i64 from, i64 until,
+                                                            const float *__restrict__ lut, int M, int K,
+                                                            u64 *__restrict__ keys, i64 n_pad) {
+  const i64 t = (i64)blockIdx.x * 256 + threadIdx.x;
+  const i64 q = blockIdx.y;
+  const i64 row = from + t;
+  u64 key = KEY_SENT;
+  if (row < until) {
+    const float *l = lut + q * M * K;
+    float d = 0.0f;
+    for (int m = 0; m < M; m++) d = __fadd_rn(d, __ldg(l + (i64)m * K + codes[(i64)m * ps + row]));
+    key = make_key(d, (uint32_t)row);
+  }
+  keys[q * n_pad + t] = key;
+}
+
 // ---- fused scan ---------------------------------------------------------------------------------
 // Persistent kernel, one 512-thread CTA per SM.  Work item = (chunk of 8192 rows, group of 4
 // queries).  For each quantizer m the group's 256-entry float4 table slice is replicated 8x in

@@ -69,11 +69,13 @@ class PQIndex:
         self.product_quantizer = product_quantizer
         h = N.vp()
         if _dev_codes is not None:
-            t = _dev_codes  # CUDA uint8 [M][stride] torch tensor, borrowed
+            t = _dev_codes  # CUDA uint8 (K <= 256) or uint16 [M][stride] torch tensor, borrowed
             self._keepalive = t
             self.length = int(length)
-            N.check(N.lib().gulon_index_create_dev(product_quantizer.handle, t.data_ptr(),
-                                                   self.length, t.stride(0), C.byref(h)))
+            fn = N.lib().gulon_index_create16_dev if t.element_size() == 2 else N.lib().gulon_index_create_dev
+            if (t.element_size() == 2) != (product_quantizer.num_clusters > 256):
+                raise ValueError("16-bit codes are for more than 256 clusters, 8-bit codes for up to 256")
+            N.check(fn(product_quantizer.handle, t.data_ptr(), self.length, t.stride(0), C.byref(h)))
         else:
             if not isinstance(data, EncodedMatrix):
                 raise ValueError("expected an EncodedMatrix")
@@ -81,8 +83,12 @@ class PQIndex:
                 raise ValueError("one code plane per quantizer expected")
             self._keepalive = None
             self.length = data.length
-            N.check(N.lib().gulon_index_create(product_quantizer.handle, data.codes.ctypes.data,
-                                               data.length, data.length, C.byref(h)))
+            wide = product_quantizer.num_clusters > 256
+            if (data.codes.dtype == np.uint16) != wide:
+                raise ValueError("16-bit codes are for more than 256 clusters, 8-bit codes for up to 256")
+            fn = N.lib().gulon_index_create16 if wide else N.lib().gulon_index_create
+            N.check(fn(product_quantizer.handle, data.codes.ctypes.data, data.length, data.length,
+                       C.byref(h)))
         self.data = data
         self._handle = h
 

@@ -19,37 +19,32 @@ from .vectors import Matrix, subvector_windows
 
 def coder_width(num_clusters):
     """ProductQuantizer.coderFactory, G/ProductQuantizer.scala:11-16: 32 - nlz(K - 1), rounded up to a
-    supported coder (G/Coder.scala:35-45).  The kernels of this library keep one byte per centroid id,
-    so K <= 256 (coders 0, 2, 4, 8); the 10/12/16-bit coders exist in `coder.py` for the packed format
-    only."""
+    supported coder (G/Coder.scala:35-45).  On the device ids are one byte up to K = 256 (coders 0, 2, 4,
+    8: the fast scan kernels) and 16 bits above (the BytePlus coders 10, 12, 16: plain-table scan)."""
     w = max_width(num_clusters)
     f = factory_for(w)
     if f is None:
         raise ValueError("too many clusters: %d" % num_clusters)
-    if f.width > 8:
-        raise ValueError("too many clusters: %d (the scan kernels of this build hold one byte per "
-                         "centroid id: K <= 256)" % num_clusters)
     return f.width
 
 
 class EncodedMatrix:
     """G/EncodedMatrix.scala:11-51: one packed `Code` per quantizer, each holding the ids of all N rows.
 
-    `codes` is the unpacked view the kernels use -- uint8 [M][N], one byte per id -- whatever the
-    coder's packed width; `encodings` / `unwrapped_encodings` are the reference's packed planes."""
+    `codes` is the unpacked view the kernels use -- [M][N], uint8 for widths <= 8, uint16 for the BytePlus
+    widths -- whatever the coder's packed width; `encodings` / `unwrapped_encodings` are the reference's
+    packed planes."""
 
     def __init__(self, coder, encodings):
         self.coder = coder
+        dt = np.uint8 if coder.width <= 8 else np.uint16
         if isinstance(encodings, np.ndarray) and encodings.ndim == 2 and coder.width == 8:
             self.codes = np.ascontiguousarray(encodings, np.uint8)
         elif isinstance(encodings, np.ndarray) and encodings.ndim != 2:
             raise ValueError("expected codes [M][N]")
         else:
             planes = [coder.unpack(coder.wrap_code(e) if e is not None else None) for e in encodings]
-            if coder.width > 8:
-                raise ValueError("unsupported width: %d (one byte per centroid id: width <= 8)" % coder.width)
-            self.codes = (np.stack(planes).astype(np.uint8) if planes
-                          else np.zeros((0, coder.length), np.uint8))
+            self.codes = (np.stack(planes).astype(dt) if planes else np.zeros((0, coder.length), dt))
         if self.codes.ndim != 2:
             raise ValueError("expected codes [M][N]")
 
@@ -58,7 +53,7 @@ class EncodedMatrix:
         """uint8 [M][N] ids -> EncodedMatrix with `coder`'s packing."""
         m = cls.__new__(cls)
         m.coder = coder
-        m.codes = np.ascontiguousarray(planes, np.uint8)
+        m.codes = np.ascontiguousarray(planes, np.uint8 if coder.width <= 8 else np.uint16)
         if m.codes.ndim != 2:
             raise ValueError("expected codes [M][N]")
         return m
@@ -226,9 +221,10 @@ class ProductQuantizer:
         if x.ndim != 2 or x.shape[1] != self.dimension:
             raise ValueError("expected [N][%d] vectors" % self.dimension)
         M = len(self.quantizers)
-        codes = np.zeros((M, x.shape[0]), np.uint8)
-        N.check(N.lib().gulon_pq_encode(self._handle, x.ctypes.data, x.shape[0], x.shape[1],
-                                        N.TIE_LOWEST, codes.ctypes.data))
+        wide = self.num_clusters > 256
+        codes = np.zeros((M, x.shape[0]), np.uint16 if wide else np.uint8)
+        fn = N.lib().gulon_pq_encode16 if wide else N.lib().gulon_pq_encode
+        N.check(fn(self._handle, x.ctypes.data, x.shape[0], x.shape[1], N.TIE_LOWEST, codes.ctypes.data))
         return EncodedMatrix.from_planes(self.coder_factory(x.shape[0]), codes)
 
     def encode_dev(self, x, out=None, stream=None):
@@ -237,12 +233,14 @@ class ProductQuantizer:
         n = x.shape[0]
         M = len(self.quantizers)
         stride = (n + 15) // 16 * 16
+        wide = self.num_clusters > 256
         if out is None:
-            out = torch.zeros((M, max(stride, 16)), dtype=torch.uint8, device=x.device)
+            out = torch.zeros((M, max(stride, 16)), dtype=torch.uint16 if wide else torch.uint8,
+                              device=x.device)
         st = torch.cuda.current_stream(x.device).cuda_stream if stream is None else stream
         ld = x.stride(0) if n > 1 else max(x.shape[1], 1)
-        N.check(N.lib().gulon_pq_encode_dev(self._handle, x.data_ptr(), n, ld, N.TIE_LOWEST,
-                                            out.data_ptr(), out.stride(0), st))
+        fn = N.lib().gulon_pq_encode16_dev if wide else N.lib().gulon_pq_encode_dev
+        N.check(fn(self._handle, x.data_ptr(), n, ld, N.TIE_LOWEST, out.data_ptr(), out.stride(0), st))
         return out
 
     def decode(self, encoded):
@@ -252,11 +250,12 @@ class ProductQuantizer:
             codes = encoded.codes
             one = False
         else:
-            codes = np.ascontiguousarray(encoded).astype(np.uint8).reshape(-1, 1)
+            codes = np.ascontiguousarray(encoded).reshape(-1, 1)
             one = True
+        wide = self.num_clusters > 256
         n = codes.shape[1]
         out = np.zeros((n, self.dimension), np.float32)
-        codes = np.ascontiguousarray(codes)
-        N.check(N.lib().gulon_pq_decode(self._handle, codes.ctypes.data, n, n, out.ctypes.data,
-                                        self.dimension))
+        codes = np.ascontiguousarray(codes.astype(np.uint16 if wide else np.uint8))
+        fn = N.lib().gulon_pq_decode16 if wide else N.lib().gulon_pq_decode
+        N.check(fn(self._handle, codes.ctypes.data, n, n, out.ctypes.data, self.dimension))
         return out[0] if one else Matrix(out)

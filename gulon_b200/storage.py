@@ -5,9 +5,9 @@ G/EncodedMatrix.scala:38-51).
 
 An index file written by the reference CLI loads straight into device-resident code planes
 (`repeated bytes encodings` ARE the plane-major uint8 planes the scan kernels read), and an index built
-here can be written for the reference to read.  Code widths 0, 2, 4 and 8 (K <= 256) are supported:
-packed planes (Coder2 / Coder4, G/Coder.scala:99-127) are unpacked to one byte per id on load and
-packed again on write; the BytePlus widths (K > 256) are refused like everywhere else in this library.
+here can be written for the reference to read.  Every code width of the reference is supported: packed
+planes (Coder2 / Coder4 / BytePlus, G/Coder.scala:99-168) are unpacked on load -- to one byte per id up
+to 256 clusters, 16 bits above -- and packed again on write.
 
 Two layers: `encode_index` / `decode_index` work on plain dicts of numpy arrays (no GPU needed; the
 CPU tests pin them against google.protobuf with the same schema), `to_protobuf` / `from_protobuf`
@@ -360,8 +360,6 @@ def _pq_index_from_dict(v):
     from .quantizer import EncodedMatrix, ProductQuantizer
     pqd, data = v["product_quantizer"], v["data"]
     cd = make_coder(data["code_width"], data["length"])          # "unsupported width" as the reference
-    if cd.width > 8:
-        raise ValueError("unsupported width: %d (one byte per centroid id: width <= 8)" % cd.width)
     M, K = len(pqd["quantizers"]), pqd["num_clusters"]
     D = sum(q["dimension"] for q in pqd["quantizers"])
     dmax = max([q["dimension"] for q in pqd["quantizers"]] + [1])
@@ -375,18 +373,21 @@ def _pq_index_from_dict(v):
         cb[m, :, :q["dimension"]] = q["centroids"]
         at += q["dimension"]
     pq = ProductQuantizer.from_codebook(cb, D)
-    want = getattr(cd, "bytes_per_code", 0)
+    want = getattr(cd, "bytes_per_code", 0) if cd.width <= 8 else cd.length + cd.lsb.bytes_per_code
     if len(data["encodings"]) != M or any(len(p) != want for p in data["encodings"]):
         raise ValueError("one code plane of %d bytes per quantizer expected" % want)
-    codes = (np.stack([cd.unpack(p) for p in data["encodings"]]).astype(np.uint8) if M
-             else np.zeros((0, data["length"]), np.uint8))
+    dt = np.uint8 if K <= 256 else np.uint16
+    if (cd.width > 8) != (K > 256):
+        raise ValueError("code width %d does not match numClusters = %d" % (cd.width, K))
+    codes = (np.stack([cd.unpack(p) for p in data["encodings"]]).astype(dt) if M
+             else np.zeros((0, data["length"]), dt))
     if codes.size and int(codes.max()) >= max(K, 1):
         raise ValueError("centroid id %d out of range (numClusters = %d)" % (int(codes.max()), K))
     # the planes go straight to HBM (16-byte padded stride); the host copy stays for decode / lookup
     import torch
     dev = torch.device("cuda", torch.cuda.current_device())
     stride = max(16, (data["length"] + 15) // 16 * 16)
-    planes = torch.zeros((M, stride), dtype=torch.uint8, device=dev)
+    planes = torch.zeros((M, stride), dtype=torch.uint8 if K <= 256 else torch.uint16, device=dev)
     if data["length"]:
         planes[:, :data["length"]] = torch.from_numpy(codes).to(dev)
     ix = PQIndex.from_device_codes(pq, planes, data["length"])

@@ -197,6 +197,13 @@ int gulon_pq_encode(gulon_codebook_t cb, const float *X, int64_t N, int64_t ld, 
 /* Device-resident form: dX device [N][ld], dcodes device uint8 [M][plane_stride]. */
 int gulon_pq_encode_dev(gulon_codebook_t cb, const float *dX, int64_t N, int64_t ld,
                         int32_t tie_mode, uint8_t *dcodes, int64_t plane_stride, void *stream);
+/* The same with 16-bit centroid ids (K <= 65536). */
+int gulon_pq_encode16(gulon_codebook_t cb, const float *X, int64_t N, int64_t ld, int32_t tie_mode,
+                      uint16_t *codes);
+int gulon_pq_encode16_dev(gulon_codebook_t cb, const float *dX, int64_t N, int64_t ld,
+                          int32_t tie_mode, uint16_t *dcodes, int64_t plane_stride, void *stream);
+int gulon_pq_decode16(gulon_codebook_t cb, const uint16_t *codes, int64_t N, int64_t plane_stride,
+                      float *out, int64_t ldo);
 /* ProductQuantizer#decode(EncodedMatrix), :58-78. codes host [M][N] -> out host [N][ldo]. */
 int gulon_pq_decode(gulon_codebook_t cb, const uint8_t *codes, int64_t N, int64_t plane_stride,
                     float *out, int64_t ldo);
@@ -208,6 +215,13 @@ int gulon_index_create(gulon_codebook_t cb, const uint8_t *codes, int64_t N, int
 /* Adopts device codes (borrowed). plane_stride must be a multiple of 16 and dcodes 16-byte aligned. */
 int gulon_index_create_dev(gulon_codebook_t cb, const uint8_t *dcodes, int64_t N,
                            int64_t plane_stride, gulon_index_t *out);
+/* Wide indexes: 256 < K <= 65536, the reference's BytePlus coders (G/Coder.scala:142-168).  The ids
+ * cross the boundary unpacked, one uint16 per (quantizer, row); plane_stride counts elements.  Queries
+ * go through gulon_pq_query / gulon_pq_query_dev like any index (plain-table scan + selection). */
+int gulon_index_create16(gulon_codebook_t cb, const uint16_t *codes, int64_t N, int64_t plane_stride,
+                         gulon_index_t *out);
+int gulon_index_create16_dev(gulon_codebook_t cb, const uint16_t *dcodes, int64_t N,
+                             int64_t plane_stride, gulon_index_t *out);
 int gulon_index_info(gulon_index_t ix, int64_t *N, int32_t *M, int32_t *K, int32_t *D);
 int gulon_index_destroy(gulon_index_t ix);
 

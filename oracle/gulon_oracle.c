@@ -291,46 +291,6 @@ void go_pq_train(const float *X, int64_t N, int64_t ld, int D, int M, int K, int
   free(from); free(dim);
 }
 
-/*
- * ProductQuantizer.encode, G/ProductQuantizer.scala:25-35 + Coder8, G/Coder.scala:129-140:
- * per subspace the whole-array assign (one Random(0) per subspace over all N rows), then
- * code[i] = (byte) idx.  Output plane-major uint8 [M][N] (G/EncodedMatrix.scala:11-23).
- */
-void go_pq_encode(const float *X, int64_t N, int64_t ld, int D, int M, int K,
-                  const float *codebook, int tie_mode, int nthreads, uint8_t *codes,
-                  int64_t *tie_stats) {
-  int32_t *from = (int32_t *)malloc(sizeof(int32_t) * (size_t)M);
-  int32_t *dim = (int32_t *)malloc(sizeof(int32_t) * (size_t)M);
-  int dmax = go_subvectors(D, M, from, dim);
-  (void)nthreads;
-#ifdef _OPENMP
-#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads > 0 ? nthreads : 1)
-#endif
-  for (int m = 0; m < M; m++) {
-    int32_t *a = (int32_t *)calloc((size_t)(N > 0 ? N : 1), sizeof(int32_t));
-    go_assign(X, N, ld, from[m], dim[m], codebook + (int64_t)m * K * dmax, dmax, K, 0, tie_mode,
-              1, a, tie_stats);
-    uint8_t *plane = codes + (int64_t)m * N;
-    for (int64_t i = 0; i < N; i++) plane[i] = (uint8_t)a[i];
-    free(a);
-  }
-  free(from); free(dim);
-}
-
-/* ProductQuantizer.decode, G/ProductQuantizer.scala:58-78.                                    */
-void go_pq_decode(const uint8_t *codes, int64_t N, int64_t plane_stride, int D, int M, int K,
-                  const float *codebook, float *out, int64_t ldo) {
-  int32_t *from = (int32_t *)malloc(sizeof(int32_t) * (size_t)M);
-  int32_t *dim = (int32_t *)malloc(sizeof(int32_t) * (size_t)M);
-  int dmax = go_subvectors(D, M, from, dim);
-  for (int m = 0; m < M; m++)
-    for (int64_t i = 0; i < N; i++) {
-      const float *c = codebook + ((int64_t)m * K + codes[(int64_t)m * plane_stride + i]) * dmax;
-      for (int j = 0; j < dim[m]; j++) out[i * ldo + from[m] + j] = c[j];
-    }
-  free(from); free(dim);
-}
-
 /* Index.prepareQuery, G/Index.scala:352-383: LUT[q][m][i] = sum_k fl(d*d), d = q[k+from]-c[k]. */
 void go_prepare_query(const float *queries, int64_t Q, int64_t ldq, int D, int M, int K,
                       const float *codebook, float *lut) {
@@ -438,51 +398,16 @@ static void topk_insert(go_topk *t, int32_t key, float v) {
   t->values[i] = v; t->keys[i] = key; t->size += 1;
 }
 
-/*
- * PQIndex.distances + batchQuery, G/Index.scala:393-440: DB blocks of 4096 rows; per query
- * ds[r] = 0; for j = 0..M-1 (outer): ds[r] += LUT[j][code_j[from+r]]; then rows ascending into
- * the heap.  lut is [Q][M][K]; codes plane-major with plane stride `plane_stride`.
- * Output: ids/dists [Q][k] ascending, sizes [Q].
- */
-void go_batch_query(const float *lut, int64_t Q, int M, int K, const uint8_t *codes,
-                    int64_t plane_stride, int64_t from, int64_t until, int k, int topk_mode,
-                    int nthreads, int32_t *ids, float *dists, int32_t *sizes) {
-  (void)nthreads;
-#ifdef _OPENMP
-#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads > 0 ? nthreads : 1)
-#endif
-  for (int64_t q = 0; q < Q; q++) {
-    const float *pq = lut + q * M * K;
-    float ds[4096];
-    go_heap *h = go_heap_new(k);
-    go_topk t;
-    t.keys = (int32_t *)malloc(sizeof(int32_t) * (size_t)(k > 0 ? k : 1));
-    t.values = (float *)malloc(sizeof(float) * (size_t)(k > 0 ? k : 1));
-    t.cap = k; t.size = 0;
-    for (int64_t i = from; i < until;) {
-      int bs = (int)(until - i < 4096 ? until - i : 4096);
-      for (int r = 0; r < bs; r++) ds[r] = 0.0f;
-      for (int j = 0; j < M; j++) {
-        const float *qds = pq + (int64_t)j * K;
-        const uint8_t *code = codes + (int64_t)j * plane_stride + i;
-        for (int r = 0; r < bs; r++) ds[r] += qds[code[r]];
-      }
-      if (topk_mode == GO_TOPK_LITERAL)
-        for (int r = 0; r < bs; r++) go_heap_update(h, (int32_t)(i + r), ds[r]);
-      else
-        for (int r = 0; r < bs; r++) topk_insert(&t, (int32_t)(i + r), ds[r]);
-      i += bs;
-    }
-    if (topk_mode == GO_TOPK_LITERAL) {
-      sizes[q] = go_heap_drain(h, ids + q * k, dists + q * k);
-    } else {
-      sizes[q] = t.size;
-      memcpy(ids + q * k, t.keys, sizeof(int32_t) * (size_t)t.size);
-      memcpy(dists + q * k, t.values, sizeof(float) * (size_t)t.size);
-    }
-    go_heap_free(h); free(t.keys); free(t.values);
-  }
-}
+#define GO_CODE_T uint8_t
+#define GO_NAME(f) f
+#include "go_codes.inc"
+#undef GO_CODE_T
+#undef GO_NAME
+#define GO_CODE_T uint16_t
+#define GO_NAME(f) f##16
+#include "go_codes.inc"
+#undef GO_CODE_T
+#undef GO_NAME
 
 /* MathUtils.distanceSq(x, y), G/MathUtils.scala:85-95: dx = y_i - x_i; sumSq += dx*dx.        */
 float go_distance_sq(const float *x, const float *y, int dim) {

@@ -142,11 +142,12 @@ def compute_clusters(X, frm, until, K, max_iter, seed=0, literal=True):
 
 
 def pq_encode(X, codebooks, literal=True):
-    """G/ProductQuantizer.scala:25-35 + Coder8; codebooks = list of (from, centroids)."""
+    """G/ProductQuantizer.scala:25-35 + the coder's getIndex(buildCode(.)) round trip (ids unchanged for
+    ids < numClusters); codebooks = list of (from, centroids).  One byte per id up to 256 centroids."""
     planes = []
     for frm, Cm in codebooks:
         a = assign(X, frm, frm + Cm.shape[1], Cm, literal=literal)
-        planes.append((a & 0xFF).astype(np.uint8))
+        planes.append(a.astype(np.uint8 if len(Cm) <= 256 else np.uint16))
     return np.stack(planes)
 
 

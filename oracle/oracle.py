@@ -18,8 +18,8 @@ TOPK_LITERAL, TOPK_CANONICAL = 0, 1
 
 
 def build(force=False):
-    src = os.path.join(_HERE, "gulon_oracle.c")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("gulon_oracle.c", "go_codes.inc")]
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
     return _SO
 
@@ -158,22 +158,24 @@ def pq_encode(X, cb, tie_mode=TIE_LITERAL, nthreads=1, stats=None):
     cb = _f32(cb)
     N, D = X.shape
     M, K, _ = cb.shape
-    codes = np.zeros((M, N), np.uint8)
+    # one byte per centroid id up to K = 256 (Coder8 and narrower), 16 bits above (BytePlus coders)
+    codes = np.zeros((M, N), np.uint8 if K <= 256 else np.uint16)
     st = np.zeros(2, np.int64)
-    lib().go_pq_encode(_p(X), i64(N), i64(D), int(D), M, K, _p(cb), int(tie_mode), int(nthreads),
-                       _p(codes), _p(st))
+    fn = lib().go_pq_encode if K <= 256 else lib().go_pq_encode16
+    fn(_p(X), i64(N), i64(D), int(D), M, K, _p(cb), int(tie_mode), int(nthreads), _p(codes), _p(st))
     if stats is not None:
         stats += st
     return codes
 
 
 def pq_decode(codes, cb, D):
-    codes = np.ascontiguousarray(codes, np.uint8)
     cb = _f32(cb)
-    M, N = codes.shape
     K = cb.shape[1]
+    codes = np.ascontiguousarray(codes, np.uint8 if K <= 256 else np.uint16)
+    M, N = codes.shape
     out = np.zeros((N, D), np.float32)
-    lib().go_pq_decode(_p(codes), i64(N), i64(N), int(D), M, K, _p(cb), _p(out), i64(D))
+    fn = lib().go_pq_decode if K <= 256 else lib().go_pq_decode16
+    fn(_p(codes), i64(N), i64(N), int(D), M, K, _p(cb), _p(out), i64(D))
     return out
 
 
@@ -189,15 +191,16 @@ def prepare_query(queries, cb):
 
 def batch_query(lut, codes, k, frm=0, until=None, topk_mode=TOPK_CANONICAL, nthreads=1):
     lut = _f32(lut)
-    codes = np.ascontiguousarray(codes, np.uint8)
     Q, M, K = lut.shape
+    codes = np.ascontiguousarray(codes, np.uint8 if K <= 256 else np.uint16)
     N = codes.shape[1]
     until = N if until is None else until
     ids = np.full((Q, max(k, 1)), -1, np.int32)
     ds = np.full((Q, max(k, 1)), np.inf, np.float32)
     sz = np.zeros(Q, np.int32)
-    lib().go_batch_query(_p(lut), i64(Q), M, K, _p(codes), i64(N), i64(frm), i64(until), int(k),
-                         int(topk_mode), int(nthreads), _p(ids), _p(ds), _p(sz))
+    fn = lib().go_batch_query if K <= 256 else lib().go_batch_query16
+    fn(_p(lut), i64(Q), M, K, _p(codes), i64(N), i64(frm), i64(until), int(k),
+       int(topk_mode), int(nthreads), _p(ids), _p(ds), _p(sz))
     return ids[:, :k], ds[:, :k], sz
 
 

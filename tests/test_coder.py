@@ -69,9 +69,8 @@ def test_max_width_and_cluster_limits():
     # G/ProductQuantizer.scala:11-16
     assert [C.max_width(k) for k in (1, 2, 3, 4, 5, 16, 17, 256, 257, 65536, 65537)] == \
         [0, 1, 2, 2, 3, 4, 5, 8, 9, 16, 17]
-    assert [coder_width(k) for k in (1, 2, 4, 5, 16, 17, 256)] == [0, 2, 2, 4, 4, 8, 8]
-    with pytest.raises(ValueError, match="too many clusters"):
-        coder_width(257)            # a 10-bit coder in the reference; one byte per id here
+    assert [coder_width(k) for k in (1, 2, 4, 5, 16, 17, 256, 257, 1024, 1025, 4096, 4097, 65536)] == \
+        [0, 2, 2, 4, 4, 8, 8, 10, 10, 12, 12, 16, 16]
     with pytest.raises(ValueError, match="too many clusters: 65537"):
         coder_width(65537)          # G/ProductQuantizer.scala:13-15
 

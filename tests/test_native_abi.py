@@ -58,7 +58,7 @@ def test_coder_width():
     # width of ProductQuantizer#coderFactory: 32 - nlz(K - 1) rounded up to a supported coder
     assert [coder_width(k) for k in (1, 2, 3, 4, 16, 17, 255, 256)] == [0, 2, 2, 2, 4, 8, 8, 8]
     with pytest.raises(ValueError):
-        coder_width(257)   # "too many clusters" for the shipped Coder8
+        coder_width(65537)   # "too many clusters", G/ProductQuantizer.scala:13-15
 
 
 def test_no_cpu_fallback(native):
