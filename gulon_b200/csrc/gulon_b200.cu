@@ -69,11 +69,18 @@ struct gulon_index_s {
   int rowcodes_state = 0;     // 0 not tried, 1 ready, -1 unavailable (no memory): planes are used
   Selector sel, sel_boot, sel2;
   // lower-bound subset size learned from the survivor rate of earlier launches (0: none yet)
+  // size of the lower-bound subset, steered by the measured time per (row, query) pair of earlier
+  // main-stage launches on this index (hill climbing; see scan_batch)
   int ml_hint = 0, ml_hint_M = 0;
-  unsigned long long *h_stats = nullptr;  // pinned: [0..2] stats of the last main stage, [3] its pairs / 1024
-  cudaEvent_t stats_ev = nullptr;
-  bool stats_pending = false;
-  int stats_ml = 0;
+  cudaEvent_t tm_ev0 = nullptr, tm_ev1 = nullptr;
+  bool tm_pending = false;
+  int tm_ml = 0;           // subset size of the launch being timed
+  double tm_pairs = 0;     // its (row, query) pairs
+  int ml_best = 0;         // best subset size known and its cost (ms per 1e9 pairs)
+  double ml_best_cost = 0;
+  int ml_dir = -1, ml_reversals = 0, ml_hold = 0, ml_hold_len = 24;
+  long long tm_shape = 0, ml_shape = 0;  // (tiles, rows) of the timed launch / of the launches compared
+  int ml_shape_miss = 0;
   ~gulon_index_s() {
     if (owned && codes) cudaFree((void *)codes);
     if (owned && codes16) cudaFree((void *)codes16);
@@ -83,8 +90,8 @@ struct gulon_index_s {
     qlut.release(); mins.release(); qp.release(); boot_tail.release(); plists.release();
     pstats.release(); boot_keys.release(); spread.release(); msel.release(); merged2.release();
     sel2.release(); sufmin.release(); rowcodes.release();
-    if (h_stats) cudaFreeHost(h_stats);
-    if (stats_ev) cudaEventDestroy(stats_ev);
+    if (tm_ev0) cudaEventDestroy(tm_ev0);
+    if (tm_ev1) cudaEventDestroy(tm_ev1);
     h_q.release(); h_ids.release(); h_dists.release(); h_sizes.release();
     sel.release(); sel_boot.release();
   }
@@ -98,7 +105,7 @@ std::atomic<long long> g_query_batch{0};      // 0 = auto (multiple of 16 * #SM)
 std::atomic<long long> g_simple_scratch{1LL << 30};
 std::atomic<long long> g_encode_chunk{1 << 20};  // rows per H2D chunk in gulon_pq_encode
 std::atomic<long long> g_fused_min_rows{16384};
-std::atomic<long long> g_boot_rows{0};           // rows scanned exactly to seed the pruned scan; 0 = range / 64 in [8192, 65536]
+std::atomic<long long> g_boot_rows{0};           // rows scanned exactly to seed the pruned scan; 0 = range / 128 in [8192, 32768]
 std::atomic<long long> g_pruned_min_rows{1 << 18};
 std::atomic<long long> g_pruned_bits{0};         // 0 = auto, 8 or 16: width of the lower-bound fields
 std::atomic<long long> g_pruned_words{0};        // 0 = auto, 1/2/4: 32-bit words per table entry
@@ -1091,24 +1098,87 @@ int scan_batch(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 fr
     if (want > 0) {
       ML = (int)std::min<long long>(want, M);
     } else {
-      // feedback: fold in the survivor rate of the previous launch on this index, if it is known
-      if (ix->stats_pending && cudaEventQuery(ix->stats_ev) == cudaSuccess) {
-        ix->stats_pending = false;
-        const double pairs = (double)ix->h_stats[3] * 1024.0;
-        if (pairs > 0 && ix->ml_hint_M == M && ix->stats_ml == ix->ml_hint) {
-          const double rate = (double)ix->h_stats[0] / pairs;
-          int h = ix->ml_hint;
-          // measured on the c2 shape (profiles/README.md, round 1d): the launch is fastest where
-          // about 2e-4 of the pairs survive; fewer quantizers cost more in survivor evaluation
-          // than they save in the bound pass, more quantizers the other way round
-          if (rate > 3.5e-4) h = std::min(M, h + std::max(1, h / 8));
-          else if (rate < 1.2e-4) h = std::max(std::min(M, 4), h - std::max(1, h / 6));
-          ix->ml_hint = h;
-        }
-      }
+      // Feedback by hill climbing on the measured cost.  Fewer quantizers make the bound pass cheaper
+      // and the survivor evaluation dearer; where the sum is smallest depends on the data, the range
+      // and the thresholds, so it is measured: every main-stage launch is timed with events (read
+      // back when they have landed, never waited for) and the subset size moves one step (1/8) in the
+      // direction that last helped.  Two failed probes in a row park it at the best size for 24
+      // launches, then 48, 96, ...  A cold index starts with the full bound.
       if (ix->ml_hint_M != M || ix->ml_hint <= 0) {
-        ix->ml_hint = M;  // a cold index starts with the full bound and sheds quantizers launch by launch
+        ix->ml_hint = M;
         ix->ml_hint_M = M;
+        ix->ml_best = 0;
+        ix->ml_best_cost = 0;
+        ix->ml_dir = -1;
+        ix->ml_reversals = 0;
+        ix->ml_hold = 0;
+        ix->ml_hold_len = 24;
+      }
+      if (ix->tm_pending && cudaEventQuery(ix->tm_ev1) == cudaSuccess) {
+        ix->tm_pending = false;
+        float ms = 0.f;
+        bool usable = cudaEventElapsedTime(&ms, ix->tm_ev0, ix->tm_ev1) == cudaSuccess &&
+                      ix->tm_pairs > 0 && ix->tm_ml == ix->ml_hint;
+        // costs are only comparable between launches of one shape (a short last batch fills fewer SMs)
+        if (usable && ix->ml_shape != ix->tm_shape) {
+          if (ix->ml_shape == 0 || ++ix->ml_shape_miss >= 8) {
+            ix->ml_shape = ix->tm_shape;  // a new workload: start comparing afresh from where we are
+            ix->ml_shape_miss = 0;
+            ix->ml_best = 0;
+            ix->ml_hold = 0;
+            ix->ml_hold_len = 24;
+            ix->ml_reversals = 0;
+          } else {
+            usable = false;
+          }
+        } else if (usable) {
+          ix->ml_shape_miss = 0;
+        }
+        if (usable) {
+          const double cost = (double)ms / (ix->tm_pairs * 1e-9);
+          const int lo = std::min(M, 4);
+          auto step_from = [&](int from, int dir) {
+            const int stp = std::max(1, from / 8);
+            return std::max(lo, std::min(M, from + dir * stp));
+          };
+          if (ix->ml_hold > 0) {
+            // parked at the best size: keep its cost current
+            ix->ml_hold--;
+            ix->ml_best_cost = 0.75 * ix->ml_best_cost + 0.25 * cost;
+            if (ix->ml_hold == 0) ix->ml_hint = step_from(ix->ml_best, ix->ml_dir);
+          } else if (ix->ml_best == 0) {
+            ix->ml_best = ix->ml_hint;
+            ix->ml_best_cost = cost;
+            ix->ml_hint = step_from(ix->ml_best, ix->ml_dir);
+          } else if (ix->ml_hint != ix->ml_best && cost < ix->ml_best_cost * 0.985) {
+            ix->ml_best = ix->ml_hint;  // the probe paid off: keep walking
+            ix->ml_best_cost = cost;
+            ix->ml_reversals = 0;
+            ix->ml_hold_len = 24;
+            ix->ml_hint = step_from(ix->ml_best, ix->ml_dir);
+          } else if (ix->ml_hint == ix->ml_best) {
+            ix->ml_best_cost = 0.5 * ix->ml_best_cost + 0.5 * cost;
+            ix->ml_hint = step_from(ix->ml_best, ix->ml_dir);
+          } else {
+            ix->ml_dir = -ix->ml_dir;   // the probe did not pay off: try the other side of the best
+            ix->ml_reversals++;
+            ix->ml_hint = step_from(ix->ml_best, ix->ml_dir);
+          }
+          if (ix->ml_hint == ix->ml_best && ix->ml_hold == 0) {
+            // nowhere to go on this side (range limit): counts as a failed probe
+            ix->ml_dir = -ix->ml_dir;
+            ix->ml_reversals++;
+            ix->ml_hint = step_from(ix->ml_best, ix->ml_dir);
+          }
+          if (ix->ml_reversals >= 2) {
+            // both neighbours are worse: park, and for twice as long every time that happens again (a
+            // probe next to a cliff -- unclustered data -- can cost several normal launches)
+            ix->ml_reversals = 0;
+            ix->ml_hold = ix->ml_hold_len;
+            ix->ml_hold_len = std::min(ix->ml_hold_len * 2, 4096);
+            ix->ml_hint = ix->ml_best;
+          }
+        }
       }
       ML = ix->ml_hint;
     }
@@ -1159,7 +1229,8 @@ int scan_batch(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 fr
     // (measured on the 1M-row shapes c1 / c5: 16384 boot rows beat 65536 by 3-7 %, and the pruned scan
     // beats the exact kernel 2x there; profiles/README.md round 1d)
     i64 boot_want = g_boot_rows.load();
-    if (boot_want <= 0) boot_want = std::min<i64>(65536, std::max<i64>(8192, range / 64));
+    // whole 8192-row chunks: the exact kernel pays for a chunk's table fills however few rows it holds
+    if (boot_want <= 0) boot_want = std::min<i64>(32768, std::max<i64>(8192, (range / 128) & ~8191LL));
     const i64 boot = std::min<i64>(range, std::max<i64>(boot_want, k));
     int Sb = 1;
     GCHECK(fused_lists(ix, from, from + boot, G, k, ix->lists, &Sb, st));
@@ -1186,9 +1257,9 @@ int scan_batch(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 fr
     GCHECK(ix->qp.ensure((size_t)Q4 * sizeof(pscan::QParam)));
     GCHECK(ix->boot_tail.ensure((size_t)Q4 * sizeof(u64)));
     GCHECK(ix->pstats.ensure(8 * sizeof(unsigned long long)));
-    if (!ix->h_stats) {
-      GCU(cudaMallocHost((void **)&ix->h_stats, 8 * sizeof(unsigned long long)));
-      GCU(cudaEventCreateWithFlags(&ix->stats_ev, cudaEventDisableTiming));
+    if (!ix->tm_ev0) {
+      GCU(cudaEventCreate(&ix->tm_ev0));
+      GCU(cudaEventCreate(&ix->tm_ev1));
     }
     // 2. stages over the remaining rows.  A stage quantises the tables against the best lists known
     //    so far (boot, then boot + earlier stages), scans its rows, and merges its lists into them.
@@ -1265,6 +1336,8 @@ int scan_batch(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 fr
       prm.k = k;
       prm.S = S;
       prm.Bs = Bs;
+      const bool time_it = stage == 1 && g_pruned_lb.load() == 0 && !ix->tm_pending;
+      if (time_it) GCU(cudaEventRecord(ix->tm_ev0, st));
       cudaEvent_t ev = g_t_pscan.begin(st);
 #define GULON_X(FB_, W_)                                                                        \
   if (FB == FB_ && W == W_) {                                                                   \
@@ -1275,6 +1348,13 @@ int scan_batch(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 fr
       GULON_PSCAN_VARIANTS(GULON_X)
 #undef GULON_X
       g_t_pscan.end(ev, st);
+      if (time_it) {
+        GCU(cudaEventRecord(ix->tm_ev1, st));
+        ix->tm_pending = true;
+        ix->tm_ml = sML;
+        ix->tm_pairs = (double)srange * (double)nq;
+        ix->tm_shape = (long long)T * 1000003LL + (long long)(srange >> 12) + 1;
+      }
       if (want_stats) {
         unsigned long long h[3];
         GCU(cudaMemcpyAsync(h, dstats, sizeof(h), cudaMemcpyDeviceToHost, st));
@@ -1282,18 +1362,7 @@ int scan_batch(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 fr
         for (int i = 0; i < 3; i++) g_pstats[i] += h[i];
         g_ppairs += (unsigned long long)srange * (unsigned long long)nq;
       }
-      if (stage == 1) {
-        g_last_ml = sML;
-        if (g_pruned_lb.load() == 0 && !ix->stats_pending) {
-          // survivor rate of this launch -> subset size of the next one (read when it has landed)
-          ix->h_stats[3] = (unsigned long long)(((double)srange * (double)nq) / 1024.0);
-          ix->stats_ml = sML;
-          GCU(cudaMemcpyAsync(ix->h_stats, dstats, 3 * sizeof(unsigned long long),
-                              cudaMemcpyDeviceToHost, st));
-          GCU(cudaEventRecord(ix->stats_ev, st));
-          ix->stats_pending = true;
-        }
-      }
+      if (stage == 1) g_last_ml = sML;
       // best lists so far + this stage's split lists -> best lists so far
       DevBuf &mb = stage == 0 ? ix->merged2 : ix->merged;
       Selector &sl = stage == 0 ? ix->sel2 : ix->sel;
