@@ -361,13 +361,21 @@ __global__ void __launch_bounds__(NT, 1) fused_scan_kernel(const Params p) {
       __syncthreads();
       if (tid < 4) s_cnt[tid] = 0;
     } else {
-      // Slow path (adversarial orderings only): replay the item in sub-batches of SUB_ROWS rows
-      // so that no batch can overflow; tails are re-read after every merge.
-      for (int b = 0; b < R / SUB_ROWS; ++b) {
+      // Slow path: the first item of a list (empty list: every row is a candidate) and adversarial
+      // orders.  The item is replayed in batches of sub-batches (SUB_ROWS rows each); tails are re-read
+      // after every merge, so once the first 256 rows have filled the list the later batches offer few
+      // candidates and may double in width: 1, 1, 2, 4, 8, 16 sub-batches for rows in random order.  A
+      // batch that overflows anyway (adversarial order) is retried one sub-batch at a time, which cannot
+      // overflow (SUB_ROWS <= CAP).
+      constexpr int NSUB = R / SUB_ROWS;
+      int done = 0, width = 1;
+      while (done < NSUB) {
+        const int w = width < NSUB - done ? width : NSUB - done;
         __syncthreads();
         if (tid < 4) s_cnt[tid] = 0;
         __syncthreads();
-        if (tid / (SUB_ROWS / RPT) == b) {
+        const int sb = tid / (SUB_ROWS / RPT);
+        if (sb >= done && sb < done + w) {
 #pragma unroll
           for (int q = 0; q < 4; q++) {
             const u64 tl = ldcg_u64(L0 + (i64)q * k + (k - 1));
@@ -377,17 +385,23 @@ __global__ void __launch_bounds__(NT, 1) fused_scan_kernel(const Params p) {
                 const u64 key = make_key(acc[i][q], (uint32_t)(row0 + i));
                 if (key < tl) {
                   int pos = atomicAdd(&s_cnt[q], 1);
-                  sortbuf[q * SORTN + k + pos] = key;
+                  if (pos < CAP) sortbuf[q * SORTN + k + pos] = key;
                 }
               }
             }
           }
         }
         __syncthreads();
+        if (w > 1 && (s_cnt[0] > CAP || s_cnt[1] > CAP || s_cnt[2] > CAP || s_cnt[3] > CAP)) {
+          width = 1;  // nothing was merged: retry this stretch one sub-batch at a time
+          continue;
+        }
         if (warp < 4) {
           const int n = s_cnt[warp];
           if (n > 0) warp_merge(sortbuf + warp * SORTN, L0 + (i64)warp * k, k, n, lane);
         }
+        done += w;
+        if (done > 1) width = 2 * w;
       }
       __syncthreads();
       if (tid < 4) s_cnt[tid] = 0;

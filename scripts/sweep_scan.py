@@ -51,7 +51,7 @@ def main():
     for cfg in a.cfgs or ["30:0", "15:32"]:
         parts = [int(v) for v in cfg.split(":")]
         lb, sdiv = parts[0], parts[1]
-        boot = parts[2] if len(parts) > 2 else 65536
+        boot = parts[2] if len(parts) > 2 else 0
         g.set_option("query_batch", parts[3] if len(parts) > 3 else 0)
         g.set_option("pruned_lb_quantizers", lb)
         g.set_option("pruned_stage_div", sdiv)
