@@ -105,7 +105,7 @@ std::atomic<long long> g_query_batch{0};      // 0 = auto (multiple of 16 * #SM)
 std::atomic<long long> g_simple_scratch{1LL << 30};
 std::atomic<long long> g_encode_chunk{1 << 20};  // rows per H2D chunk in gulon_pq_encode
 std::atomic<long long> g_fused_min_rows{16384};
-std::atomic<long long> g_boot_rows{0};           // rows scanned exactly to seed the pruned scan; 0 = range / 128 in [8192, 32768]
+std::atomic<long long> g_boot_rows{0};           // rows scanned exactly to seed the pruned scan; 0 = range / 64 in [8192, 32768], whole 8192-row chunks
 std::atomic<long long> g_pruned_min_rows{1 << 18};
 std::atomic<long long> g_pruned_bits{0};         // 0 = auto, 8 or 16: width of the lower-bound fields
 std::atomic<long long> g_pruned_words{0};        // 0 = auto, 1/2/4: 32-bit words per table entry
@@ -1170,6 +1170,11 @@ int scan_batch(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 fr
             ix->ml_reversals++;
             ix->ml_hint = step_from(ix->ml_best, ix->ml_dir);
           }
+          static const bool dbg = getenv("GULON_DEBUG_ML") != nullptr;
+          if (dbg)
+            fprintf(stderr, "[gulon ml] measured ml=%d cost=%.4f -> best=%d (%.4f) next=%d dir=%d rev=%d hold=%d\n",
+                    ix->tm_ml, cost, ix->ml_best, ix->ml_best_cost, ix->ml_hint, ix->ml_dir,
+                    ix->ml_reversals, ix->ml_hold);
           if (ix->ml_reversals >= 2) {
             // both neighbours are worse: park, and for twice as long every time that happens again (a
             // probe next to a cliff -- unclustered data -- can cost several normal launches)
@@ -1230,7 +1235,7 @@ int scan_batch(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 fr
     // beats the exact kernel 2x there; profiles/README.md round 1d)
     i64 boot_want = g_boot_rows.load();
     // whole 8192-row chunks: the exact kernel pays for a chunk's table fills however few rows it holds
-    if (boot_want <= 0) boot_want = std::min<i64>(32768, std::max<i64>(8192, (range / 128) & ~8191LL));
+    if (boot_want <= 0) boot_want = std::min<i64>(32768, std::max<i64>(8192, (range / 64) & ~8191LL));
     const i64 boot = std::min<i64>(range, std::max<i64>(boot_want, k));
     int Sb = 1;
     GCHECK(fused_lists(ix, from, from + boot, G, k, ix->lists, &Sb, st));
@@ -1269,8 +1274,9 @@ int scan_batch(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 fr
     const long long sdiv = g_pruned_stage_div.load();
     i64 stageA = 0;
     if (ML < M && sdiv > 0) {
-      stageA = round_up(prange / sdiv, RI);
-      if (stageA < 8 * (i64)RI || stageA >= prange) stageA = 0;
+      // at least 4 items per CTA
+      stageA = std::max<i64>(round_up(prange / sdiv, RI), 4 * (i64)RI);
+      if (stageA >= prange) stageA = 0;
     }
     const int nsm = sm_count();
     const bool want_stats = g_profile.load() != 0;

@@ -112,7 +112,7 @@ int gulon_get_device(int32_t *device);
 int gulon_device_sync(void);
 /* Tuning options (results never depend on them).  Scan: "scan_impl" (GULON_SCAN_*), "query_batch",
  * "pruned_min_rows" (ranges shorter than this use the exact kernel; default 262144), "boot_rows"
- * (0 = range / 128 clamped to [8192, 32768]), "pruned_bits" (0 auto | 8 | 16), "pruned_words"
+ * (0 = range / 64 in whole 8192-row chunks, clamped to [8192, 32768]), "pruned_bits" (0 auto | 8 | 16), "pruned_words"
  * (0 auto | 1 | 2 | 4), "pruned_lb_quantizers" (0 = measured-cost feedback per index, else the
  * number of quantizers the lower bound sums), "pruned_stage_div" (first stage = range / div rows,
  * 0 = one stage), "pruned_rowcodes" (row-major copy of the codes for the survivor evaluation).
