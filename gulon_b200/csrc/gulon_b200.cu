@@ -79,6 +79,7 @@ struct gulon_index_s {
   int ml_best = 0;         // best subset size known and its cost (ms per 1e9 pairs)
   double ml_best_cost = 0;
   int ml_dir = -1, ml_reversals = 0, ml_hold = 0, ml_hold_len = 24;
+  bool ml_fine = false;    // parked once: later probes move by one quantizer
   long long tm_shape = 0, ml_shape = 0;  // (tiles, rows) of the timed launch / of the launches compared
   int ml_shape_miss = 0;
   ~gulon_index_s() {
@@ -1103,7 +1104,8 @@ int scan_batch(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 fr
       // and the thresholds, so it is measured: every main-stage launch is timed with events (read
       // back when they have landed, never waited for) and the subset size moves one step (1/8) in the
       // direction that last helped.  Two failed probes in a row park it at the best size for 24
-      // launches, then 48, 96, ...  A cold index starts with the full bound.
+      // launches, then 48, 96, ..., and later probes move by a single quantizer.  A cold index starts
+      // with the full bound.
       if (ix->ml_hint_M != M || ix->ml_hint <= 0) {
         ix->ml_hint = M;
         ix->ml_hint_M = M;
@@ -1113,6 +1115,7 @@ int scan_batch(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 fr
         ix->ml_reversals = 0;
         ix->ml_hold = 0;
         ix->ml_hold_len = 24;
+        ix->ml_fine = false;
       }
       if (ix->tm_pending && cudaEventQuery(ix->tm_ev1) == cudaSuccess) {
         ix->tm_pending = false;
@@ -1128,6 +1131,7 @@ int scan_batch(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 fr
             ix->ml_hold = 0;
             ix->ml_hold_len = 24;
             ix->ml_reversals = 0;
+            ix->ml_fine = false;
           } else {
             usable = false;
           }
@@ -1138,7 +1142,7 @@ int scan_batch(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 fr
           const double cost = (double)ms / (ix->tm_pairs * 1e-9);
           const int lo = std::min(M, 4);
           auto step_from = [&](int from, int dir) {
-            const int stp = std::max(1, from / 8);
+            const int stp = ix->ml_fine ? 1 : std::max(1, from / 8);
             return std::max(lo, std::min(M, from + dir * stp));
           };
           if (ix->ml_hold > 0) {
@@ -1179,6 +1183,7 @@ int scan_batch(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 fr
             // both neighbours are worse: park, and for twice as long every time that happens again (a
             // probe next to a cliff -- unclustered data -- can cost several normal launches)
             ix->ml_reversals = 0;
+            ix->ml_fine = true;
             ix->ml_hold = ix->ml_hold_len;
             ix->ml_hold_len = std::min(ix->ml_hold_len * 2, 4096);
             ix->ml_hint = ix->ml_best;
