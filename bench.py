@@ -50,6 +50,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-recall", action="store_true")
     ap.add_argument("--opt", action="append", default=[], help="library option name=value")
+    ap.add_argument("--row-shards", type=int, default=0,
+                    help="row shards R of the code planes (0 = gulon_b200.sharded.shard_plan); the other "
+                         "factor of the world size splits the query batch")
     return ap.parse_args()
 
 
@@ -160,7 +163,7 @@ def main():
     import torch.distributed as dist
     import gulon_b200 as g
     from gulon_b200 import _native as N
-    from gulon_b200.sharded import ShardedPQIndex, shard_bounds
+    from gulon_b200.sharded import ShardedPQIndex, shard_bounds, shard_plan
     from gulon_b200.synth import Mixture
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -201,8 +204,10 @@ def main():
     train_s = time.perf_counter() - t0
     del xt
 
+    # (R row shards) x (C query groups) over the ranks: gulon_b200.sharded.shard_plan
+    R, Cq = shard_plan(a.rows, world) if a.row_shards <= 0 else (a.row_shards, world // a.row_shards)
     # this rank's row shard of the database, encoded chunk by chunk (rows independent: no exchange)
-    lo, hi = shard_bounds(a.rows, world)[rank]
+    lo, hi = shard_bounds(a.rows, R)[rank % R]
     n_local = hi - lo
     stride = (max(n_local, 1) + 15) // 16 * 16
     codes = torch.zeros((M, stride), dtype=torch.uint8, device=dev)
@@ -242,7 +247,7 @@ def main():
         g.set_option("profile", 0)
         del x
     ix = g.PQIndex.from_device_codes(pq, codes, n_local)
-    sh = ShardedPQIndex(ix, lo)
+    sh = ShardedPQIndex(ix, lo, plan=(R, Cq)) if world > 1 else ShardedPQIndex(ix, lo)
     queries = mix.rows(0, Q, stream_seed=1)
 
     def step_dev():
@@ -295,8 +300,7 @@ def main():
         if world == 1:
             r = ix.batch_query(k, q_np)          # gulon_pq_query: H2D + scan + D2H inside
             return r.keys, r.values
-        qd = q_host.to(dev, non_blocking=True)
-        ids, ds, _ = sh.batch_query(k, qd)
+        ids, ds, _ = sh.batch_query(k, q_host)   # each rank copies its slice of the pinned batch to HBM
         return ids.cpu(), ds.cpu()
 
     step_e2e()
@@ -398,13 +402,17 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(workload(a), sharding="row shards of the code planes per GPU, "
-                           "all-gather + (distance,id) merge" if world > 1 else "single GPU",
+            "config": dict(workload(a), sharding=("%d row shard(s) of the code planes x %d query group(s) "
+                           "(gulon_b200.sharded.shard_plan: shards keep >= 8M rows); all-gather + "
+                           "(distance,id) merge inside a group, all-gather of the slices across groups"
+                           % (R, Cq)) if world > 1 else "single GPU",
                            l2="inputs larger than L2: 300 MB code planes + per-tile lookup tables "
                               "> 126 MB; no flush needed"),
             "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": Q * D * 4,
-                    "d2h_bytes_per_step": Q * k * 8 + (Q * 4 if world == 1 else 0),
+            # whole job: every query group copies its slice of the batch to each of its R row shards;
+            # every rank reads the assembled (ids, distances) back
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": R * Q * D * 4,
+                    "d2h_bytes_per_step": world * Q * k * 8 + (Q * 4 if world == 1 else 0),
                     "ms_per_step": e2e_ms / a.steps, "ids_equal_device_path": same},
             "gpu_launches": launches,
             "encode": dict({"value": enc_rows / (enc_ns * 1e-9) if enc_ns else None, "unit": "vectors/s",

@@ -126,7 +126,9 @@ class NativeOps:
     """The device ops of the sharded scan: the CUDA library (the only product implementation)."""
 
     def __init__(self, index):
+        import torch
         self.index = index
+        self.device = torch.device("cuda", torch.cuda.current_device())
 
     def local_query(self, k, queries, id_offset):
         return self.index.batch_query_dev(k, queries, id_offset=id_offset)
@@ -143,31 +145,91 @@ class NativeOps:
         return oi, od, oz
 
 
+def shard_plan(n_rows, world, min_rows_per_shard=8_000_000):
+    """(R, C) with R * C == world: R row shards of the code planes x C query groups.
+
+    The pruned scan is most efficient on long row ranges (its thresholds tighten with the rows a CTA has
+    seen, and the per-launch table builds amortise over the range), and code planes are small (M bytes
+    per row: 300 MB at 10M x m=30), so an index is split into as many row shards as keep
+    `min_rows_per_shard` rows each and the remaining factor of the world size splits the QUERY batch:
+    10M rows on 8 GPUs -> 1 shard x 8 query groups (every rank holds the planes, scans 1/8 of the queries);
+    100M rows on 8 GPUs -> 8 row shards x 1; 40M rows on 8 GPUs -> 4 x 2."""
+    if world < 1:
+        raise ValueError("need world >= 1")
+    R = 1
+    for r in range(1, world + 1):
+        if world % r == 0 and n_rows // r >= min_rows_per_shard:
+            R = r
+    return R, world // R
+
+
 class ShardedPQIndex:
-    """A PQIndex whose code planes are row-sharded over the ranks of a process group.
+    """A PQIndex spread over the ranks of the default process group by a (R, C) plan (`shard_plan`):
+    rank = query_group * R + row_shard.  The ranks of a query group hold the R contiguous row shards of
+    the code planes; each scans its shard for the group's slice of the query batch, one all-gather +
+    (distance, id) merge inside the group gives the slice's answer, and one all-gather across the groups
+    assembles the batch: identical results on every rank.  plan = (world, 1) is plain row sharding.
 
     `ops` provides `local_query(k, queries, id_offset)` -> (ids, dists, sizes) tensors and
     `merge(ids_all [S][Q][k], dists_all, k)`; the default is the CUDA library.
     """
 
-    def __init__(self, local_index, row_offset, group=None, ops=None):
+    def __init__(self, local_index, row_offset, group=None, ops=None, plan=None):
         import torch.distributed as dist
         self.dist = dist
-        self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.R, self.C = plan if plan is not None else (self.world, 1)
+        if self.R * self.C != self.world:
+            raise ValueError("plan %r does not factor the world size %d" % ((self.R, self.C), self.world))
+        self.row_shard, self.query_group = self.rank % self.R, self.rank // self.R
+        self.row_group = group      # ranks holding the shards of one index copy
+        self.col_group = None       # ranks holding the same shard, one per query group
+        if self.C > 1:
+            if group is not None:
+                raise ValueError("a (R, C) plan with C > 1 spans the default process group")
+            # every rank creates every group, in the same order
+            rows = [dist.new_group(ranks=[c * self.R + i for i in range(self.R)]) for c in range(self.C)]
+            cols = [dist.new_group(ranks=[c * self.R + i for c in range(self.C)]) for i in range(self.R)]
+            self.row_group = rows[self.query_group]
+            self.col_group = cols[self.row_shard]
         self.row_offset = int(row_offset)
         self.ops = ops if ops is not None else NativeOps(local_index)
 
+    def query_slice(self, Q):
+        """rows [lo, hi) of a Q-query batch this rank's query group answers, and the padded slice length."""
+        per = -(-Q // self.C)
+        lo = min(self.query_group * per, Q)
+        return lo, min(lo + per, Q), per
+
     def batch_query(self, k, queries):
-        """queries: the same [Q][D] tensor on every rank.  Returns merged (ids, dists, sizes)."""
+        """queries: the same [Q][D] tensor on every rank (a host tensor is sliced before it is copied to
+        the device).  Returns merged (ids, dists, sizes) for the whole batch on every rank."""
         import torch
-        ids, ds, _ = self.ops.local_query(k, queries, self.row_offset)
-        if self.world == 1:
+        Q = queries.shape[0]
+        lo, hi, per = self.query_slice(Q)
+        mine = queries[lo:hi]
+        if not mine.is_cuda and hasattr(self.ops, "device"):
+            mine = mine.to(self.ops.device, non_blocking=True)
+        if mine.shape[0] < per:      # equal slice lengths for the collectives
+            pad = torch.zeros((per - mine.shape[0], queries.shape[1]), dtype=mine.dtype, device=mine.device)
+            mine = torch.cat((mine, pad))
+        ids, ds, sz = self.ops.local_query(k, mine, self.row_offset)
+        if self.R > 1:
+            # rank-major concatenation along dim 0 == [R][per][k]
+            ids_all = torch.empty((self.R * per, k), dtype=ids.dtype, device=ids.device)
+            ds_all = torch.empty((self.R * per, k), dtype=ds.dtype, device=ds.device)
+            self.dist.all_gather_into_tensor(ids_all, ids.contiguous(), group=self.row_group)
+            self.dist.all_gather_into_tensor(ds_all, ds.contiguous(), group=self.row_group)
+            ids, ds, sz = self.ops.merge(ids_all.view(self.R, per, k), ds_all.view(self.R, per, k), k)
+        elif self.world == 1:
             return self.ops.merge(ids.unsqueeze(0), ds.unsqueeze(0), k)
-        Q = ids.shape[0]
-        # rank-major concatenation along dim 0 == [world][Q][k]
-        ids_all = torch.empty((self.world * Q, k), dtype=ids.dtype, device=ids.device)
-        ds_all = torch.empty((self.world * Q, k), dtype=ds.dtype, device=ds.device)
-        self.dist.all_gather_into_tensor(ids_all, ids.contiguous(), group=self.group)
-        self.dist.all_gather_into_tensor(ds_all, ds.contiguous(), group=self.group)
-        return self.ops.merge(ids_all.view(self.world, Q, k), ds_all.view(self.world, Q, k), k)
+        if self.C > 1:
+            out = []
+            for t in (ids, ds, sz):
+                t = t.contiguous()
+                full = torch.empty((self.C * per,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+                self.dist.all_gather_into_tensor(full, t, group=self.col_group)
+                out.append(full[:Q])
+            ids, ds, sz = out
+        return ids, ds, sz
