@@ -1101,8 +1101,8 @@ int scan_batch(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 fr
     } else {
       // Feedback by hill climbing on the measured cost.  Fewer quantizers make the bound pass cheaper
       // and the survivor evaluation dearer; where the sum is smallest depends on the data, the range
-      // and the thresholds, so it is measured: every main-stage launch is timed with events (read
-      // back when they have landed, never waited for) and the subset size moves one step (1/8) in the
+      // and the thresholds, so it is measured: every main-stage launch is timed with events and the
+      // subset size moves one step (1/8) in the
       // direction that last helped.  Two failed probes in a row park it at the best size for 24
       // launches, then 48, 96, ..., and later probes move by a single quantizer.  A cold index starts
       // with the full bound.
@@ -1117,6 +1117,12 @@ int scan_batch(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 fr
         ix->ml_hold_len = 24;
         ix->ml_fine = false;
       }
+      // While it is still searching (not parked) the controller waits for the timed launch before it
+      // picks the next size: callers enqueue many launches ahead of the GPU, and a search that only
+      // advanced when the host happened to fall behind would take hundreds of launches.  The wait
+      // ends when the previous main-stage kernel does (the GPU idles for one launch latency); a parked
+      // controller never waits.
+      if (ix->tm_pending && ix->ml_hold == 0) cudaEventSynchronize(ix->tm_ev1);
       if (ix->tm_pending && cudaEventQuery(ix->tm_ev1) == cudaSuccess) {
         ix->tm_pending = false;
         float ms = 0.f;
@@ -1147,9 +1153,7 @@ int scan_batch(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 fr
           };
           if (ix->ml_hold > 0) {
             // parked at the best size: keep its cost current
-            ix->ml_hold--;
             ix->ml_best_cost = 0.75 * ix->ml_best_cost + 0.25 * cost;
-            if (ix->ml_hold == 0) ix->ml_hint = step_from(ix->ml_best, ix->ml_dir);
           } else if (ix->ml_best == 0) {
             ix->ml_best = ix->ml_hint;
             ix->ml_best_cost = cost;
@@ -1189,6 +1193,16 @@ int scan_batch(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 fr
             ix->ml_hint = ix->ml_best;
           }
         }
+      }
+      // parked: count launches; when the time is up probe one step away from the best size
+      if (ix->ml_hold > 0 && --ix->ml_hold == 0 && ix->ml_best > 0) {
+        const int stp = ix->ml_fine ? 1 : std::max(1, ix->ml_best / 8);
+        int probe = std::max(std::min(M, 4), std::min(M, ix->ml_best + ix->ml_dir * stp));
+        if (probe == ix->ml_best) {
+          ix->ml_dir = -ix->ml_dir;
+          probe = std::max(std::min(M, 4), std::min(M, ix->ml_best + ix->ml_dir * stp));
+        }
+        ix->ml_hint = probe;
       }
       ML = ix->ml_hint;
     }
