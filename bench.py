@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--rows", type=int, default=10_000_000)
     ap.add_argument("--dim", type=int, default=300)
-    ap.add_argument("--m", type=int, default=30)
+    ap.add_argument("--m", "--subquantizers", dest="m", type=int, default=30)
     ap.add_argument("--queries", type=int, default=100_000)
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--train-rows", type=int, default=262_144)
