@@ -20,6 +20,11 @@ object GulonNative {
   val codebookExport = fn("gulon_codebook_export", JAVA_INT, ADDRESS, ADDRESS)
   val pqEncode      = fn("gulon_pq_encode", JAVA_INT, ADDRESS, ADDRESS, JAVA_LONG, JAVA_LONG, JAVA_INT, ADDRESS)
   val indexCreate   = fn("gulon_index_create", JAVA_INT, ADDRESS, ADDRESS, JAVA_LONG, JAVA_LONG, ADDRESS)
+  // more than 256 clusters (BytePlus coders, G/Coder.scala:142-168): ids cross unpacked, one Short each
+  val pqEncode16    = fn("gulon_pq_encode16", JAVA_INT, ADDRESS, ADDRESS, JAVA_LONG, JAVA_LONG, JAVA_INT, ADDRESS)
+  val pqDecode16    = fn("gulon_pq_decode16", JAVA_INT, ADDRESS, ADDRESS, JAVA_LONG, JAVA_LONG, ADDRESS, JAVA_LONG)
+  val indexCreate16 = fn("gulon_index_create16", JAVA_INT, ADDRESS, ADDRESS, JAVA_LONG, JAVA_LONG, ADDRESS)
+  val setOption     = fn("gulon_set_option", JAVA_INT, ADDRESS, JAVA_LONG)
   val pqQuery       = fn("gulon_pq_query", JAVA_INT, ADDRESS, ADDRESS, JAVA_LONG, JAVA_LONG, JAVA_INT,
                          JAVA_LONG, JAVA_LONG, JAVA_INT, JAVA_LONG, ADDRESS, ADDRESS, ADDRESS)
 
