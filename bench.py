@@ -377,6 +377,13 @@ def main():
                                 "frac": gathers * ((fb // 8) if use_p else 4) / smem_peak_bytes,
                                 "note": "table reads from shared memory: the binding resource "
                                         "(128 B/clk/SM crossbar)"}}
+        if use_p and world == 1 and (a.rows, a.dim, a.m, a.k) == (10_000_000, 300, 30, 10):
+            # one `ncu --set full` capture of the main-stage launch of this workload (2368 queries x 9.6M
+            # rows, bound over 15 quantizers): profiles/r01e_pruned_scan_lb15_ncu_full.csv.  That launch's
+            # algorithmic bytes are 148 tiles x 9.6M rows x 30 planes = 42.8 GB; it streams 15 planes.
+            roof["traffic"] = 16.401e9 + 0.006e9
+            roof["traffic_source"] = ("dram__bytes_read.sum + dram__bytes_write.sum of the main-stage launch, "
+                                      "profiles/r01e_pruned_scan_lb15_ncu_full.csv (not measured in this run)")
         if use_p and pstats["pairs"]:
             roof["pruning"] = {"survivor_rate": pstats["survivors"] / pstats["pairs"],
                                "list_candidates": pstats["candidates"],
