@@ -14,7 +14,7 @@ _ROOT = os.path.dirname(_HERE)
 SO_PATH = os.path.join(_HERE, "libgulon_b200.so")
 _SRC_DIR = os.path.join(_HERE, "csrc")
 _SOURCES = ["gulon_b200.cu"]
-_HEADERS = ["common.cuh", "kmeans.cuh", "scan.cuh", "select.cuh", "pscan.cuh", "tcassign.cuh", "kupdate.cuh"]
+_HEADERS = ["common.cuh", "kmeans.cuh", "scan.cuh", "select.cuh", "pscan.cuh", "tcassign.cuh", "kupdate.cuh", "mlctl.h"]
 
 OK, EINVAL, ECUDA, ENOMEM, ENODEVICE, ECOMM, EUNSUPPORTED, ESTATE = 0, -1, -2, -3, -4, -5, -6, -7
 TIE_LOWEST = 1

@@ -13,6 +13,7 @@
 #include <memory>
 
 #include "common.cuh"
+#include "mlctl.h"
 #include "kmeans.cuh"
 #include "pscan.cuh"
 #include "scan.cuh"
@@ -71,17 +72,12 @@ struct gulon_index_s {
   // lower-bound subset size learned from the survivor rate of earlier launches (0: none yet)
   // size of the lower-bound subset, steered by the measured time per (row, query) pair of earlier
   // main-stage launches on this index (hill climbing; see scan_batch)
-  int ml_hint = 0, ml_hint_M = 0;
+  gulon::MlController mlc;
   cudaEvent_t tm_ev0 = nullptr, tm_ev1 = nullptr;
   bool tm_pending = false;
   int tm_ml = 0;           // subset size of the launch being timed
   double tm_pairs = 0;     // its (row, query) pairs
-  int ml_best = 0;         // best subset size known and its cost (ms per 1e9 pairs)
-  double ml_best_cost = 0;
-  int ml_dir = -1, ml_reversals = 0, ml_hold = 0, ml_hold_len = 24;
-  bool ml_fine = false;    // parked once: later probes move by one quantizer
-  long long tm_shape = 0, ml_shape = 0;  // (tiles, rows) of the timed launch / of the launches compared
-  int ml_shape_miss = 0;
+  long long tm_shape = 0;  // its (tiles, rows)
   ~gulon_index_s() {
     if (owned && codes) cudaFree((void *)codes);
     if (owned && codes16) cudaFree((void *)codes16);
@@ -1099,112 +1095,30 @@ int scan_batch(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 fr
     if (want > 0) {
       ML = (int)std::min<long long>(want, M);
     } else {
-      // Feedback by hill climbing on the measured cost.  Fewer quantizers make the bound pass cheaper
-      // and the survivor evaluation dearer; where the sum is smallest depends on the data, the range
-      // and the thresholds, so it is measured: every main-stage launch is timed with events and the
-      // subset size moves one step (1/8) in the
-      // direction that last helped.  Two failed probes in a row park it at the best size for 24
-      // launches, then 48, 96, ..., and later probes move by a single quantizer.  A cold index starts
-      // with the full bound.
-      if (ix->ml_hint_M != M || ix->ml_hint <= 0) {
-        ix->ml_hint = M;
-        ix->ml_hint_M = M;
-        ix->ml_best = 0;
-        ix->ml_best_cost = 0;
-        ix->ml_dir = -1;
-        ix->ml_reversals = 0;
-        ix->ml_hold = 0;
-        ix->ml_hold_len = 24;
-        ix->ml_fine = false;
-      }
+      // Feedback by hill climbing on the measured cost: gulon::MlController (mlctl.h).
+      gulon::MlController &c = ix->mlc;
+      if (c.M != M || c.hint <= 0) c.reset(M);
       // While it is still searching (not parked) the controller waits for the timed launch before it
       // picks the next size: callers enqueue many launches ahead of the GPU, and a search that only
       // advanced when the host happened to fall behind would take hundreds of launches.  The wait
       // ends when the previous main-stage kernel does (the GPU idles for one launch latency); a parked
       // controller never waits.
-      if (ix->tm_pending && ix->ml_hold == 0) cudaEventSynchronize(ix->tm_ev1);
+      if (ix->tm_pending && c.searching()) cudaEventSynchronize(ix->tm_ev1);
       if (ix->tm_pending && cudaEventQuery(ix->tm_ev1) == cudaSuccess) {
         ix->tm_pending = false;
         float ms = 0.f;
-        bool usable = cudaEventElapsedTime(&ms, ix->tm_ev0, ix->tm_ev1) == cudaSuccess &&
-                      ix->tm_pairs > 0 && ix->tm_ml == ix->ml_hint;
-        // costs are only comparable between launches of one shape (a short last batch fills fewer SMs)
-        if (usable && ix->ml_shape != ix->tm_shape) {
-          if (ix->ml_shape == 0 || ++ix->ml_shape_miss >= 8) {
-            ix->ml_shape = ix->tm_shape;  // a new workload: start comparing afresh from where we are
-            ix->ml_shape_miss = 0;
-            ix->ml_best = 0;
-            ix->ml_hold = 0;
-            ix->ml_hold_len = 24;
-            ix->ml_reversals = 0;
-            ix->ml_fine = false;
-          } else {
-            usable = false;
-          }
-        } else if (usable) {
-          ix->ml_shape_miss = 0;
-        }
-        if (usable) {
+        if (cudaEventElapsedTime(&ms, ix->tm_ev0, ix->tm_ev1) == cudaSuccess && ix->tm_pairs > 0) {
           const double cost = (double)ms / (ix->tm_pairs * 1e-9);
-          const int lo = std::min(M, 4);
-          auto step_from = [&](int from, int dir) {
-            const int stp = ix->ml_fine ? 1 : std::max(1, from / 8);
-            return std::max(lo, std::min(M, from + dir * stp));
-          };
-          if (ix->ml_hold > 0) {
-            // parked at the best size: keep its cost current
-            ix->ml_best_cost = 0.75 * ix->ml_best_cost + 0.25 * cost;
-          } else if (ix->ml_best == 0) {
-            ix->ml_best = ix->ml_hint;
-            ix->ml_best_cost = cost;
-            ix->ml_hint = step_from(ix->ml_best, ix->ml_dir);
-          } else if (ix->ml_hint != ix->ml_best && cost < ix->ml_best_cost * 0.985) {
-            ix->ml_best = ix->ml_hint;  // the probe paid off: keep walking
-            ix->ml_best_cost = cost;
-            ix->ml_reversals = 0;
-            ix->ml_hold_len = 24;
-            ix->ml_hint = step_from(ix->ml_best, ix->ml_dir);
-          } else if (ix->ml_hint == ix->ml_best) {
-            ix->ml_best_cost = 0.5 * ix->ml_best_cost + 0.5 * cost;
-            ix->ml_hint = step_from(ix->ml_best, ix->ml_dir);
-          } else {
-            ix->ml_dir = -ix->ml_dir;   // the probe did not pay off: try the other side of the best
-            ix->ml_reversals++;
-            ix->ml_hint = step_from(ix->ml_best, ix->ml_dir);
-          }
-          if (ix->ml_hint == ix->ml_best && ix->ml_hold == 0) {
-            // nowhere to go on this side (range limit): counts as a failed probe
-            ix->ml_dir = -ix->ml_dir;
-            ix->ml_reversals++;
-            ix->ml_hint = step_from(ix->ml_best, ix->ml_dir);
-          }
+          c.on_measurement(ix->tm_ml, cost, ix->tm_shape);
           static const bool dbg = getenv("GULON_DEBUG_ML") != nullptr;
           if (dbg)
             fprintf(stderr, "[gulon ml] measured ml=%d cost=%.4f -> best=%d (%.4f) next=%d dir=%d rev=%d hold=%d\n",
-                    ix->tm_ml, cost, ix->ml_best, ix->ml_best_cost, ix->ml_hint, ix->ml_dir,
-                    ix->ml_reversals, ix->ml_hold);
-          if (ix->ml_reversals >= 2) {
-            // both neighbours are worse: park, and for twice as long every time that happens again (a
-            // probe next to a cliff -- unclustered data -- can cost several normal launches)
-            ix->ml_reversals = 0;
-            ix->ml_fine = true;
-            ix->ml_hold = ix->ml_hold_len;
-            ix->ml_hold_len = std::min(ix->ml_hold_len * 2, 4096);
-            ix->ml_hint = ix->ml_best;
-          }
+                    ix->tm_ml, cost, c.best, c.best_cost, c.hint, c.dir, c.reversals, c.hold);
+        } else {
+          cudaGetLastError();
         }
       }
-      // parked: count launches; when the time is up probe one step away from the best size
-      if (ix->ml_hold > 0 && --ix->ml_hold == 0 && ix->ml_best > 0) {
-        const int stp = ix->ml_fine ? 1 : std::max(1, ix->ml_best / 8);
-        int probe = std::max(std::min(M, 4), std::min(M, ix->ml_best + ix->ml_dir * stp));
-        if (probe == ix->ml_best) {
-          ix->ml_dir = -ix->ml_dir;
-          probe = std::max(std::min(M, 4), std::min(M, ix->ml_best + ix->ml_dir * stp));
-        }
-        ix->ml_hint = probe;
-      }
-      ML = ix->ml_hint;
+      ML = c.next_launch();
     }
   }
   int FB = (int)g_pruned_bits.load();
