@@ -1292,7 +1292,8 @@ int scan_batch(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 fr
         ix->tm_pending = true;
         ix->tm_ml = sML;
         ix->tm_pairs = (double)srange * (double)nq;
-        ix->tm_shape = (long long)T * 1000003LL + (long long)(srange >> 12) + 1;
+        // (the whole pruned range, not this stage's share: the full bound runs without a first stage)
+        ix->tm_shape = (long long)T * 1000003LL + (long long)(prange >> 12) + 1;
       }
       if (want_stats) {
         unsigned long long h[3];
