@@ -125,7 +125,7 @@ def reference_arm(a):
     dmax = -(-D // M)
     cb = rng.normal(size=(M, K, dmax)).astype(np.float32)
     codes = rng.integers(0, K, (M, a.rows), dtype=np.uint8)
-    nq = a.cpu_queries or 2 * T
+    nq = a.cpu_queries or 16 * T      # ~2 s of work per step on 16 cores at the c2 shape
     Q = rng.normal(size=(nq, D)).astype(np.float32)
 
     def step():
