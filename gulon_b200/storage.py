@@ -319,6 +319,32 @@ class SortedIndex:
             return None
         return self.vector_index.decode(i)
 
+    # -- Index.sorted, G/Index.scala:107-113 ---------------------------------------------------------
+    @staticmethod
+    def build(words, matrix, quantizer, normalized=False):
+        """Encode the rows of `matrix` (one per word, words ascending as in WordVectors.Sorted) with
+        `quantizer` and wrap them as a full-scan index."""
+        from .index import PQIndex
+        from .vectors import Matrix
+        m = matrix if isinstance(matrix, Matrix) else Matrix(matrix)
+        words = list(words)
+        if len(words) != m.rows:
+            raise ValueError("one word per row expected")
+        if any(a > b for a, b in zip(words[:-1], words[1:])):
+            raise ValueError("words must be sorted (KeyIndex.Sorted looks them up by binary search)")
+        return SortedIndex(words, PQIndex(quantizer, quantizer.encode(m)), normalized)
+
+    def query_by_word(self, k, word):
+        """Index#queryByWord, G/Index.scala:44-45: None for an unknown word."""
+        v = self.lookup(word)
+        return None if v is None else self.query(k, v)
+
+    def results(self, k, vectors):
+        """Index.Result per query, G/Index.scala:62-94: [(word, squared distance), ...] ascending."""
+        r = self.batch_query(k, vectors)
+        return [[(self.words[int(i)], float(d)) for i, d in zip(r.keys[q, :r.size[q]], r.values[q, :r.size[q]])]
+                for q in range(len(r))]
+
 
 def _pq_index_dict(vector_index):
     pq = vector_index.product_quantizer

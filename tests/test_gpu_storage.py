@@ -99,3 +99,30 @@ def test_small_codebooks_use_the_packed_coders(g, oracle, tmp_path, K):
     for r in (a, b):
         assert np.array_equal(r.keys, wi) and np.array_equal(r.values.view(np.uint32), wd.view(np.uint32))
     assert storage.to_protobuf(back) == raw
+
+
+def test_sorted_index_builder_and_word_queries(g, oracle):
+    """Index.sorted (G/Index.scala:107-113), queryByWord (:44-45) and Index.Result (:62-94)."""
+    from gulon_b200 import storage
+    rng = np.random.default_rng(13)
+    n, D, M = 3000, 16, 4
+    X = clustered(rng, n, D)
+    pq = g.ProductQuantizer.train(g.Matrix(X), g.ProductQuantizerConfig(256, M, 3))
+    words = ["w%05d" % i for i in range(n)]
+    ix = storage.SortedIndex.build(words, X, pq)
+    assert ix.size == n and ix.dimension == D
+    assert np.array_equal(ix.vector_index.data.codes, oracle.pq_encode(X, pq.codebook(), tie_mode=oracle.TIE_LOWEST))
+    with pytest.raises(ValueError, match="sorted"):
+        storage.SortedIndex.build(words[::-1], X, pq)
+    with pytest.raises(ValueError, match="one word per row"):
+        storage.SortedIndex.build(words[:-1], X, pq)
+    r = ix.query_by_word(5, "w00123")
+    # the decoded row is at ADC distance 0 from its own code; the lowest id among identical codes leads
+    assert r[1][0] == 0.0 and r[0][0] <= 123
+    assert np.array_equal(ix.vector_index.data.codes[:, r[0][0]], ix.vector_index.data.codes[:, 123])
+    assert ix.query_by_word(5, "nope") is None
+    Q = clustered(rng, 4, D)
+    res = ix.results(3, Q)
+    wi, wd, ws = oracle.pq_query(Q, pq.codebook(), ix.vector_index.data.codes, 3)
+    assert [[w for w, _ in row] for row in res] == [[words[i] for i in row] for row in wi.tolist()]
+    assert np.array_equal(np.array([[d for _, d in row] for row in res], np.float32).view(np.uint32), wd.view(np.uint32))
