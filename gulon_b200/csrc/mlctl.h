@@ -4,9 +4,10 @@
 // Fewer quantizers make the bound pass cheaper and the survivor evaluation dearer; where the sum is
 // smallest depends on the data, the range and the thresholds, so it is measured.  Every main-stage
 // launch is timed; its cost (ms per 1e9 (row, query) pairs) is fed to `on_measurement`, and the size
-// moves one step (1/8 of the current size) in the direction that last helped.  Two failed probes in a
-// row park the controller at the best size for 24 launches (then 48, 96, ... up to 4096), and once it has
-// parked, probes move by a single quantizer.  Only launches of one shape (tiles, rows) are compared;
+// moves one step in the direction that last helped: an eighth of the current size, a quarter once a probe
+// has paid off and until one fails (the failed quarter step is retried as an eighth from the best size
+// before the other side is tried).  Two failed probes in a row park the controller at the best size for
+// 24 launches (then 48, 96, ... up to 4096), and once it has parked, probes move by a single quantizer.  Only launches of one shape (tiles, rows) are compared;
 // after 8 consecutive measurements of another shape the search restarts from the current size.  A cold
 // controller starts with every quantizer (the bound of round 1b).
 #pragma once
@@ -23,13 +24,15 @@ struct MlController {
   int reversals = 0;         // failed probes since the last success
   int hold = 0;              // launches left before the next probe (parked while > 0)
   int hold_len = 24;
+  bool coarse = false;       // a probe has paid off and none has failed yet: quarter steps
+  bool failed = false;       // a probe has failed since the search (re)started
   bool fine = false;         // parked once: probes move by one quantizer
   long long shape = 0;       // shape key of the launches being compared
   int shape_miss = 0;
 
   int lo() const { return std::min(M, 4); }
   int step_from(int from, int d) const {
-    const int stp = fine ? 1 : std::max(1, from / 8);
+    const int stp = fine ? 1 : std::max(1, from / (coarse ? 4 : 8));
     return std::max(lo(), std::min(M, from + d * stp));
   }
   void restart_search() {
@@ -39,6 +42,8 @@ struct MlController {
     hold = 0;
     hold_len = 24;
     fine = false;
+    coarse = false;
+    failed = false;
   }
   // (re)initialise for a codebook of M quantizers
   void reset(int M_) {
@@ -74,17 +79,23 @@ struct MlController {
       best_cost = cost;
       hint = step_from(best, dir);
     } else if (hint != best && cost < best_cost * 0.985) {
-      best = hint;  // the probe paid off: keep walking
+      best = hint;  // the probe paid off: keep walking, faster while nothing has failed
       best_cost = cost;
       reversals = 0;
       hold_len = 24;
+      if (!failed && !fine) coarse = true;
       hint = step_from(best, dir);
     } else if (hint == best) {
       best_cost = 0.5 * best_cost + 0.5 * cost;
       hint = step_from(best, dir);
+    } else if (coarse) {
+      coarse = false;  // a quarter step overshot: try an eighth from the best size, same direction
+      failed = true;
+      hint = step_from(best, dir);
     } else {
       dir = -dir;  // the probe did not pay off: try the other side of the best
       reversals++;
+      failed = true;
       hint = step_from(best, dir);
     }
     if (hint == best) {
