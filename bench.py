@@ -46,7 +46,8 @@ def parse():
     ap.add_argument("--train-rows", type=int, default=262_144)
     ap.add_argument("--train-iters", type=int, default=8)
     ap.add_argument("--recall-queries", type=int, default=200)
-    ap.add_argument("--cpu-queries", type=int, default=0, help="0 = 2 x host threads")
+    ap.add_argument("--cpu-queries", type=int, default=0,
+                    help="queries of the CPU sample (0 = about 10 s of host work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-recall", action="store_true")
     ap.add_argument("--opt", action="append", default=[], help="library option name=value")
@@ -393,7 +394,9 @@ def main():
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         from oracle import oracle as o
         T = o.num_threads()
-        nq = a.cpu_queries or 2 * T
+        # ~10 s of host work at the c2 shape (about 100 queries/s on 16 cores); every sampled query's ids and
+        # distances are also compared with the GPU's
+        nq = min(Q, a.cpu_queries or max(64, int(64 * T * (3e8 / max(1.0, float(n_local) * M)))))
         cb = pq.codebook()
         hc = codes[:, :n_local].cpu().numpy()
         t0 = time.perf_counter()
