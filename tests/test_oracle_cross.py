@@ -126,3 +126,36 @@ def test_exact_nn_and_normalize_match_numpy(oracle):
     nc = oracle.normalize(X)
     for i in (0, 17, 199):
         assert nc[i].tobytes() == npo.normalize(X[i]).tobytes()
+
+
+def test_wide_ids_match_numpy(oracle):
+    """More than 256 centroids: the C oracle's 16-bit twins (oracle/go_codes.inc compiled for uint16_t)
+    against the numpy restatement, encode / decode / tables / scan, literal and canonical rules."""
+    rng = np.random.default_rng(5)
+    N, D, M, K, Q, k = 260, 7, 3, 300, 3, 6
+    X = _data(rng, N, D)
+    frm, dim, dmax = oracle.subvectors(D, M)
+    cb = np.zeros((M, K, dmax), np.float32)
+    for m in range(M):
+        cb[m, :, :dim[m]] = _data(rng, K, dim[m])
+    cb[2, 299] = cb[2, 7]                                 # a duplicate beyond id 255: tie rule on wide ids
+    cbl = _cb_list(cb, frm, dim)
+    for literal in (True, False):
+        tie = oracle.TIE_LITERAL if literal else oracle.TIE_LOWEST
+        codes_c = oracle.pq_encode(X, cb, tie_mode=tie, nthreads=2)
+        codes_n = npo.pq_encode(X, cbl, literal=literal)
+        assert codes_c.dtype == np.uint16 and (codes_c == codes_n).all()
+    codes = oracle.pq_encode(X, cb, tie_mode=oracle.TIE_LOWEST)
+    assert codes.max() > 255
+    dec = oracle.pq_decode(codes, cb, D)
+    for m in range(M):
+        assert np.array_equal(dec[:, frm[m]:frm[m] + dim[m]], cb[m, codes[m], :dim[m]])
+    qs = _data(rng, Q, D)
+    lut_c = oracle.prepare_query(qs, cb)
+    assert lut_c.tobytes() == npo.prepare_query(qs, cbl).tobytes()
+    for literal in (True, False):
+        mode = oracle.TOPK_LITERAL if literal else oracle.TOPK_CANONICAL
+        ids, ds, sz = oracle.batch_query(lut_c, codes, k, topk_mode=mode, nthreads=2)
+        ref = npo.batch_query(lut_c, codes, k, literal=literal)
+        for q in range(Q):
+            assert ids[q].tolist() == ref[q][0].tolist() and ds[q].tobytes() == ref[q][1].tobytes()
