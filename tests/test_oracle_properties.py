@@ -1,0 +1,177 @@
+"""The reference's OWN test properties, restated with hypothesis against the oracle (CPU only):
+T/KMeansSpec.scala:23-72, T/ProductQuantizerSpec.scala:15-104, T/TopKHeapSpec.scala:16-52,
+T/IndexSpec.scala (exact kNN over decoded vectors).  The reference holds no golden vectors; its
+ScalaCheck properties are the only behaviour its tests pin, so the oracle has to satisfy them in its
+LITERAL mode (java.util.Random tie breaks, binary-heap top-k).  Generators follow T/Generators.scala:
+clusters with centroid and per-dimension scale in [-5, 5], points = centroid + gaussian * scale."""
+import numpy as np
+from hypothesis import given, settings, strategies as st
+
+f32 = np.float32
+
+
+@st.composite
+def gen_vectors(draw, min_d=2, max_d=12):
+    """Generators.genVectorsOfN: k clusters (2..15) of >= 1 points each in d dimensions."""
+    d = draw(st.integers(min_d, max_d))
+    k = draw(st.integers(2, 8))
+    seed = draw(st.integers(0, 2 ** 31 - 1))
+    rng = np.random.default_rng(seed)
+    cents = rng.uniform(-5, 5, (k, d)).astype(f32)
+    scales = rng.uniform(-5, 5, (k, d)).astype(f32)
+    sizes = [draw(st.integers(1, 12)) for _ in range(k)]
+    pts = np.concatenate([cents[i] + rng.standard_normal((n, d)).astype(f32) * scales[i]
+                          for i, n in enumerate(sizes)]).astype(f32)
+    return pts, cents
+
+
+def objective(o, X, C):
+    """KMeansSpec.objective: assign (literal: one Random(0) for the call), float sum of distanceSq."""
+    a = o.assign(X, 0, X.shape[1], C, tie_mode=o.TIE_LITERAL)
+    s = f32(0)
+    for i in range(len(X)):
+        s = f32(s + f32(o.distance_sq(X[i], C[a[i]])))
+    return float(s)
+
+
+def iterate(o, X, C, iters):
+    """KMeans#iterate, G/KMeans.scala:100-106: assignments array reused across iterations."""
+    K, d = C.shape
+    a = np.zeros(len(X), np.int32)
+    for _ in range(iters):
+        a = o.assign(X, 0, d, C, tie_mode=o.TIE_LITERAL, prev=a)
+        C = o.from_assignment(X, 0, d, a, K)
+    return C
+
+
+@settings(max_examples=40, deadline=None)
+@given(gen_vectors())
+def test_compute_clusters_converges(oracle, gv):
+    X, cents = gv
+    r = oracle.compute_clusters(X, 0, X.shape[1], len(cents), 100, seed=0, tie_mode=oracle.TIE_LITERAL)
+    assert r["converged"]
+
+
+@settings(max_examples=40, deadline=None)
+@given(gen_vectors())
+def test_iterate_progresses_towards_minimum(oracle, gv):
+    X, cents = gv
+    K = len(cents)
+    c0, _ = oracle.kmeans_init(X, 0, X.shape[1], K, seed=0)
+    o0 = objective(oracle, X, c0)
+    c = c0
+    prev = o0
+    for iters in (1, 3, 7, 11):
+        c = iterate(oracle, X, c, iters)
+        cur = objective(oracle, X, c)
+        # KMeansSpec asserts o_i >= o_{i+1} on Float sums; allow the rounding of the two sums
+        assert cur <= prev * (1 + 1e-5) + 1e-6, (iters, prev, cur)
+        prev = cur
+
+
+@settings(max_examples=40, deadline=None)
+@given(gen_vectors())
+def test_does_not_get_stuck_when_clusters_are_not_distinct(oracle, gv):
+    X, cents = gv
+    K, d = len(cents), X.shape[1]
+    a0 = np.zeros(len(X), np.int32)                      # all vectors assigned to cluster 0
+    k0 = oracle.from_assignment(X, 0, d, a0, K)          # K - 1 empty clusters: all-zero centroids
+    k1 = iterate(oracle, X, k0, 1)
+    a1 = oracle.assign(X, 0, d, k1, tie_mode=oracle.TIE_LITERAL)
+    if not np.array_equal(a0, a1):
+        assert objective(oracle, X, k0) > objective(oracle, X, k1)
+
+
+@st.composite
+def gen_pq(draw):
+    D = draw(st.integers(2, 14))
+    M = draw(st.integers(1, D))
+    K = draw(st.sampled_from([1, 2, 3, 5, 16, 40]))
+    seed = draw(st.integers(0, 2 ** 31 - 1))
+    rng = np.random.default_rng(seed)
+    from oracle import oracle as o
+    frm, dim, dmax = o.subvectors(D, M)
+    cb = np.zeros((M, K, dmax), f32)
+    for m in range(M):
+        cb[m, :, :dim[m]] = rng.uniform(-5, 5, (K, dim[m]))
+    return D, M, K, cb, rng
+
+
+@settings(max_examples=60, deadline=None)
+@given(gen_pq(), st.integers(1, 20))
+def test_decode_encode_is_idempotent_and_decode_selects_centroids(oracle, pq, n):
+    D, M, K, cb, rng = pq
+    X = rng.uniform(-6, 6, (n, D)).astype(f32)
+    e1 = oracle.pq_encode(X, cb, tie_mode=oracle.TIE_LITERAL)
+    d1 = oracle.pq_decode(e1, cb, D)
+    d2 = oracle.pq_decode(oracle.pq_encode(d1, cb, tie_mode=oracle.TIE_LITERAL), cb, D)
+    assert np.allclose(d1, d2, rtol=1e-3, atol=1e-3)      # TestUtils.nearlyEqualMatrices
+    # "decode selects centroids": codes 0..K-1 decode to the centroids themselves
+    codes = np.tile(np.arange(K, dtype=np.uint8), (M, 1))
+    dec = oracle.pq_decode(codes, cb, D)
+    frm, dim, _ = oracle.subvectors(D, M)
+    for m in range(M):
+        assert np.array_equal(dec[:, frm[m]:frm[m] + dim[m]], cb[m, :, :dim[m]])
+
+
+@settings(max_examples=60, deadline=None)
+@given(gen_pq(), st.integers(1, 12))
+def test_encode_selects_closest_encoding(oracle, pq, n_rand):
+    D, M, K, cb, rng = pq
+    p = rng.uniform(-6, 6, (1, D)).astype(f32)
+    p0 = oracle.pq_decode(oracle.pq_encode(p, cb, tie_mode=oracle.TIE_LITERAL), cb, D)[0]
+    d = np.sqrt(oracle.distance_sq(p[0], p0))
+    rand_codes = rng.integers(0, K, (M, n_rand)).astype(np.uint8)
+    for r in oracle.pq_decode(rand_codes, cb, D):
+        # the score off - 2*dot is not the rounded distance itself: ProductQuantizerSpec allows for that
+        assert d <= np.sqrt(oracle.distance_sq(p[0], r)) * (1 + 1e-4) + 1e-4
+
+
+finite = st.floats(-1e6, 1e6, width=32)
+
+
+@settings(max_examples=150, deadline=None)
+@given(st.lists(st.tuples(st.integers(-1000, 1000), finite), max_size=40, unique_by=lambda kv: kv[1]),
+       st.integers(1, 90))
+def test_heap_gets_first_k_values(oracle, kvs, k):
+    h = oracle.Heap(k)
+    for key, v in kvs:
+        h.update(key, v)
+    ids, ds = h.drain()
+    want = sorted(kvs, key=lambda kv: kv[1])[:k]
+    assert ids.tolist() == [kv[0] for kv in want]
+    assert ds.tolist() == [float(f32(kv[1])) for kv in want]
+
+
+@settings(max_examples=100, deadline=None)
+@given(st.lists(st.lists(st.tuples(st.integers(-1000, 1000), finite), max_size=15), max_size=6),
+       st.integers(1, 60))
+def test_heap_merge(oracle, groups, k):
+    vals = [kv[1] for g in groups for kv in g]
+    if len(set(vals)) != len(vals):
+        return                                             # ties: heap-structure dependent
+    h = oracle.Heap(k)
+    for g in groups:
+        h0 = oracle.Heap(k)
+        for key, v in g:
+            h0.update(key, v)
+        h.merge(h0)
+    ids, ds = h.drain()
+    want = sorted((kv for g in groups for kv in g), key=lambda kv: kv[1])[:k]
+    assert ids.tolist() == [kv[0] for kv in want]
+
+
+@settings(max_examples=40, deadline=None)
+@given(gen_pq(), st.integers(5, 60), st.integers(1, 8))
+def test_index_query_is_exact_knn_over_decoded_vectors(oracle, pq, n, k):
+    """T/IndexSpec.scala: the PQ index returns the exact nearest neighbours of the DECODED vectors (ADC
+    distance == squared distance to the reconstruction, up to fp32 summation order)."""
+    D, M, K, cb, rng = pq
+    X = rng.uniform(-6, 6, (n, D)).astype(f32)
+    codes = oracle.pq_encode(X, cb, tie_mode=oracle.TIE_LOWEST)
+    dec = oracle.pq_decode(codes, cb, D)
+    q = rng.uniform(-6, 6, (1, D)).astype(f32)
+    ids, ds, sz = oracle.pq_query(q, cb, codes, k, topk_mode=oracle.TOPK_LITERAL)
+    ei, ed, es = oracle.exact_nn(dec, q, k, topk_mode=oracle.TOPK_LITERAL)
+    assert sz[0] == es[0] == min(k, n)
+    assert np.allclose(ds[0, :sz[0]], ed[0, :es[0]], rtol=1e-4, atol=1e-4)
