@@ -44,7 +44,7 @@ def iterate(o, X, C, iters):
     return C
 
 
-@settings(max_examples=40, deadline=None)
+@settings(max_examples=40, deadline=None, derandomize=True)
 @given(gen_vectors())
 def test_compute_clusters_converges(oracle, gv):
     X, cents = gv
@@ -52,7 +52,7 @@ def test_compute_clusters_converges(oracle, gv):
     assert r["converged"]
 
 
-@settings(max_examples=40, deadline=None)
+@settings(max_examples=40, deadline=None, derandomize=True)
 @given(gen_vectors())
 def test_iterate_progresses_towards_minimum(oracle, gv):
     X, cents = gv
@@ -69,7 +69,7 @@ def test_iterate_progresses_towards_minimum(oracle, gv):
         prev = cur
 
 
-@settings(max_examples=40, deadline=None)
+@settings(max_examples=40, deadline=None, derandomize=True)
 @given(gen_vectors())
 def test_does_not_get_stuck_when_clusters_are_not_distinct(oracle, gv):
     X, cents = gv
@@ -97,7 +97,7 @@ def gen_pq(draw):
     return D, M, K, cb, rng
 
 
-@settings(max_examples=60, deadline=None)
+@settings(max_examples=60, deadline=None, derandomize=True)
 @given(gen_pq(), st.integers(1, 20))
 def test_decode_encode_is_idempotent_and_decode_selects_centroids(oracle, pq, n):
     D, M, K, cb, rng = pq
@@ -114,7 +114,7 @@ def test_decode_encode_is_idempotent_and_decode_selects_centroids(oracle, pq, n)
         assert np.array_equal(dec[:, frm[m]:frm[m] + dim[m]], cb[m, :, :dim[m]])
 
 
-@settings(max_examples=60, deadline=None)
+@settings(max_examples=60, deadline=None, derandomize=True)
 @given(gen_pq(), st.integers(1, 12))
 def test_encode_selects_closest_encoding(oracle, pq, n_rand):
     D, M, K, cb, rng = pq
@@ -130,7 +130,7 @@ def test_encode_selects_closest_encoding(oracle, pq, n_rand):
 finite = st.floats(-1e6, 1e6, width=32)
 
 
-@settings(max_examples=150, deadline=None)
+@settings(max_examples=150, deadline=None, derandomize=True)
 @given(st.lists(st.tuples(st.integers(-1000, 1000), finite), max_size=40, unique_by=lambda kv: kv[1]),
        st.integers(1, 90))
 def test_heap_gets_first_k_values(oracle, kvs, k):
@@ -143,7 +143,7 @@ def test_heap_gets_first_k_values(oracle, kvs, k):
     assert ds.tolist() == [float(f32(kv[1])) for kv in want]
 
 
-@settings(max_examples=100, deadline=None)
+@settings(max_examples=100, deadline=None, derandomize=True)
 @given(st.lists(st.lists(st.tuples(st.integers(-1000, 1000), finite), max_size=15), max_size=6),
        st.integers(1, 60))
 def test_heap_merge(oracle, groups, k):
@@ -161,7 +161,7 @@ def test_heap_merge(oracle, groups, k):
     assert ids.tolist() == [kv[0] for kv in want]
 
 
-@settings(max_examples=40, deadline=None)
+@settings(max_examples=40, deadline=None, derandomize=True)
 @given(gen_pq(), st.integers(5, 60), st.integers(1, 8))
 def test_index_query_is_exact_knn_over_decoded_vectors(oracle, pq, n, k):
     """T/IndexSpec.scala: the PQ index returns the exact nearest neighbours of the DECODED vectors (ADC
@@ -177,7 +177,7 @@ def test_index_query_is_exact_knn_over_decoded_vectors(oracle, pq, n, k):
     assert np.allclose(ds[0, :sz[0]], ed[0, :es[0]], rtol=1e-4, atol=1e-4)
 
 
-@settings(max_examples=60, deadline=None)
+@settings(max_examples=60, deadline=None, derandomize=True)
 @given(gen_pq(), st.integers(5, 60), st.integers(1, 8))
 def test_sorted_index_queries_encoded_nearest_neighbours(oracle, pq, n, k):
     """T/IndexSpec.scala:24-43: results re-sorted by (distance, rank in the exact answer) name exactly the exact
@@ -201,7 +201,7 @@ def test_sorted_index_queries_encoded_nearest_neighbours(oracle, pq, n, k):
     assert sorted(w for w, _ in actual) == sorted(expected)
 
 
-@settings(max_examples=60, deadline=None)
+@settings(max_examples=60, deadline=None, derandomize=True)
 @given(gen_pq(), st.integers(1, 50))
 def test_query_by_word_finds_word(oracle, pq, n):
     """T/IndexSpec.scala:45-71: querying a row's own decoded vector with k = (largest group of identical
