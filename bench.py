@@ -206,9 +206,10 @@ def main():
     del xt
 
     # (R row shards) x (C query groups) over the ranks: gulon_b200.sharded.shard_plan
-    R, Cq = shard_plan(a.rows, world) if a.row_shards <= 0 else (a.row_shards, world // a.row_shards)
+    n_shards, n_groups = shard_plan(a.rows, world) if a.row_shards <= 0 else \
+        (a.row_shards, world // a.row_shards)
     # this rank's row shard of the database, encoded chunk by chunk (rows independent: no exchange)
-    lo, hi = shard_bounds(a.rows, R)[rank % R]
+    lo, hi = shard_bounds(a.rows, n_shards)[rank % n_shards]
     n_local = hi - lo
     stride = (max(n_local, 1) + 15) // 16 * 16
     codes = torch.zeros((M, stride), dtype=torch.uint8, device=dev)
@@ -248,7 +249,7 @@ def main():
         g.set_option("profile", 0)
         del x
     ix = g.PQIndex.from_device_codes(pq, codes, n_local)
-    sh = ShardedPQIndex(ix, lo, plan=(R, Cq)) if world > 1 else ShardedPQIndex(ix, lo)
+    sh = ShardedPQIndex(ix, lo, plan=(n_shards, n_groups)) if world > 1 else ShardedPQIndex(ix, lo)
     queries = mix.rows(0, Q, stream_seed=1)
 
     def step_dev():
@@ -415,13 +416,13 @@ def main():
             "config": dict(workload(a), sharding=("%d row shard(s) of the code planes x %d query group(s) "
                            "(gulon_b200.sharded.shard_plan: shards keep >= 8M rows); all-gather + "
                            "(distance,id) merge inside a group, all-gather of the slices across groups"
-                           % (R, Cq)) if world > 1 else "single GPU",
+                           % (n_shards, n_groups)) if world > 1 else "single GPU",
                            l2="inputs larger than L2: 300 MB code planes + per-tile lookup tables "
                               "> 126 MB; no flush needed"),
             "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
             # whole job: every query group copies its slice of the batch to each of its R row shards;
             # every rank reads the assembled (ids, distances) back
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": R * Q * D * 4,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n_shards * Q * D * 4,
                     "d2h_bytes_per_step": world * Q * k * 8 + (Q * 4 if world == 1 else 0),
                     "ms_per_step": e2e_ms / a.steps, "ids_equal_device_path": same},
             "gpu_launches": launches,
