@@ -14,7 +14,8 @@ _ROOT = os.path.dirname(_HERE)
 SO_PATH = os.path.join(_HERE, "libgulon_b200.so")
 _SRC_DIR = os.path.join(_HERE, "csrc")
 _SOURCES = ["gulon_b200.cu"]
-_HEADERS = ["common.cuh", "kmeans.cuh", "scan.cuh", "select.cuh", "pscan.cuh", "tcassign.cuh", "kupdate.cuh", "mlctl.h"]
+_HEADERS = ["common.cuh", "kmeans.cuh", "scan.cuh", "select.cuh", "pscan.cuh", "tcassign.cuh", "kupdate.cuh", "mlctl.h",
+            "synth.cuh", "synth_spec.h"]
 
 OK, EINVAL, ECUDA, ENOMEM, ENODEVICE, ECOMM, EUNSUPPORTED, ESTATE = 0, -1, -2, -3, -4, -5, -6, -7
 TIE_LOWEST = 1
@@ -90,6 +91,14 @@ class Progress(C.Structure):
 
 PROGRESS_FN = C.CFUNCTYPE(None, vp, C.POINTER(Progress))
 
+
+class SynthParams(C.Structure):
+    """gulon_synth_params_t == gs_params (csrc/synth_spec.h)."""
+    _fields_ = [("seed", C.c_uint64), ("D", i32), ("centres", i32), ("latent", i32), ("nonneg", i32),
+                ("noise", C.c_float), ("eps", C.c_float), ("span", C.c_float),
+                ("inv_sqrt_latent", C.c_float)]
+
+
 # every symbol include/gulon_b200.h declares: name -> (restype, argtypes)
 SIGNATURES = {
     "gulon_version": (C.c_int, []),
@@ -98,6 +107,8 @@ SIGNATURES = {
     "gulon_set_device": (C.c_int, [i32]),
     "gulon_get_device": (C.c_int, [C.POINTER(i32)]),
     "gulon_device_sync": (C.c_int, []),
+    "gulon_init": (C.c_int, [vp, i32]),
+    "gulon_shutdown": (C.c_int, []),
     "gulon_set_option": (C.c_int, [C.c_char_p, i64]),
     "gulon_get_counter": (C.c_int, [C.c_char_p, C.POINTER(i64)]),
     "gulon_subvectors": (C.c_int, [i32, i32, vp, vp]),
@@ -138,6 +149,12 @@ SIGNATURES = {
     "gulon_pq_query": (C.c_int, [vp, vp, i64, i64, i32, i64, i64, i32, i64, vp, vp, vp]),
     "gulon_pq_query_dev": (C.c_int, [vp, vp, i64, i64, i32, i64, i64, i32, i64, vp, vp, vp, vp]),
     "gulon_topk_merge_dev": (C.c_int, [vp, vp, i32, i64, i32, vp, vp, vp, vp]),
+    "gulon_pq_query_sharded_dev": (C.c_int, [vp, C.POINTER(Comm), C.POINTER(Comm), vp, i64, i64, i32,
+                                             i32, i64, vp, vp, vp, vp]),
+    "gulon_pq_query_sharded": (C.c_int, [vp, C.POINTER(Comm), C.POINTER(Comm), vp, i64, i64, i32, i32,
+                                         i64, vp, vp, vp]),
+    "gulon_synth_tables_dev": (C.c_int, [C.POINTER(SynthParams), vp, vp, vp]),
+    "gulon_synth_rows_dev": (C.c_int, [C.POINTER(SynthParams), i64, i64, i64, vp, vp, vp, i64, vp]),
     "gulon_exact_topk": (C.c_int, [vp, vp, i64, i64, i32, i64, i64, vp, vp, vp]),
     "gulon_rerank": (C.c_int, [vp, vp, i64, i64, vp, i32, i32, vp, vp, vp]),
 }

@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <map>
 #include <memory>
+#include <set>
 
 #include "common.cuh"
 #include "mlctl.h"
@@ -20,8 +21,33 @@
 #include "select.cuh"
 #include "tcassign.cuh"
 #include "kupdate.cuh"
+#include "synth.cuh"
 
 using namespace gulon;
+
+// Scratch that lives in a handle is reused by the next call, which may arrive on another stream (the
+// mutex that guards it is released when the work is ENQUEUED, not when it finishes).  Every user
+// brackets its work with enter()/leave(): a caller on a different stream first waits, on the device,
+// for the previous user's last kernel.  Calls on one stream are ordered by the stream itself.
+struct StreamChain {
+  cudaEvent_t ev = nullptr;
+  cudaStream_t last = nullptr;
+  bool used = false;
+  int enter(cudaStream_t st) {
+    if (used && st != last) GCU(cudaStreamWaitEvent(st, ev, 0));
+    return GULON_OK;
+  }
+  int leave(cudaStream_t st) {
+    if (!ev) GCU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    GCU(cudaEventRecord(ev, st));
+    last = st;
+    used = true;
+    return GULON_OK;
+  }
+  ~StreamChain() {
+    if (ev) cudaEventDestroy(ev);
+  }
+};
 
 // ---- handles --------------------------------------------------------------------------------
 struct gulon_points_s {
@@ -60,8 +86,12 @@ struct gulon_index_s {
   i64 N = 0, ps = 0;
   bool owned = false;
   DevBuf lutW;
-  std::mutex mu;  // guards the scratch below: one query batch in flight per index handle
+  std::mutex mu;  // guards the scratch below while a query batch is being enqueued
+  StreamChain chain;   // ... and orders batches that arrive on different streams (see StreamChain)
   std::mutex mu_host;  // guards the host-call staging buffers
+  std::mutex mu_sh;    // guards the scratch of the sharded query (gulon_pq_query_sharded*)
+  StreamChain chain_sh;
+  DevBuf sh_send, sh_recv, sh_slice, sh_all, sh_q;
   DevBuf h_q, h_ids, h_dists, h_sizes;
   DevBuf lutI, keys, lists, qbuf, ids, dists, sizes, merged;
   DevBuf qlut, mins, qp, boot_tail, plists, pstats, boot_keys, spread, msel, merged2, sufmin;
@@ -91,6 +121,7 @@ struct gulon_index_s {
     if (tm_ev1) cudaEventDestroy(tm_ev1);
     h_q.release(); h_ids.release(); h_dists.release(); h_sizes.release();
     sel.release(); sel_boot.release();
+    sh_send.release(); sh_recv.release(); sh_slice.release(); sh_all.release(); sh_q.release();
   }
 };
 
@@ -193,6 +224,21 @@ int sm_count() {
   }
   return cached;
 }
+
+// Opt-in to > 48 KB of dynamic shared memory.  The attribute is PER DEVICE (and per function): a
+// host that drives several GPUs from one process (gulon_set_device per thread) needs it on each.
+int smem_optin(const void *func, size_t bytes) {
+  static std::mutex mu;
+  static std::set<std::pair<const void *, int>> done;
+  int dev = 0;
+  GCU(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  if (done.count({func, dev})) return GULON_OK;
+  GCU(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  done.insert({func, dev});
+  return GULON_OK;
+}
+#define GOPTIN(kern, bytes) GCHECK(smem_optin(reinterpret_cast<const void *>(kern), (bytes)))
 
 // ---- java.util.Random (JDK javadoc algorithm) -- seeds KMeans.init, G/KMeans.scala:188-196 ----
 struct JRandom {
@@ -361,10 +407,7 @@ int launch_assign_tc_dim(const float *dX, i64 N, i64 ld, const float *cb, const 
   if (tc.prep)
     GLAUNCH(tca::tc_prep_kernel, (unsigned)nsub, 256, 0, st, cb, off, dsubs, ddim, K, dmax, blobs);
   auto kern = tca::tc_assign_kernel<DIM, OutT>;
-  static std::once_flag once;  // one per instantiation
-  std::call_once(once, [&] {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tca::SMEM_BYTES);
-  });
+  GOPTIN(kern, tca::SMEM_BYTES);
   CUtensorMap map;
   GCHECK(make_row_map(dX, N, ld, ncols, tca::TM, &map));
   tca::Params p;
@@ -470,10 +513,7 @@ int launch_assign(const float *dX, i64 N, i64 ld, const float *cb, const float *
   const size_t smem = (size_t)AG_KB * dim * sizeof(float);
   GREQUIRE(smem <= 200 * 1024, "window width %d too large for the generic assignment kernel", dim);
   auto kern = assign_generic_kernel<OutT>;
-  static std::once_flag once;  // one per OutT instantiation
-  std::call_once(once, [&] {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  });
+  GOPTIN(kern, 200 * 1024);
   dim3 grid((unsigned)ceil_div(N, 128), (unsigned)nsub);
   GLAUNCH(kern, grid, 128, smem, st, dX, N, ld, cb, off, K, dmax, dsubs, dfrom, ddim, out,
           out_stride);
@@ -603,10 +643,7 @@ struct Problems {
     CUtensorMap map;
     GCHECK(make_row_map(dX, N, ld, ncols, upd::ROWS, &map));
     auto kern = upd::update_fixed_kernel<DIM>;
-    static std::once_flag once;
-    std::call_once(once, [&] {
-      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, upd::smem_bytes(DIM));
-    });
+    GOPTIN(kern, upd::smem_bytes(DIM));
     upd::Params p;
     p.N = N;
     const int sms = sm_count();
@@ -660,11 +697,7 @@ struct Problems {
       GREQUIRE(need(W) <= 200 * 1024,
                "K=%d x width=%d does not fit the shared-memory segmented sum; use "
                "GULON_UPDATE_RUNNING_MEAN", K, w);
-      static std::once_flag once;
-      std::call_once(once, [] {
-        cudaFuncSetAttribute(update_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             200 * 1024);
-      });
+      GOPTIN(update_partial_kernel, 200 * 1024);
       int B = (int)std::max<i64>(1, std::min<i64>(ceil_div(296, ns), ceil_div(N, 2048)));
       GCHECK(part_sum.ensure((size_t)ns * B * K * dmax * sizeof(float)));
       GCHECK(part_cnt.ensure((size_t)ns * B * K * sizeof(int32_t)));
@@ -713,11 +746,8 @@ struct Problems {
     GREQUIRE(N < (1LL << 31), "N too large for the running-mean update");
     const int tiles = (int)std::max<i64>(1, ceil_div(N, RM_TILE));
     GREQUIRE((size_t)4 * K * sizeof(int) <= 200 * 1024, "K=%d too large for the running-mean update", K);
-    static std::once_flag once;
-    std::call_once(once, [] {
-      cudaFuncSetAttribute(rm_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      cudaFuncSetAttribute(rm_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    });
+    GOPTIN(rm_scatter_kernel, 200 * 1024);
+    GOPTIN(rm_hist_kernel, 200 * 1024);
     return for_each_width(subs, st, [&](int w, const int32_t *ds, int ns) -> int {
       GCHECK(tile_hist.ensure((size_t)ns * tiles * K * sizeof(int32_t)));
       GCHECK(base.ensure((size_t)ns * K * sizeof(int32_t)));
@@ -901,6 +931,43 @@ int train_problems(Problems &pr, gulon_points_t p, const int32_t *seeds, int max
   return GULON_OK;
 }
 
+// Centroid ids must be < K: the reference fails with ArrayIndexOutOfBounds on the first lookup of a
+// bad id (G/Index.scala:401-406); here an id >= K would read outside a table.  One max-reduction
+// over the planes when an index is created.
+template <typename T>
+__global__ void max_code_kernel(const T *__restrict__ codes, i64 ps, i64 N, int M,
+                                unsigned int *__restrict__ out) {
+  unsigned int mx = 0;
+  const i64 total = (i64)M * N;
+  for (i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (i64)gridDim.x * blockDim.x) {
+    const i64 m = t / N, r = t % N;
+    const unsigned int c = codes[m * ps + r];
+    mx = c > mx ? c : mx;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned int v = __shfl_xor_sync(0xffffffffu, mx, o);
+    mx = v > mx ? v : mx;
+  }
+  if ((threadIdx.x & 31) == 0 && mx > 0) atomicMax(out, mx);
+}
+template <typename T>
+int validate_codes_dev(const T *dcodes, i64 ps, i64 N, int M, int K) {
+  if (N <= 0 || (sizeof(T) == 1 && K >= 256) || (sizeof(T) == 2 && K >= 65536)) return GULON_OK;
+  DevBuf mx;
+  int rc = [&]() -> int {
+    GCHECK(mx.ensure(sizeof(unsigned int)));
+    GCU(cudaMemsetAsync(mx.p, 0, sizeof(unsigned int), 0));
+    const unsigned grid = (unsigned)std::max<i64>(1, std::min<i64>(8LL * sm_count(), ceil_div((i64)M * N, 256)));
+    GLAUNCH(max_code_kernel<T>, grid, 256, 0, 0, dcodes, ps, N, M, mx.as<unsigned int>());
+    unsigned int h = 0;
+    GCU(cudaMemcpy(&h, mx.p, sizeof(h), cudaMemcpyDeviceToHost));
+    GREQUIRE((int)h < K, "centroid id %u >= K=%d in the code planes", h, K);
+    return GULON_OK;
+  }();
+  mx.release();
+  return rc;
+}
+
 int make_codebook(int D, int M, int K, gulon_codebook_t *out) {
   GREQUIRE(D >= 1 && M >= 1 && K >= 1, "codebook needs D, M, K >= 1 (D=%d M=%d K=%d)", D, M, K);
   GREQUIRE(M <= D, "more quantizers (%d) than dimensions (%d)", M, D);
@@ -996,11 +1063,7 @@ int fused_lists(gulon_index_t ix, i64 from, i64 until, int G, int k, DevBuf &lis
   const i64 range = until - from;
   const int Q4 = G * 4;
   GREQUIRE(k <= fscan::KMAX, "fused scan supports k <= %d (k=%d)", fscan::KMAX, k);
-  static std::once_flag once;
-  std::call_once(once, [] {
-    cudaFuncSetAttribute(fscan::fused_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         fscan::SMEM_BYTES);
-  });
+  GOPTIN(fscan::fused_scan_kernel, fscan::SMEM_BYTES);
   const int nsm = sm_count();
   int Bs = std::min(G, nsm);
   int S = std::max(1, nsm / Bs);
@@ -1149,17 +1212,14 @@ int scan_batch(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 fr
     GREQUIRE(M <= pscan::MSEL_MAX, "pruned scan supports M <= %d (M=%d)", pscan::MSEL_MAX, M);
     GREQUIRE(FB == 16 || 127 / ML >= 1, "8-bit pruned scan needs <= 127 quantizers in the bound (%d)", ML);
 #define GULON_PSCAN_VARIANTS(X) X(8, 4) X(8, 2) X(8, 1) X(16, 4) X(16, 2)
-    static std::once_flag once;
-    std::call_once(once, [] {
 #define GULON_X(FB_, W_)                                                                        \
-  {                                                                                             \
+  if (FB == FB_ && W == W_) {                                                                   \
     auto kern = pscan::pruned_scan_kernel<FB_, W_>;                                             \
     using CfgT = pscan::Cfg<FB_, W_>;                                                           \
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgT::SMEM_BYTES);  \
+    GOPTIN(kern, CfgT::SMEM_BYTES);                                                             \
   }
-      GULON_PSCAN_VARIANTS(GULON_X)
+    GULON_PSCAN_VARIANTS(GULON_X)
 #undef GULON_X
-    });
     const int T = G / (QT / 4);
     const int RI = pscan::NT * (64 / W);  // rows per work item
     g_last_qt = QT;
@@ -1362,23 +1422,174 @@ int query_dev(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 fro
   if (nq <= 0) return GULON_OK;
   if (k == 0 || until == from) return fill_empty(nq, k, d_ids, d_dists, d_sizes, st);
   std::lock_guard<std::mutex> lock(ix->mu);
+  GCHECK(ix->chain.enter(st));
   const int D = ix->cb->D;
   i64 qb = g_query_batch.load();
   if (qb <= 0) qb = (i64)sm_count() * 16;
   qb = std::min<i64>(round_up(qb, 16), 32768);
-  for (i64 q0 = 0; q0 < nq; q0 += qb) {
-    const i64 nb = std::min<i64>(qb, nq - q0);
-    const float *q = dQ + q0 * ldq;
-    i64 ql = ldq;
-    if (normalize) {
-      GCHECK(ix->qbuf.ensure((size_t)nb * D * sizeof(float)));
-      GCHECK(normalize_dev(q, nb, D, ldq, ix->qbuf.as<float>(), D, st));
-      q = ix->qbuf.as<float>();
-      ql = D;
+  const int rc = [&]() -> int {
+    for (i64 q0 = 0; q0 < nq; q0 += qb) {
+      const i64 nb = std::min<i64>(qb, nq - q0);
+      const float *q = dQ + q0 * ldq;
+      i64 ql = ldq;
+      if (normalize) {
+        GCHECK(ix->qbuf.ensure((size_t)nb * D * sizeof(float)));
+        GCHECK(normalize_dev(q, nb, D, ldq, ix->qbuf.as<float>(), D, st));
+        q = ix->qbuf.as<float>();
+        ql = D;
+      }
+      GCHECK(scan_batch(ix, q, nb, ql, k, from, until, id_offset, d_ids + q0 * k, d_dists + q0 * k,
+                        d_sizes ? d_sizes + q0 : nullptr, st));
     }
-    GCHECK(scan_batch(ix, q, nb, ql, k, from, until, id_offset, d_ids + q0 * k, d_dists + q0 * k,
-                      d_sizes ? d_sizes + q0 : nullptr, st));
+    return GULON_OK;
+  }();
+  GCHECK(ix->chain.leave(st));  // also after a failure: kernels already enqueued still use the scratch
+  return rc;
+}
+
+
+// ---- shard merge (TopKHeap#merge, G/TopKHeap.scala:44-53) -------------------------------------
+// Scratch per DEVICE (a thread bound to another GPU must not touch this one's memory), handed from
+// stream to stream by a StreamChain.
+struct MergeScratch {
+  std::mutex mu;
+  StreamChain chain;
+  DevBuf keys;
+  Selector sel;
+};
+MergeScratch &merge_scratch() {
+  static std::mutex mu;
+  static std::map<int, std::unique_ptr<MergeScratch>> per_dev;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(mu);
+  auto &slot = per_dev[dev];
+  if (!slot) slot.reset(new MergeScratch);
+  return *slot;
+}
+
+// S result sets, shard s at element offset s * shard_stride of d_ids / d_dists, each [nq][k].
+int merge_shards(const int32_t *d_ids, const float *d_dists, int S, i64 shard_stride, i64 nq, int k,
+                 int32_t *d_out_ids, float *d_out_dists, int32_t *d_out_sizes, cudaStream_t st) {
+  if (nq == 0) return GULON_OK;
+  MergeScratch &ms = merge_scratch();
+  std::lock_guard<std::mutex> lock(ms.mu);
+  GCHECK(ms.chain.enter(st));
+  const int rc = [&]() -> int {
+    const i64 stride = round_up((i64)S * k, SEL_CHUNK);
+    const i64 qb = std::max<i64>(1, (256LL << 20) / (stride * 8));
+    GCHECK(ms.keys.ensure((size_t)std::min<i64>(qb, nq) * stride * sizeof(u64)));
+    for (i64 q0 = 0; q0 < nq; q0 += qb) {
+      const i64 nb = std::min<i64>(qb, nq - q0);
+      for (i64 y0 = 0; y0 < nb; y0 += 32768) {
+        const i64 ny = std::min<i64>(32768, nb - y0);
+        dim3 gg((unsigned)ceil_div(stride, 256), (unsigned)ny);
+        GLAUNCH(pack_results_kernel, gg, 256, 0, st, d_ids, d_dists, S, shard_stride, k, q0 + y0,
+                ms.keys.as<u64>() + (size_t)y0 * stride, stride);
+      }
+      u64 *res;
+      i64 rs;
+      GCHECK(ms.sel.run(ms.keys.as<u64>(), stride, nb, k, st, &res, &rs));
+      GCHECK(unpack(res, rs, nb, k, 0, d_out_ids + q0 * k, d_out_dists + q0 * k,
+                    d_out_sizes ? d_out_sizes + q0 : nullptr, st));
+    }
+    return GULON_OK;
+  }();
+  GCHECK(ms.chain.leave(st));
+  return rc;
+}
+
+// ---- sharded PQIndex#batchQuery ---------------------------------------------------------------
+// slices [C][per][2k+1] words (ids | dists | size per query) -> ids / dists / sizes [nq]...
+__global__ void scatter_slices_kernel(const int32_t *__restrict__ all, int C, i64 per, int k, i64 nq,
+                                      int32_t *__restrict__ ids, float *__restrict__ dists,
+                                      int32_t *__restrict__ sizes) {
+  const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nq * (k + 1)) return;
+  const i64 q = t / (k + 1);
+  const int i = (int)(t % (k + 1));
+  const i64 c = q / per, ql = q % per;
+  const int32_t *blk = all + c * per * (2 * k + 1);
+  if (i < k) {
+    ids[q * k + i] = blk[ql * k + i];
+    dists[q * k + i] = __int_as_float(blk[per * k + ql * k + i]);
+  } else if (sizes) {
+    sizes[q] = blk[2 * per * k + ql];
   }
+}
+
+// The queries of this rank's query group are dq[0, n_mine) (already on the device); `per` is the
+// padded slice length every group uses; the whole batch has nq queries.
+int sharded_query(gulon_index_t ix, const gulon_comm_t *row_comm, const gulon_comm_t *query_comm,
+                  const float *dq, i64 n_mine, i64 per, i64 nq, i64 ldq, int k, int normalize,
+                  i64 row_offset, int32_t *d_ids, float *d_dists, int32_t *d_sizes, cudaStream_t st) {
+  const int R = row_comm ? row_comm->world : 1;
+  const int C = query_comm ? query_comm->world : 1;
+  std::lock_guard<std::mutex> lock(ix->mu_sh);
+  GCHECK(ix->chain_sh.enter(st));
+  const int rc = [&]() -> int {
+    // 1. local scan of this rank's row shard: [ids | dists] of the padded slice (global row ids)
+    const size_t blk = (size_t)per * k;  // elements per array
+    GCHECK(ix->sh_send.ensure(2 * blk * 4));
+    int32_t *l_ids = ix->sh_send.as<int32_t>();
+    float *l_dists = reinterpret_cast<float *>(l_ids + blk);
+    GCHECK(ix->sh_slice.ensure((2 * blk + (size_t)per) * 4));
+    int32_t *s_ids = ix->sh_slice.as<int32_t>();
+    float *s_dists = reinterpret_cast<float *>(s_ids + blk);
+    int32_t *s_sizes = s_ids + 2 * blk;
+    const bool direct = C == 1;  // the merged slice IS the result
+    int32_t *m_ids = direct ? d_ids : s_ids;
+    float *m_dists = direct ? d_dists : s_dists;
+    int32_t *m_sizes = direct ? d_sizes : s_sizes;
+    int32_t *q_ids = R > 1 ? l_ids : m_ids;
+    float *q_dists = R > 1 ? l_dists : m_dists;
+    int32_t *q_sizes = R > 1 ? nullptr : m_sizes;
+    if (n_mine < per)
+      GCHECK(fill_empty(per - n_mine, k, q_ids + n_mine * k, q_dists + n_mine * k,
+                        q_sizes ? q_sizes + n_mine : nullptr, st));
+    if (n_mine > 0)
+      GCHECK(query_dev(ix, dq, n_mine, ldq, k, 0, ix->N, normalize, row_offset, q_ids, q_dists,
+                       q_sizes, st));
+    // 2. the R shards of the group exchange their candidates; every rank merges (TopKHeap#merge)
+    if (R > 1) {
+      GREQUIRE(row_comm->allgather, "row_comm has no allgather hook");
+      GCHECK(ix->sh_recv.ensure((size_t)R * 2 * blk * 4));
+      if (row_comm->allgather(row_comm->user, l_ids, ix->sh_recv.p, (i64)(2 * blk * 4), st) != 0)
+        return fail(GULON_ECOMM, "allgather hook failed (row shards)");
+      const int32_t *a_ids = ix->sh_recv.as<int32_t>();
+      const float *a_dists = reinterpret_cast<const float *>(a_ids + blk);
+      GCHECK(merge_shards(a_ids, a_dists, R, (i64)(2 * blk), per, k, m_ids, m_dists, m_sizes, st));
+    }
+    // 3. the C query groups exchange their slices
+    if (C > 1) {
+      GREQUIRE(query_comm->allgather, "query_comm has no allgather hook");
+      const size_t words = 2 * blk + (size_t)per;
+      GCHECK(ix->sh_all.ensure((size_t)C * words * 4));
+      if (query_comm->allgather(query_comm->user, s_ids, ix->sh_all.p, (i64)(words * 4), st) != 0)
+        return fail(GULON_ECOMM, "allgather hook failed (query groups)");
+      const i64 t = nq * (k + 1);
+      GLAUNCH(scatter_slices_kernel, (unsigned)ceil_div(t, 256), 256, 0, st, ix->sh_all.as<int32_t>(),
+              C, per, k, nq, d_ids, d_dists, d_sizes);
+    }
+    return GULON_OK;
+  }();
+  GCHECK(ix->chain_sh.leave(st));
+  return rc;
+}
+
+int check_sharded_args(gulon_index_t ix, const gulon_comm_t *row_comm, const gulon_comm_t *query_comm,
+                       i64 nq, i64 ldq, int k, i64 row_offset) {
+  GREQUIRE(ix, "null handle");
+  GREQUIRE(!ix->codes16, "the sharded query serves 8-bit indexes");
+  GREQUIRE(nq >= 0 && k >= 1, "nq must be >= 0 and k >= 1 (nq=%lld k=%d)", (long long)nq, k);
+  GREQUIRE(ldq >= ix->cb->D, "query leading dimension %lld < dimension %d", (long long)ldq, ix->cb->D);
+  GREQUIRE(!row_comm || (row_comm->world >= 1 && row_comm->rank >= 0 && row_comm->rank < row_comm->world),
+           "bad row_comm rank/world");
+  GREQUIRE(!query_comm ||
+               (query_comm->world >= 1 && query_comm->rank >= 0 && query_comm->rank < query_comm->world),
+           "bad query_comm rank/world");
+  GREQUIRE(row_offset >= 0 && row_offset + ix->N < (1LL << 31),
+           "global row ids are Int in the reference: row_offset + N must be < 2^31");
   return GULON_OK;
 }
 
@@ -1415,6 +1626,35 @@ int gulon_get_device(int32_t *device) {
 }
 int gulon_device_sync(void) {
   GCHECK(need_device());
+  GCU(cudaDeviceSynchronize());
+  return GULON_OK;
+}
+
+int gulon_init(const int32_t *devices, int32_t n) {
+  GREQUIRE(n >= 0 && (devices || n == 0), "bad device list");
+  GCHECK(need_device());
+  int count = 0, cur = 0;
+  GCU(cudaGetDeviceCount(&count));
+  GCU(cudaGetDevice(&cur));
+  for (int i = 0; i < n; i++) {
+    GREQUIRE(devices[i] >= 0 && devices[i] < count, "device %d does not exist (%d visible)", devices[i], count);
+    int major = 0;
+    GCU(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, devices[i]));
+    if (major != 10)
+      return fail(GULON_EUNSUPPORTED, "device %d has compute capability %d.x: libgulon_b200 is built for "
+                  "sm_100a only", devices[i], major);
+    GCU(cudaSetDevice(devices[i]));
+    GCU(cudaFree(nullptr));  // create the context now, not inside the first timed call
+  }
+  GCU(cudaSetDevice(cur));
+  return GULON_OK;
+}
+int gulon_shutdown(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    return GULON_OK;
+  }
   GCU(cudaDeviceSynchronize());
   return GULON_OK;
 }
@@ -1955,6 +2195,7 @@ int gulon_index_create(gulon_codebook_t cb, const uint8_t *codes, int64_t N, int
   if (N > 0)
     GCU(cudaMemcpy2D(d, (size_t)ix->ps, codes, (size_t)plane_stride, (size_t)N, (size_t)cb->M,
                      cudaMemcpyHostToDevice));
+  GCHECK(validate_codes_dev<uint8_t>(ix->codes, ix->ps, N, cb->M, cb->K));
   *out = ix.release();
   return GULON_OK;
 }
@@ -1970,6 +2211,7 @@ int gulon_index_create_dev(gulon_codebook_t cb, const uint8_t *dcodes, int64_t N
   GREQUIRE(cb->K <= 256, "Coder8 needs K <= 256 (K=%d)", cb->K);
   GREQUIRE(N < (1LL << 31), "row ids are Int in the reference: N must be < 2^31");
   GCHECK(need_device());
+  GCHECK(validate_codes_dev<uint8_t>(dcodes, plane_stride, N, cb->M, cb->K));
   gulon_index_s *ix = new gulon_index_s;
   ix->cb = cb;
   ix->codes = dcodes;
@@ -2025,6 +2267,7 @@ int gulon_index_create16_dev(gulon_codebook_t cb, const uint16_t *dcodes, int64_
   GREQUIRE(cb->K <= 65536, "too many clusters: %d", cb->K);
   GREQUIRE(N < (1LL << 31), "row ids are Int in the reference: N must be < 2^31");
   GCHECK(need_device());
+  GCHECK(validate_codes_dev<uint16_t>(dcodes, plane_stride, N, cb->M, cb->K));
   gulon_index_s *ix = new gulon_index_s;
   ix->cb = cb;
   ix->codes16 = dcodes;
@@ -2164,30 +2407,89 @@ int gulon_topk_merge_dev(const int32_t *d_ids, const float *d_dists, int32_t S, 
   GREQUIRE(S >= 1 && nq >= 0 && k >= 1, "bad merge shape S=%d nq=%lld k=%d", S, (long long)nq, k);
   GREQUIRE((d_ids && d_dists && d_out_ids && d_out_dists) || nq == 0, "null argument");
   GCHECK(need_device());
+  return merge_shards(d_ids, d_dists, S, (i64)nq * k, nq, k, d_out_ids, d_out_dists, d_out_sizes,
+                      (cudaStream_t)stream);
+}
+
+int gulon_pq_query_sharded_dev(gulon_index_t ix, const gulon_comm_t *row_comm,
+                               const gulon_comm_t *query_comm, const float *dqueries, int64_t nq,
+                               int64_t ldq, int32_t k, int32_t normalize, int64_t row_offset,
+                               int32_t *d_ids, float *d_dists, int32_t *d_sizes, void *stream) {
+  GCHECK(check_sharded_args(ix, row_comm, query_comm, nq, ldq, k, row_offset));
+  GREQUIRE((dqueries && d_ids && d_dists) || nq == 0, "null argument");
+  GCHECK(need_device());
   if (nq == 0) return GULON_OK;
-  cudaStream_t st = (cudaStream_t)stream;
-  // process-wide scratch guarded by a mutex: merges are short
-  static std::mutex mu;
-  static DevBuf keys;
-  static Selector sel;
-  std::lock_guard<std::mutex> lock(mu);
-  const i64 stride = round_up((i64)S * k, SEL_CHUNK);
-  const i64 qb = std::max<i64>(1, (256LL << 20) / (stride * 8));
-  GCHECK(keys.ensure((size_t)std::min<i64>(qb, nq) * stride * sizeof(u64)));
-  for (i64 q0 = 0; q0 < nq; q0 += qb) {
-    const i64 nb = std::min<i64>(qb, nq - q0);
-    for (i64 y0 = 0; y0 < nb; y0 += 32768) {
-      const i64 ny = std::min<i64>(32768, nb - y0);
-      dim3 gg((unsigned)ceil_div(stride, 256), (unsigned)ny);
-      GLAUNCH(pack_results_kernel, gg, 256, 0, st, d_ids, d_dists, S, nq, k, q0 + y0,
-              keys.as<u64>() + (size_t)y0 * stride, stride);
-    }
-    u64 *res;
-    i64 rs;
-    GCHECK(sel.run(keys.as<u64>(), stride, nb, k, st, &res, &rs));
-    GCHECK(unpack(res, rs, nb, k, 0, d_out_ids + q0 * k, d_out_dists + q0 * k,
-                  d_out_sizes ? d_out_sizes + q0 : nullptr, st));
-  }
+  const int C = query_comm ? query_comm->world : 1, g = query_comm ? query_comm->rank : 0;
+  const i64 per = ceil_div(nq, C), lo = std::min<i64>((i64)g * per, nq), hi = std::min<i64>(lo + per, nq);
+  return sharded_query(ix, row_comm, query_comm, dqueries + lo * ldq, hi - lo, per, nq, ldq, k,
+                       normalize, row_offset, d_ids, d_dists, d_sizes, (cudaStream_t)stream);
+}
+
+int gulon_pq_query_sharded(gulon_index_t ix, const gulon_comm_t *row_comm,
+                           const gulon_comm_t *query_comm, const float *queries, int64_t nq,
+                           int64_t ldq, int32_t k, int32_t normalize, int64_t row_offset,
+                           int32_t *out_ids, float *out_dists, int32_t *out_sizes) {
+  GCHECK(check_sharded_args(ix, row_comm, query_comm, nq, ldq, k, row_offset));
+  GREQUIRE((queries && out_ids && out_dists) || nq == 0, "null argument");
+  GCHECK(need_device());
+  if (nq == 0) return GULON_OK;
+  const int D = ix->cb->D;
+  const int C = query_comm ? query_comm->world : 1, g = query_comm ? query_comm->rank : 0;
+  const i64 per = ceil_div(nq, C), lo = std::min<i64>((i64)g * per, nq), hi = std::min<i64>(lo + per, nq);
+  std::unique_lock<std::mutex> lock(ix->mu_host);
+  // only this group's slice of the batch crosses PCIe; the assembled answer comes back whole
+  GCHECK(ix->h_q.ensure((size_t)std::max<i64>(hi - lo, 1) * D * sizeof(float)));
+  GCHECK(ix->h_ids.ensure((size_t)nq * k * sizeof(int32_t)));
+  GCHECK(ix->h_dists.ensure((size_t)nq * k * sizeof(float)));
+  GCHECK(ix->h_sizes.ensure((size_t)nq * sizeof(int32_t)));
+  if (hi > lo)
+    GCU(cudaMemcpy2DAsync(ix->h_q.p, (size_t)D * 4, queries + lo * ldq, (size_t)ldq * 4, (size_t)D * 4,
+                          (size_t)(hi - lo), cudaMemcpyHostToDevice, 0));
+  GCHECK(sharded_query(ix, row_comm, query_comm, ix->h_q.as<float>(), hi - lo, per, nq, D, k, normalize,
+                       row_offset, ix->h_ids.as<int32_t>(), ix->h_dists.as<float>(),
+                       ix->h_sizes.as<int32_t>(), 0));
+  GCU(cudaMemcpyAsync(out_ids, ix->h_ids.p, (size_t)nq * k * sizeof(int32_t), cudaMemcpyDeviceToHost, 0));
+  GCU(cudaMemcpyAsync(out_dists, ix->h_dists.p, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, 0));
+  if (out_sizes)
+    GCU(cudaMemcpyAsync(out_sizes, ix->h_sizes.p, (size_t)nq * sizeof(int32_t), cudaMemcpyDeviceToHost, 0));
+  GCU(cudaStreamSynchronize(0));
+  return GULON_OK;
+}
+
+/* Synthetic data of SURVEY.md 8d (benchmark / test tooling; CPU twin: oracle/synth.c). */
+int gulon_synth_tables_dev(const gulon_synth_params_t *prm, float *d_centres, float *d_map, void *stream) {
+  GREQUIRE(prm && prm->D >= 1 && prm->centres >= 0 && prm->latent >= 0 && prm->latent <= synth::LMAX,
+           "bad synth parameters");
+  GREQUIRE(prm->centres == 0 || d_centres, "null centre table");
+  GREQUIRE(prm->latent == 0 || d_map, "null map table");
+  GCHECK(need_device());
+  if (prm->centres == 0) return GULON_OK;
+  gs_params p;
+  static_assert(sizeof(gs_params) == sizeof(gulon_synth_params_t), "synth parameter layouts differ");
+  memcpy(&p, prm, sizeof(p));
+  const i64 W = p.latent > 0 ? p.latent : p.D;
+  const i64 total = (i64)p.centres * W + (i64)p.latent * p.D;
+  GLAUNCH(synth::tables_kernel, (unsigned)std::min<i64>(ceil_div(total, 256), 4096), 256, 0,
+          (cudaStream_t)stream, p, d_centres, d_map);
+  return GULON_OK;
+}
+
+int gulon_synth_rows_dev(const gulon_synth_params_t *prm, int64_t stream_id, int64_t lo, int64_t n,
+                         const float *d_centres, const float *d_map, float *d_out, int64_t ld,
+                         void *stream) {
+  GREQUIRE(prm && prm->D >= 1 && prm->centres >= 0 && prm->latent >= 0 && prm->latent <= synth::LMAX,
+           "bad synth parameters");
+  GREQUIRE(n >= 0 && lo >= 0 && ld >= prm->D && stream_id >= 0, "bad synth row range");
+  GREQUIRE(n == 0 || d_out, "null output");
+  GREQUIRE(prm->centres == 0 || d_centres, "null centre table");
+  GREQUIRE(prm->latent == 0 || d_map, "null map table");
+  GCHECK(need_device());
+  if (n == 0) return GULON_OK;
+  gs_params p;
+  memcpy(&p, prm, sizeof(p));
+  const unsigned grid = (unsigned)std::min<i64>(ceil_div(n, synth::ROWS), 16LL * sm_count());
+  GLAUNCH(synth::rows_kernel, grid, 256, 0, (cudaStream_t)stream, p, (i64)stream_id, (i64)lo, (i64)n,
+          d_centres, d_map, d_out, (i64)ld);
   return GULON_OK;
 }
 

@@ -101,10 +101,12 @@ __global__ void gather_lists_kernel(const u64 *__restrict__ lists, int S, i64 ro
   }
 }
 
-// (ids, dists) [S][rows][k] -> keys [.][stride] for result rows q_base + blockIdx.y; id < 0
-// marks an empty slot
+// (ids, dists) of S shards, shard s at element offset s * shard_stride, each [rows][k] -> keys
+// [.][stride] for result rows q_base + blockIdx.y; id < 0 marks an empty slot.  shard_stride =
+// rows * k for plain [S][rows][k] arrays; the all-gathered [ids | dists] blocks of the sharded query
+// use 2 * rows * k.
 __global__ void pack_results_kernel(const int32_t *__restrict__ ids,
-                                    const float *__restrict__ dists, int S, i64 rows, int k,
+                                    const float *__restrict__ dists, int S, i64 shard_stride, int k,
                                     i64 q_base, u64 *__restrict__ keys, i64 stride) {
   const i64 q = q_base + blockIdx.y;
   for (i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x; t < stride;
@@ -112,7 +114,7 @@ __global__ void pack_results_kernel(const int32_t *__restrict__ ids,
     u64 v = KEY_SENT;
     if (t < (i64)S * k) {
       int s = (int)(t / k), i = (int)(t % k);
-      i64 at = ((i64)s * rows + q) * k + i;
+      i64 at = (i64)s * shard_stride + q * k + i;
       int32_t id = ids[at];
       if (id >= 0) v = make_key(dists[at], (uint32_t)id);
     }

@@ -62,42 +62,59 @@ class TorchComm:
         self.device = torch.device(device)
         self.calls = {"allreduce_f32": 0, "allreduce_i32": 0, "allgather": 0}
 
-        def ar_f32(_u, buf, n, _stream):
-            return self._allreduce(buf, n, "<f4", "allreduce_f32")
+        def ar_f32(_u, buf, n, stream):
+            return self._allreduce(buf, n, "<f4", "allreduce_f32", stream)
 
-        def ar_i32(_u, buf, n, _stream):
-            return self._allreduce(buf, n, "<i4", "allreduce_i32")
+        def ar_i32(_u, buf, n, stream):
+            return self._allreduce(buf, n, "<i4", "allreduce_i32", stream)
 
-        def ag(_u, send, recv, nbytes, _stream):
+        def ag(_u, send, recv, nbytes, stream):
             try:
-                s = _view(send, nbytes, "|u1", self.device)
-                r = _view(recv, nbytes * self.world, "|u1", self.device)
-                dist.all_gather_into_tensor(r, s, group=self.group)
+                with self._on(stream):
+                    s = _view(send, nbytes, "|u1", self.device)
+                    r = _view(recv, nbytes * self.world, "|u1", self.device)
+                    dist.all_gather_into_tensor(r, s, group=self.group)
                 self.calls["allgather"] += 1
+                self.bytes["allgather"] += int(nbytes)
                 return 0
-            except Exception:  # surfaced by the library as GULON_EINVAL "hook failed"
+            except Exception:  # surfaced by the library as GULON_ECOMM "hook failed"
                 return 1
 
-        def ar_i64(_u, buf, n, _stream):
-            return self._allreduce(buf, n, "<i8", "allreduce_i64")
+        def ar_i64(_u, buf, n, stream):
+            return self._allreduce(buf, n, "<i8", "allreduce_i64", stream)
 
-        def ar_max(_u, buf, n, _stream):
-            return self._allreduce(buf, n, "<f4", "allreduce_max_f32", op=dist.ReduceOp.MAX)
+        def ar_max(_u, buf, n, stream):
+            return self._allreduce(buf, n, "<f4", "allreduce_max_f32", stream, op=dist.ReduceOp.MAX)
 
         self.calls["allreduce_i64"] = 0
         self.calls["allreduce_max_f32"] = 0
+        self.bytes = {k: 0 for k in self.calls}      # payload per rank, summed over the calls
         self._cbs = (N.Comm.ALLREDUCE_F32(ar_f32), N.Comm.ALLREDUCE_I32(ar_i32), N.Comm.ALLGATHER(ag),
                      N.Comm.ALLREDUCE_I64(ar_i64), N.Comm.ALLREDUCE_MAX_F32(ar_max))
         self.struct = N.Comm(self.rank, self.world, self._cbs[0], self._cbs[1], self._cbs[2], None,
                              self._cbs[3], self._cbs[4])
 
-    def _allreduce(self, buf, n, typestr, name, op=None):
+    def _on(self, stream):
+        """The hooks must enqueue on the library's stream: make it torch's current stream for the call
+        (NCCL orders its own stream against the current one).  Host buffers (gloo) need nothing."""
+        import contextlib
+        import torch
+        if self.device.type != "cuda":
+            return contextlib.nullcontext()
+        cur = torch.cuda.current_stream(self.device)
+        if int(stream or 0) == cur.cuda_stream:
+            return contextlib.nullcontext()
+        return torch.cuda.stream(torch.cuda.ExternalStream(int(stream or 0), device=self.device))
+
+    def _allreduce(self, buf, n, typestr, name, stream=None, op=None):
         try:
             if n > 0:
-                t = _view(buf, n, typestr, self.device)
-                self.dist.all_reduce(t, op=op if op is not None else self.dist.ReduceOp.SUM,
-                                     group=self.group)
+                with self._on(stream):
+                    t = _view(buf, n, typestr, self.device)
+                    self.dist.all_reduce(t, op=op if op is not None else self.dist.ReduceOp.SUM,
+                                         group=self.group)
             self.calls[name] += 1
+            self.bytes[name] += int(n) * int(typestr[-1])
             return 0
         except Exception:
             return 1
@@ -123,12 +140,43 @@ def merge_topk_host(ids, dists, k):
 
 
 class NativeOps:
-    """The device ops of the sharded scan: the CUDA library (the only product implementation)."""
+    """The device ops of the sharded scan: the CUDA library (the only product implementation).
+    `ShardedPQIndex` drives it through ONE C entry point, gulon_pq_query_sharded[_dev] (local scan ->
+    allgather hook -> (distance, id) merge -> allgather of the query slices), so a JVM host gets the
+    same multi-GPU path without Python; `local_query` / `merge` remain for callers that compose the
+    steps themselves."""
 
     def __init__(self, index):
         import torch
         self.index = index
         self.device = torch.device("cuda", torch.cuda.current_device())
+
+    def sharded_query(self, k, queries, row_comm, query_comm, row_offset, normalize=False):
+        """queries: CUDA float32 [Q][D] tensor -> (ids, dists, sizes) CUDA tensors; or a host array /
+        CPU tensor -> numpy arrays (only this rank's query slice crosses PCIe)."""
+        import torch
+        rc = C.byref(row_comm.struct) if row_comm is not None else None
+        qc = C.byref(query_comm.struct) if query_comm is not None else None
+        if isinstance(queries, torch.Tensor) and queries.is_cuda:
+            q = queries
+            nq = q.shape[0]
+            ids = torch.empty((nq, k), dtype=torch.int32, device=q.device)
+            ds = torch.empty((nq, k), dtype=torch.float32, device=q.device)
+            sz = torch.empty((nq,), dtype=torch.int32, device=q.device)
+            ld = q.stride(0) if nq > 1 else max(q.shape[1], 1)
+            N.check(N.lib().gulon_pq_query_sharded_dev(
+                self.index.handle, rc, qc, q.data_ptr(), nq, ld, k, int(bool(normalize)), row_offset,
+                ids.data_ptr(), ds.data_ptr(), sz.data_ptr(), torch.cuda.current_stream(q.device).cuda_stream))
+            return ids, ds, sz
+        q = queries.numpy() if isinstance(queries, torch.Tensor) else np.ascontiguousarray(queries, np.float32)
+        nq = q.shape[0]
+        ids = np.empty((nq, k), np.int32)
+        ds = np.empty((nq, k), np.float32)
+        sz = np.empty((nq,), np.int32)
+        N.check(N.lib().gulon_pq_query_sharded(
+            self.index.handle, rc, qc, q.ctypes.data, nq, q.strides[0] // 4 if nq > 1 else q.shape[1], k,
+            int(bool(normalize)), row_offset, ids.ctypes.data, ds.ctypes.data, sz.ctypes.data))
+        return ids, ds, sz
 
     def local_query(self, k, queries, id_offset):
         return self.index.batch_query_dev(k, queries, id_offset=id_offset)
@@ -195,6 +243,13 @@ class ShardedPQIndex:
             self.col_group = cols[self.row_shard]
         self.row_offset = int(row_offset)
         self.ops = ops if ops is not None else NativeOps(local_index)
+        self.row_comm = self.col_comm = None
+        if isinstance(self.ops, NativeOps) and self.world > 1:
+            # exchange hooks of the C entry point, one gulon_comm_t per process group
+            if self.R > 1:
+                self.row_comm = TorchComm(group=self.row_group, device=self.ops.device)
+            if self.C > 1:
+                self.col_comm = TorchComm(group=self.col_group, device=self.ops.device)
 
     def query_slice(self, Q):
         """rows [lo, hi) of a Q-query batch this rank's query group answers, and the padded slice length."""
@@ -206,6 +261,9 @@ class ShardedPQIndex:
         """queries: the same [Q][D] tensor on every rank (a host tensor is sliced before it is copied to
         the device).  Returns merged (ids, dists, sizes) for the whole batch on every rank."""
         import torch
+        if isinstance(self.ops, NativeOps):
+            return self.ops.sharded_query(k, queries, self.row_comm, self.col_comm, self.row_offset)
+        # the same orchestration spelled out over stand-in ops (CPU tests of the host logic)
         Q = queries.shape[0]
         lo, hi, per = self.query_slice(Q)
         mine = queries[lo:hi]
@@ -222,8 +280,6 @@ class ShardedPQIndex:
             self.dist.all_gather_into_tensor(ids_all, ids.contiguous(), group=self.row_group)
             self.dist.all_gather_into_tensor(ds_all, ds.contiguous(), group=self.row_group)
             ids, ds, sz = self.ops.merge(ids_all.view(self.R, per, k), ds_all.view(self.R, per, k), k)
-        elif self.world == 1:
-            return self.ops.merge(ids.unsqueeze(0), ds.unsqueeze(0), k)
         if self.C > 1:
             out = []
             for t in (ids, ds, sz):

@@ -110,6 +110,11 @@ int gulon_device_count(int32_t *n);
 int gulon_set_device(int32_t device); /* device used by the calling thread's later calls */
 int gulon_get_device(int32_t *device);
 int gulon_device_sync(void);
+/* Optional: validates the devices a host will use (they must exist and be sm_100) and creates their
+ * contexts up front; the calling thread's current device is unchanged.  gulon_shutdown waits for the
+ * current device's outstanding work.  Handles are destroyed explicitly, not by gulon_shutdown. */
+int gulon_init(const int32_t *devices, int32_t n);
+int gulon_shutdown(void);
 /* Tuning options (results never depend on them).  Scan: "scan_impl" (GULON_SCAN_*), "query_batch",
  * "pruned_min_rows" (ranges shorter than this use the exact kernel; default 262144), "boot_rows"
  * (0 = range / 64 in whole 8192-row chunks, clamped to [8192, 32768]), "pruned_bits" (0 auto | 8 | 16), "pruned_words"
@@ -248,10 +253,42 @@ int gulon_pq_query_dev(gulon_index_t ix, const float *dqueries, int64_t nq, int6
  * TopKHeap#merge across shards (G/TopKHeap.scala:44-53; T/TopKHeapSpec.scala:33-52): merges S
  * result sets laid out [S][nq][k] (as produced by an all-gather of per-rank gulon_pq_query_dev
  * outputs) into [nq][k] by (distance, id).  Device pointers.
+ *
+ * Threading: handles may be used from several threads and streams.  The scratch memory inside a
+ * handle (and the per-device scratch of this merge) serves one call at a time: calls are serialised
+ * by a mutex while they enqueue, and a call that arrives on a DIFFERENT stream than the previous one
+ * first waits on the device (cudaStreamWaitEvent) for the previous call's last kernel.  Concurrent
+ * callers therefore get correct results but no overlap on one handle; use one index handle per
+ * stream for overlap.  A handle belongs to the device that was current when it was created.
  */
 int gulon_topk_merge_dev(const int32_t *d_ids, const float *d_dists, int32_t S, int64_t nq,
                          int32_t k, int32_t *d_out_ids, float *d_out_dists, int32_t *d_out_sizes,
                          void *stream);
+
+/*
+ * PQIndex#batchQuery over an index whose rows are sharded across processes (one process per GPU).
+ * The reference merges per-range heaps in GroupedIndex#query (G/Index.scala:273-281) with
+ * TopKHeap#merge (G/TopKHeap.scala:44-53); this entry point is that merge across GPUs:
+ *   1. this rank scans ITS row shard (`ix`; global row id = local id + row_offset) for the queries of
+ *      its query group;
+ *   2. row_comm->allgather exchanges the k candidates per query between the ranks that hold the row
+ *      shards of one copy of the index (80 B per query, rank and k = 10); every rank merges them by
+ *      (distance, id);
+ *   3. query_comm->allgather (optional) assembles the batch when the ranks are also split into query
+ *      groups: group g = query_comm->rank answers queries [g*per, (g+1)*per), per = ceil(nq / groups).
+ * row_comm / query_comm may be NULL (or world == 1) when that dimension is not split.  EVERY rank
+ * passes the same batch and receives the whole answer.  The hooks receive device buffers and the
+ * stream; a failing hook gives GULON_ECOMM.  _dev: device pointers, asynchronous on `stream`.
+ * The host form copies only this rank's query slice to the device.
+ */
+int gulon_pq_query_sharded_dev(gulon_index_t ix, const gulon_comm_t *row_comm,
+                               const gulon_comm_t *query_comm, const float *dqueries, int64_t nq,
+                               int64_t ldq, int32_t k, int32_t normalize, int64_t row_offset,
+                               int32_t *d_ids, float *d_dists, int32_t *d_sizes, void *stream);
+int gulon_pq_query_sharded(gulon_index_t ix, const gulon_comm_t *row_comm,
+                           const gulon_comm_t *query_comm, const float *queries, int64_t nq,
+                           int64_t ldq, int32_t k, int32_t normalize, int64_t row_offset,
+                           int32_t *out_ids, float *out_dists, int32_t *out_sizes);
 
 /* Index.exactNearestNeighbours, G/Index.scala:209-229 (+ MathUtils.distanceSq, G/MathUtils.scala:85-95). */
 int gulon_exact_topk(gulon_points_t p, const float *queries, int64_t nq, int64_t ldq, int32_t k,
@@ -267,6 +304,24 @@ int gulon_exact_topk(gulon_points_t p, const float *queries, int64_t nq, int64_t
 int gulon_rerank(gulon_points_t p, const float *queries, int64_t nq, int64_t ldq,
                  const int32_t *cand_ids, int32_t R, int32_t k, int32_t *out_ids,
                  float *out_dists, int32_t *out_sizes);
+
+/* ---- synthetic data (benchmark / test tooling; not part of the reference path) --------------- */
+/*
+ * The data sets of the benchmark configurations as a pure function of (seed, stream,
+ * row, column): gulon_b200/csrc/synth_spec.h.  The CPU twin (oracle/synth.c) gives identical bits, so
+ * bench.py's reference arm rebuilds on host cores the very index the GPU arm measures.  Tables:
+ * d_centres [centres][latent or D], d_map [latent][D].  Rows [lo, lo+n) of stream `stream_id` ->
+ * d_out [n][ld].
+ */
+typedef struct gulon_synth_params {
+  uint64_t seed;
+  int32_t D, centres, latent, nonneg;
+  float noise, eps, span, inv_sqrt_latent;
+} gulon_synth_params_t;
+int gulon_synth_tables_dev(const gulon_synth_params_t *prm, float *d_centres, float *d_map, void *stream);
+int gulon_synth_rows_dev(const gulon_synth_params_t *prm, int64_t stream_id, int64_t lo, int64_t n,
+                         const float *d_centres, const float *d_map, float *d_out, int64_t ld,
+                         void *stream);
 
 #ifdef __cplusplus
 }

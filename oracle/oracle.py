@@ -18,7 +18,8 @@ TOPK_LITERAL, TOPK_CANONICAL = 0, 1
 
 
 def build(force=False):
-    srcs = [os.path.join(_HERE, f) for f in ("gulon_oracle.c", "go_codes.inc")]
+    srcs = [os.path.join(_HERE, f) for f in ("gulon_oracle.c", "go_codes.inc", "synth.c",
+                                             "../gulon_b200/csrc/synth_spec.h")]
     if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
     return _SO
@@ -391,3 +392,34 @@ def grouped_query(queries, cents, offsets, n, cb, codes, k, strategy, normalized
             ids[qi, j] = i
             ds[qi, j] = np.float32(d)
     return ids, ds, sz
+
+
+# ---- CPU twin of the synthetic-data generator (oracle/synth.c; spec: gulon_b200/csrc/synth_spec.h) ----
+class SynthParams(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("D", i32), ("centres", i32), ("latent", i32), ("nonneg", i32),
+                ("noise", C.c_float), ("eps", C.c_float), ("span", C.c_float),
+                ("inv_sqrt_latent", C.c_float)]
+
+
+class SynthMixture:
+    """Same data as gulon_b200.synth.Mixture, on host cores (identical bits)."""
+
+    def __init__(self, D, centres=4096, noise=0.5, seed=20261018, nonneg=False, span=1.0, latent=32,
+                 eps=0.05):
+        L = latent if (latent and centres > 0) else 0
+        inv = np.float32(1.0 / np.sqrt(np.float64(L))) if L else np.float32(0.0)
+        self.p = SynthParams(int(seed), int(D), int(centres), int(L), int(bool(nonneg)), float(noise),
+                             float(eps), float(span), float(inv))
+        self.D = D
+        W = L if L > 0 else D
+        self.c = np.zeros((max(centres, 1), W), np.float32)
+        self.P = np.zeros((max(L, 1), D), np.float32)
+        lib().go_synth_tables(C.byref(self.p), _p(self.c), _p(self.P))
+
+    def rows(self, lo, hi, stream_seed=0, out=None, nthreads=0):
+        n = hi - lo
+        if out is None:
+            out = np.empty((n, self.D), np.float32)
+        lib().go_synth_rows(C.byref(self.p), i64(stream_seed), i64(lo), i64(n), _p(self.c), _p(self.P),
+                            _p(out), i64(out.strides[0] // 4 if n > 0 else self.D), i32(nthreads))
+        return out
