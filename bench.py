@@ -8,17 +8,32 @@ recall@10 on a 10M x 300-d PQ index; encode vectors/sec as a secondary figure).
 A "step" is one PQIndex.batchQuery of the whole query batch (100k queries, top-10) over the
 index: ADC lookup-table build + uint8 code scan + top-k (+ all-gather merge when sharded).
 `value` is timed with the queries and the index resident in HBM; `e2e` goes through the host
-C-ABI call (gulon_pq_query) with host query/result buffers.  Data are synthetic
-(word-embedding-shaped Gaussian mixture, gulon_b200/synth.py), codebooks are trained by the
-library itself.  Between timed steps nothing is cached on purpose: the code planes (300 MB) and the
-lookup tables of a query batch (> 70 MB per 2368-query tile) exceed the 126 MB L2 together, see
-config.l2.
+C-ABI call (gulon_pq_query / gulon_pq_query_sharded) with host query/result buffers.  Data are
+synthetic (gulon_b200/csrc/synth_spec.h: a pure function of seed, row and column, identical on the
+device and on host cores), codebooks are trained by the library itself.  Between timed steps
+nothing is cached on purpose: the code planes (300 MB) and the lookup tables of a query batch
+(> 70 MB per 2368-query tile) exceed the 126 MB L2 together, see config.l2.
+
+Besides the headline the line carries, each with its own roofline / CPU baseline:
+  encode      resident and end-to-end (host buffers) encode rates, oracle encode on host cores
+  train_c3    configs[2]: k-means codebook training over all rows, 25 Lloyd iterations, rows sharded
+              over the ranks with one all-reduce of sums / counts per iteration (world > 1)
+  row_sharded configs[3]-shaped (world > 1): 12.5M x 128-d rows PER GPU, m = 16, code planes sharded by
+              rows, NCCL all-gather + (distance, id) merge of every rank's k candidates, checked
+              against the oracle on a query sample
+  rerank_c5   configs[4]-shaped: 1M x 1000-d, m = 100, PQ top-R candidates + exact fp32 re-rank
+
+The reference arm (`--impl reference`) rebuilds THE SAME index on host cores -- same synthetic rows,
+the oracle's k-means and encode (bit-identical to the GPU's by the parity tests; `index_digest` in
+both lines proves it for the run) -- and times the reference's prepareQuery + batchQuery on it.
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -30,6 +45,7 @@ if ROOT not in sys.path:
 
 METRIC = "queries/sec at fixed recall@10 on 10Mx300-d PQ index"
 UNIT = "queries/s"
+SEED = 20261018
 
 
 def parse():
@@ -50,17 +66,69 @@ def parse():
                     help="queries of the CPU sample (0 = about 10 s of host work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-recall", action="store_true")
+    ap.add_argument("--no-extra-legs", action="store_true",
+                    help="headline only: skip train_c3 / row_sharded / rerank_c5 and the encode e2e/cpu legs")
     ap.add_argument("--opt", action="append", default=[], help="library option name=value")
     ap.add_argument("--row-shards", type=int, default=0,
-                    help="row shards R of the code planes (0 = gulon_b200.sharded.shard_plan); the other "
-                         "factor of the world size splits the query batch")
+                    help="row shards R of the code planes (0 = shard_plan); the other factor of the "
+                         "world size splits the query batch")
+    ap.add_argument("--c3-iters", type=int, default=25)
+    ap.add_argument("--rs-rows-per-gpu", type=int, default=12_500_000)
+    ap.add_argument("--rs-queries", type=int, default=100_000)
+    ap.add_argument("--c5-rows", type=int, default=1_000_000)
+    ap.add_argument("--c5-queries", type=int, default=10_000)
+    ap.add_argument("--c5-candidates", type=int, default=100)
     return ap.parse_args()
 
 
-def workload(a):
-    return {"workload": "configs[1]: %dx%d-d word-embedding-shaped synthetic vectors, PQ m=%dx256, "
-                        "top-%d query batch of %d" % (a.rows, a.dim, a.m, a.k, a.queries),
-            "rows": a.rows, "dim": a.dim, "m": a.m, "clusters": 256, "k": a.k, "queries": a.queries}
+def shard_plan(n_rows, world, min_rows_per_shard=8_000_000):
+    """(R row shards, C query groups), R * C == world -- the rule of gulon_b200.sharded.shard_plan,
+    restated so that the reference arm prints the same `config` without importing the package."""
+    R = 1
+    for r in range(1, world + 1):
+        if world % r == 0 and n_rows // r >= min_rows_per_shard:
+            R = r
+    return R, world // R
+
+
+def config_of(a, world):
+    """Identical in both arms (the driver compares them)."""
+    R, Cq = shard_plan(a.rows, world) if a.row_shards <= 0 else (a.row_shards, world // a.row_shards)
+    c2 = (a.rows, a.dim, a.m, a.k, a.queries) == (10_000_000, 300, 30, 10, 100_000)
+    return {"workload": "%s: %dx%d-d word-embedding-shaped synthetic vectors, PQ m=%dx256, top-%d query "
+                        "batch of %d" % ("configs[1]" if c2 else "custom shape (not a BASELINE config)",
+                                         a.rows, a.dim, a.m, a.k, a.queries),
+            "rows": a.rows, "dim": a.dim, "m": a.m, "clusters": 256, "k": a.k, "queries": a.queries,
+            "data": "gulon_b200/csrc/synth_spec.h seed %d: 4096-centre mixture in a 32-d latent space mapped "
+                    "to %d-d; queries = stream 1 of the same mixture" % (SEED, a.dim),
+            "codebook": "trained on rows [0, %d), %d Lloyd iterations, running-mean update, ties to the "
+                        "lowest index" % (min(a.train_rows, a.rows), a.train_iters),
+            "sharding": ("%d row shard(s) of the code planes x %d query group(s); all-gather + (distance,id) "
+                         "merge inside a group, all-gather of the slices across groups" % (R, Cq))
+            if world > 1 else "single GPU",
+            "l2": "inputs larger than L2: code planes (%d MB) + per-tile lookup tables > 126 MB; no flush "
+                  "needed" % (a.rows * a.m // 1_000_000)}
+
+
+def index_digest(codebook, codes):
+    h = hashlib.sha256()
+    h.update(np.ascontiguousarray(codebook, np.float32).tobytes())
+    h.update(np.ascontiguousarray(codes).tobytes())
+    return h.hexdigest()[:16]
+
+
+def probe_jvm():
+    """is there a JVM toolchain on this box?"""
+    out = {}
+    for tool, arg in (("java", "-version"), ("javac", "-version"), ("scala", "-version"), ("sbt", "--version")):
+        try:
+            r = subprocess.run([tool, arg], capture_output=True, text=True, timeout=20)
+            out[tool] = ((r.stderr or r.stdout).strip().splitlines() or ["?"])[0][:80]
+        except FileNotFoundError:
+            out[tool] = "not found"
+        except Exception as e:  # pragma: no cover
+            out[tool] = "error: %s" % type(e).__name__
+    return out
 
 
 # ---- clocks -------------------------------------------------------------------------------
@@ -114,127 +182,509 @@ class ClockSampler:
 
 
 # ---- reference arm: the reference algorithm (C restatement; no JVM in the image) on host cores ---
+def build_index_cpu(a, o, T):
+    """The index of the GPU arm, rebuilt on host cores: same synthetic rows, the oracle's
+    ProductQuantizer.apply (seed = quantizer index, running mean, lowest-index ties) and #encode.
+    Cached under the temp directory: the driver runs this arm once per GPU count on the same box."""
+    rows, D, M = a.rows, a.dim, a.m
+    tag = "gulon_ref_index_%dx%d_m%d_t%dx%d_s%d" % (rows, D, M, a.train_rows, a.train_iters, SEED)
+    for base in ("/dev/shm", tempfile.gettempdir()):
+        path = os.path.join(base, tag + ".npz")
+        if os.path.exists(path):
+            try:
+                z = np.load(path)
+                return z["cb"], z["codes"], "cache hit (%s)" % path, 0.0
+            except Exception:
+                pass
+    t0 = time.perf_counter()
+    mix = o.SynthMixture(D, seed=SEED)
+    xt = mix.rows(0, min(a.train_rows, rows), nthreads=T)
+    cb, _, _ = o.pq_train(xt, M, 256, a.train_iters, tie_mode=o.TIE_LOWEST, nthreads=T)
+    del xt
+    codes = np.empty((M, rows), np.uint8)
+    CH = 250_000
+    buf = np.empty((CH, D), np.float32)
+    for r0 in range(0, rows, CH):
+        n = min(CH, rows - r0)
+        x = mix.rows(r0, r0 + n, out=buf[:n], nthreads=T)
+        codes[:, r0:r0 + n] = o.pq_encode(x, cb, tie_mode=o.TIE_LOWEST, nthreads=T)
+    dt = time.perf_counter() - t0
+    note = "built in %.0f s" % dt
+    for base in ("/dev/shm", tempfile.gettempdir()):
+        try:
+            st = os.statvfs(base)
+            if st.f_bavail * st.f_frsize < codes.nbytes + cb.nbytes + (64 << 20):
+                continue
+            tmp = os.path.join(base, tag + ".%d.tmp.npz" % os.getpid())
+            np.savez(tmp, cb=cb, codes=codes)
+            os.replace(tmp, os.path.join(base, tag + ".npz"))
+            note += ", cached in %s" % base
+            break
+        except Exception:
+            continue
+    return cb, codes, note, dt
+
+
 def reference_arm(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     from oracle import oracle as o
     o.build()
-    T = o.num_threads()
-    rng = np.random.default_rng(20261018)
-    M, K, D = a.m, 256, a.dim
-    dmax = -(-D // M)
-    cb = rng.normal(size=(M, K, dmax)).astype(np.float32)
-    codes = rng.integers(0, K, (M, a.rows), dtype=np.uint8)
-    nq = a.cpu_queries or 16 * T      # ~2 s of work per step on 16 cores at the c2 shape
-    Q = rng.normal(size=(nq, D)).astype(np.float32)
+    T = o.host_cores()
+    cb, codes, how, build_s = build_index_cpu(a, o, T)
+    nq = min(a.queries, a.cpu_queries or 8 * T)     # ~1 s of work per step on 16 cores at the c2 shape
+    Q = o.SynthMixture(a.dim, seed=SEED).rows(0, nq, stream_seed=1, nthreads=T)   # the first nq queries
 
     def step():
         # Index.prepareQuery + PQIndex.batchQuery; one task per query as G/Tests.scala:109-121
         return o.pq_query(Q, cb, codes, a.k, topk_mode=o.TOPK_LITERAL, nthreads=T)
 
-    for _ in range(min(a.warmup, 1)):
+    for _ in range(a.warmup):
         step()
     t0 = time.perf_counter()
     for _ in range(a.steps):
-        step()
+        ids, ds, _ = step()
     dt = time.perf_counter() - t0
     v = nq * a.steps / dt
-    sample = "%d queries x full %d-row index per step, literal TopKHeap" % (nq, a.rows)
+    sample = ("the first %d of the %d queries x the full %d-row index per step, literal TopKHeap"
+              % (nq, a.queries, a.rows))
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus,
-        "steps": a.steps, "warmup": min(a.warmup, 1), "ms_per_step": 1e3 * dt / a.steps,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * dt / a.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": workload(a),
+        "data": "synthetic", "config": config_of(a, a.gpus),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": T, "kind": "port", "sample": sample,
                          "note": "C restatement of the reference algorithm (oracle/); the "
-                                 "reference is Scala/JVM and no JDK exists in this image"},
+                                 "reference is Scala/JVM and no JDK exists in this image",
+                         "threads_from": "os.sched_getaffinity (not OMP_NUM_THREADS)"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "index": {"digest": index_digest(cb, codes), "how": how,
+                  "note": "same rows, codebook and codes as the GPU arm (compare `index.digest`)"},
+        "jvm_probe": probe_jvm(),
         "gpu_launches": 0}))
     return 0
 
 
 # ---- own arm ---------------------------------------------------------------------------------
-def main():
-    a = parse()
-    if a.impl == "reference":
-        return reference_arm(a)
+class Ctx:
+    """What every leg needs: ranks, device, timing helpers."""
 
-    import torch
-    import torch.distributed as dist
-    import gulon_b200 as g
-    from gulon_b200 import _native as N
-    from gulon_b200.sharded import ShardedPQIndex, shard_bounds, shard_plan
-    from gulon_b200.synth import Mixture
+    def __init__(self, a):
+        import torch
+        import torch.distributed as dist
+        import gulon_b200 as g
+        from gulon_b200 import _native as N
+        self.a, self.torch, self.dist, self.g, self.N = a, torch, dist, g, N
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if g.device_count() < 1:
+            raise SystemExit("bench.py needs a CUDA device: gulon_b200 has no CPU fallback")
+        torch.cuda.set_device(self.local)
+        N.check(N.lib().gulon_set_device(self.local))
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        self.peak = float(peaks.get("hbm_gbs", 6650.0))
+        self.peak_source = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+        self.cores = None
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if g.device_count() < 1:
-        raise SystemExit("bench.py needs a CUDA device: gulon_b200 has no CPU fallback")
-    torch.cuda.set_device(local)
-    N.check(N.lib().gulon_set_device(local))
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if world == 1:
+    def max_over_ranks(self, x):
+        if self.world == 1:
             return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
-    for kv in a.opt:
-        name, val = kv.split("=")
-        g.set_option(name, int(val))
-    D, M, K, k, Q = a.dim, a.m, 256, a.k, a.queries
-    mix = Mixture(D, device=dev)
+    def timed(self, fn, steps, warmup):
+        """W untimed + K timed calls bracketed by barrier + synchronize; ms for the K calls, max over ranks."""
+        torch = self.torch
+        out = None
+        for _ in range(warmup):
+            out = fn()
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        self.barrier()
+        wall = (time.perf_counter() - t0) * 1e3
+        return self.max_over_ranks(max(e0.elapsed_time(e1), 0.0)), self.max_over_ranks(wall), out
 
-    # codebooks: trained by the library on the first rows of the data set (same on every rank)
-    xt = mix.rows(0, min(a.train_rows, a.rows))
-    t0 = time.perf_counter()
-    pq = g.ProductQuantizer.train(g.DevicePoints.from_torch(xt),
-                                  g.ProductQuantizerConfig(K, M, a.train_iters))
-    torch.cuda.synchronize()
-    train_s = time.perf_counter() - t0
-    del xt
+    def gather_codes(self, codes, n_local, bounds):
+        """The row shards of the code planes, concatenated on rank 0 (host uint8 [M][N]); None elsewhere."""
+        torch, dist = self.torch, self.dist
+        if self.world == 1 or len(bounds) == 1:      # one shard: rank 0 already holds every row
+            return codes[:, :n_local].cpu().numpy() if self.rank == 0 else None
+        per = max(hi - lo for lo, hi in bounds)
+        M = codes.shape[0]
+        mine = torch.zeros((M, per), dtype=torch.uint8, device=self.dev)
+        mine[:, :n_local] = codes[:, :n_local]
+        parts = [torch.empty_like(mine) for _ in range(len(bounds))] if self.rank == 0 else None
+        if len(bounds) == self.world:
+            dist.gather(mine, parts, dst=0)
+        else:      # R shards replicated over C groups: ranks 0..R-1 hold one full copy
+            grp_ranks = list(range(len(bounds)))
+            grp = dist.new_group(ranks=grp_ranks)
+            if self.rank in grp_ranks:
+                dist.gather(mine, parts, dst=0, group=grp)
+        if self.rank != 0:
+            return None
+        return np.concatenate([p[:, :hi - lo].cpu().numpy() for p, (lo, hi) in zip(parts, bounds)], axis=1)
 
-    # (R row shards) x (C query groups) over the ranks: gulon_b200.sharded.shard_plan
-    n_shards, n_groups = shard_plan(a.rows, world) if a.row_shards <= 0 else \
-        (a.row_shards, world // a.row_shards)
-    # this rank's row shard of the database, encoded chunk by chunk (rows independent: no exchange)
-    lo, hi = shard_bounds(a.rows, n_shards)[rank % n_shards]
+
+def encode_shard(cx, pq, mix, lo, hi, keep=None, time_it=True):
+    """Encodes global rows [lo, hi) chunk by chunk into device code planes (rows independent: no
+    exchange between ranks).  Returns (codes [M][stride], stride, ns, rows_timed)."""
+    torch, N = cx.torch, cx.N
+    M, D = len(pq.quantizers), pq.dimension
     n_local = hi - lo
     stride = (max(n_local, 1) + 15) // 16 * 16
-    codes = torch.zeros((M, stride), dtype=torch.uint8, device=dev)
-    keep_x = world == 1 and not a.no_recall
-    X = torch.empty((n_local, D), dtype=torch.float32, device=dev) if keep_x else None
+    codes = torch.zeros((M, stride), dtype=torch.uint8, device=cx.dev)
     CH = 1 << 20
-    enc_ns, enc_rows = 0.0, 0
+    ns, rows = 0.0, 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     st = torch.cuda.current_stream().cuda_stream
+    buf = None if keep is not None else torch.empty((min(CH, max(n_local, 1)), D), dtype=torch.float32,
+                                                    device=cx.dev)
     for r0 in range(0, n_local, CH):
         n = min(CH, n_local - r0)
-        x = mix.rows(lo + r0, lo + r0 + n, out=X[r0:r0 + n] if keep_x else None)
+        x = mix.rows(lo + r0, lo + r0 + n, out=keep[r0:r0 + n] if keep is not None else buf[:n])
         e0.record()
         N.check(N.lib().gulon_pq_encode_dev(pq.handle, x.data_ptr(), n, D, N.TIE_LOWEST,
                                             codes.data_ptr() + r0, stride, st))
         e1.record()
         torch.cuda.synchronize()
-        if r0 > 0 or n_local <= CH:          # first chunk is the warm-up
-            enc_ns += e0.elapsed_time(e1) * 1e6
-            enc_rows += n
-        del x
+        if time_it and (r0 > 0 or n_local <= CH):          # first chunk is the warm-up
+            ns += e0.elapsed_time(e1) * 1e6
+            rows += n
+    return codes, stride, ns, rows
+
+
+def scan_roofline(cx, M, Q, steps, n_local, clk, prof_ms, shape_key=None):
+    """Roofline of the dominant scan kernel from the library's per-launch event timers (profile = 1)."""
+    N = cx.N
+    scan_ns, scan_l = N.counter("scan_kernel_ns"), N.counter("scan_kernel_launches")
+    p_ns, p_l = N.counter("pscan_kernel_ns"), N.counter("pscan_kernel_launches")
+    f_ns, f_l = N.counter("pscan_first_kernel_ns"), N.counter("pscan_first_kernel_launches")
+    pst = {nm: N.counter("pscan_" + nm) for nm in ("survivors", "candidates", "slow_items", "pairs", "main_pairs")}
+    ml = N.counter("pscan_lb_quantizers") or M
+    use_p = p_l > 0 and p_ns >= scan_ns
+    k_ns, k_l = (p_ns, p_l) if use_p else (scan_ns, scan_l)
+    if k_l <= 0:
+        return None
+    fb = 8 if 127 // ml >= 3 else 16
+    QT = (N.counter("pscan_qt") or 128 // fb) if use_p else 4
+    rows_main = (pst["main_pairs"] / (steps * Q)) if use_p else n_local
+    # algorithmic bytes (SURVEY 8d): one pass over ALL M code planes of the scanned rows per tile of QT
+    # queries whose tables share shared memory
+    alg = steps * -(-Q // QT) * rows_main * M / k_l
+    sec = k_ns * 1e-9 / k_l
+    ach = alg / sec / 1e9
+    lookups = steps * Q * rows_main * (ml if use_p else M) / (k_ns * 1e-9)
+    bpe = (fb // 8) if use_p else 4
+    clk_mhz = (clk or {}).get("sm_mhz") or 1965.0
+    smem_peak = 148 * 128 * clk_mhz * 1e6
+    roof = {"bound": "hbm", "achieved": ach, "peak": cx.peak, "unit": "GB/s", "frac": ach / cx.peak,
+            "traffic": None, "kernel": "pscan::pruned_scan_kernel (main stage)" if use_p else "fscan::fused_scan_kernel",
+            "peak_source": cx.peak_source,
+            "algorithmic_bytes_per_launch": alg, "launch_seconds": sec, "launches": k_l, "query_tile": QT,
+            "lower_bound_quantizers": ml if use_p else None,
+            "note": ("algorithmic bytes count all M code planes per pass (SURVEY 8d); the pruned kernel streams only "
+                     "the planes its lower bound sums, so `achieved` is work done per second, not bytes moved; the "
+                     "binding resource is the shared-memory crossbar, see smem_gather") if use_p else None,
+            "kernel_share_of_step": k_ns * 1e-6 / prof_ms,
+            "other_kernels_share_of_step": {"first_stage_pruned": f_ns * 1e-6 / prof_ms,
+                                            "exact_kernel_boot_rows" if use_p else "pruned": (scan_ns if use_p else p_ns) * 1e-6 / prof_ms},
+            "timed_in": "a repeat of the K steps with the kernel timers on (%.1f ms per step; the timed region "
+                        "runs without them)" % (prof_ms / steps),
+            "smem_gather": {"bytes_per_entry": bpe, "achieved_GBps": lookups * bpe / 1e9,
+                            "peak_GBps": smem_peak / 1e9, "frac": lookups * bpe / smem_peak,
+                            "note": "table reads from shared memory: the binding resource (128 B/clk/SM crossbar)"}}
+    # dram bytes of the main-stage launch from the committed `ncu --set full` capture of this workload
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "scan_traffic.json")))
+        key = "%s_q%d" % (shape_key, QT * 148)
+        if use_p and cx.world == 1 and shape_key and key in tr:
+            t = tr[key]
+            roof["traffic"] = t["dram_bytes_per_launch"]
+            roof["traffic_source"] = t["source"]
+            roof["traffic_algorithmic_bytes_same_launch"] = t["algorithmic_bytes_per_launch"]
+            roof["dram_frac"] = t["dram_bytes_per_launch"] / t["launch_seconds"] / 1e9 / cx.peak
+    except Exception:
+        pass
+    if use_p and pst["pairs"]:
+        roof["pruning"] = {"survivor_rate": pst["survivors"] / pst["pairs"], "list_candidates": pst["candidates"],
+                           "slow_path_items": pst["slow_items"]}
+    return roof
+
+
+def leg_train_c3(cx, mix, X_full):
+    """configs[2]: ProductQuantizer.apply over ALL rows, 25 Lloyd iterations, sum-mode update; rows
+    sharded over the ranks, one all-reduce of the fixed-point sums / counts / changed-count per
+    iteration through the gulon_comm_t hooks (NCCL).  At world > 1 rank 0 repeats the training alone
+    and compares the centroids bit for bit."""
+    torch, g, N, a = cx.torch, cx.g, cx.N, cx.a
+    from gulon_b200.sharded import TorchComm, shard_bounds
+    rows, D, M = a.rows, a.dim, a.m
+    lo, hi = shard_bounds(rows, cx.world)[cx.rank]
+    X = X_full if (X_full is not None and cx.world == 1) else mix.rows(lo, hi)
+    pts = g.DevicePoints.from_torch(X)
+    cfg = g.ProductQuantizerConfig(256, M, a.c3_iters, update_mode=g.UPDATE_SUM)
+    comm = TorchComm(device=cx.dev) if cx.world > 1 else None
+
+    def run():
+        if comm is None:
+            return g.ProductQuantizer.train(pts, cfg)
+        return g.ProductQuantizer.train(pts, cfg, comm=comm.struct, n_total=rows, row_offset=lo)
+
+    run()                                   # warm-up: allocations, tensor maps, NCCL channels
+    calls0 = dict(comm.calls) if comm else {}
+    bytes0 = dict(comm.bytes) if comm else {}
+    ms, wall, pq = cx.timed(run, 1, 0)
+    sec = max(ms, wall) * 1e-3
+    updates = N.counter("train_updates")
+    alg = (updates + 1) * rows * D * 4.0      # the matrix is read at least once per Lloyd iteration
+    out = {"config": "configs[2]: %dx%d-d, m=%dx256, max %d Lloyd iterations, sum-mode update" % (rows, D, M, a.c3_iters),
+           "seconds": sec, "n_gpus": cx.world, "centroid_updates": updates, "assignment_passes": updates + 1,
+           "row_iterations_per_s": rows * (updates + 1) / sec,
+           "roofline": {"bound": "hbm", "unit": "GB/s", "peak": cx.peak * cx.world,
+                        "achieved": alg / sec / 1e9, "frac": alg / sec / 1e9 / (cx.peak * cx.world),
+                        "algorithmic_bytes_per_pass": rows * D * 4,
+                        "note": "N*D*4 bytes per Lloyd iteration (one read of the matrix); whole training time"}}
+    if comm:
+        d = {k: comm.calls[k] - calls0.get(k, 0) for k in comm.calls}
+        b = {k: comm.bytes[k] - bytes0.get(k, 0) for k in comm.bytes}
+        out["allreduce_calls"] = sum(v for k, v in d.items() if k.startswith("allreduce"))
+        out["allreduce_calls_by_kind"] = d
+        out["bytes_per_allreduce"] = {k: (b[k] // d[k] if d[k] else 0) for k in d if k.startswith("allreduce")}
+        cb = pq.codebook()
+        # every rank must hold the same centroids
+        t = torch.from_numpy(cb.view(np.int32).astype(np.int64)).to(cx.dev)
+        mn, mx = t.clone(), t.clone()
+        cx.dist.all_reduce(mn, op=cx.dist.ReduceOp.MIN)
+        cx.dist.all_reduce(mx, op=cx.dist.ReduceOp.MAX)
+        out["centroids_equal_on_all_ranks"] = bool(torch.equal(mn, mx))
+        if cx.rank == 0:
+            del pts
+            Xa = X_full if X_full is not None else mix.rows(0, rows)
+            single = g.ProductQuantizer.train(g.DevicePoints.from_torch(Xa), cfg)
+            out["centroids_equal_single_rank"] = bool(np.array_equal(cb.view(np.uint32),
+                                                                     single.codebook().view(np.uint32)))
+            del Xa
+        cx.barrier()
+    return out
+
+
+def leg_train_cpu(cx, o, T):
+    """The reference's ProductQuantizer.apply on host cores over a bounded sample (oracle port)."""
+    a = cx.a
+    n, it = 65_536, 2
+    x = o.SynthMixture(a.dim, seed=SEED).rows(0, n, nthreads=T)
+    t0 = time.perf_counter()
+    _, nu, _ = o.pq_train(x, a.m, 256, it, tie_mode=o.TIE_LOWEST, nthreads=T)
+    dt = time.perf_counter() - t0
+    passes = float(np.mean(nu)) + 1
+    return {"value": n * passes / dt, "unit": "row-iterations/s", "cores": T, "kind": "port",
+            "sample": "%d rows x %d-d, m=%d, max %d iterations (%.1f assignment passes on average), running mean"
+                      % (n, a.dim, a.m, it, passes)}
+
+
+def leg_row_sharded(cx, clk_unused):
+    """configs[3]-shaped: rs_rows_per_gpu x 128-d SIFT-shaped rows PER GPU, m = 16 x 256, the code planes
+    sharded by rows, every rank's k candidates merged by one NCCL all-gather + (distance, id) merge
+    (gulon_pq_query_sharded_dev).  Weak scaling in the index size; the query batch is fixed."""
+    torch, g, N, a, dist = cx.torch, cx.g, cx.N, cx.a, cx.dist
+    from gulon_b200.sharded import ShardedPQIndex, shard_bounds
+    from gulon_b200.synth import Mixture
+    D, M, k, Q = 128, 16, a.k, a.rs_queries
+    rows = a.rs_rows_per_gpu * cx.world
+    mix = Mixture(D, centres=16384, nonneg=True, span=40.0, seed=SEED + 4, device=cx.dev)
+    xt = mix.rows(0, min(a.train_rows, rows))
+    pq = g.ProductQuantizer.train(g.DevicePoints.from_torch(xt), g.ProductQuantizerConfig(256, M, a.train_iters))
+    del xt
+    bounds = shard_bounds(rows, cx.world)
+    lo, hi = bounds[cx.rank]
+    codes, stride, enc_ns, enc_rows = encode_shard(cx, pq, mix, lo, hi)
+    ix = g.PQIndex.from_device_codes(pq, codes, hi - lo)
+    sh = ShardedPQIndex(ix, lo, plan=(cx.world, 1))
+    queries = mix.rows(0, Q, stream_seed=1)
+    W, K = min(a.warmup, 2), min(a.steps, 3)
+    ms, _, out = cx.timed(lambda: sh.batch_query(k, queries), K, W)
+    value = Q * K / (ms * 1e-3)
+    # the same steps without the exchange: local scan of this rank's shard only
+    ms_local, _, _ = cx.timed(lambda: ix.batch_query_dev(k, queries, id_offset=lo), K, 1)
+    # the exchange alone: all-gather of [ids | dists] + merge of `world` candidate lists
+    send = torch.zeros((2 * Q * k,), dtype=torch.int32, device=cx.dev)
+    recv = torch.zeros((cx.world * 2 * Q * k,), dtype=torch.int32, device=cx.dev)
+    ms_ag, _, _ = cx.timed(lambda: dist.all_gather_into_tensor(recv, send), K, 1)
+    ids_all = torch.zeros((cx.world, Q, k), dtype=torch.int32, device=cx.dev)
+    ds_all = torch.rand((cx.world, Q, k), dtype=torch.float32, device=cx.dev).sort(dim=2).values
+    oi = torch.empty((Q, k), dtype=torch.int32, device=cx.dev)
+    od = torch.empty((Q, k), dtype=torch.float32, device=cx.dev)
+    st = torch.cuda.current_stream().cuda_stream
+    ms_mg, _, _ = cx.timed(lambda: N.check(N.lib().gulon_topk_merge_dev(
+        ids_all.data_ptr(), ds_all.data_ptr(), cx.world, Q, k, oi.data_ptr(), od.data_ptr(), None, st)), K, 1)
+    del send, recv, ids_all, ds_all
+    # roofline of the main-stage kernel on this rank (every rank runs the same shapes)
+    g.set_option("profile", 1)
+    pms, _, _ = cx.timed(lambda: sh.batch_query(k, queries), K, 0)
+    roof = scan_roofline(cx, M, Q, K, hi - lo, None, pms)
+    g.set_option("profile", 0)
+    # end to end: host queries in, host answers out on every rank
+    q_host = torch.empty((Q, D), dtype=torch.float32, pin_memory=True)
+    q_host.copy_(queries)
+    torch.cuda.synchronize()
+    q_np = q_host.numpy()
+    ms_e, wall_e, res = cx.timed(lambda: sh.batch_query(k, q_np), K, 1)
+    e2e = Q * K / (max(ms_e, wall_e) * 1e-3)
+    same = bool(np.array_equal(out[0].cpu().numpy(), res[0]))
+    line = {"config": "configs[3]-shaped: %d x %d-d SIFT-shaped rows (%d per GPU), m=%dx256, top-%d batch of %d queries, "
+                      "%d row shards, NCCL all-gather + (distance,id) merge" % (rows, D, a.rs_rows_per_gpu, M, k, Q, cx.world),
+            "value": value, "unit": UNIT, "ms_per_step": ms / K, "steps": K, "warmup": W, "scaling": "weak (rows per GPU fixed)",
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": cx.world * Q * D * 4,
+                    "d2h_bytes_per_step": cx.world * Q * (k * 8 + 4), "ids_equal_device_path": same},
+            "local_scan_ms": ms_local / K, "exchange_ms": (ms - ms_local) / K,
+            "allgather_ms": ms_ag / K, "allgather_bytes_per_rank": 2 * Q * k * 4, "merge_ms": ms_mg / K,
+            "roofline": roof,
+            "encode": {"value": enc_rows / (enc_ns * 1e-9) if enc_ns else None, "unit": "vectors/s per GPU",
+                       "aggregate": cx.world * enc_rows / (enc_ns * 1e-9) if enc_ns else None}}
+    # oracle check of a query sample over the CONCATENATED shards (rank 0, all host cores)
+    nqc = 8
+    full = cx.gather_codes(codes, hi - lo, bounds)
+    if cx.rank == 0:
+        from oracle import oracle as o
+        T = o.host_cores()
+        t0 = time.perf_counter()
+        ci, cd, _ = o.pq_query(q_np[:nqc], pq.codebook(), full, k, topk_mode=o.TOPK_CANONICAL, nthreads=T)
+        dt = time.perf_counter() - t0
+        gi, gd = out[0][:nqc].cpu().numpy(), out[1][:nqc].cpu().numpy()
+        line["matches_oracle"] = bool(np.array_equal(ci, gi) and np.array_equal(cd.view(np.uint32), gd.view(np.uint32)))
+        line["cpu_baseline"] = {"value": nqc / dt, "unit": UNIT, "cores": T, "kind": "port",
+                                "sample": "%d queries x the concatenated %d-row index" % (nqc, rows)}
+        del full
+    cx.barrier()
+    return line
+
+
+def leg_rerank_c5(cx):
+    """configs[4]-shaped: 1M x 1000-d entity embeddings, m = 100 x 256: batched encode, PQ top-R
+    candidates, exact fp32 re-rank of the candidates against the raw vectors (rows sharded over the
+    ranks; candidates are re-ranked by the rank that owns the row, then merged)."""
+    torch, g, N, a, dist = cx.torch, cx.g, cx.N, cx.a, cx.dist
+    from gulon_b200.sharded import ShardedPQIndex, shard_bounds
+    from gulon_b200.synth import Mixture
+    from gulon_b200.pipeline import RerankPipeline
+    D, M, k, Q, R = 1000, 100, a.k, a.c5_queries, a.c5_candidates
+    rows = a.c5_rows
+    mix = Mixture(D, seed=SEED + 5, device=cx.dev)
+    xt = mix.rows(0, min(65_536, rows))
+    pq = g.ProductQuantizer.train(g.DevicePoints.from_torch(xt), g.ProductQuantizerConfig(256, M, 4))
+    del xt
+    bounds = shard_bounds(rows, cx.world)
+    lo, hi = bounds[cx.rank]
+    X = torch.empty((hi - lo, D), dtype=torch.float32, device=cx.dev)
+    codes, stride, enc_ns, enc_rows = encode_shard(cx, pq, mix, lo, hi, keep=X)
+    pipe = RerankPipeline(pq, codes, X, lo, hi - lo, world=cx.world)
+    queries = mix.rows(0, Q, stream_seed=1)
+    W, K = min(a.warmup, 2), min(a.steps, 3)
+    ms, _, out = cx.timed(lambda: pipe.query(k, R, queries), K, W)
+    value = Q * K / (ms * 1e-3)
+    ms_r, _, _ = cx.timed(lambda: pipe.rerank_only(k, R, queries), K, 1)
+    line = {"config": "configs[4]-shaped: %dx%d-d, m=%dx256, %d queries: PQ top-%d -> exact fp32 re-rank -> top-%d"
+                      % (rows, D, M, Q, R, k),
+            "value": value, "unit": UNIT, "ms_per_step": ms / K, "n_gpus": cx.world,
+            "encode": {"value": cx.world * enc_rows / (enc_ns * 1e-9) if enc_ns else None, "unit": "vectors/s",
+                       "roofline": {"bound": "hbm", "unit": "GB/s", "peak": cx.peak,
+                                    "achieved": enc_rows * (D * 4 + M) / enc_ns if enc_ns else None,
+                                    "frac": enc_rows * (D * 4 + M) / enc_ns / cx.peak if enc_ns else None}},
+            "rerank": {"ms_per_step": ms_r / K,
+                       "roofline": {"bound": "hbm", "unit": "GB/s", "peak": cx.peak * cx.world,
+                                    "algorithmic_bytes_per_query": R * D * 4,
+                                    "achieved": Q * R * D * 4 / (ms_r / K * 1e-3) / 1e9,
+                                    "frac": Q * R * D * 4 / (ms_r / K * 1e-3) / 1e9 / (cx.peak * cx.world)}}}
+    nqc = 16
+    if cx.world == 1 and not a.no_cpu_baseline:
+        from oracle import oracle as o
+        T = o.host_cores()
+        hc = codes[:, :hi - lo].cpu().numpy()
+        qn = queries[:nqc].cpu().numpy()
+        cbh = pq.codebook()
+        t0 = time.perf_counter()
+        ci, _, _ = o.pq_query(qn, cbh, hc, R, topk_mode=o.TOPK_CANONICAL, nthreads=T)
+        dt = time.perf_counter() - t0
+        want_i = np.full((nqc, k), -1, np.int32)
+        want_d = np.full((nqc, k), np.inf, np.float32)
+        for q in range(nqc):
+            cand = np.sort(ci[q][ci[q] >= 0])
+            xc = X[torch.from_numpy(cand.astype(np.int64)).to(cx.dev)].cpu().numpy()   # only the candidate rows
+            t1 = time.perf_counter()
+            ei, ed, _ = o.exact_nn(xc, qn[q:q + 1], k, topk_mode=o.TOPK_CANONICAL)
+            dt += time.perf_counter() - t1
+            want_i[q, :len(ei[0])] = cand[ei[0]]
+            want_d[q, :len(ed[0])] = ed[0]
+        gi, gd = out[0][:nqc].cpu().numpy(), out[1][:nqc].cpu().numpy()
+        line["matches_oracle"] = bool(np.array_equal(want_i, gi) and np.array_equal(want_d.view(np.uint32), gd.view(np.uint32)))
+        line["cpu_baseline"] = {"value": nqc / dt, "unit": UNIT, "cores": T, "kind": "port",
+                                "sample": "%d queries: oracle PQ top-%d over %d rows + exact distances of the candidates"
+                                          % (nqc, R, rows)}
+    return line
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        return reference_arm(a)
+
+    cx = Ctx(a)
+    torch, dist, g, N = cx.torch, cx.dist, cx.g, cx.N
+    from gulon_b200.sharded import ShardedPQIndex, shard_bounds
+    from gulon_b200.synth import Mixture
+    world, rank, dev = cx.world, cx.rank, cx.dev
+
+    for kv in a.opt:
+        name, val = kv.split("=")
+        g.set_option(name, int(val))
+    D, M, K, k, Q = a.dim, a.m, 256, a.k, a.queries
+    mix = Mixture(D, seed=SEED, device=dev)
+
+    # codebooks: trained by the library on the first rows of the data set (same on every rank)
+    xt = mix.rows(0, min(a.train_rows, a.rows))
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    pq = g.ProductQuantizer.train(g.DevicePoints.from_torch(xt),
+                                  g.ProductQuantizerConfig(K, M, a.train_iters))
+    torch.cuda.synchronize()
+    train_s = time.perf_counter() - t0
+    train_passes = N.counter("train_updates") + 1
+    del xt
+
+    # (R row shards) x (C query groups) over the ranks
+    n_shards, n_groups = shard_plan(a.rows, world) if a.row_shards <= 0 else (a.row_shards, world // a.row_shards)
+    bounds = shard_bounds(a.rows, n_shards)
+    lo, hi = bounds[rank % n_shards]
+    n_local = hi - lo
+    keep_x = world == 1 and (not a.no_recall or not a.no_extra_legs)
+    X = torch.empty((n_local, D), dtype=torch.float32, device=dev) if keep_x else None
+    codes, stride, enc_ns, enc_rows = encode_shard(cx, pq, mix, lo, hi, keep=X)
+    st = torch.cuda.current_stream().cuda_stream
     # candidate statistics of the tensor-core encode (one untimed chunk, profile counters on)
     enc_stats = None
     if n_local > 0:
-        n = min(CH, n_local)
+        n = min(1 << 20, n_local)
         x = X[:n] if keep_x else mix.rows(lo, lo + n)
         g.set_option("profile", 1)
         N.check(N.lib().gulon_pq_encode_dev(pq.handle, x.data_ptr(), n, D, N.TIE_LOWEST,
@@ -249,7 +699,7 @@ def main():
         g.set_option("profile", 0)
         del x
     ix = g.PQIndex.from_device_codes(pq, codes, n_local)
-    sh = ShardedPQIndex(ix, lo, plan=(n_shards, n_groups)) if world > 1 else ShardedPQIndex(ix, lo)
+    sh = ShardedPQIndex(ix, lo, plan=(n_shards, n_groups)) if world > 1 else None
     queries = mix.rows(0, Q, stream_seed=1)
 
     def step_dev():
@@ -258,39 +708,21 @@ def main():
     # warm-up, then the timed region
     for _ in range(a.warmup):
         step_dev()
-    barrier()
+    cx.barrier()
     launches0 = g.kernel_launches()
-    clocks = ClockSampler(local)
+    clocks = ClockSampler(cx.local)
     if rank == 0:
         clocks.start()
-    barrier()
-    e0.record()
-    for _ in range(a.steps):
-        out = step_dev()
-    e1.record()
-    barrier()
-    ms = max_over_ranks(e0.elapsed_time(e1))
+    ms, _, out = cx.timed(step_dev, a.steps, 0)
     clk = clocks.stop() if rank == 0 else None
     launches = g.kernel_launches() - launches0
-    # the same K steps once more with the library's kernel timers and counters on (they add an event pair
-    # per kernel and a host sync per scan stage, so they stay out of the timed region above); the
-    # roofline's kernel time, launch count and survivor statistics come from this pass
-    g.set_option("profile", 1)
-    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    p0.record()
-    for _ in range(a.steps):
-        step_dev()
-    p1.record()
-    barrier()
-    prof_ms = p0.elapsed_time(p1)
-    scan_ns = N.counter("scan_kernel_ns")
-    scan_launches = N.counter("scan_kernel_launches")
-    pscan_ns = N.counter("pscan_kernel_ns")
-    pscan_launches = N.counter("pscan_kernel_launches")
-    pstats = {nm: N.counter("pscan_" + nm) for nm in ("survivors", "candidates", "slow_items", "pairs")}
-    lb_quantizers = N.counter("pscan_lb_quantizers")
-    g.set_option("profile", 0)
     value = Q * a.steps / (ms * 1e-3)
+    # the same K steps once more with the library's kernel timers and counters on (they add an event pair
+    # per kernel and a host sync per scan stage, so they stay out of the timed region above)
+    g.set_option("profile", 1)
+    prof_ms, _, _ = cx.timed(step_dev, a.steps, 0)
+    roof = scan_roofline(cx, M, Q, a.steps, n_local, clk, prof_ms, shape_key="%dx%d_m%d" % (a.rows, D, M))
+    g.set_option("profile", 0)
 
     # e2e: the host-facing call, host query buffer in, host (ids, distances) out, every step
     q_host = torch.empty((Q, D), dtype=torch.float32, pin_memory=True)
@@ -302,140 +734,142 @@ def main():
         if world == 1:
             r = ix.batch_query(k, q_np)          # gulon_pq_query: H2D + scan + D2H inside
             return r.keys, r.values
-        ids, ds, _ = sh.batch_query(k, q_host)   # each rank copies its slice of the pinned batch to HBM
-        return ids.cpu(), ds.cpu()
+        ids, ds, _ = sh.batch_query(k, q_np)     # gulon_pq_query_sharded: this rank's slice H2D, whole answer D2H
+        return ids, ds
 
-    step_e2e()
-    barrier()
-    t0 = time.perf_counter()
-    e0.record()
-    for _ in range(a.steps):
-        res = step_e2e()
-    e1.record()
-    barrier()
-    e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3))
+    e_ms, e_wall, res = cx.timed(step_e2e, a.steps, 1)
+    e2e_ms = max(e_ms, e_wall)
     e2e_value = Q * a.steps / (e2e_ms * 1e-3)
 
-    # results of both paths must agree (same kernels, same inputs)
     ids_dev = out[0].cpu().numpy()
+    dist_dev = out[1].cpu().numpy()
     same = bool(np.array_equal(ids_dev, np.asarray(res[0])))
 
     extra = {}
     # recall@10 per G/Tests.scala:18-41 on a query sample (single GPU: raw vectors are resident)
-    if keep_x and rank == 0:
+    if keep_x and rank == 0 and not a.no_recall:
         from gulon_b200.index import rerank
-        R = min(a.recall_queries, Q)
-        qs = q_np[:R]
+        Rq = min(a.recall_queries, Q)
+        qs = q_np[:Rq]
         pts = g.DevicePoints.from_torch(X)
         gt = g.exact_nearest_neighbours(pts, qs, k)
-        ex = rerank(pts, qs, ids_dev[:R], k)            # exact distances of the returned keys
+        ex = rerank(pts, qs, ids_dev[:Rq], k)            # exact distances of the returned keys
         kth = gt.values[:, k - 1]
-        tp = [(ex.values[i][ex.keys[i] >= 0] <= kth[i]).sum() for i in range(R)]
-        extra["recall_at_10"] = {"mean": float(np.mean(tp)) / k, "queries": R,
+        tp = [(ex.values[i][ex.keys[i] >= 0] <= kth[i]).sum() for i in range(Rq)]
+        extra["recall_at_10"] = {"mean": float(np.mean(tp)) / k, "queries": Rq,
                                  "definition": "G/Tests.scala:18-41, eps=0"}
         del pts
 
-    # roofline of the dominant kernel (fused scan): algorithmic bytes = one pass over this rank's
-    # code planes per tile of Qt = 4 queries whose lookup tables share shared memory
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    roof = None
-    use_p = pscan_launches > 0 and pscan_ns >= scan_ns
-    k_ns, k_launches = (pscan_ns, pscan_launches) if use_p else (scan_ns, scan_launches)
-    if k_launches > 0:
-        # algorithmic bytes: one pass over the scanned code planes per tile of Qt
-        # queries whose tables share shared memory (Qt = 8 pruned kernel, 4 exact kernel)
-        ml = lb_quantizers or M                  # quantizers summed by the lower bound (main stage)
-        fb = 8 if 127 // ml >= 3 else 16         # the library's automatic field width
-        QT = (N.counter("pscan_qt") or 128 // fb) if use_p else 4
-        rows_scanned = (pstats["pairs"] / (a.steps * Q)) if use_p else n_local
-        alg_bytes = a.steps * -(-Q // QT) * rows_scanned * M / k_launches
-        sec = k_ns * 1e-9 / k_launches
-        ach = alg_bytes / sec / 1e9
-        # table reads actually issued: the bound pass reads ml of the M quantizers
-        gathers = a.steps * Q * rows_scanned * (ml if use_p else M) / (k_ns * 1e-9)
-        clk_mhz = (clk or {}).get("sm_mhz") or 1965.0
-        smem_peak_bytes = 148 * 128 * clk_mhz * 1e6
-        roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": None, "kernel": "pruned_scan_kernel" if use_p else "fused_scan_kernel",
-                "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
-                "algorithmic_bytes_per_launch": alg_bytes, "launch_seconds": sec,
-                "launches": k_launches, "query_tile": QT,
-                "lower_bound_quantizers": ml if use_p else None,
-                "note": "algorithmic bytes count all M code planes per pass (SURVEY 8d); the pruned kernel "
-                        "streams only the planes its lower bound sums, so `achieved` is work done per "
-                        "second, not bytes moved" if use_p else None,
-                "kernel_share_of_step": k_ns * 1e-6 / prof_ms,
-                "other_scan_kernel_share_of_step": (scan_ns if use_p else pscan_ns) * 1e-6 / prof_ms,
-                "timed_in": "a repeat of the K steps with the kernel timers on (%.1f ms per step; the "
-                            "timed region runs without them)" % (prof_ms / a.steps),
-                "smem_gather": {"bytes_per_entry": (fb // 8) if use_p else 4,
-                                "achieved_GBps": gathers * ((fb // 8) if use_p else 4) / 1e9,
-                                "peak_GBps": smem_peak_bytes / 1e9,
-                                "frac": gathers * ((fb // 8) if use_p else 4) / smem_peak_bytes,
-                                "note": "table reads from shared memory: the binding resource "
-                                        "(128 B/clk/SM crossbar)"}}
-        if use_p and world == 1 and (a.rows, a.dim, a.m, a.k) == (10_000_000, 300, 30, 10):
-            # one `ncu --set full` capture of the main-stage launch of this workload (2368 queries x 9.6M
-            # rows, bound over 15 quantizers): profiles/r01e_pruned_scan_lb15_ncu_full.csv.  That launch's
-            # algorithmic bytes are 148 tiles x 9.6M rows x 30 planes = 42.8 GB; it streams 15 planes.
-            roof["traffic"] = 16.401e9 + 0.006e9
-            roof["traffic_source"] = ("dram__bytes_read.sum + dram__bytes_write.sum of the main-stage launch, "
-                                      "profiles/r01e_pruned_scan_lb15_ncu_full.csv (not measured in this run)")
-        if use_p and pstats["pairs"]:
-            roof["pruning"] = {"survivor_rate": pstats["survivors"] / pstats["pairs"],
-                               "list_candidates": pstats["candidates"],
-                               "slow_path_items": pstats["slow_items"]}
-
+    # ---- CPU baseline + oracle check of the headline (rank 0) --------------------------------------
     cpu = None
-    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+    digest = None
+    enc_cpu = None
+    train_cpu = None
+    o = None
+    T = 0
+    if rank == 0 and not a.no_cpu_baseline:
         from oracle import oracle as o
-        T = o.num_threads()
-        # ~10 s of host work at the c2 shape (about 100 queries/s on 16 cores); every sampled query's ids and
-        # distances are also compared with the GPU's
-        nq = min(Q, a.cpu_queries or max(64, int(64 * T * (3e8 / max(1.0, float(n_local) * M)))))
+        o.build()
+        T = o.host_cores()
+    full_codes = cx.gather_codes(codes, n_local, bounds) if not a.no_cpu_baseline else None
+    if o is not None:
+        # ~10 s of host work at the c2 shape on one GPU (about 7 queries/s per core); 16 queries at world > 1
+        per_s = 3e8 / max(1.0, float(a.rows) * M)
+        nq = a.cpu_queries or (max(64, int(64 * T * per_s)) if world == 1 else 16)
+        nq = min(Q, nq)
         cb = pq.codebook()
-        hc = codes[:, :n_local].cpu().numpy()
+        digest = index_digest(cb, full_codes)
         t0 = time.perf_counter()
-        ci, cd, _ = o.pq_query(q_np[:nq], cb, hc, k, topk_mode=o.TOPK_CANONICAL, nthreads=T)
+        ci, cd, _ = o.pq_query(q_np[:nq], cb, full_codes, k, topk_mode=o.TOPK_CANONICAL, nthreads=T)
         dt = time.perf_counter() - t0
+        ok = bool(np.array_equal(ci, ids_dev[:nq]) and np.array_equal(cd.view(np.uint32), dist_dev[:nq].view(np.uint32)))
         cpu = {"value": nq / dt, "unit": UNIT, "cores": T, "kind": "port",
-               "sample": "%d of the %d queries x the full %d-row index" % (nq, Q, n_local),
-               "matches_gpu": bool(np.array_equal(ci, ids_dev[:nq]) and
-                                   np.array_equal(cd, out[1][:nq].cpu().numpy()))}
+               "sample": "the first %d of the %d queries x the full %d-row index" % (nq, Q, a.rows),
+               "matches_gpu": ok, "threads_from": "os.sched_getaffinity"}
+        if world > 1:      # the CPU baseline proper is an N = 1 figure; at N > 1 this is the parity check
+            extra["oracle_check"] = dict(cpu, note="sharded answer (NCCL path) against the oracle over the whole index")
+            cpu = None
+        if not a.no_extra_legs:
+            # encode on host cores: ProductQuantizer#encode over a row sample, M subspace tasks in parallel
+            ne = 100_000
+            xs = o.SynthMixture(D, seed=SEED).rows(0, min(ne, a.rows), nthreads=T)
+            t0 = time.perf_counter()
+            hc = o.pq_encode(xs, cb, tie_mode=o.TIE_LOWEST, nthreads=T)
+            dt = time.perf_counter() - t0
+            enc_cpu = {"value": len(xs) / dt, "unit": "vectors/s", "cores": T, "kind": "port",
+                       "sample": "rows [0, %d) of the data set" % len(xs),
+                       "matches_gpu": bool(lo == 0 and np.array_equal(hc, full_codes[:, :len(xs)]))}
+            train_cpu = leg_train_cpu(cx, o, T)
+        del full_codes
+    cx.barrier()
+
+    # ---- encode end to end: host rows in, host codes out (gulon_pq_encode) ---------------------------
+    enc_e2e = None
+    if not a.no_extra_legs and rank == 0:
+        ne = min(1 << 20, a.rows)
+        xh = torch.empty((ne, D), dtype=torch.float32, pin_memory=True)
+        xh.copy_(X[:ne] if keep_x else mix.rows(0, ne))
+        torch.cuda.synchronize()
+        xn = xh.numpy()
+        hc = np.empty((M, ne), np.uint8)
+        fn = N.lib().gulon_pq_encode
+        N.check(fn(pq.handle, xn.ctypes.data, ne, D, N.TIE_LOWEST, hc.ctypes.data))
+        t0 = time.perf_counter()
+        reps = 3
+        for _ in range(reps):
+            N.check(fn(pq.handle, xn.ctypes.data, ne, D, N.TIE_LOWEST, hc.ctypes.data))
+        dt = (time.perf_counter() - t0) / reps
+        enc_e2e = {"value": ne / dt, "unit": "vectors/s", "rows": ne, "h2d_bytes_per_step": ne * D * 4,
+                   "d2h_bytes_per_step": ne * M, "pcie_GBps": ne * (D * 4 + M) / dt / 1e9,
+                   "codes_equal_device_path": bool(lo == 0 and np.array_equal(
+                       hc, codes[:, :ne].cpu().numpy()))}
+        del xh
+    cx.barrier()
+
+    # ---- other legs ---------------------------------------------------------------------------------
+    legs = {}
+    if not a.no_extra_legs:
+        del ix, sh
+        legs["train_c3"] = leg_train_c3(cx, mix, X)
+        if train_cpu:
+            legs["train_c3"]["cpu_baseline"] = train_cpu
+        X = None
+        torch.cuda.empty_cache()
+        if world > 1:
+            legs["row_sharded"] = leg_row_sharded(cx, clk)
+        try:
+            legs["rerank_c5"] = leg_rerank_c5(cx)
+        except ImportError as e:      # pragma: no cover
+            legs["rerank_c5"] = {"unavailable": str(e)}
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(workload(a), sharding=("%d row shard(s) of the code planes x %d query group(s) "
-                           "(gulon_b200.sharded.shard_plan: shards keep >= 8M rows); all-gather + "
-                           "(distance,id) merge inside a group, all-gather of the slices across groups"
-                           % (n_shards, n_groups)) if world > 1 else "single GPU",
-                           l2="inputs larger than L2: 300 MB code planes + per-tile lookup tables "
-                              "> 126 MB; no flush needed"),
+            "config": config_of(a, world),
             "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
             # whole job: every query group copies its slice of the batch to each of its R row shards;
-            # every rank reads the assembled (ids, distances) back
+            # every rank reads the assembled (ids, distances, sizes) back
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n_shards * Q * D * 4,
-                    "d2h_bytes_per_step": world * Q * k * 8 + (Q * 4 if world == 1 else 0),
+                    "d2h_bytes_per_step": world * Q * (k * 8 + 4),
                     "ms_per_step": e2e_ms / a.steps, "ids_equal_device_path": same},
             "gpu_launches": launches,
-            "encode": dict({"value": enc_rows / (enc_ns * 1e-9) if enc_ns else None, "unit": "vectors/s",
-                            "rows": enc_rows, "resident": True,
-                            "roofline": {"bound": "hbm", "unit": "GB/s", "peak": peak,
+            "index": {"digest": digest, "note": "sha256 of codebook + code planes; equals the reference arm's"},
+            "encode": dict({"value": world * enc_rows / (enc_ns * 1e-9) if enc_ns else None, "unit": "vectors/s",
+                            "rows": enc_rows, "resident": True, "n_gpus": world,
+                            "roofline": {"bound": "hbm", "unit": "GB/s", "peak": cx.peak,
                                          "achieved": enc_rows * (D * 4 + M) / enc_ns if enc_ns else None,
-                                         "frac": enc_rows * (D * 4 + M) / enc_ns / peak if enc_ns else None,
-                                         "algorithmic_bytes_per_vector": D * 4 + M}},
+                                         "frac": enc_rows * (D * 4 + M) / enc_ns / cx.peak if enc_ns else None,
+                                         "algorithmic_bytes_per_vector": D * 4 + M},
+                            "e2e": enc_e2e, "cpu_baseline": enc_cpu},
                            **(enc_stats or {})),
-            "train": {"rows": min(a.train_rows, a.rows), "iters": a.train_iters, "seconds": train_s},
+            "train": {"rows": min(a.train_rows, a.rows), "iters": a.train_iters, "seconds": train_s,
+                      "assignment_passes": train_passes, "note": "the codebook of the index (running-mean update)"},
+            "jvm_probe": probe_jvm(),
         }
         line.update(extra)
+        line.update(legs)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

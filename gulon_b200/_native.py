@@ -86,7 +86,8 @@ class Comm(C.Structure):
 class Progress(C.Structure):
     """gulon_progress_t == KMeans.ProgressReport (G/KMeans.scala:119-127)."""
     _fields_ = [("quantizer", i32), ("num_iterations", i32), ("max_iterations", i32),
-                ("step_mean", C.c_float), ("step_stddev", C.c_float), ("converged", i32)]
+                ("step_mean", C.c_float), ("step_stddev", C.c_float), ("converged", i32),
+                ("step_count", i32), ("step_s", C.c_float)]
 
 
 PROGRESS_FN = C.CFUNCTYPE(None, vp, C.POINTER(Progress))
@@ -153,6 +154,11 @@ SIGNATURES = {
                                              i32, i64, vp, vp, vp, vp]),
     "gulon_pq_query_sharded": (C.c_int, [vp, C.POINTER(Comm), C.POINTER(Comm), vp, i64, i64, i32, i32,
                                          i64, vp, vp, vp]),
+    "gulon_rerank_dev": (C.c_int, [vp, vp, i64, i64, vp, i32, i32, i64, vp, vp, vp, vp]),
+    "gulon_pq_rerank_query_dev": (C.c_int, [vp, vp, C.POINTER(Comm), vp, i64, i64, i32, i32, i32, i64,
+                                            vp, vp, vp, vp]),
+    "gulon_pq_rerank_query": (C.c_int, [vp, vp, C.POINTER(Comm), vp, i64, i64, i32, i32, i32, i64,
+                                        vp, vp, vp]),
     "gulon_synth_tables_dev": (C.c_int, [C.POINTER(SynthParams), vp, vp, vp]),
     "gulon_synth_rows_dev": (C.c_int, [C.POINTER(SynthParams), i64, i64, i64, vp, vp, vp, i64, vp]),
     "gulon_exact_topk": (C.c_int, [vp, vp, i64, i64, i32, i64, i64, vp, vp, vp]),

@@ -111,6 +111,9 @@ __host__ __device__ inline uint32_t f2ord(float f) {
   uint32_t u;
   memcpy(&u, &f, 4);
 #endif
+  // every NaN orders as the largest value (after +inf), whatever its sign or payload: the keys then
+  // form a total order.  (The reference heap's treatment of NaN is order-dependent, G/TopKHeap.scala:69-79.)
+  if ((u & 0x7fffffffu) > 0x7f800000u) u = 0x7fffffffu;
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 __host__ __device__ inline float ord2f(uint32_t o) {

@@ -91,7 +91,7 @@ struct gulon_index_s {
   std::mutex mu_host;  // guards the host-call staging buffers
   std::mutex mu_sh;    // guards the scratch of the sharded query (gulon_pq_query_sharded*)
   StreamChain chain_sh;
-  DevBuf sh_send, sh_recv, sh_slice, sh_all, sh_q;
+  DevBuf sh_send, sh_recv, sh_slice, sh_all, sh_q, sh_cand;
   DevBuf h_q, h_ids, h_dists, h_sizes;
   DevBuf lutI, keys, lists, qbuf, ids, dists, sizes, merged;
   DevBuf qlut, mins, qp, boot_tail, plists, pstats, boot_keys, spread, msel, merged2, sufmin;
@@ -122,6 +122,7 @@ struct gulon_index_s {
     h_q.release(); h_ids.release(); h_dists.release(); h_sizes.release();
     sel.release(); sel_boot.release();
     sh_send.release(); sh_recv.release(); sh_slice.release(); sh_all.release(); sh_q.release();
+    sh_cand.release();
   }
 };
 
@@ -146,6 +147,9 @@ std::atomic<long long> g_assign_tc_min_rows{4096};
 std::atomic<long long> g_update_fixed{1};        // GULON_UPDATE_SUM as the exact fixed-point sum when possible
 std::atomic<unsigned long long> g_tc_stats[3];   // candidate (row, chunk) pairs, overflow tiles, (row, window) pairs
 std::atomic<long long> g_last_qt{0};             // queries per tile of the last pruned launch
+std::atomic<long long> g_train_updates{0};       // last training: centroid updates of the longest-running window
+std::atomic<long long> g_train_window_passes{0}; // last training: (window, assignment pass) pairs
+std::atomic<unsigned long long> g_ppairs_main{0}; // (row, query) pairs of main-stage pruned launches
 std::atomic<unsigned long long> g_pstats[3];     // survivors, list candidates, slow-path items
 std::atomic<unsigned long long> g_ppairs{0};     // (row, query) pairs offered to the pruned kernel
 
@@ -198,7 +202,7 @@ struct KernelTimer {
     launches = 0;
   }
 };
-KernelTimer g_t_scan, g_t_assign, g_t_pscan;
+KernelTimer g_t_scan, g_t_assign, g_t_pscan, g_t_pscan_first;  // pscan: main stage; first: the short full-bound stage
 
 int need_device() {
   int n = 0;
@@ -239,6 +243,17 @@ int smem_optin(const void *func, size_t bytes) {
   return GULON_OK;
 }
 #define GOPTIN(kern, bytes) GCHECK(smem_optin(reinterpret_cast<const void *>(kern), (bytes)))
+
+// cudaMemcpy2D[Async] with rows that are contiguous on both sides is one linear copy; the runtime does
+// not always collapse it (1M rows of 1200 B took 1.1 s through the 2-D path: one DMA descriptor per row).
+inline cudaError_t copy2d(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width,
+                          size_t height, cudaMemcpyKind kind, cudaStream_t st, bool async) {
+  if (height == 0 || width == 0) return cudaSuccess;
+  if (dpitch == width && spitch == width)
+    return async ? cudaMemcpyAsync(dst, src, width * height, kind, st) : cudaMemcpy(dst, src, width * height, kind);
+  return async ? cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, kind, st)
+               : cudaMemcpy2D(dst, dpitch, src, spitch, width, height, kind);
+}
 
 // ---- java.util.Random (JDK javadoc algorithm) -- seeds KMeans.init, G/KMeans.scala:188-196 ----
 struct JRandom {
@@ -776,7 +791,7 @@ struct Problems {
 // SummaryStatsBuilder over MathUtils.distance of centroid pairs: KMeans.stepSize,
 // G/KMeans.scala:160-168 with G/MathUtils.scala:46-57,85-98 (host side, fp32 as the reference).
 void step_size(const float *prev, const float *next, int K, int dim, int ldc, float *mean,
-               float *stddev) {
+               float *stddev, int32_t *count = nullptr, float *s_out = nullptr) {
   volatile float m = 0.0f, s = 0.0f;
   int n = 0;
   for (int i = 0; i < K; i++) {
@@ -797,6 +812,8 @@ void step_size(const float *prev, const float *next, int K, int dim, int ldc, fl
   }
   *mean = m;
   *stddev = n > 0 ? (float)sqrt((double)(s / (float)n)) : 0.0f;
+  if (count) *count = n;
+  if (s_out) *s_out = s;
 }
 
 // The driver loop of KMeans.computeClusters for `pr.n` windows at once; every window keeps its own
@@ -860,7 +877,7 @@ int train_problems(Problems &pr, gulon_points_t p, const int32_t *seeds, int max
                         cudaMemcpyDeviceToHost, st));
     GCU(cudaStreamSynchronize(st));
     for (int s = 0; s < n; s++) {
-      gulon_progress_t r = {quantizer_base + s, 0, max_iter, 0.0f, 0.0f, 0};
+      gulon_progress_t r = {quantizer_base + s, 0, max_iter, 0.0f, 0.0f, 0, 0, 0.0f};
       report(user, &r);
     }
   }
@@ -911,9 +928,9 @@ int train_problems(Problems &pr, gulon_points_t p, const int32_t *seeds, int max
       upd[s] += 1;
       conv[s] = c;
       if (report) {
-        gulon_progress_t r = {quantizer_base + s, iter[s], max_iter, 0.0f, 0.0f, c};
+        gulon_progress_t r = {quantizer_base + s, iter[s], max_iter, 0.0f, 0.0f, c, 0, 0.0f};
         step_size(h_prev.data() + (size_t)s * K * dmax, h_next.data() + (size_t)s * K * dmax, K,
-                  pr.dim[s], dmax, &r.step_mean, &r.step_stddev);
+                  pr.dim[s], dmax, &r.step_mean, &r.step_stddev, &r.step_count, &r.step_s);
         report(user, &r);
         memcpy(h_prev.data() + (size_t)s * K * dmax, h_next.data() + (size_t)s * K * dmax,
                (size_t)K * dmax * sizeof(float));
@@ -924,10 +941,15 @@ int train_problems(Problems &pr, gulon_points_t p, const int32_t *seeds, int max
     active.swap(still);
   }
   GCU(cudaStreamSynchronize(st));
+  long long umax = 0, wp = 0;
   for (int s = 0; s < n; s++) {
     if (n_updates) n_updates[s] = upd[s];
     if (converged) converged[s] = conv[s];
+    umax = std::max<long long>(umax, upd[s]);
+    wp += upd[s] + 1;
   }
+  g_train_updates = umax;
+  g_train_window_passes = wp;
   return GULON_OK;
 }
 
@@ -1337,7 +1359,8 @@ int scan_batch(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 fr
       prm.Bs = Bs;
       const bool time_it = stage == 1 && g_pruned_lb.load() == 0 && !ix->tm_pending;
       if (time_it) GCU(cudaEventRecord(ix->tm_ev0, st));
-      cudaEvent_t ev = g_t_pscan.begin(st);
+      KernelTimer &ktm = stage == 1 ? g_t_pscan : g_t_pscan_first;
+      cudaEvent_t ev = ktm.begin(st);
 #define GULON_X(FB_, W_)                                                                        \
   if (FB == FB_ && W == W_) {                                                                   \
     auto kern = pscan::pruned_scan_kernel<FB_, W_>;                                             \
@@ -1346,7 +1369,7 @@ int scan_batch(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 fr
   }
       GULON_PSCAN_VARIANTS(GULON_X)
 #undef GULON_X
-      g_t_pscan.end(ev, st);
+      ktm.end(ev, st);
       if (time_it) {
         GCU(cudaEventRecord(ix->tm_ev1, st));
         ix->tm_pending = true;
@@ -1361,6 +1384,7 @@ int scan_batch(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 fr
         GCU(cudaStreamSynchronize(st));
         for (int i = 0; i < 3; i++) g_pstats[i] += h[i];
         g_ppairs += (unsigned long long)srange * (unsigned long long)nq;
+        if (stage == 1) g_ppairs_main += (unsigned long long)srange * (unsigned long long)nq;
       }
       if (stage == 1) g_last_ml = sML;
       // best lists so far + this stage's split lists -> best lists so far
@@ -1520,14 +1544,12 @@ __global__ void scatter_slices_kernel(const int32_t *__restrict__ all, int C, i6
 
 // The queries of this rank's query group are dq[0, n_mine) (already on the device); `per` is the
 // padded slice length every group uses; the whole batch has nq queries.
-int sharded_query(gulon_index_t ix, const gulon_comm_t *row_comm, const gulon_comm_t *query_comm,
-                  const float *dq, i64 n_mine, i64 per, i64 nq, i64 ldq, int k, int normalize,
-                  i64 row_offset, int32_t *d_ids, float *d_dists, int32_t *d_sizes, cudaStream_t st) {
+int sharded_query_body(gulon_index_t ix, const gulon_comm_t *row_comm, const gulon_comm_t *query_comm,
+                       const float *dq, i64 n_mine, i64 per, i64 nq, i64 ldq, int k, int normalize,
+                       i64 row_offset, int32_t *d_ids, float *d_dists, int32_t *d_sizes, cudaStream_t st) {
   const int R = row_comm ? row_comm->world : 1;
   const int C = query_comm ? query_comm->world : 1;
-  std::lock_guard<std::mutex> lock(ix->mu_sh);
-  GCHECK(ix->chain_sh.enter(st));
-  const int rc = [&]() -> int {
+  {
     // 1. local scan of this rank's row shard: [ids | dists] of the padded slice (global row ids)
     const size_t blk = (size_t)per * k;  // elements per array
     GCHECK(ix->sh_send.ensure(2 * blk * 4));
@@ -1572,6 +1594,96 @@ int sharded_query(gulon_index_t ix, const gulon_comm_t *row_comm, const gulon_co
               C, per, k, nq, d_ids, d_dists, d_sizes);
     }
     return GULON_OK;
+  }
+}
+
+int sharded_query(gulon_index_t ix, const gulon_comm_t *row_comm, const gulon_comm_t *query_comm,
+                  const float *dq, i64 n_mine, i64 per, i64 nq, i64 ldq, int k, int normalize,
+                  i64 row_offset, int32_t *d_ids, float *d_dists, int32_t *d_sizes, cudaStream_t st) {
+  std::lock_guard<std::mutex> lock(ix->mu_sh);
+  GCHECK(ix->chain_sh.enter(st));
+  const int rc = sharded_query_body(ix, row_comm, query_comm, dq, n_mine, per, nq, ldq, k, normalize,
+                                    row_offset, d_ids, d_dists, d_sizes, st);
+  GCHECK(ix->chain_sh.leave(st));
+  return rc;
+}
+
+// exact re-rank of candidate lists against the rows this device owns: [nq][R] global ids -> [nq][k]
+int rerank_dev(gulon_points_t p, const float *dq, i64 nq, i64 ldq, const int32_t *d_cand, int R, int k,
+               i64 id_lo, int32_t *d_ids, float *d_dists, int32_t *d_sizes, DevBuf &keys, Selector &sel,
+               cudaStream_t st) {
+  if (nq <= 0) return GULON_OK;
+  if (k == 0 || R == 0) return fill_empty(nq, k, d_ids, d_dists, d_sizes, st);
+  const int D = p->D;
+  GREQUIRE((size_t)D * sizeof(float) <= 48 * 1024, "dimension %d too large for rerank", D);
+  if (R <= RERANK_RMAX) {
+    int P = 2;
+    while (P < R) P <<= 1;
+    const size_t smem = (size_t)P * sizeof(u64) + (size_t)D * sizeof(float);
+    GOPTIN(rerank_topk_kernel, 64 * 1024);
+    for (i64 q0 = 0; q0 < nq; q0 += 1 << 30) {
+      const i64 nb = std::min<i64>(1 << 30, nq - q0);
+      GLAUNCH(rerank_topk_kernel, (unsigned)nb, 128, smem, st, p->d, p->ld, D, p->N, id_lo, dq + q0 * ldq,
+              ldq, d_cand + q0 * R, R, P, k, d_ids + q0 * k, d_dists + q0 * k, d_sizes ? d_sizes + q0 : nullptr);
+    }
+    return GULON_OK;
+  }
+  GREQUIRE(id_lo == 0, "re-rank of more than %d candidates per query is single-shard only", RERANK_RMAX);
+  const i64 n_pad = round_up(R, SEL_CHUNK);
+  i64 qb = std::max<i64>(1, g_simple_scratch.load() / (8 * n_pad));
+  qb = std::min<i64>(std::min<i64>(qb, nq), 32768);
+  GCHECK(keys.ensure((size_t)qb * n_pad * sizeof(u64)));
+  for (i64 q0 = 0; q0 < nq; q0 += qb) {
+    const i64 nb = std::min<i64>(qb, nq - q0);
+    dim3 grid((unsigned)(n_pad / 128), (unsigned)nb);
+    GLAUNCH(rerank_keys_kernel, grid, 128, (size_t)D * sizeof(float), st, p->d, p->ld, D, p->N, dq + q0 * ldq,
+            ldq, d_cand + q0 * R, R, keys.as<u64>(), n_pad);
+    u64 *res;
+    i64 rs;
+    GCHECK(sel.run(keys.as<u64>(), n_pad, nb, k, st, &res, &rs));
+    GCHECK(unpack(res, rs, nb, k, 0, d_ids + q0 * k, d_dists + q0 * k, d_sizes ? d_sizes + q0 : nullptr, st));
+  }
+  return GULON_OK;
+}
+
+// PQ top-R over the row-sharded index -> exact re-rank on the owner of each row -> top-k merge.
+// dq: the whole batch on the device.
+int rerank_query(gulon_index_t ix, gulon_points_t pts, const gulon_comm_t *row_comm, const float *dq, i64 nq,
+                 i64 ldq, int k, int R, int normalize, i64 row_offset, int32_t *d_ids, float *d_dists,
+                 int32_t *d_sizes, cudaStream_t st) {
+  const int Rw = row_comm ? row_comm->world : 1;
+  std::lock_guard<std::mutex> lock(ix->mu_sh);
+  GCHECK(ix->chain_sh.enter(st));
+  const int rc = [&]() -> int {
+    const size_t cblk = (size_t)nq * R, kblk = (size_t)nq * k;
+    GCHECK(ix->sh_cand.ensure(2 * cblk * 4));
+    int32_t *c_ids = ix->sh_cand.as<int32_t>();
+    float *c_dists = reinterpret_cast<float *>(c_ids + cblk);
+    // 1. the GLOBAL PQ top-R of every query, on every rank (one exchange)
+    GCHECK(sharded_query_body(ix, row_comm, nullptr, dq, nq, nq, nq, ldq, R, normalize, row_offset, c_ids,
+                              c_dists, nullptr, st));
+    const float *q = dq;
+    i64 ql = ldq;
+    if (normalize) {   // exact distances are taken against the normalised query, as SortedIndex.prepare does
+      GCHECK(ix->sh_q.ensure((size_t)nq * pts->D * sizeof(float)));
+      GCHECK(normalize_dev(dq, nq, pts->D, ldq, ix->sh_q.as<float>(), pts->D, st));
+      q = ix->sh_q.as<float>();
+      ql = pts->D;
+    }
+    // 2. every rank re-ranks the candidates whose raw vectors it holds
+    if (Rw == 1)
+      return rerank_dev(pts, q, nq, ql, c_ids, R, k, row_offset, d_ids, d_dists, d_sizes, ix->keys, ix->sel2, st);
+    GCHECK(ix->sh_send.ensure(2 * kblk * 4));
+    int32_t *l_ids = ix->sh_send.as<int32_t>();
+    float *l_dists = reinterpret_cast<float *>(l_ids + kblk);
+    GCHECK(rerank_dev(pts, q, nq, ql, c_ids, R, k, row_offset, l_ids, l_dists, nullptr, ix->keys, ix->sel2, st));
+    // 3. second exchange: the k exact candidates of every rank, merged by (distance, id)
+    GCHECK(ix->sh_recv.ensure((size_t)Rw * 2 * kblk * 4));
+    if (row_comm->allgather(row_comm->user, l_ids, ix->sh_recv.p, (i64)(2 * kblk * 4), st) != 0)
+      return fail(GULON_ECOMM, "allgather hook failed (re-ranked candidates)");
+    const int32_t *a_ids = ix->sh_recv.as<int32_t>();
+    return merge_shards(a_ids, reinterpret_cast<const float *>(a_ids + kblk), Rw, (i64)(2 * kblk), nq, k, d_ids,
+                        d_dists, d_sizes, st);
   }();
   GCHECK(ix->chain_sh.leave(st));
   return rc;
@@ -1688,8 +1800,10 @@ int gulon_set_option(const char *name, int64_t value) {
     g_t_scan.reset();
     g_t_assign.reset();
     g_t_pscan.reset();
+    g_t_pscan_first.reset();
     for (int i = 0; i < 3; i++) g_pstats[i] = 0;
     g_ppairs = 0;
+    g_ppairs_main = 0;
   } else if (s == "boot_rows") {
     GREQUIRE(value >= 0, "boot_rows must be >= 0 (0 = auto)");
     g_boot_rows = value;
@@ -1735,6 +1849,19 @@ int gulon_get_counter(const char *name, int64_t *value) {
   if (s == "pscan_kernel_ns" || s == "pscan_kernel_launches") {
     g_t_pscan.drain();
     *value = s == "pscan_kernel_ns" ? (int64_t)g_t_pscan.ns : g_t_pscan.launches;
+    return GULON_OK;
+  }
+  if (s == "pscan_first_kernel_ns" || s == "pscan_first_kernel_launches") {
+    g_t_pscan_first.drain();
+    *value = s == "pscan_first_kernel_ns" ? (int64_t)g_t_pscan_first.ns : g_t_pscan_first.launches;
+    return GULON_OK;
+  }
+  if (s == "pscan_main_pairs") {
+    *value = (int64_t)g_ppairs_main.load();
+    return GULON_OK;
+  }
+  if (s == "train_updates" || s == "train_window_passes") {
+    *value = s == "train_updates" ? g_train_updates.load() : g_train_window_passes.load();
     return GULON_OK;
   }
   if (s == "pscan_survivors" || s == "pscan_candidates" || s == "pscan_slow_items") {
@@ -1791,8 +1918,8 @@ int gulon_points_create(const float *X, int64_t N, int32_t D, int64_t ld, gulon_
       return fail(GULON_ENOMEM, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
     }
     if (p->ld != D) cudaMemset(p->d, 0, bytes);
-    e = cudaMemcpy2D(p->d, (size_t)p->ld * 4, X, (size_t)ld * 4, (size_t)D * 4, (size_t)N,
-                     cudaMemcpyHostToDevice);
+    e = copy2d(p->d, (size_t)p->ld * 4, X, (size_t)ld * 4, (size_t)D * 4, (size_t)N,
+                     cudaMemcpyHostToDevice, 0, false);
     if (e != cudaSuccess) {
       cudaFree(p->d);
       return fail(GULON_ECUDA, "cudaMemcpy2D failed: %s", cudaGetErrorString(e));
@@ -1849,8 +1976,8 @@ int gulon_normalize(const float *X, int64_t N, int32_t D, int64_t ld, float *out
   GCHECK(gulon_points_create(X, N, D, ld, &p));
   int rc = gulon_points_normalize(p);
   if (rc == GULON_OK && N > 0) {
-    cudaError_t e = cudaMemcpy2D(out, (size_t)ldo * 4, p->d, (size_t)p->ld * 4, (size_t)D * 4,
-                                 (size_t)N, cudaMemcpyDeviceToHost);
+    cudaError_t e = copy2d(out, (size_t)ldo * 4, p->d, (size_t)p->ld * 4, (size_t)D * 4,
+                                 (size_t)N, cudaMemcpyDeviceToHost, 0, false);
     if (e != cudaSuccess) rc = fail(GULON_ECUDA, "cudaMemcpy2D failed: %s", cudaGetErrorString(e));
   }
   gulon_points_destroy(p);
@@ -2088,11 +2215,11 @@ static int pq_encode_host(gulon_codebook_t cb, const float *X, int64_t N, int64_
   int b = 0;
   for (i64 r0 = 0; r0 < N; r0 += chunk, b ^= 1) {
     const i64 n = std::min<i64>(chunk, N - r0);
-    GCU(cudaMemcpy2DAsync(r.dx[b], (size_t)Dp * 4, X + r0 * ld, (size_t)ld * 4, (size_t)D * 4,
-                          (size_t)n, cudaMemcpyHostToDevice, r.st[b]));
+    GCU(copy2d(r.dx[b], (size_t)Dp * 4, X + r0 * ld, (size_t)ld * 4, (size_t)D * 4,
+                          (size_t)n, cudaMemcpyHostToDevice, r.st[b], true));
     GCHECK(encode_dev(cb, r.dx[b], n, Dp, r.dc[b], cps, r.st[b]));
-    GCU(cudaMemcpy2DAsync(codes + r0, (size_t)N * sizeof(CodeT), r.dc[b], (size_t)cps * sizeof(CodeT),
-                          (size_t)n * sizeof(CodeT), (size_t)M, cudaMemcpyDeviceToHost, r.st[b]));
+    GCU(copy2d(codes + r0, (size_t)N * sizeof(CodeT), r.dc[b], (size_t)cps * sizeof(CodeT),
+                          (size_t)n * sizeof(CodeT), (size_t)M, cudaMemcpyDeviceToHost, r.st[b], true));
     // buffer pair b is reused two chunks later on the same stream, so reuse is stream-ordered
   }
   GCU(cudaStreamSynchronize(r.st[0]));
@@ -2142,14 +2269,14 @@ static int pq_decode_host(gulon_codebook_t cb, const CodeT *codes, int64_t N, in
   int rc = [&]() -> int {
     GCHECK(dc.ensure((size_t)cb->M * N * sizeof(CodeT)));
     GCHECK(dout.ensure((size_t)N * cb->D * sizeof(float)));
-    GCU(cudaMemcpy2D(dc.p, (size_t)N * sizeof(CodeT), codes, (size_t)plane_stride * sizeof(CodeT),
-                     (size_t)N * sizeof(CodeT), (size_t)cb->M, cudaMemcpyHostToDevice));
+    GCU(copy2d(dc.p, (size_t)N * sizeof(CodeT), codes, (size_t)plane_stride * sizeof(CodeT),
+                     (size_t)N * sizeof(CodeT), (size_t)cb->M, cudaMemcpyHostToDevice, 0, false));
     dim3 block(32, 8);
     GLAUNCH(decode_kernel<CodeT>, (unsigned)ceil_div(N, 8), block, 0, 0, dc.as<CodeT>(), N, N,
             cb->cb.as<float>(), cb->dfrom.as<int32_t>(), cb->ddim.as<int32_t>(), cb->M, cb->K,
             cb->dmax, dout.as<float>(), (i64)cb->D);
-    GCU(cudaMemcpy2D(out, (size_t)ldo * 4, dout.p, (size_t)cb->D * 4, (size_t)cb->D * 4, (size_t)N,
-                     cudaMemcpyDeviceToHost));
+    GCU(copy2d(out, (size_t)ldo * 4, dout.p, (size_t)cb->D * 4, (size_t)cb->D * 4, (size_t)N,
+                     cudaMemcpyDeviceToHost, 0, false));
     return GULON_OK;
   }();
   dc.release();
@@ -2193,8 +2320,8 @@ int gulon_index_create(gulon_codebook_t cb, const uint8_t *codes, int64_t N, int
   ix->codes = d;
   GCU(cudaMemset(d, 0, (size_t)cb->M * ix->ps));
   if (N > 0)
-    GCU(cudaMemcpy2D(d, (size_t)ix->ps, codes, (size_t)plane_stride, (size_t)N, (size_t)cb->M,
-                     cudaMemcpyHostToDevice));
+    GCU(copy2d(d, (size_t)ix->ps, codes, (size_t)plane_stride, (size_t)N, (size_t)cb->M,
+                     cudaMemcpyHostToDevice, 0, false));
   GCHECK(validate_codes_dev<uint8_t>(ix->codes, ix->ps, N, cb->M, cb->K));
   *out = ix.release();
   return GULON_OK;
@@ -2251,8 +2378,8 @@ int gulon_index_create16(gulon_codebook_t cb, const uint16_t *codes, int64_t N, 
   ix->codes16 = d;
   GCU(cudaMemset(d, 0, bytes));
   if (N > 0)
-    GCU(cudaMemcpy2D(d, (size_t)ix->ps * 2, codes, (size_t)plane_stride * 2, (size_t)N * 2,
-                     (size_t)cb->M, cudaMemcpyHostToDevice));
+    GCU(copy2d(d, (size_t)ix->ps * 2, codes, (size_t)plane_stride * 2, (size_t)N * 2,
+                     (size_t)cb->M, cudaMemcpyHostToDevice, 0, false));
   *out = ix.release();
   return GULON_OK;
 }
@@ -2309,8 +2436,8 @@ int gulon_prepare_query(gulon_codebook_t cb, const float *queries, int64_t nq, i
     float *dl = dq + (size_t)qw * D;
     for (i64 q0 = 0; q0 < nq; q0 += qw) {
       const i64 nb = std::min<i64>(qw, nq - q0);
-      GCU(cudaMemcpy2DAsync(dq, (size_t)D * 4, queries + q0 * ldq, (size_t)ldq * 4, (size_t)D * 4,
-                            (size_t)nb, cudaMemcpyHostToDevice, 0));
+      GCU(copy2d(dq, (size_t)D * 4, queries + q0 * ldq, (size_t)ldq * 4, (size_t)D * 4,
+                            (size_t)nb, cudaMemcpyHostToDevice, 0, true));
       dim3 lg((unsigned)ceil_div(K, 256), (unsigned)M, (unsigned)nb);
       GLAUNCH(lut_wide_kernel, lg, 256, 0, 0, dq, (i64)D, cb->cb.as<float>(), cb->dfrom.as<int32_t>(),
               cb->ddim.as<int32_t>(), M, K, cb->dmax, dl);
@@ -2327,8 +2454,8 @@ int gulon_prepare_query(gulon_codebook_t cb, const float *queries, int64_t nq, i
   float *dl = dq + (size_t)qb * D;
   for (i64 q0 = 0; q0 < nq; q0 += qb) {
     const i64 nb = std::min<i64>(qb, nq - q0);
-    GCU(cudaMemcpy2DAsync(dq, (size_t)D * 4, queries + q0 * ldq, (size_t)ldq * 4, (size_t)D * 4,
-                          (size_t)nb, cudaMemcpyHostToDevice, 0));
+    GCU(copy2d(dq, (size_t)D * 4, queries + q0 * ldq, (size_t)ldq * 4, (size_t)D * 4,
+                          (size_t)nb, cudaMemcpyHostToDevice, 0, true));
     dim3 lg((unsigned)ceil_div(nb, 4), (unsigned)M);
     GLAUNCH(lut_build_kernel, lg, 256, 0, 0, dq, (i64)D, nb, cb->cb.as<float>(),
             cb->dfrom.as<int32_t>(), cb->ddim.as<int32_t>(), M, K, cb->dmax,
@@ -2375,8 +2502,8 @@ int gulon_pq_query(gulon_index_t ix, const float *queries, int64_t nq, int64_t l
   float *dq = ix->h_q.as<float>();
   int32_t *di = ix->h_ids.as<int32_t>(), *dz = ix->h_sizes.as<int32_t>();
   float *dd = ix->h_dists.as<float>();
-  GCU(cudaMemcpy2DAsync(dq, (size_t)D * 4, queries, (size_t)ldq * 4, (size_t)D * 4, (size_t)nq,
-                        cudaMemcpyHostToDevice, 0));
+  GCU(copy2d(dq, (size_t)D * 4, queries, (size_t)ldq * 4, (size_t)D * 4, (size_t)nq,
+                        cudaMemcpyHostToDevice, 0, true));
   GCHECK(query_dev(ix, dq, nq, D, k, from, until, normalize, id_offset, di, dd, dz, 0));
   if (k > 0) {
     GCU(cudaMemcpyAsync(out_ids, di, (size_t)nq * k * sizeof(int32_t), cudaMemcpyDeviceToHost, 0));
@@ -2443,8 +2570,8 @@ int gulon_pq_query_sharded(gulon_index_t ix, const gulon_comm_t *row_comm,
   GCHECK(ix->h_dists.ensure((size_t)nq * k * sizeof(float)));
   GCHECK(ix->h_sizes.ensure((size_t)nq * sizeof(int32_t)));
   if (hi > lo)
-    GCU(cudaMemcpy2DAsync(ix->h_q.p, (size_t)D * 4, queries + lo * ldq, (size_t)ldq * 4, (size_t)D * 4,
-                          (size_t)(hi - lo), cudaMemcpyHostToDevice, 0));
+    GCU(copy2d(ix->h_q.p, (size_t)D * 4, queries + lo * ldq, (size_t)ldq * 4, (size_t)D * 4,
+                          (size_t)(hi - lo), cudaMemcpyHostToDevice, 0, true));
   GCHECK(sharded_query(ix, row_comm, query_comm, ix->h_q.as<float>(), hi - lo, per, nq, D, k, normalize,
                        row_offset, ix->h_ids.as<int32_t>(), ix->h_dists.as<float>(),
                        ix->h_sizes.as<int32_t>(), 0));
@@ -2520,8 +2647,8 @@ int gulon_exact_topk(gulon_points_t p, const float *queries, int64_t nq, int64_t
     } else {
       GREQUIRE((size_t)D * sizeof(float) <= 48 * 1024, "dimension %d too large for exact_topk", D);
       GCHECK(dq.ensure((size_t)nq * D * sizeof(float)));
-      GCU(cudaMemcpy2DAsync(dq.p, (size_t)D * 4, queries, (size_t)ldq * 4, (size_t)D * 4,
-                            (size_t)nq, cudaMemcpyHostToDevice, 0));
+      GCU(copy2d(dq.p, (size_t)D * 4, queries, (size_t)ldq * 4, (size_t)D * 4,
+                            (size_t)nq, cudaMemcpyHostToDevice, 0, true));
       const i64 n_pad = round_up(range, SEL_CHUNK);
       i64 qb = std::max<i64>(1, g_simple_scratch.load() / (8 * n_pad));
       qb = std::min<i64>(std::min<i64>(qb, nq), 32768);
@@ -2569,31 +2696,15 @@ int gulon_rerank(gulon_points_t p, const float *queries, int64_t nq, int64_t ldq
     GCHECK(di.ensure(nk * sizeof(int32_t)));
     GCHECK(dd.ensure(nk * sizeof(float)));
     GCHECK(dz.ensure((size_t)nq * sizeof(int32_t)));
-    if (k == 0 || R == 0) {
-      GCHECK(fill_empty(nq, k, di.as<int32_t>(), dd.as<float>(), dz.as<int32_t>(), 0));
-    } else {
-      GREQUIRE((size_t)D * sizeof(float) <= 48 * 1024, "dimension %d too large for rerank", D);
-      GCHECK(dq.ensure((size_t)nq * D * sizeof(float)));
-      GCHECK(dc.ensure((size_t)nq * R * sizeof(int32_t)));
-      GCU(cudaMemcpy2DAsync(dq.p, (size_t)D * 4, queries, (size_t)ldq * 4, (size_t)D * 4,
-                            (size_t)nq, cudaMemcpyHostToDevice, 0));
+    GCHECK(dq.ensure((size_t)nq * D * sizeof(float)));
+    GCHECK(dc.ensure((size_t)std::max<i64>(1, nq * R) * sizeof(int32_t)));
+    if (k > 0 && R > 0) {
+      GCU(copy2d(dq.p, (size_t)D * 4, queries, (size_t)ldq * 4, (size_t)D * 4,
+                            (size_t)nq, cudaMemcpyHostToDevice, 0, true));
       GCU(cudaMemcpyAsync(dc.p, cand_ids, (size_t)nq * R * sizeof(int32_t), cudaMemcpyHostToDevice, 0));
-      const i64 n_pad = round_up(R, SEL_CHUNK);
-      i64 qb = std::max<i64>(1, g_simple_scratch.load() / (8 * n_pad));
-      qb = std::min<i64>(std::min<i64>(qb, nq), 32768);
-      GCHECK(keys.ensure((size_t)qb * n_pad * sizeof(u64)));
-      for (i64 q0 = 0; q0 < nq; q0 += qb) {
-        const i64 nb = std::min<i64>(qb, nq - q0);
-        dim3 grid((unsigned)(n_pad / 128), (unsigned)nb);
-        GLAUNCH(rerank_keys_kernel, grid, 128, (size_t)D * sizeof(float), 0, p->d, p->ld, D, p->N,
-                dq.as<float>() + q0 * D, (i64)D, dc.as<int32_t>() + q0 * R, R, keys.as<u64>(), n_pad);
-        u64 *res;
-        i64 rs;
-        GCHECK(sel.run(keys.as<u64>(), n_pad, nb, k, 0, &res, &rs));
-        GCHECK(unpack(res, rs, nb, k, 0, di.as<int32_t>() + q0 * k, dd.as<float>() + q0 * k,
-                      dz.as<int32_t>() + q0, 0));
-      }
     }
+    GCHECK(rerank_dev(p, dq.as<float>(), nq, D, dc.as<int32_t>(), R, k, 0, di.as<int32_t>(), dd.as<float>(),
+                      dz.as<int32_t>(), keys, sel, 0));
     if (k > 0) {
       GCU(cudaMemcpyAsync(out_ids, di.p, (size_t)nq * k * sizeof(int32_t), cudaMemcpyDeviceToHost, 0));
       GCU(cudaMemcpyAsync(out_dists, dd.p, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, 0));
@@ -2606,6 +2717,68 @@ int gulon_rerank(gulon_points_t p, const float *queries, int64_t nq, int64_t ldq
   dq.release(); dc.release(); keys.release(); di.release(); dd.release(); dz.release();
   sel.release();
   return rc;
+}
+
+int gulon_rerank_dev(gulon_points_t p, const float *dqueries, int64_t nq, int64_t ldq,
+                     const int32_t *d_cand_ids, int32_t R, int32_t k, int64_t id_lo, int32_t *d_ids,
+                     float *d_dists, int32_t *d_sizes, void *stream) {
+  GREQUIRE(p, "null handle");
+  GREQUIRE(nq >= 0 && R >= 0 && R <= RERANK_RMAX && k >= 0 && ldq >= p->D && id_lo >= 0,
+           "bad re-rank shape (R <= %d on the device path)", RERANK_RMAX);
+  GREQUIRE((dqueries && d_cand_ids && d_ids && d_dists) || nq == 0 || k == 0 || R == 0, "null argument");
+  GCHECK(need_device());
+  DevBuf none;
+  Selector nosel;
+  return rerank_dev(p, dqueries, nq, ldq, d_cand_ids, R, k, id_lo, d_ids, d_dists, d_sizes, none, nosel,
+                    (cudaStream_t)stream);
+}
+
+static int check_rerank_query(gulon_index_t ix, gulon_points_t pts, const gulon_comm_t *row_comm, i64 nq,
+                              i64 ldq, int k, int R, i64 row_offset) {
+  GCHECK(check_sharded_args(ix, row_comm, nullptr, nq, ldq, std::max(k, 1), row_offset));
+  GREQUIRE(pts, "null points handle");
+  GREQUIRE(pts->D == ix->cb->D && pts->N == ix->N, "the raw vectors must be the rows the index encodes "
+           "(points %lld x %d, index %lld x %d)", (long long)pts->N, pts->D, (long long)ix->N, ix->cb->D);
+  GREQUIRE(k >= 1 && R >= k && R <= RERANK_RMAX, "need 1 <= k <= R <= %d (k=%d R=%d)", RERANK_RMAX, k, R);
+  return GULON_OK;
+}
+
+int gulon_pq_rerank_query_dev(gulon_index_t ix, gulon_points_t points, const gulon_comm_t *row_comm,
+                              const float *dqueries, int64_t nq, int64_t ldq, int32_t k, int32_t R,
+                              int32_t normalize, int64_t row_offset, int32_t *d_ids, float *d_dists,
+                              int32_t *d_sizes, void *stream) {
+  GCHECK(check_rerank_query(ix, points, row_comm, nq, ldq, k, R, row_offset));
+  GREQUIRE((dqueries && d_ids && d_dists) || nq == 0, "null argument");
+  GCHECK(need_device());
+  if (nq == 0) return GULON_OK;
+  return rerank_query(ix, points, row_comm, dqueries, nq, ldq, k, R, normalize, row_offset, d_ids, d_dists,
+                      d_sizes, (cudaStream_t)stream);
+}
+
+int gulon_pq_rerank_query(gulon_index_t ix, gulon_points_t points, const gulon_comm_t *row_comm,
+                          const float *queries, int64_t nq, int64_t ldq, int32_t k, int32_t R,
+                          int32_t normalize, int64_t row_offset, int32_t *out_ids, float *out_dists,
+                          int32_t *out_sizes) {
+  GCHECK(check_rerank_query(ix, points, row_comm, nq, ldq, k, R, row_offset));
+  GREQUIRE((queries && out_ids && out_dists) || nq == 0, "null argument");
+  GCHECK(need_device());
+  if (nq == 0) return GULON_OK;
+  const int D = ix->cb->D;
+  std::unique_lock<std::mutex> lock(ix->mu_host);
+  GCHECK(ix->h_q.ensure((size_t)nq * D * sizeof(float)));
+  GCHECK(ix->h_ids.ensure((size_t)nq * k * sizeof(int32_t)));
+  GCHECK(ix->h_dists.ensure((size_t)nq * k * sizeof(float)));
+  GCHECK(ix->h_sizes.ensure((size_t)nq * sizeof(int32_t)));
+  GCU(copy2d(ix->h_q.p, (size_t)D * 4, queries, (size_t)ldq * 4, (size_t)D * 4, (size_t)nq,
+                        cudaMemcpyHostToDevice, 0, true));
+  GCHECK(rerank_query(ix, points, row_comm, ix->h_q.as<float>(), nq, D, k, R, normalize, row_offset,
+                      ix->h_ids.as<int32_t>(), ix->h_dists.as<float>(), ix->h_sizes.as<int32_t>(), 0));
+  GCU(cudaMemcpyAsync(out_ids, ix->h_ids.p, (size_t)nq * k * sizeof(int32_t), cudaMemcpyDeviceToHost, 0));
+  GCU(cudaMemcpyAsync(out_dists, ix->h_dists.p, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, 0));
+  if (out_sizes)
+    GCU(cudaMemcpyAsync(out_sizes, ix->h_sizes.p, (size_t)nq * sizeof(int32_t), cudaMemcpyDeviceToHost, 0));
+  GCU(cudaStreamSynchronize(0));
+  return GULON_OK;
 }
 
 }  // extern "C"

@@ -12,6 +12,7 @@
 #include <float.h>
 
 #include "common.cuh"
+#include "select.cuh"
 
 namespace gulon {
 
@@ -468,6 +469,101 @@ __global__ void __launch_bounds__(128) rerank_keys_kernel(const float *__restric
     }
   }
   keys[q * n_pad + t] = key;
+}
+
+// Fused re-rank: exact distances of a query's R candidates and their k best, one CTA per query, no key
+// materialisation in global memory.  cand [nq][R] holds GLOBAL row ids; this device owns rows
+// [id_lo, id_lo + N) (X row 0 = global row id_lo); ids outside (other shards' rows, or -1) are skipped.
+// Each thread walks whole rows -- the reference's sequential fp32 sum (G/MathUtils.scala:85-95) cannot
+// be split -- with 32-byte loads (one full sector per request, streamed past L1).  The keys are
+// sorted in shared memory; the k smallest go out as (global id, distance), (distance, id) ascending.
+// grid nq, block 128; dynamic shared memory: D floats + P u64, P = power of two >= R, R <= 1024.
+constexpr int RERANK_RMAX = 1024;
+__device__ __forceinline__ float4 ldg_nc_stream_f4(const float *p) {
+  float4 r;
+  asm("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+      : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__global__ void __launch_bounds__(128) rerank_topk_kernel(const float *__restrict__ X, i64 ld, int D,
+                                                          i64 N, i64 id_lo,
+                                                          const float *__restrict__ Q, i64 ldq,
+                                                          const int32_t *__restrict__ cand, int R, int P,
+                                                          int k, int32_t *__restrict__ ids,
+                                                          float *__restrict__ dists,
+                                                          int32_t *__restrict__ sizes) {
+  extern __shared__ __align__(16) unsigned char rr_smem[];
+  u64 *keys = reinterpret_cast<u64 *>(rr_smem);
+  float *sq = reinterpret_cast<float *>(rr_smem + (size_t)P * sizeof(u64));
+  const i64 q = blockIdx.x;
+  const int tid = threadIdx.x;
+  for (int j = tid; j < D; j += 128) sq[j] = Q[q * ldq + j];
+  __syncthreads();
+  const bool vec = (ld & 7) == 0 && (reinterpret_cast<uintptr_t>(X) & 31) == 0;
+  for (int t = tid; t < P; t += 128) {
+    u64 key = KEY_SENT;
+    if (t < R) {
+      const i64 gid = cand[q * R + t];
+      const i64 row = gid - id_lo;
+      if (gid >= 0 && row >= 0 && row < N) {
+        const float *x = X + row * ld;
+        float s = 0.0f;
+        int j = 0;
+        if (vec) {
+          // 128 bytes (four sectors) of the row in flight per thread and step; the loads are plain
+          // (non-volatile) so that the compiler issues a step's loads ahead of the previous step's sums
+#pragma unroll 1
+          for (; j + 32 <= D; j += 32) {
+            float4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) v[u] = ldg_nc_stream_f4(x + j + 4 * u);
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+              const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+              for (int t = 0; t < 4; t++) {
+                const float dx = __fsub_rn(sq[j + 4 * u + t], e[t]);
+                s = __fadd_rn(s, __fmul_rn(dx, dx));
+              }
+            }
+          }
+          for (; j + 8 <= D; j += 8) {
+            const float4 a = ldg_nc_stream_f4(x + j), b4 = ldg_nc_stream_f4(x + j + 4);
+            const float e[8] = {a.x, a.y, a.z, a.w, b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+              const float dx = __fsub_rn(sq[j + u], e[u]);
+              s = __fadd_rn(s, __fmul_rn(dx, dx));
+            }
+          }
+        }
+        for (; j < D; j++) {
+          const float dx = __fsub_rn(sq[j], x[j]);
+          s = __fadd_rn(s, __fmul_rn(dx, dx));
+        }
+        key = make_key(s, (uint32_t)gid);
+      }
+    }
+    keys[t] = key;
+  }
+  block_bitonic_sort(keys, P, tid, 128);
+  int cnt = 0;
+  for (int i = tid; i < k; i += 128) {
+    const u64 key = i < P ? keys[i] : KEY_SENT;
+    const bool ok = key != KEY_SENT;
+    ids[q * k + i] = ok ? (int32_t)(uint32_t)key : -1;
+    dists[q * k + i] = ok ? ord2f((uint32_t)(key >> 32)) : __int_as_float(0x7f800000);
+    cnt += ok;
+  }
+  if (sizes) {
+    // block-wide count of valid slots
+    __shared__ int s_cnt;
+    if (tid == 0) s_cnt = 0;
+    __syncthreads();
+    if (cnt) atomicAdd(&s_cnt, cnt);
+    __syncthreads();
+    if (tid == 0) sizes[q] = s_cnt;
+  }
 }
 
 // codes [M][ps] -> out [N][ldo]: ProductQuantizer.decode, G/ProductQuantizer.scala:58-78

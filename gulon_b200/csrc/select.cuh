@@ -76,7 +76,7 @@ __global__ void unpack_keys_kernel(const u64 *__restrict__ keys, i64 stride, i64
   if (q >= rows) return;
   int cnt = 0;
   for (int i = threadIdx.x; i < k; i += 32) {
-    u64 key = keys[q * stride + i];
+    u64 key = i < stride ? keys[q * stride + i] : KEY_SENT;   // k may exceed the keys a row has
     bool ok = key != KEY_SENT;
     if (ids) ids[q * k + i] = ok ? (int32_t)((i64)(uint32_t)key + id_offset) : -1;
     if (dists) dists[q * k + i] = ok ? ord2f((uint32_t)(key >> 32)) : __int_as_float(0x7f800000);
@@ -133,6 +133,38 @@ __global__ void fill_empty_kernel(i64 nq, int k, int32_t *__restrict__ ids,
   if (sizes && t < nq) sizes[t] = 0;
 }
 
+// ---- any k: full merge sort of a row's keys ------------------------------------------------------
+// The chunked selection above keeps k <= SEL_CHUNK / 2 keys per chunk.  The reference's TopKHeap takes
+// any k (k > N returns every row, sorted: G/TopKHeap.scala:69-79); for k beyond the chunk limit the keys
+// of a row are sorted completely: 4096-key chunks by the bitonic kernel (kk = SEL_CHUNK keeps a whole
+// chunk), then log2(chunks) merge passes in which every key finds its place by one binary search in
+// the partner run (lower bound from the left run, upper bound from the right: stable, a bijection
+// even among equal sentinel keys).  8 B x (1 + log2) per key: a correctness path, not a fast one.
+__global__ void __launch_bounds__(256) merge_pass_kernel(const u64 *__restrict__ in, u64 *__restrict__ out,
+                                                         i64 stride, i64 run) {
+  const i64 row = blockIdx.y;
+  const u64 *src = in + row * stride;
+  u64 *dst = out + row * stride;
+  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < stride; i += (i64)gridDim.x * blockDim.x) {
+    const i64 r = i / run;
+    const i64 base = (r & ~1LL) * run;
+    const bool left = (r & 1) == 0;
+    const i64 o0 = left ? base + run : base;                       // partner run [o0, o1)
+    i64 o1 = o0 + run;
+    if (o0 > stride) o1 = o0;
+    if (o1 > stride) o1 = stride;
+    const u64 key = src[i];
+    i64 lo = o0, hi = o1 > o0 ? o1 : o0;
+    while (lo < hi) {                                              // left: #partner < key; right: #partner <= key
+      const i64 mid = (lo + hi) >> 1;
+      const u64 v = src[mid];
+      if (left ? v < key : v <= key) lo = mid + 1; else hi = mid;
+    }
+    const i64 own0 = left ? base : base + run;
+    dst[base + (i - own0) + (lo - o0)] = key;
+  }
+}
+
 // Runs selection passes until every row holds its k smallest keys at the front of the result.
 // keys_a: [rows][stride_a] input (stride_a multiple of SEL_CHUNK); scratch buffers ping-pong.
 // On return *result / *result_stride describe where the answer lives.
@@ -142,10 +174,8 @@ struct Selector {
           i64 *result_stride, u64 *final_out = nullptr, i64 final_stride = 0) {
     GREQUIRE(k >= 1, "k must be >= 1");
     GREQUIRE(stride_a % SEL_CHUNK == 0, "internal: key stride not a multiple of %d", SEL_CHUNK);
-    GREQUIRE(k <= SEL_CHUNK / 2 || stride_a == SEL_CHUNK,
-             "k=%d too large: this build supports k <= %d, or any k when the scanned range has "
-             "at most %d rows", k, SEL_CHUNK / 2, SEL_CHUNK);
     GREQUIRE(rows <= 65535 * 64LL, "internal: too many selection rows");
+    if (k > SEL_CHUNK / 2 && stride_a > SEL_CHUNK) return run_sort(keys_a, stride_a, rows, st, result, result_stride);
     int kk = k < SEL_CHUNK ? k : SEL_CHUNK;
     u64 *in = keys_a;
     i64 in_stride = stride_a;
@@ -181,6 +211,32 @@ struct Selector {
       in_stride = out_stride;
       phase++;
     }
+  }
+  // full sort of every row (any k): see merge_pass_kernel
+  int run_sort(u64 *keys_a, i64 stride, i64 rows, cudaStream_t st, u64 **result, i64 *result_stride) {
+    GCHECK(ping.ensure((size_t)rows * (size_t)stride * sizeof(u64)));
+    GCHECK(pong.ensure((size_t)rows * (size_t)stride * sizeof(u64)));
+    const i64 chunks = stride / SEL_CHUNK;
+    for (i64 r0 = 0; r0 < rows; r0 += 65535) {
+      const i64 nr = rows - r0 < 65535 ? rows - r0 : 65535;
+      dim3 grid((unsigned)chunks, (unsigned)nr);
+      GLAUNCH(select_pass_kernel, grid, SEL_NT, 0, st, keys_a + r0 * stride, stride,
+              ping.as<u64>() + r0 * stride, stride, SEL_CHUNK);
+    }
+    u64 *in = ping.as<u64>(), *out = pong.as<u64>();
+    for (i64 run = SEL_CHUNK; run < stride; run <<= 1) {
+      for (i64 r0 = 0; r0 < rows; r0 += 65535) {
+        const i64 nr = rows - r0 < 65535 ? rows - r0 : 65535;
+        dim3 grid((unsigned)(ceil_div(stride, 256) < 4096 ? ceil_div(stride, 256) : 4096), (unsigned)nr);
+        GLAUNCH(merge_pass_kernel, grid, 256, 0, st, in + r0 * stride, out + r0 * stride, stride, run);
+      }
+      u64 *t = in;
+      in = out;
+      out = t;
+    }
+    *result = in;
+    *result_stride = stride;
+    return GULON_OK;
   }
   void release() {
     ping.release();

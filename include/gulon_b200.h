@@ -100,6 +100,10 @@ typedef struct gulon_progress {
   int32_t max_iterations;
   float step_mean, step_stddev; /* SummaryStats of centroid displacement, G/KMeans.scala:160-168 */
   int32_t converged;
+  /* the SummaryStats(count, mean, s) triple itself (G/MathUtils.scala:5), so that a host can rebuild
+   * the reference's value exactly: count = number of centroids, s = sum of squared deviations */
+  int32_t step_count;
+  float step_s;
 } gulon_progress_t;
 typedef void (*gulon_progress_fn)(void *user, const gulon_progress_t *report);
 
@@ -304,6 +308,34 @@ int gulon_exact_topk(gulon_points_t p, const float *queries, int64_t nq, int64_t
 int gulon_rerank(gulon_points_t p, const float *queries, int64_t nq, int64_t ldq,
                  const int32_t *cand_ids, int32_t R, int32_t k, int32_t *out_ids,
                  float *out_dists, int32_t *out_sizes);
+
+/* Device-resident re-rank.  cand ids are GLOBAL row ids; this device's points are global rows
+ * [id_lo, id_lo + N): candidates outside (another shard's rows, or -1) are skipped.  One fused kernel
+ * per query (exact distances + top-k in shared memory); R <= 1024. */
+int gulon_rerank_dev(gulon_points_t p, const float *dqueries, int64_t nq, int64_t ldq,
+                     const int32_t *d_cand_ids, int32_t R, int32_t k, int64_t id_lo, int32_t *d_ids,
+                     float *d_dists, int32_t *d_sizes, void *stream);
+
+/*
+ * The re-ranked query as ONE call (BASELINE configs[4]: "PQ candidates + brute-force fp32 re-rank"):
+ *   1. PQIndex#batchQuery for the R best PQ candidates of every query (G/Index.scala:414-440); with
+ *      row_comm the index is row-sharded and the candidates are the GLOBAL top-R (as
+ *      gulon_pq_query_sharded);
+ *   2. MathUtils.distanceSq (G/MathUtils.scala:85-95) between the query and the raw vector of every
+ *      candidate -- Index.exactNearestNeighbours restricted to the candidates (G/Index.scala:209-229),
+ *      the exact-distance step of G/Tests.scala:24-37 -- computed by the rank that owns the row
+ *      (`points` are the raw vectors of exactly the rows `ix` encodes);
+ *   3. the k best by (exact distance, id); sharded: one more all-gather + merge.
+ * Every rank passes the same batch and receives the whole answer.  1 <= k <= R <= 1024.
+ */
+int gulon_pq_rerank_query_dev(gulon_index_t ix, gulon_points_t points, const gulon_comm_t *row_comm,
+                              const float *dqueries, int64_t nq, int64_t ldq, int32_t k, int32_t R,
+                              int32_t normalize, int64_t row_offset, int32_t *d_ids, float *d_dists,
+                              int32_t *d_sizes, void *stream);
+int gulon_pq_rerank_query(gulon_index_t ix, gulon_points_t points, const gulon_comm_t *row_comm,
+                          const float *queries, int64_t nq, int64_t ldq, int32_t k, int32_t R,
+                          int32_t normalize, int64_t row_offset, int32_t *out_ids, float *out_dists,
+                          int32_t *out_sizes);
 
 /* ---- synthetic data (benchmark / test tooling; not part of the reference path) --------------- */
 /*

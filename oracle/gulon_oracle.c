@@ -382,17 +382,26 @@ int go_heap_drain(go_heap *h, int32_t *ids, float *dists) {
   return n;
 }
 
-/* Canonical bounded top-k: sorted ascending by (value, key); insert keeps lexicographic order. */
+/* Canonical bounded top-k: sorted ascending by (value, key); insert keeps lexicographic order.
+ * The order on values is TOTAL: every NaN ranks after +inf (all NaNs equal).  The reference heap has
+ * no defined behaviour for NaN (`root > v` is false both ways, G/TopKHeap.scala:69-79: what it keeps
+ * depends on the insertion order); the canonical rule, which is the GPU library's, must be a total
+ * order or the result would depend on the scan order too. */
 typedef struct { int32_t *keys; float *values; int cap; int size; } go_topk;
+static inline int topk_less(float a, int32_t ka, float b, int32_t kb) {
+  const int na = a != a, nb = b != b;
+  if (na || nb) return na != nb ? nb : ka < kb;
+  return a < b || (a == b && ka < kb);
+}
 static void topk_insert(go_topk *t, int32_t key, float v) {
   if (t->cap <= 0) return;
   if (t->size == t->cap) {
     float lv = t->values[t->size - 1]; int32_t lk = t->keys[t->size - 1];
-    if (!(v < lv || (v == lv && key < lk))) return;
+    if (!topk_less(v, key, lv, lk)) return;
     t->size -= 1;
   }
   int i = t->size;
-  while (i > 0 && (t->values[i - 1] > v || (t->values[i - 1] == v && t->keys[i - 1] > key))) {
+  while (i > 0 && topk_less(v, key, t->values[i - 1], t->keys[i - 1])) {
     t->values[i] = t->values[i - 1]; t->keys[i] = t->keys[i - 1]; i--;
   }
   t->values[i] = v; t->keys[i] = key; t->size += 1;

@@ -53,7 +53,16 @@ i32 = C.c_int32
 
 
 def num_threads():
+    """OpenMP's default team size -- obeys OMP_NUM_THREADS (torchrun exports 1); prefer host_cores()."""
     return int(lib().go_num_threads())
+
+
+def host_cores():
+    """Host cores this process may run on; every oracle call takes an explicit `nthreads`."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
 
 
 class JRandom:

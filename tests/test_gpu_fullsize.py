@@ -1,9 +1,16 @@
-"""GPU: BASELINE.json's full shapes through size-independent properties (no oracle at this size):
-pruned scan == exact fused scan == any-k selection scan, range split + merge == whole scan
-(TopKHeap#merge, T/TopKHeapSpec.scala:33-52), a decoded row finds its own code at distance 0
-(T/IndexSpec.scala:62-73 analogue), encode is idempotent on decoded rows and independent of the kernel
-(tensor-core filter vs exact CUDA cores), (distance, id) order of every result.  Data are generated on the
-device (gulon_b200.synth) so nothing large crosses PCIe."""
+"""GPU: BASELINE.json's full shapes (c1 1M x 100, c2 10M x 300, a c4 shard 12.5M x 128, c5 1M x 1000).
+
+Against the ORACLE at full size (`check_against_oracle`): PQIndex.batchQuery of 8 sampled queries over
+the whole index (ids and distance bits), ProductQuantizer#encode of a 50 000-row slice taken from the
+middle of the data set (codes byte-equal; the rows are regenerated on host cores by the CPU twin of
+the data generator, oracle/synth.c), and the trained codebook of the index itself (bit-equal to the
+oracle's ProductQuantizer.apply on the same training rows).
+
+And through size-independent properties over thousands of queries: pruned scan == exact fused scan ==
+any-k selection scan, range split + merge == whole scan (TopKHeap#merge, T/TopKHeapSpec.scala:33-52),
+a decoded row finds its own code at distance 0 (T/IndexSpec.scala:62-73 analogue), encode is
+idempotent on decoded rows and independent of the kernel (tensor-core filter vs exact CUDA cores),
+(distance, id) order of every result.  Data are generated on the device (gulon_b200.synth)."""
 import numpy as np
 import pytest
 
@@ -23,7 +30,7 @@ def build(g, rows, D, M, centres=4096, nonneg=False, train_rows=131072, iters=4)
     from gulon_b200 import _native as N
     from gulon_b200.synth import Mixture
     dev = torch.device("cuda", 0)
-    mix = Mixture(D, device=dev, centres=centres, nonneg=nonneg)
+    mix = Mixture(D, device=dev, centres=centres, nonneg=nonneg, span=40.0 if nonneg else 1.0)
     xt = mix.rows(0, train_rows)
     pq = g.ProductQuantizer.train(g.DevicePoints.from_torch(xt), g.ProductQuantizerConfig(256, M, iters))
     del xt
@@ -39,6 +46,28 @@ def build(g, rows, D, M, centres=4096, nonneg=False, train_rows=131072, iters=4)
         torch.cuda.synchronize()
         del x
     return mix, pq, codes, g.PQIndex.from_device_codes(pq, codes, rows)
+
+
+def check_against_oracle(g, oracle, mix, pq, codes, rows, D, Q, ids, ds, k=10, train_rows=None, iters=None):
+    """The oracle over the FULL index on a query sample, over a mid-data-set slice for encode, and
+    (when the training protocol is given) for the codebook itself."""
+    T = oracle.host_cores()
+    cb = pq.codebook()
+    hc = codes[:, :rows].cpu().numpy()
+    nq = Q.shape[0]
+    pick = np.unique(np.linspace(0, nq - 1, 8).astype(np.int64))
+    qs = Q[pick].cpu().numpy()
+    oi, od, _ = oracle.pq_query(qs, cb, hc, k, topk_mode=oracle.TOPK_CANONICAL, nthreads=T)
+    assert np.array_equal(oi, ids[pick])
+    assert np.array_equal(od.view(np.uint32), ds[pick].view(np.uint32))
+    twin = oracle.SynthMixture(D, **mix.kw)
+    lo = (rows // 2) | 1                                    # an odd offset: unaligned chunk starts
+    x = twin.rows(lo, lo + 50_000, nthreads=T)
+    assert np.array_equal(oracle.pq_encode(x, cb, tie_mode=oracle.TIE_LOWEST, nthreads=T), hc[:, lo:lo + 50_000])
+    if train_rows:
+        xt = twin.rows(0, train_rows, nthreads=T)
+        want, _, _ = oracle.pq_train(xt, cb.shape[0], 256, iters, tie_mode=oracle.TIE_LOWEST, nthreads=T)
+        assert np.array_equal(want.view(np.uint32), cb.view(np.uint32))
 
 
 def query(g, ix, k, Q, impl=None, frm=0, until=None, **opts):
@@ -135,19 +164,29 @@ def check_encode_properties(g, mix, pq, codes, rows, D):
             assert ((a - b) ** 2).sum() <= 1e-5 * ((a ** 2).sum() + (b ** 2).sum()), (m, i)
 
 
-def test_c2_shape_10m_x_300(g):
+def test_c1_shape_1m_x_100_iid(g, oracle):
+    """configs[0]: iid unit-variance rows (no cluster structure: the lower bound prunes least here)."""
+    rows, D, M = 1_000_000, 100, 10
+    mix, pq, codes, ix = build(g, rows, D, M, centres=0, train_rows=32768, iters=2)
+    Q, ids, ds = check_scan_properties(g, mix, pq, codes, ix, rows, nq=1200, n_exact=64)
+    check_against_oracle(g, oracle, mix, pq, codes, rows, D, Q, ids, ds, train_rows=32768, iters=2)
+
+
+def test_c2_shape_10m_x_300(g, oracle):
     rows, D, M = 10_000_000, 300, 30
     mix, pq, codes, ix = build(g, rows, D, M)
-    check_scan_properties(g, mix, pq, codes, ix, rows)
+    Q, ids, ds = check_scan_properties(g, mix, pq, codes, ix, rows)
+    check_against_oracle(g, oracle, mix, pq, codes, rows, D, Q, ids, ds)
     check_encode_properties(g, mix, pq, codes, rows, D)
 
 
-def test_c5_shape_1m_x_1000_with_rerank(g):
+def test_c5_shape_1m_x_1000_with_rerank(g, oracle):
     import torch
     from gulon_b200.index import rerank
     rows, D, M = 1_000_000, 1000, 100
     mix, pq, codes, ix = build(g, rows, D, M, train_rows=65536, iters=3)
     Q, ids, ds = check_scan_properties(g, mix, pq, codes, ix, rows, nq=1200, n_exact=64)
+    check_against_oracle(g, oracle, mix, pq, codes, rows, D, Q, ids, ds)
     check_encode_properties(g, mix, pq, codes, rows, D)
     # re-rank (c5): exact distances of 100 PQ candidates; the re-ranked top-10 are the 10 smallest exact
     # distances among the candidates, ascending, and the exact nearest neighbour of a database row is itself
@@ -157,16 +196,19 @@ def test_c5_shape_1m_x_1000_with_rerank(g):
     cand, _ = query(g, ix, 100, Q[:32])
     rr = rerank(pts, qs, cand.astype(np.int32), 10)
     for q in range(32):
-        d = ((X[torch.from_numpy(cand[q].astype(np.int64)).cuda()] - Q[q]) ** 2).sum(1).cpu().numpy()
-        want = set(cand[q][np.argsort(d, kind="stable")[:10]])
-        assert len(want & set(rr.keys[q])) >= 9                      # fp32 summation order may swap a near-tie
-        assert np.all(np.diff(rr.values[q]) >= 0)
+        # the oracle's exactNearestNeighbours over the candidate rows (MathUtils.distanceSq, sequential fp32)
+        c = np.sort(cand[q])
+        xh = X[torch.from_numpy(c.astype(np.int64)).cuda()].cpu().numpy()
+        ei, ed, _ = oracle.exact_nn(xh, qs[q:q + 1], 10, topk_mode=oracle.TOPK_CANONICAL)
+        assert np.array_equal(c[ei[0]], rr.keys[q])
+        assert np.array_equal(ed[0].view(np.uint32), rr.values[q].view(np.uint32))
     self_rows = np.array([5, 77_777, rows - 1])
     nn = g.exact_nearest_neighbours(pts, X[torch.from_numpy(self_rows).cuda()].cpu().numpy(), 1)
     assert np.array_equal(nn.keys[:, 0], self_rows) and np.all(nn.values[:, 0] == 0.0)
 
 
-def test_c4_shard_shape_12m5_x_128(g):
+def test_c4_shard_shape_12m5_x_128(g, oracle):
     rows, D, M = 12_500_000, 128, 16
     mix, pq, codes, ix = build(g, rows, D, M, centres=16384, nonneg=True)
-    check_scan_properties(g, mix, pq, codes, ix, rows, nq=1200, n_exact=64)
+    Q, ids, ds = check_scan_properties(g, mix, pq, codes, ix, rows, nq=1200, n_exact=64)
+    check_against_oracle(g, oracle, mix, pq, codes, rows, D, Q, ids, ds)
