@@ -145,6 +145,7 @@ std::atomic<long long> g_last_ml{0};             // quantizers in the lower boun
 std::atomic<long long> g_assign_impl{GULON_ASSIGN_AUTO};  // exact CUDA-core kernel or tcgen05 filter + exact recheck
 std::atomic<long long> g_assign_tc_min_rows{4096};
 std::atomic<long long> g_update_fixed{1};        // GULON_UPDATE_SUM as the exact fixed-point sum when possible
+std::atomic<long long> g_train_fused{1};         // sum mode: assignment + sums + changed count in one pass over the matrix
 std::atomic<unsigned long long> g_tc_stats[3];   // candidate (row, chunk) pairs, overflow tiles, (row, window) pairs
 std::atomic<long long> g_last_qt{0};             // queries per tile of the last pruned launch
 std::atomic<long long> g_train_updates{0};       // last training: centroid updates of the longest-running window
@@ -329,17 +330,23 @@ struct TcCtx {
   DevBuf *groups = nullptr;       // scratch for the group table when d_groups is null
   const int32_t *d_groups = nullptr;  // prepared group table (codebooks)
   int n_groups = 0;
+  // fused Lloyd pass (tca::tc_assign_kernel<.., true>): fixed-point sums, counts, changed rows
+  bool fuse = false;
+  const float *scale = nullptr;
+  unsigned long long *sums = nullptr;
+  int32_t *counts = nullptr, *bad = nullptr, *diff = nullptr;
 };
 
 // Groups of up to GRP_MAX windows that are adjacent in the row, so that one TMA box (32 floats from
 // the 16-byte boundary below the first window) serves them all.
-std::vector<int32_t> build_tc_groups(const int32_t *subs, int n, const int32_t *from, int dim) {
+std::vector<int32_t> build_tc_groups(const int32_t *subs, int n, const int32_t *from, int dim,
+                                     int grp_max = tca::GRP_MAX) {
   std::vector<int32_t> g;
   int i = 0;
   while (i < n) {
     const int m0 = from[subs[i]] & 3;
     int cnt = 1;
-    while (cnt < tca::GRP_MAX && i + cnt < n && from[subs[i + cnt]] == from[subs[i + cnt - 1]] + dim &&
+    while (cnt < grp_max && i + cnt < n && from[subs[i + cnt]] == from[subs[i + cnt - 1]] + dim &&
            m0 + (cnt + 1) * dim <= tca::BOX_COLS)
       cnt++;
     for (int j = 0; j < tca::GRP_MAX; j++) g.push_back(j < cnt ? subs[i + j] : -1);
@@ -389,7 +396,7 @@ bool tc_eligible(const float *dX, i64 N, i64 ld, int K, int dim) {
 }
 
 // Approximate scores on tcgen05, exact recheck of the candidate chunks.
-template <int DIM, typename OutT>
+template <int DIM, typename OutT, bool FUSE = false>
 int launch_assign_tc_dim(const float *dX, i64 N, i64 ld, const float *cb, const float *off, int K,
                          int dmax, const int32_t *dsubs, int nsub, const int32_t *dfrom,
                          const int32_t *ddim, TcCtx &tc, OutT *out, i64 out_stride,
@@ -402,7 +409,7 @@ int launch_assign_tc_dim(const float *dX, i64 N, i64 ld, const float *cb, const 
   const int32_t *d_groups = tc.d_groups;
   int n_groups = tc.n_groups;
   if (!d_groups) {
-    std::vector<int32_t> g = build_tc_groups(tc.hsubs, nsub, tc.hfrom, DIM);
+    std::vector<int32_t> g = build_tc_groups(tc.hsubs, nsub, tc.hfrom, DIM, FUSE ? tca::FUSE_GRP : tca::GRP_MAX);
     n_groups = (int)(g.size() / tca::GRP_MAX);
     GCHECK(upload(*tc.groups, g, st));
     d_groups = tc.groups->as<int32_t>();
@@ -421,11 +428,18 @@ int launch_assign_tc_dim(const float *dX, i64 N, i64 ld, const float *cb, const 
   }
   if (tc.prep)
     GLAUNCH(tca::tc_prep_kernel, (unsigned)nsub, 256, 0, st, cb, off, dsubs, ddim, K, dmax, blobs);
-  auto kern = tca::tc_assign_kernel<DIM, OutT>;
-  GOPTIN(kern, tca::SMEM_BYTES);
+  auto kern = tca::tc_assign_kernel<DIM, OutT, FUSE>;
+  constexpr int kSmem = FUSE ? tca::fuse_smem_bytes(DIM) : tca::SMEM_BYTES;
+  GOPTIN(kern, kSmem);
   CUtensorMap map;
   GCHECK(make_row_map(dX, N, ld, ncols, tca::TM, &map));
   tca::Params p;
+  p.scale = tc.scale;
+  p.sums = tc.sums;
+  p.counts = tc.counts;
+  p.bad = tc.bad;
+  p.diff = tc.diff;
+  p.dmax = dmax;
   p.N = N;
   // rows per work unit: at least ~16 units per CTA, at most 8192 rows
   const int sms = sm_count();
@@ -456,7 +470,7 @@ int launch_assign_tc_dim(const float *dX, i64 N, i64 ld, const float *cb, const 
   const i64 units = ceil_div(N, ur) * n_groups;
   const unsigned grid = (unsigned)std::min<i64>(units, sms);
   cudaEvent_t ev = g_t_assign.begin(st);
-  GLAUNCH(kern, grid, tca::NT, tca::SMEM_BYTES, st, map, p);
+  GLAUNCH(kern, grid, tca::NT, kSmem, st, map, p);
   g_t_assign.end(ev, st);
   if (dbg_host) {
     cudaError_t e = cudaStreamSynchronize(st);
@@ -497,6 +511,23 @@ int launch_assign(const float *dX, i64 N, i64 ld, const float *cb, const float *
            "assign_impl=tensor needs K <= %d, window width <= %d, a 16-byte aligned matrix and a row "
            "stride that is a multiple of 4 floats (K=%d, width=%d, ld=%lld)", tca::TN,
            (tca::KP - 3) / 3, K, dim, (long long)ld);
+  if constexpr (sizeof(OutT) == 4) {
+    if (tc && tc->fuse) {
+      GREQUIRE(tc_ok, "internal: fused Lloyd pass on a shape the tensor path does not take");
+      switch (dim) {
+#define GULON_CASE(DD)                                                                                 \
+  case DD:                                                                                             \
+    return launch_assign_tc_dim<DD, OutT, true>(dX, N, ld, cb, off, K, dmax, dsubs, nsub, dfrom, ddim, \
+                                                *tc, out, out_stride, st);
+        GULON_CASE(1) GULON_CASE(2) GULON_CASE(3) GULON_CASE(4) GULON_CASE(5) GULON_CASE(6)
+        GULON_CASE(7) GULON_CASE(8) GULON_CASE(9) GULON_CASE(10) GULON_CASE(11) GULON_CASE(12)
+        GULON_CASE(13) GULON_CASE(14) GULON_CASE(15)
+#undef GULON_CASE
+        default:
+          return fail(GULON_EINVAL, "internal: fused Lloyd pass with window width %d", dim);
+      }
+    }
+  }
   if constexpr (sizeof(OutT) != 2)  // 16-bit codes mean K > 256: never tensor-eligible
   if (tc_ok && (impl == GULON_ASSIGN_TENSOR ||
                 (impl == GULON_ASSIGN_AUTO && N >= g_assign_tc_min_rows.load()))) {
@@ -608,6 +639,39 @@ struct Problems {
       return launch_assign<int32_t>(dX, N, ld, cb.as<float>(), off.as<float>(), K, dmax, ds, ns,
                                     dfrom.as<int32_t>(), ddim.as<int32_t>(), w, &ctx, out,
                                     out_stride, st);
+    });
+  }
+  // One fused Lloyd pass over the windows `subs`: assignments (in place: `inout` holds the previous ones),
+  // fixed-point sums / counts of the NEW assignments, rows changed per window (pr.diff).  Needs `fixed`.
+  bool can_fuse(const float *dX, i64 N, i64 ld) const {
+    if (!fixed || g_assign_impl.load() == GULON_ASSIGN_EXACT || !g_train_fused.load()) return false;
+    for (int s2 = 0; s2 < n; s2++)
+      if (!tc_eligible(dX, N, ld, K, dim[s2])) return false;
+    return true;
+  }
+  int assign_fused(const float *dX, i64 N, i64 ld, const std::vector<int32_t> &subs, int32_t *inout,
+                   i64 stride, cudaStream_t st) {
+    GCU(cudaMemsetAsync(sums64.p, 0, (size_t)n * K * dmax * sizeof(unsigned long long), st));
+    GCU(cudaMemsetAsync(counts.p, 0, (size_t)n * K * sizeof(int32_t), st));
+    GCU(cudaMemsetAsync(bad.p, 0, (size_t)n * K * sizeof(int32_t), st));
+    GCU(cudaMemsetAsync(diff.p, 0, (size_t)n * sizeof(int32_t), st));
+    if (N <= 0) return GULON_OK;
+    return for_each_width(subs, st, [&](int w, const int32_t *ds, int ns) {
+      TcCtx ctx;
+      ctx.blobs = &tc;
+      ctx.n_windows = n;
+      ctx.prep = true;
+      ctx.hsubs = h_cur;
+      ctx.hfrom = from.data();
+      ctx.groups = &tc_groups;
+      ctx.fuse = true;
+      ctx.scale = scale.as<float>();
+      ctx.sums = sums64.as<unsigned long long>();
+      ctx.counts = counts.as<int32_t>();
+      ctx.bad = bad.as<int32_t>();
+      ctx.diff = diff.as<int32_t>();
+      return launch_assign<int32_t>(dX, N, ld, cb.as<float>(), off.as<float>(), K, dmax, ds, ns,
+                                    dfrom.as<int32_t>(), ddim.as<int32_t>(), w, &ctx, inout, stride, st);
     });
   }
   // GULON_UPDATE_SUM as an exact fixed-point sum (kupdate.cuh): finds the per-window scale with one
@@ -860,14 +924,25 @@ int train_problems(Problems &pr, gulon_points_t p, const int32_t *seeds, int max
     ~Guard() { a.release(); b.release(); c.release(); }
   } guard{a_prev, a_next, d_active};
   const i64 astride = std::max<i64>(N, 1);
-  GCHECK(a_prev.ensure((size_t)n * astride * sizeof(int32_t)));
-  GCHECK(a_next.ensure((size_t)n * astride * sizeof(int32_t)));
   GCHECK(d_active.ensure((size_t)n * sizeof(int32_t)));
 
   std::vector<int32_t> active(n);
   for (int s = 0; s < n; s++) active[s] = s;
   if (update_mode == GULON_UPDATE_SUM && g_update_fixed.load()) GCHECK(pr.prepare_fixed(p->d, N, p->ld, comm, st));
-  GCHECK(pr.assign(p->d, N, p->ld, active, a_prev.as<int32_t>(), astride, st));
+  // Sum mode on tensor-eligible shapes: ONE pass over the matrix per Lloyd iteration.  The pass that
+  // assigns with the current centroids also accumulates the fixed-point sums of the NEW assignments (the
+  // next update's input) and counts the rows that changed; assignments live in one buffer, updated in
+  // place.  Every rank of a sharded run takes the same branch (the shapes are the same everywhere; a
+  // rank without rows launches nothing).
+  const bool fused = update_mode == GULON_UPDATE_SUM && pr.can_fuse(p->d, std::max<i64>(N, 1), p->ld);
+  GCHECK(a_prev.ensure((size_t)n * astride * sizeof(int32_t)));
+  if (!fused) GCHECK(a_next.ensure((size_t)n * astride * sizeof(int32_t)));
+  if (fused) {
+    GCU(cudaMemsetAsync(a_prev.p, 0xFF, (size_t)n * astride * sizeof(int32_t), st));  // "no previous assignment"
+    GCHECK(pr.assign_fused(p->d, N, p->ld, active, a_prev.as<int32_t>(), astride, st));
+  } else {
+    GCHECK(pr.assign(p->d, N, p->ld, active, a_prev.as<int32_t>(), astride, st));
+  }
 
   std::vector<float> h_prev, h_next;
   if (report) {
@@ -892,21 +967,26 @@ int train_problems(Problems &pr, gulon_points_t p, const int32_t *seeds, int max
     if (update_mode == GULON_UPDATE_RUNNING_MEAN) {
       GCHECK(pr.running_mean(p->d, N, p->ld, a_prev.as<int32_t>(), astride, active, st));
     } else {
-      GCHECK(pr.partial_sums(p->d, N, p->ld, a_prev.as<int32_t>(), astride, active, st));
+      // (fused: the sums of the previous pass's assignments are already there)
+      if (!fused) GCHECK(pr.partial_sums(p->d, N, p->ld, a_prev.as<int32_t>(), astride, active, st));
       if (sharded) GCHECK(pr.allreduce_sums(comm, st));
       GCHECK(pr.finalize(d_active.as<int32_t>(), st));
     }
     GCHECK(pr.offsets(st));
     // assignments = next.parAssign(vecs); converged = Arrays.equals(prev, assignments)
-    GCHECK(pr.assign(p->d, N, p->ld, active, a_next.as<int32_t>(), astride, st));
-    GCU(cudaMemsetAsync(pr.diff.p, 0, (size_t)n * sizeof(int32_t), st));
-    if (N > 0) {
-      GCHECK(pr.for_each_width(active, st, [&](int, const int32_t *ds, int ns) -> int {
-        dim3 grid((unsigned)std::min<i64>(ceil_div(N, 1024), 1184), (unsigned)ns);
-        GLAUNCH(count_diff_kernel, grid, 256, 0, st, a_prev.as<int32_t>(), a_next.as<int32_t>(), N,
-                astride, ds, pr.diff.as<int32_t>());
-        return GULON_OK;
-      }));
+    if (fused) {
+      GCHECK(pr.assign_fused(p->d, N, p->ld, active, a_prev.as<int32_t>(), astride, st));
+    } else {
+      GCHECK(pr.assign(p->d, N, p->ld, active, a_next.as<int32_t>(), astride, st));
+      GCU(cudaMemsetAsync(pr.diff.p, 0, (size_t)n * sizeof(int32_t), st));
+      if (N > 0) {
+        GCHECK(pr.for_each_width(active, st, [&](int, const int32_t *ds, int ns) -> int {
+          dim3 grid((unsigned)std::min<i64>(ceil_div(N, 1024), 1184), (unsigned)ns);
+          GLAUNCH(count_diff_kernel, grid, 256, 0, st, a_prev.as<int32_t>(), a_next.as<int32_t>(), N,
+                  astride, ds, pr.diff.as<int32_t>());
+          return GULON_OK;
+        }));
+      }
     }
     if (sharded) {
       GREQUIRE(comm->allreduce_sum_i32(comm->user, pr.diff.as<int32_t>(), (i64)n, st) == 0,
@@ -921,9 +1001,10 @@ int train_problems(Problems &pr, gulon_points_t p, const int32_t *seeds, int max
     // carry the new assignments of the active windows forward (inactive windows are frozen)
     std::vector<int32_t> still;
     for (int32_t s : active) {
-      GCU(cudaMemcpyAsync(a_prev.as<int32_t>() + (size_t)s * astride,
-                          a_next.as<int32_t>() + (size_t)s * astride, (size_t)N * sizeof(int32_t),
-                          cudaMemcpyDeviceToDevice, st));
+      if (!fused)
+        GCU(cudaMemcpyAsync(a_prev.as<int32_t>() + (size_t)s * astride,
+                            a_next.as<int32_t>() + (size_t)s * astride, (size_t)N * sizeof(int32_t),
+                            cudaMemcpyDeviceToDevice, st));
       const int c = h_diff[s] == 0;
       upd[s] += 1;
       conv[s] = c;
@@ -1496,6 +1577,13 @@ MergeScratch &merge_scratch() {
 int merge_shards(const int32_t *d_ids, const float *d_dists, int S, i64 shard_stride, i64 nq, int k,
                  int32_t *d_out_ids, float *d_out_dists, int32_t *d_out_sizes, cudaStream_t st) {
   if (nq == 0) return GULON_OK;
+  if ((i64)S * k <= MERGE_WARP_MAX) {   // short lists: one warp per query, no scratch
+    int P = 2;
+    while (P < S * k) P <<= 1;
+    GLAUNCH(merge_results_small_kernel, (unsigned)ceil_div(nq, 4), 128, (size_t)4 * P * sizeof(u64), st, d_ids,
+            d_dists, S, shard_stride, k, (i64)nq, P, d_out_ids, d_out_dists, d_out_sizes);
+    return GULON_OK;
+  }
   MergeScratch &ms = merge_scratch();
   std::lock_guard<std::mutex> lock(ms.mu);
   GCHECK(ms.chain.enter(st));
@@ -1791,6 +1879,8 @@ int gulon_set_option(const char *name, int64_t value) {
     g_assign_impl = value;
   } else if (s == "update_fixed") {
     g_update_fixed = value ? 1 : 0;
+  } else if (s == "train_fused") {
+    g_train_fused = value ? 1 : 0;
   } else if (s == "assign_tc_min_rows") {
     GREQUIRE(value >= 0, "assign_tc_min_rows must be >= 0");
     g_assign_tc_min_rows = value;

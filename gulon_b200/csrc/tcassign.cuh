@@ -64,6 +64,17 @@ __host__ __device__ constexpr int off_slot(int dim) { return ((dim + 1 + 3) & ~3
 static_assert(off_slot(15) < CB_LD, "offset slot outside the centroid row");
 constexpr int BAR_BYTES = 256;
 constexpr int SMEM_BYTES = NRAW * RAW_BYTES + 2 * A_BYTES + GRP_MAX * BLOB_BYTES + BAR_BYTES;
+// Fused Lloyd pass (assignment + fixed-point cluster sums + changed count, one read of the matrix):
+// units hold at most FUSE_GRP windows, and the room of the third operand blob holds the shared-memory
+// accumulators of kupdate.cuh: per window LO[256][DIM], HI[256][DIM], CNT[256], BAD[256] 32-bit words.
+constexpr int FUSE_GRP = 2;
+constexpr int FUSE_KMAX = 256;
+constexpr int FUSE_FIX_BITS = 28;
+__host__ __device__ constexpr int fuse_wstride(int dim) { return 2 * FUSE_KMAX * dim + 2 * FUSE_KMAX; }
+__host__ __device__ constexpr int fuse_smem_bytes(int dim) {
+  return NRAW * RAW_BYTES + 2 * A_BYTES + FUSE_GRP * BLOB_BYTES + FUSE_GRP * fuse_wstride(dim) * 4 + BAR_BYTES;
+}
+static_assert(fuse_smem_bytes(15) <= 232448, "the fused pass must fit the 227 KB of an sm_100 CTA");
 
 static_assert(BLOB_BYTES % 16 == 0, "bulk copies move multiples of 16 bytes");
 static_assert(NCH == 32, "the candidate mask is one 32-bit word");
@@ -81,6 +92,13 @@ struct Params {
   i64 out_stride;
   unsigned long long *stats;    // [0] candidate (row, chunk) pairs
   volatile int *dbg;            // host-mapped breadcrumbs [warp][8] of CTA 0 (diagnostics), or null
+  // fused Lloyd pass only (FUSE): `out` is int32 and holds the PREVIOUS assignments on entry
+  const float *scale;           // [M] 2^S of the fixed-point sums (kupdate.cuh)
+  unsigned long long *sums;     // [M][K][dmax] biased fixed-point sums (RED.ADD.64 at the end of a unit)
+  int32_t *counts;              // [M][K]
+  int32_t *bad;                 // [M][K]
+  int32_t *diff;                // [M] rows whose assignment changed
+  int dmax;
 };
 
 // ---- PTX helpers ---------------------------------------------------------------------------------
@@ -111,6 +129,14 @@ __device__ __forceinline__ bool mb_try(uint64_t *b, uint32_t parity) {
 }
 // A hand-off that never arrives is a bug in the pipeline: trap (the launch fails with an error and
 // the breadcrumbs) instead of hanging the device.  Legitimate waits are microseconds long.
+//
+// Polling discipline (measured, round 2).  The ncu source page of the encode kernel shows 44 % of the
+// executed warp instructions in these wait loops (SYNCS / BRA / ISETP / VIADD / NANOSLEEP.SYNCS: a waiter
+// suspended with the hardware hint is woken by every mbarrier event of the CTA and polls again).  Both
+// alternatives were measured on the c2 encode and are slower: a fixed back-off (__nanosleep 32..256 ns
+// between polls) 524 M vectors/s -- the hand-offs sit on the critical path, a late wake-up stalls the
+// two-accumulator pipeline; a pure test_wait spin 484 M -- the spinners take the issue slots.  The
+// suspend-hint wait below gives 737 M.
 __device__ __forceinline__ void mb_wait(uint64_t *b, uint32_t parity) {
   for (uint32_t spins = 0; !mb_try(b, parity); spins++)
     if (spins > (1u << 22)) __trap();
@@ -358,17 +384,26 @@ __device__ __forceinline__ void load_window(const unsigned char *row_base, int s
 }
 
 // ---- the kernel ----------------------------------------------------------------------------------
-template <int DIM, typename OutT>
+// FUSE: one Lloyd pass.  Besides the assignment the sweep thread (which holds the row's window in
+// registers) adds the row into the fixed-point sums of its new cluster -- the arithmetic of
+// upd::update_fixed_kernel, bit for bit -- and counts the rows whose assignment differs from the one
+// `out` held on entry (KMeans.computeClusters' `Arrays.equals(prev, next)`, G/KMeans.scala:144-154).
+// Three passes over the matrix per iteration (assign, update, compare) become one.
+template <int DIM, typename OutT, bool FUSE = false>
 __global__ void __launch_bounds__(NT, 1) tc_assign_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
   static_assert(3 * DIM + 3 <= KP, "window too wide for the 48-slot contraction");
   static_assert(DIM <= BOX_COLS - 3, "a window at any alignment must fit one box");
+  static_assert(!FUSE || sizeof(OutT) == 4, "the fused pass works on int32 assignments");
   constexpr int DO = off_slot(DIM) + 1;  // floats of a centroid row the exact loop reads
   constexpr int W_MMA = 4 + 4 * NWG, W_TMA = W_MMA + 1;
+  constexpr int NBLOB = FUSE ? FUSE_GRP : GRP_MAX;
+  constexpr int WSTRIDE = fuse_wstride(DIM);
   extern __shared__ __align__(1024) unsigned char smem[];  // the 128-byte swizzle needs 1024-byte aligned tiles
   unsigned char *raw_s = smem;                                // NRAW raw tiles, 1024-byte aligned
   unsigned char *a_s = raw_s + NRAW * RAW_BYTES;              // 2 A tiles
-  unsigned char *blob_s = a_s + 2 * A_BYTES;                  // GRP_MAX blobs
-  uint64_t *bars = reinterpret_cast<uint64_t *>(blob_s + GRP_MAX * BLOB_BYTES);
+  unsigned char *blob_s = a_s + 2 * A_BYTES;                  // NBLOB blobs
+  unsigned int *acc_s = reinterpret_cast<unsigned int *>(blob_s + NBLOB * BLOB_BYTES);  // FUSE: accumulators
+  uint64_t *bars = reinterpret_cast<uint64_t *>(blob_s + NBLOB * BLOB_BYTES + (FUSE ? FUSE_GRP * WSTRIDE * 4 : 0));
   uint64_t *blob_full = bars;         // 1
   uint64_t *blob_empty = bars + 1;    // 1
   uint64_t *raw_full = bars + 2;      // NRAW
@@ -409,6 +444,8 @@ __global__ void __launch_bounds__(NT, 1) tc_assign_kernel(const __grid_constant_
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   TC_DBG(0, 1);
+  if constexpr (FUSE)
+    for (int t = tid; t < FUSE_GRP * WSTRIDE; t += NT) acc_s[t] = 0;
   if (warp == W_MMA) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sa(tmem_base_s)), "r"(512)
                  : "memory");
@@ -550,6 +587,12 @@ __global__ void __launch_bounds__(NT, 1) tc_assign_kernel(const __grid_constant_
         mb_arrive(raw_empty + rb);
       };
       unsigned n_pairs = 0;
+      int chg[FUSE_GRP] = {0, 0};   // FUSE: rows of this thread whose assignment changed, per window slot
+      float scl[FUSE_GRP] = {0.0f, 0.0f};
+      if constexpr (FUSE) {
+#pragma unroll
+        for (int ws = 0; ws < FUSE_GRP; ws++) scl[ws] = ws < nw ? p.scale[gw[ws]] : 0.0f;
+      }
       int rel = 0;  // next row block this warp has not released yet
       int t = (int)(((wg - tile) % NWG + NWG) % NWG);
       int b = t / nw, w = t - b * nw;
@@ -626,6 +669,10 @@ __global__ void __launch_bounds__(NT, 1) tc_assign_kernel(const __grid_constant_
         const i64 row = r_begin + (i64)b * TM + r;
         if (row >= r_end) mask = 0;
         n_pairs += __popc(mask);
+        int prev_a = 0;   // FUSE: the row's previous assignment (loaded now, compared after the recheck)
+        if constexpr (FUSE) {
+          if (row < r_end) prev_a = reinterpret_cast<const int32_t *>(p.out)[(i64)gw[w] * p.out_stride + row];
+        }
         // ---- exact evaluation of the candidate chunks ----
         // Reference rule: ascending k, strict '<' from Float.MaxValue = the (score, k)-lexicographic
         // minimum over accepted scores.  The 8 centroids of a chunk are visited in a per-lane rotated
@@ -635,6 +682,55 @@ __global__ void __launch_bounds__(NT, 1) tc_assign_kernel(const __grid_constant_
         const float *cbs = reinterpret_cast<const float *>(blob + B_BYTES);
         float best = FLT_MAX;
         int idx = 0;
+        // One candidate chunk (99 % of the rows): a second, FUSED fp32 filter before the literal
+        // arithmetic.  With u = 2^-24 and A_k = sum |x_j c_kj| <= |x||c_k|, the reference's unfused score is
+        // within 2 (DIM + 1) u A_k + u |s_k| of the real value and s~_k = fma(-2, fma-chain(x, c_k), off_k)
+        // within 2 DIM u A_k + u |s_k|, so the two evaluations of ONE centroid disagree by at most
+        //   D = (4 DIM + 2) u |x| max|c| + 2 u max|s|  <=  2^-18 |x| max|c| + 2^-23 max|s|     (DIM <= 15).
+        // If exactly one centroid k* of the chunk has s~ within tol >= 2 D of the chunk minimum, then for
+        // every other j: s_j >= s~_j - D > s~_k* + tol - D >= s_k* + tol - 2 D >= s_k*, strictly: k* IS the
+        // reference's argmin and no exact tie exists.  tol = 2^-16 |x| max|c| + 2^-20 (|min| + max|off|)
+        // is more than 4 D.  88 fused operations replace 176 unfused ones.  Anything else -- several
+        // centroids within tol (duplicates, near ties), NaN / huge scores, several candidate chunks --
+        // takes the literal path below.
+        if (!all && (mask & (mask - 1)) == 0 && mask != 0) {
+          const int c = __ffs(mask) - 1;
+          const float *cc = cbs + c * CHUNK_FLOATS;
+          const int rot = (5 * (lane - c)) & 7;
+          float sf[CH];
+#pragma unroll
+          for (int step = 0; step < CH; step++) {
+            const int i = (step + rot) & 7;
+            float cv[DO];
+#pragma unroll
+            for (int j4 = 0; j4 < DO / 4; j4++) {
+              const float4 q = *reinterpret_cast<const float4 *>(cc + i * CB_LD + 4 * j4);
+              cv[4 * j4 + 0] = q.x; cv[4 * j4 + 1] = q.y; cv[4 * j4 + 2] = q.z; cv[4 * j4 + 3] = q.w;
+            }
+            float d = 0.0f;
+#pragma unroll
+            for (int j = 0; j < DIM; j++) d = fmaf(x[j], cv[j], d);
+            sf[step] = fmaf(-2.0f, d, cv[DO - 1]);
+          }
+          float m = min3(sf[0], sf[1], sf[2]);
+          m = min3(m, sf[3], sf[4]);
+          m = min3(m, sf[5], sf[6]);
+          m = fminf(m, sf[7]);
+          const float tol = sqrtf(n2) * 1.001f * meta[0] * (1.0f / 65536.0f) +
+                            (fabsf(m) + meta[1]) * (1.0f / 1048576.0f) + 1e-30f;
+          const float lim = m + tol;
+          int near = 0, at = 0;
+#pragma unroll
+          for (int step = 0; step < CH; step++) {
+            const bool in = sf[step] <= lim;
+            near += in ? 1 : 0;
+            at = in ? step : at;
+          }
+          if (near == 1 && m < 1.0e37f && m > -1.0e37f) {
+            idx = c * CH + ((at + rot) & 7);
+            mask = 0;   // decided
+          }
+        }
         while (mask) {
           const int c = __ffs(mask) - 1;
           mask &= mask - 1;
@@ -673,6 +769,32 @@ __global__ void __launch_bounds__(NT, 1) tc_assign_kernel(const __grid_constant_
           }
         }
         if (row < r_end) reinterpret_cast<OutT *>(p.out)[(i64)gw[w] * p.out_stride + row] = (OutT)idx;
+        if constexpr (FUSE) {
+          if (row < r_end) {
+            // upd::update_fixed_kernel's accumulation: v = round(x 2^S) + 2^28 into 64-bit sums kept as two
+            // 32-bit words; all low-word atomics first (their returns in flight together), carries after
+            unsigned int *lo = acc_s + w * WSTRIDE + idx * DIM;
+            unsigned int *hi = lo + FUSE_KMAX * DIM;
+            const float sc_w = w == 0 ? scl[0] : scl[1];
+            bool bad = false;
+            unsigned int v[DIM], old[DIM];
+#pragma unroll
+            for (int j = 0; j < DIM; j++) {
+              const float sx = x[j] * sc_w;                // exact: a power of two
+              const bool ok = fabsf(sx) <= 268435456.0f;    // finite and within 2^28 (always, for finite x)
+              bad = bad || !ok;
+              v[j] = ok ? (unsigned int)(__float2int_rn(sx) + (1 << FUSE_FIX_BITS)) : 0u;
+            }
+#pragma unroll
+            for (int j = 0; j < DIM; j++) old[j] = atomicAdd(lo + j, v[j]);
+#pragma unroll
+            for (int j = 0; j < DIM; j++)
+              if (old[j] + v[j] < old[j]) atomicAdd(hi + j, 1u);  // carry out of the low word
+            atomicAdd(acc_s + w * WSTRIDE + 2 * FUSE_KMAX * DIM + idx, 1u);
+            if (bad) atomicOr(acc_s + w * WSTRIDE + 2 * FUSE_KMAX * DIM + FUSE_KMAX + idx, 1u);
+            if (w == 0) chg[0] += prev_a != idx; else chg[1] += prev_a != idx;
+          }
+        }
         TC_DBG(4, 100 + t);
         // next tile of this group
         w += NWG;
@@ -690,6 +812,41 @@ __global__ void __launch_bounds__(NT, 1) tc_assign_kernel(const __grid_constant_
       if (p.stats) {
         n_pairs = __reduce_add_sync(0xffffffffu, n_pairs);
         if (lane == 0) atomicAdd(p.stats, (unsigned long long)n_pairs);
+      }
+      if constexpr (FUSE) {
+        // flush the unit's sums (and clear them for the next unit): the 16 sweep warps only
+        constexpr int NSW = 4 * NWG * 32;
+        const int st = tid - 128;
+#pragma unroll
+        for (int ws = 0; ws < FUSE_GRP; ws++) {
+          const int c = __reduce_add_sync(0xffffffffu, chg[ws]);
+          if (lane == 0 && c && ws < nw) atomicAdd(p.diff + gw[ws], c);
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(NSW) : "memory");
+        for (int ws = 0; ws < nw; ws++) {
+          unsigned int *lo = acc_s + ws * WSTRIDE, *hi = lo + FUSE_KMAX * DIM, *cnt = hi + FUSE_KMAX * DIM,
+                       *bd = cnt + FUSE_KMAX;
+          const int m = gw[ws];
+          for (int t2 = st; t2 < p.K * DIM; t2 += NSW) {
+            const unsigned long long v = ((unsigned long long)hi[t2] << 32) | lo[t2];
+            if (v) {
+              atomicAdd(p.sums + ((i64)m * p.K + t2 / DIM) * p.dmax + t2 % DIM, v);
+              lo[t2] = 0;
+              hi[t2] = 0;
+            }
+          }
+          for (int t2 = st; t2 < p.K; t2 += NSW) {
+            if (cnt[t2]) {
+              atomicAdd(p.counts + (i64)m * p.K + t2, (int)cnt[t2]);
+              cnt[t2] = 0;
+            }
+            if (bd[t2]) {
+              atomicOr(p.bad + (i64)m * p.K + t2, 1);
+              bd[t2] = 0;
+            }
+          }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(NSW) : "memory");
       }
     }
     tile += n_tiles;

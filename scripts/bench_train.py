@@ -1,6 +1,6 @@
 """Resident-data timing of ProductQuantizer.train (k-means codebook training, c3 shape).
 
-usage: python scripts/bench_train.py [rows] [D] [M] [iters] [update_mode: 0 running mean | 1 sum]
+usage: python scripts/bench_train.py [rows] [D] [M] [iters] [update_mode: 0 running mean | 1 sum] [fused: 1 | 0]
 Prints one JSON line: seconds, Lloyd passes, rows*windows assigned per second.
 """
 import json
@@ -22,6 +22,8 @@ def main():
     M = int(sys.argv[3]) if len(sys.argv) > 3 else 30
     iters = int(sys.argv[4]) if len(sys.argv) > 4 else 25
     mode = int(sys.argv[5]) if len(sys.argv) > 5 else 1
+    fused = int(sys.argv[6]) if len(sys.argv) > 6 else 1
+    g.set_option("train_fused", fused)
     dev = torch.device("cuda", 0)
     X = Mixture(D, device=dev).rows(0, rows)
     pts = g.DevicePoints.from_torch(X)
@@ -35,7 +37,7 @@ def main():
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
     passes = len(seen)
-    print(json.dumps({"rows": rows, "D": D, "M": M, "max_iters": iters, "update_mode": mode, "seconds": dt,
+    print(json.dumps({"rows": rows, "D": D, "M": M, "max_iters": iters, "update_mode": mode, "fused": fused, "seconds": dt,
                       "reports": passes, "GB_per_pass": rows * D * 4 / 1e9,
                       "s_per_iter": dt / max(1, iters + 1)}))
 

@@ -202,3 +202,59 @@ def test_sharded_training_is_bit_identical_to_one_rank(g):
             assert np.array_equal(out[r][0].view(np.uint32), one.centroids.view(np.uint32)), (world, r)
             assert out[r][1] == info1
             assert calls[r]["i64"] > 0 and calls[r]["mx"] == 1
+
+
+# ---- fused Lloyd pass (assignment + sums + changed count in one read of the matrix) -------------------
+@pytest.mark.parametrize("n,D,M,K,iters", [
+    (50000, 40, 4, 256, 6),        # width 10, the BASELINE width
+    (30000, 37, 5, 100, 5),        # ragged windows: widths 8 and 7, K < 256
+    (4097, 16, 2, 256, 3),         # width 8, a 1-row last tile
+    (200, 30, 3, 16, 4),           # fewer rows than one tile
+    (20000, 45, 3, 256, 4),        # width 15: the largest the tensor path takes
+    (70000, 300, 30, 256, 3),      # c2 / c3 shape: 30 windows, 15 units of 2 per row range
+    (9000, 128, 16, 256, 25),      # c4 shape, runs to convergence or 25 iterations
+])
+def test_fused_lloyd_pass_equals_three_pass_training(g, n, D, M, K, iters):
+    """ProductQuantizer.apply in sum mode: the fused pass (tca::tc_assign_kernel<.., true>) against the
+    round-1 sequence assign -> update_fixed -> count_diff.  Same integer sums, same assignments, so the
+    centroids, the iteration counts and the convergence flags are identical."""
+    rng = np.random.default_rng(n + D)
+    X = clustered(rng, n, D, centres=40)
+    X[7] = X[3]
+    pts = g.Matrix(X).device()
+    out = {}
+    for fused in (0, 1):
+        reports = {}
+        cfg = g.ProductQuantizerConfig(K, M, iters, update_mode=g.UPDATE_SUM,
+                                       report=lambda r: reports.update(
+                                           {i: (k.num_iterations, k.converged) for i, k in enumerate(r.kmeans_reports)}))
+        g.set_option("train_fused", fused)
+        try:
+            launches0 = g.kernel_launches()
+            out[fused] = (g.ProductQuantizer.train(pts, cfg).codebook(), dict(reports), g.kernel_launches() - launches0)
+        finally:
+            g.set_option("train_fused", 1)
+    assert np.array_equal(out[0][0].view(np.uint32), out[1][0].view(np.uint32))
+    assert out[0][1] == out[1][1]
+    assert out[1][2] < out[0][2]          # fewer launches: no update / compare kernels
+
+
+def test_fused_single_window_with_offset_and_duplicates(g, oracle):
+    """KMeans.computeClusters on a column window that starts off the 16-byte grid, with duplicate rows
+    (exact score ties -> lowest index) -- fused == three-pass, and the assignments of the result equal the
+    oracle's for the returned centroids."""
+    rng = np.random.default_rng(4)
+    n, D = 12000, 23
+    X = clustered(rng, n, D, centres=6)
+    X[100:200] = X[0]
+    out = []
+    for fused in (0, 1):
+        g.set_option("train_fused", fused)
+        try:
+            km, info = g.KMeans.compute_clusters(g.Vectors(g.Matrix(X), 5, 16),
+                                                 g.KMeansConfig(64, 12, seed=3, update_mode=g.UPDATE_SUM),
+                                                 return_info=True)
+        finally:
+            g.set_option("train_fused", 1)
+        out.append((km.centroids.copy(), info))
+    assert np.array_equal(out[0][0].view(np.uint32), out[1][0].view(np.uint32)) and out[0][1] == out[1][1]
