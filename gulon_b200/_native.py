@@ -161,6 +161,8 @@ SIGNATURES = {
                                         vp, vp, vp]),
     "gulon_synth_tables_dev": (C.c_int, [C.POINTER(SynthParams), vp, vp, vp]),
     "gulon_synth_rows_dev": (C.c_int, [C.POINTER(SynthParams), i64, i64, i64, vp, vp, vp, i64, vp]),
+    "gulon_grouped_query_dev": (C.c_int, [vp, vp, i64, i64, vp, i32, vp, vp, vp, vp, i64, i32, i32,
+                                          vp, vp, vp, vp]),
     "gulon_exact_topk": (C.c_int, [vp, vp, i64, i64, i32, i64, i64, vp, vp, vp]),
     "gulon_rerank": (C.c_int, [vp, vp, i64, i64, vp, i32, i32, vp, vp, vp]),
 }

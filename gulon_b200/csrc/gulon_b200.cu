@@ -67,6 +67,9 @@ struct gulon_codebook_s {
   std::map<int, DevBuf> d_by_dim;
   std::mutex mu;
   DevBuf scratch_q, scratch_lut;  // gulon_prepare_query staging
+  // gulon_pq_encode staging, kept across calls (no cudaMalloc / cudaFree / stream creation per call)
+  cudaStream_t enc_st[2] = {nullptr, nullptr};
+  DevBuf enc_x[2], enc_c[2];
   DevBuf tc;                      // tensor-core assignment operands (tcassign.cuh)
   std::map<int, DevBuf> tc_groups;  // per window width: groups of adjacent windows
   std::map<int, int> tc_ngroups;
@@ -76,6 +79,11 @@ struct gulon_codebook_s {
     cb.release(); off.release(); dfrom.release(); ddim.release();
     for (auto &kv : d_by_dim) kv.second.release();
     scratch_q.release(); scratch_lut.release();
+    for (int i = 0; i < 2; i++) {
+      enc_x[i].release();
+      enc_c[i].release();
+      if (enc_st[i]) cudaStreamDestroy(enc_st[i]);
+    }
   }
 };
 
@@ -96,6 +104,7 @@ struct gulon_index_s {
   DevBuf lutI, keys, lists, qbuf, ids, dists, sizes, merged;
   DevBuf qlut, mins, qp, boot_tail, plists, pstats, boot_keys, spread, msel, merged2, sufmin;
   DevBuf rowcodes;            // row-major copy of the planes, built by the first pruned scan
+  DevBuf kacc, kfloor;        // k-chunked scans: accumulated keys [Q4][k], last key of the previous pass [Q4]
   i64 rcs = 0;
   int rowcodes_state = 0;     // 0 not tried, 1 ready, -1 unavailable (no memory): planes are used
   Selector sel, sel_boot, sel2;
@@ -116,7 +125,7 @@ struct gulon_index_s {
     ids.release(); dists.release(); sizes.release(); merged.release();
     qlut.release(); mins.release(); qp.release(); boot_tail.release(); plists.release();
     pstats.release(); boot_keys.release(); spread.release(); msel.release(); merged2.release();
-    sel2.release(); sufmin.release(); rowcodes.release();
+    sel2.release(); sufmin.release(); rowcodes.release(); kacc.release(); kfloor.release();
     if (tm_ev0) cudaEventDestroy(tm_ev0);
     if (tm_ev1) cudaEventDestroy(tm_ev1);
     h_q.release(); h_ids.release(); h_dists.release(); h_sizes.release();
@@ -132,7 +141,7 @@ namespace {
 std::atomic<long long> g_scan_impl{GULON_SCAN_AUTO};
 std::atomic<long long> g_query_batch{0};      // 0 = auto (multiple of 16 * #SM)
 std::atomic<long long> g_simple_scratch{1LL << 30};
-std::atomic<long long> g_encode_chunk{1 << 20};  // rows per H2D chunk in gulon_pq_encode
+std::atomic<long long> g_encode_chunk{1 << 18};  // rows per H2D chunk in gulon_pq_encode (two chunks in flight)
 std::atomic<long long> g_fused_min_rows{16384};
 std::atomic<long long> g_boot_rows{0};           // rows scanned exactly to seed the pruned scan; 0 = range / 64 in [8192, 32768], whole 8192-row chunks
 std::atomic<long long> g_pruned_min_rows{1 << 18};
@@ -1161,7 +1170,7 @@ int fill_empty(i64 nq, int k, int32_t *ids, float *dists, int32_t *sizes, cudaSt
 
 // Launches the fused exact scan of [from, until) for G query groups; lists [S][G*4][k].
 int fused_lists(gulon_index_t ix, i64 from, i64 until, int G, int k, DevBuf &lists, int *S_out,
-                cudaStream_t st) {
+                cudaStream_t st, const u64 *floor = nullptr) {
   gulon_codebook_t cb = ix->cb;
   const i64 range = until - from;
   const int Q4 = G * 4;
@@ -1191,6 +1200,7 @@ int fused_lists(gulon_index_t ix, i64 from, i64 until, int G, int k, DevBuf &lis
   prm.S = S;
   prm.Bs = Bs;
   prm.lists = lists.as<u64>();
+  prm.floor = floor;
   cudaEvent_t ev = g_t_scan.begin(st);
   GLAUNCH(fscan::fused_scan_kernel, (unsigned)(S * Bs), fscan::NT, fscan::SMEM_BYTES, st, prm);
   g_t_scan.end(ev, st);
@@ -1212,6 +1222,11 @@ int collapse_lists(DevBuf &lists, int S, int Q4, int k, DevBuf &merged, Selector
   GLAUNCH(gather_lists_kernel, gg, 256, 0, st, lists.as<u64>(), S, (i64)Q4, k, merged.as<u64>(), ms);
   return sel.run(merged.as<u64>(), ms, Q4, k, st, keys, stride);
 }
+
+// k beyond the in-kernel list size (128) runs the fast kernels in passes of <= 128: a pass only admits keys
+// greater than the last key of the previous pass (`floor`), so it returns the NEXT 128 of the (distance,
+// id) order.  The reference's recall harness defaults reach k = 1000 (G/Tests.scala:53): 8 passes.
+constexpr int KCHUNK_MAX = 1024;
 
 // One batch of queries (device, already normalised if the metric asks for it) over [from, until).
 // Caller holds ix->mu.
@@ -1245,9 +1260,9 @@ int scan_batch(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 fr
   }
   long long impl = g_scan_impl.load();
   if (impl == GULON_SCAN_AUTO) {
-    if (k <= pscan::KMAX && M <= 1024 && range >= g_pruned_min_rows.load())
+    if (k <= KCHUNK_MAX && M <= 1024 && range >= g_pruned_min_rows.load())
       impl = GULON_SCAN_PRUNED;
-    else if (k <= fscan::KMAX && range >= g_fused_min_rows.load())
+    else if (k <= KCHUNK_MAX && range >= g_fused_min_rows.load())
       impl = GULON_SCAN_FUSED;
     else
       impl = GULON_SCAN_SIMPLE;
@@ -1301,193 +1316,224 @@ int scan_batch(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 fr
   GLAUNCH(lut_build_kernel, lg, 256, 0, st, dQ, ldq, nq, cb->cb.as<float>(),
           cb->dfrom.as<int32_t>(), cb->ddim.as<int32_t>(), M, K, cb->dmax, ix->lutI.as<float4>());
 
-  if (impl == GULON_SCAN_FUSED) {
-    int S = 1;
-    GCHECK(fused_lists(ix, from, until, G, k, ix->lists, &S, st));
-    u64 *res;
-    i64 rs;
-    GCHECK(collapse_lists(ix->lists, S, Q4, k, ix->merged, ix->sel, &res, &rs, st));
-    return unpack(res, rs, nq, k, id_offset, d_ids, d_dists, d_sizes, st);
-  }
+  if (impl == GULON_SCAN_FUSED || impl == GULON_SCAN_PRUNED) {
+    const int k_all = k;
+    // one pass of a fast kernel: the k best keys greater than `floor` (null: the k best) -> res [Q4][rs]
+    auto fast_pass = [&](int k, const u64 *floor, u64 *&res, i64 &rs) -> int {
+    if (impl == GULON_SCAN_FUSED) {
+      int S = 1;
+      GCHECK(fused_lists(ix, from, until, G, k, ix->lists, &S, st, floor));
+      GCHECK(collapse_lists(ix->lists, S, Q4, k, ix->merged, ix->sel, &res, &rs, st));
+      return GULON_OK;
+    }
 
-  if (impl == GULON_SCAN_PRUNED) {
-    GREQUIRE(k <= pscan::KMAX, "pruned scan supports k <= %d (k=%d)", pscan::KMAX, k);
-    GREQUIRE(M <= pscan::MSEL_MAX, "pruned scan supports M <= %d (M=%d)", pscan::MSEL_MAX, M);
-    GREQUIRE(FB == 16 || 127 / ML >= 1, "8-bit pruned scan needs <= 127 quantizers in the bound (%d)", ML);
-#define GULON_PSCAN_VARIANTS(X) X(8, 4) X(8, 2) X(8, 1) X(16, 4) X(16, 2)
-#define GULON_X(FB_, W_)                                                                        \
-  if (FB == FB_ && W == W_) {                                                                   \
-    auto kern = pscan::pruned_scan_kernel<FB_, W_>;                                             \
-    using CfgT = pscan::Cfg<FB_, W_>;                                                           \
-    GOPTIN(kern, CfgT::SMEM_BYTES);                                                             \
-  }
-    GULON_PSCAN_VARIANTS(GULON_X)
-#undef GULON_X
-    const int T = G / (QT / 4);
-    const int RI = pscan::NT * (64 / W);  // rows per work item
-    g_last_qt = QT;
-    // 1. exact scan of the boot rows -> one sorted list per query (its tail is tau0)
-    // (measured on the 1M-row shapes c1 / c5: 16384 boot rows beat 65536 by 3-7 %, and the pruned scan
-    // beats the exact kernel 2x there; profiles/README.md round 1d)
-    i64 boot_want = g_boot_rows.load();
-    // whole 8192-row chunks: the exact kernel pays for a chunk's table fills however few rows it holds
-    if (boot_want <= 0) boot_want = std::min<i64>(32768, std::max<i64>(8192, (range / 64) & ~8191LL));
-    const i64 boot = std::min<i64>(range, std::max<i64>(boot_want, k));
-    int Sb = 1;
-    GCHECK(fused_lists(ix, from, from + boot, G, k, ix->lists, &Sb, st));
-    u64 *bkeys;
-    i64 bstride;
-    GCHECK(collapse_lists(ix->lists, Sb, Q4, k, ix->boot_keys, ix->sel_boot, &bkeys, &bstride, st));
-    if (boot == range) return unpack(bkeys, bstride, nq, k, id_offset, d_ids, d_dists, d_sizes, st);
-    GCHECK(ix->mins.ensure((size_t)Q4 * M * sizeof(float)));
-    GCHECK(ix->spread.ensure((size_t)Q4 * M * sizeof(float)));
-    GCHECK(ix->sufmin.ensure((size_t)Q4 * (M + 1) * sizeof(float)));
-    if (ix->rowcodes_state == 0 && g_pruned_rowcodes.load() != 0) {
-      // the codes of a row side by side: what the survivor evaluation gathers (built once; the code
-      // planes of an index must not change after its first query)
-      ix->rcs = round_up(M, 16);
-      if (ix->rowcodes.ensure((size_t)ix->N * (size_t)ix->rcs) == GULON_OK) {
-        GLAUNCH(pscan::rowcodes_kernel, (unsigned)ceil_div(ix->N, 256), 256, 0, st, ix->codes, ix->ps,
-                ix->N, M, ix->rcs, ix->rowcodes.as<uint8_t>());
-        ix->rowcodes_state = 1;
-      } else {
-        cudaGetLastError();
-        ix->rowcodes_state = -1;
-      }
+    if (impl == GULON_SCAN_PRUNED) {
+      GREQUIRE(k <= pscan::KMAX, "pruned scan supports k <= %d (k=%d)", pscan::KMAX, k);
+      GREQUIRE(M <= pscan::MSEL_MAX, "pruned scan supports M <= %d (M=%d)", pscan::MSEL_MAX, M);
+      GREQUIRE(FB == 16 || 127 / ML >= 1, "8-bit pruned scan needs <= 127 quantizers in the bound (%d)", ML);
+  #define GULON_PSCAN_VARIANTS(X) X(8, 4) X(8, 2) X(8, 1) X(16, 4) X(16, 2)
+  #define GULON_X(FB_, W_)                                                                        \
+    if (FB == FB_ && W == W_) {                                                                   \
+      auto kern = pscan::pruned_scan_kernel<FB_, W_>;                                             \
+      using CfgT = pscan::Cfg<FB_, W_>;                                                           \
+      GOPTIN(kern, CfgT::SMEM_BYTES);                                                             \
     }
-    GCHECK(ix->qp.ensure((size_t)Q4 * sizeof(pscan::QParam)));
-    GCHECK(ix->boot_tail.ensure((size_t)Q4 * sizeof(u64)));
-    GCHECK(ix->pstats.ensure(8 * sizeof(unsigned long long)));
-    if (!ix->tm_ev0) {
-      GCU(cudaEventCreate(&ix->tm_ev0));
-      GCU(cudaEventCreate(&ix->tm_ev1));
-    }
-    // 2. stages over the remaining rows.  A stage quantises the tables against the best lists known
-    //    so far (boot, then boot + earlier stages), scans its rows, and merges its lists into them.
-    //    The first, short stage uses every quantizer; its result gives the main stage thresholds
-    //    tight enough for a lower bound over a SUBSET of the quantizers.
-    const i64 pfrom = from + boot, prange = until - pfrom;
-    const long long sdiv = g_pruned_stage_div.load();
-    i64 stageA = 0;
-    if (ML < M && sdiv > 0) {
-      // at least 4 items per CTA
-      stageA = std::max<i64>(round_up(prange / sdiv, RI), 4 * (i64)RI);
-      if (stageA >= prange) stageA = 0;
-    }
-    const int nsm = sm_count();
-    const bool want_stats = g_profile.load() != 0;
-    u64 *cur = bkeys;
-    i64 cur_stride = bstride;
-    for (int stage = stageA > 0 ? 0 : 1; stage < 2; ++stage) {
-      const i64 sfrom = stage == 0 ? pfrom : pfrom + stageA;
-      const i64 suntil = stage == 0 ? pfrom + stageA : until;
-      const i64 srange = suntil - sfrom;
-      // the first stage sums every quantizer, or as many as 8-bit fields hold with >= 3 levels each
-      const int sML = stage == 1 ? ML : (FB == 8 ? std::min(M, std::max(ML, 42)) : M);
-      GCHECK(ix->qlut.ensure((size_t)T * sML * 256 * W * sizeof(uint32_t)));
-      GCHECK(ix->msel.ensure((size_t)T * sML * sizeof(int32_t)));
-      GLAUNCH(pscan::qparams_kernel, (unsigned)G, 256, 0, st, ix->lutI.as<float4>(), M, K, nq, cur,
-              cur_stride, k, pscan::t0_units(FB, sML), ix->mins.as<float>(), ix->spread.as<float>(),
-              ix->sufmin.as<float>(), ix->qp.as<pscan::QParam>(), ix->boot_tail.as<u64>());
-      GLAUNCH(pscan::qselect_kernel, (unsigned)T, 256, 0, st, ix->spread.as<float>(),
-              ix->qp.as<pscan::QParam>(), M, sML, QT, ix->msel.as<int32_t>());
-      dim3 qg((unsigned)T, (unsigned)sML);
-      bool built = false;
-#define GULON_X(FB_, W_)                                                                        \
-  if (FB == FB_ && W == W_) {                                                                   \
-    auto kern = pscan::qlut_build_kernel<FB_, W_>;                                              \
-    GLAUNCH(kern, qg, 256, 0, st, ix->lutI.as<float4>(), ix->mins.as<float>(),                  \
-            ix->qp.as<pscan::QParam>(), ix->msel.as<int32_t>(), M, sML, K,                      \
-            ix->qlut.as<uint32_t>());                                                           \
-    built = true;                                                                               \
-  }
       GULON_PSCAN_VARIANTS(GULON_X)
-#undef GULON_X
-      GREQUIRE(built, "unsupported pruned-scan variant: %d-bit fields, %d words", FB, W);
-      int Bs = std::min(T, nsm);
-      int S = std::max(1, nsm / Bs);
-      S = (int)std::max<i64>(1, std::min<i64>(S, srange / (2 * (i64)RI)));
-      const i64 split_len = round_up(ceil_div(srange, S), 16);
-      S = (int)ceil_div(srange, split_len);
-      const size_t nl = (size_t)S * Q4 * k;
-      GCHECK(ix->plists.ensure(nl * sizeof(u64)));
-      GCU(cudaMemsetAsync(ix->plists.p, 0xFF, nl * sizeof(u64), st));
-      unsigned long long *dstats = ix->pstats.as<unsigned long long>() + 4 * stage;
-      GCU(cudaMemsetAsync(dstats, 0, 3 * sizeof(unsigned long long), st));
-      pscan::Params prm;
-      prm.codes = ix->codes;
-      prm.ps = ix->ps;
-      const bool use_rows = ix->rowcodes_state == 1 && g_pruned_rowcodes.load() != 0;
-      prm.rowcodes = use_rows ? ix->rowcodes.as<uint8_t>() : nullptr;
-      prm.rcs = ix->rcs;
-      prm.sufmin = ix->sufmin.as<float>();
-      prm.from = sfrom;
-      prm.until = suntil;
-      prm.split_len = split_len;
-      prm.qlut = ix->qlut.as<uint32_t>();
-      prm.msel = ix->msel.as<int32_t>();
-      prm.lutI = ix->lutI.as<float4>();
-      prm.qp = ix->qp.as<pscan::QParam>();
-      prm.boot_tail = ix->boot_tail.as<u64>();
-      prm.lists = ix->plists.as<u64>();
-      prm.stats = dstats;
-      prm.nq = nq;
-      prm.M = M;
-      prm.ML = sML;
-      prm.T = T;
-      prm.k = k;
-      prm.S = S;
-      prm.Bs = Bs;
-      const bool time_it = stage == 1 && g_pruned_lb.load() == 0 && !ix->tm_pending;
-      if (time_it) GCU(cudaEventRecord(ix->tm_ev0, st));
-      KernelTimer &ktm = stage == 1 ? g_t_pscan : g_t_pscan_first;
-      cudaEvent_t ev = ktm.begin(st);
-#define GULON_X(FB_, W_)                                                                        \
-  if (FB == FB_ && W == W_) {                                                                   \
-    auto kern = pscan::pruned_scan_kernel<FB_, W_>;                                             \
-    using CfgT = pscan::Cfg<FB_, W_>;                                                           \
-    GLAUNCH(kern, (unsigned)(S * Bs), pscan::NT, CfgT::SMEM_BYTES, st, prm);                    \
-  }
-      GULON_PSCAN_VARIANTS(GULON_X)
-#undef GULON_X
-      ktm.end(ev, st);
-      if (time_it) {
-        GCU(cudaEventRecord(ix->tm_ev1, st));
-        ix->tm_pending = true;
-        ix->tm_ml = sML;
-        ix->tm_pairs = (double)srange * (double)nq;
-        // (the whole pruned range, not this stage's share: the full bound runs without a first stage)
-        ix->tm_shape = (long long)T * 1000003LL + (long long)(prange >> 12) + 1;
+  #undef GULON_X
+      const int T = G / (QT / 4);
+      const int RI = pscan::NT * (64 / W);  // rows per work item
+      g_last_qt = QT;
+      // 1. exact scan of the boot rows -> one sorted list per query (its tail is tau0)
+      // (measured on the 1M-row shapes c1 / c5: 16384 boot rows beat 65536 by 3-7 %, and the pruned scan
+      // beats the exact kernel 2x there; profiles/README.md round 1d)
+      i64 boot_want = g_boot_rows.load();
+      // whole 8192-row chunks: the exact kernel pays for a chunk's table fills however few rows it holds
+      if (boot_want <= 0) boot_want = std::min<i64>(32768, std::max<i64>(8192, (range / 64) & ~8191LL));
+      const i64 boot = std::min<i64>(range, std::max<i64>(boot_want, k));
+      int Sb = 1;
+      GCHECK(fused_lists(ix, from, from + boot, G, k, ix->lists, &Sb, st, floor));
+      u64 *bkeys;
+      i64 bstride;
+      GCHECK(collapse_lists(ix->lists, Sb, Q4, k, ix->boot_keys, ix->sel_boot, &bkeys, &bstride, st));
+      if (boot == range) {
+        res = bkeys;
+        rs = bstride;
+        return GULON_OK;
       }
-      if (want_stats) {
-        unsigned long long h[3];
-        GCU(cudaMemcpyAsync(h, dstats, sizeof(h), cudaMemcpyDeviceToHost, st));
-        GCU(cudaStreamSynchronize(st));
-        for (int i = 0; i < 3; i++) g_pstats[i] += h[i];
-        g_ppairs += (unsigned long long)srange * (unsigned long long)nq;
-        if (stage == 1) g_ppairs_main += (unsigned long long)srange * (unsigned long long)nq;
+      GCHECK(ix->mins.ensure((size_t)Q4 * M * sizeof(float)));
+      GCHECK(ix->spread.ensure((size_t)Q4 * M * sizeof(float)));
+      GCHECK(ix->sufmin.ensure((size_t)Q4 * (M + 1) * sizeof(float)));
+      if (ix->rowcodes_state == 0 && g_pruned_rowcodes.load() != 0) {
+        // the codes of a row side by side: what the survivor evaluation gathers (built once; the code
+        // planes of an index must not change after its first query)
+        ix->rcs = round_up(M, 16);
+        if (ix->rowcodes.ensure((size_t)ix->N * (size_t)ix->rcs) == GULON_OK) {
+          GLAUNCH(pscan::rowcodes_kernel, (unsigned)ceil_div(ix->N, 256), 256, 0, st, ix->codes, ix->ps,
+                  ix->N, M, ix->rcs, ix->rowcodes.as<uint8_t>());
+          ix->rowcodes_state = 1;
+        } else {
+          cudaGetLastError();
+          ix->rowcodes_state = -1;
+        }
       }
-      if (stage == 1) g_last_ml = sML;
-      // best lists so far + this stage's split lists -> best lists so far
-      DevBuf &mb = stage == 0 ? ix->merged2 : ix->merged;
-      Selector &sl = stage == 0 ? ix->sel2 : ix->sel;
-      if ((i64)(S + 1) * k <= pscan::MERGE_SMALL_MAX) {
-        GCHECK(mb.ensure((size_t)Q4 * k * sizeof(u64)));
-        GLAUNCH(pscan::merge_small_kernel, (unsigned)ceil_div(Q4, 4), 128, 0, st, ix->plists.as<u64>(), S,
-                (i64)Q4, k, cur, cur_stride, mb.as<u64>());
-        cur = mb.as<u64>();
-        cur_stride = k;
-      } else {
-        const i64 ms = round_up((i64)(S + 1) * k, SEL_CHUNK);
-        GCHECK(mb.ensure((size_t)Q4 * ms * sizeof(u64)));
-        dim3 gg((unsigned)ceil_div(ms, 256), (unsigned)Q4);
-        GLAUNCH(pscan::gather_lists2_kernel, gg, 256, 0, st, ix->plists.as<u64>(), S, (i64)Q4, k, cur,
-                cur_stride, mb.as<u64>(), ms);
-        GCHECK(sl.run(mb.as<u64>(), ms, Q4, k, st, &cur, &cur_stride));
+      GCHECK(ix->qp.ensure((size_t)Q4 * sizeof(pscan::QParam)));
+      GCHECK(ix->boot_tail.ensure((size_t)Q4 * sizeof(u64)));
+      GCHECK(ix->pstats.ensure(8 * sizeof(unsigned long long)));
+      if (!ix->tm_ev0) {
+        GCU(cudaEventCreate(&ix->tm_ev0));
+        GCU(cudaEventCreate(&ix->tm_ev1));
       }
+      // 2. stages over the remaining rows.  A stage quantises the tables against the best lists known
+      //    so far (boot, then boot + earlier stages), scans its rows, and merges its lists into them.
+      //    The first, short stage uses every quantizer; its result gives the main stage thresholds
+      //    tight enough for a lower bound over a SUBSET of the quantizers.
+      const i64 pfrom = from + boot, prange = until - pfrom;
+      const long long sdiv = g_pruned_stage_div.load();
+      i64 stageA = 0;
+      if (ML < M && sdiv > 0) {
+        // at least 4 items per CTA
+        stageA = std::max<i64>(round_up(prange / sdiv, RI), 4 * (i64)RI);
+        if (stageA >= prange) stageA = 0;
+      }
+      const int nsm = sm_count();
+      const bool want_stats = g_profile.load() != 0;
+      u64 *cur = bkeys;
+      i64 cur_stride = bstride;
+      for (int stage = stageA > 0 ? 0 : 1; stage < 2; ++stage) {
+        const i64 sfrom = stage == 0 ? pfrom : pfrom + stageA;
+        const i64 suntil = stage == 0 ? pfrom + stageA : until;
+        const i64 srange = suntil - sfrom;
+        // the first stage sums every quantizer, or as many as 8-bit fields hold with >= 3 levels each
+        const int sML = stage == 1 ? ML : (FB == 8 ? std::min(M, std::max(ML, 42)) : M);
+        GCHECK(ix->qlut.ensure((size_t)T * sML * 256 * W * sizeof(uint32_t)));
+        GCHECK(ix->msel.ensure((size_t)T * sML * sizeof(int32_t)));
+        GLAUNCH(pscan::qparams_kernel, (unsigned)G, 256, 0, st, ix->lutI.as<float4>(), M, K, nq, cur,
+                cur_stride, k, pscan::t0_units(FB, sML), ix->mins.as<float>(), ix->spread.as<float>(),
+                ix->sufmin.as<float>(), ix->qp.as<pscan::QParam>(), ix->boot_tail.as<u64>());
+        GLAUNCH(pscan::qselect_kernel, (unsigned)T, 256, 0, st, ix->spread.as<float>(),
+                ix->qp.as<pscan::QParam>(), M, sML, QT, ix->msel.as<int32_t>());
+        dim3 qg((unsigned)T, (unsigned)sML);
+        bool built = false;
+  #define GULON_X(FB_, W_)                                                                        \
+    if (FB == FB_ && W == W_) {                                                                   \
+      auto kern = pscan::qlut_build_kernel<FB_, W_>;                                              \
+      GLAUNCH(kern, qg, 256, 0, st, ix->lutI.as<float4>(), ix->mins.as<float>(),                  \
+              ix->qp.as<pscan::QParam>(), ix->msel.as<int32_t>(), M, sML, K,                      \
+              ix->qlut.as<uint32_t>());                                                           \
+      built = true;                                                                               \
     }
-#undef GULON_PSCAN_VARIANTS
-    return unpack(cur, cur_stride, nq, k, id_offset, d_ids, d_dists, d_sizes, st);
+        GULON_PSCAN_VARIANTS(GULON_X)
+  #undef GULON_X
+        GREQUIRE(built, "unsupported pruned-scan variant: %d-bit fields, %d words", FB, W);
+        int Bs = std::min(T, nsm);
+        int S = std::max(1, nsm / Bs);
+        S = (int)std::max<i64>(1, std::min<i64>(S, srange / (2 * (i64)RI)));
+        const i64 split_len = round_up(ceil_div(srange, S), 16);
+        S = (int)ceil_div(srange, split_len);
+        const size_t nl = (size_t)S * Q4 * k;
+        GCHECK(ix->plists.ensure(nl * sizeof(u64)));
+        GCU(cudaMemsetAsync(ix->plists.p, 0xFF, nl * sizeof(u64), st));
+        unsigned long long *dstats = ix->pstats.as<unsigned long long>() + 4 * stage;
+        GCU(cudaMemsetAsync(dstats, 0, 3 * sizeof(unsigned long long), st));
+        pscan::Params prm;
+        prm.codes = ix->codes;
+        prm.ps = ix->ps;
+        const bool use_rows = ix->rowcodes_state == 1 && g_pruned_rowcodes.load() != 0;
+        prm.rowcodes = use_rows ? ix->rowcodes.as<uint8_t>() : nullptr;
+        prm.rcs = ix->rcs;
+        prm.sufmin = ix->sufmin.as<float>();
+        prm.from = sfrom;
+        prm.until = suntil;
+        prm.split_len = split_len;
+        prm.qlut = ix->qlut.as<uint32_t>();
+        prm.msel = ix->msel.as<int32_t>();
+        prm.lutI = ix->lutI.as<float4>();
+        prm.qp = ix->qp.as<pscan::QParam>();
+        prm.boot_tail = ix->boot_tail.as<u64>();
+        prm.floor = floor;
+        prm.lists = ix->plists.as<u64>();
+        prm.stats = dstats;
+        prm.nq = nq;
+        prm.M = M;
+        prm.ML = sML;
+        prm.T = T;
+        prm.k = k;
+        prm.S = S;
+        prm.Bs = Bs;
+        const bool time_it = stage == 1 && g_pruned_lb.load() == 0 && !ix->tm_pending;
+        if (time_it) GCU(cudaEventRecord(ix->tm_ev0, st));
+        KernelTimer &ktm = stage == 1 ? g_t_pscan : g_t_pscan_first;
+        cudaEvent_t ev = ktm.begin(st);
+  #define GULON_X(FB_, W_)                                                                        \
+    if (FB == FB_ && W == W_) {                                                                   \
+      auto kern = pscan::pruned_scan_kernel<FB_, W_>;                                             \
+      using CfgT = pscan::Cfg<FB_, W_>;                                                           \
+      GLAUNCH(kern, (unsigned)(S * Bs), pscan::NT, CfgT::SMEM_BYTES, st, prm);                    \
+    }
+        GULON_PSCAN_VARIANTS(GULON_X)
+  #undef GULON_X
+        ktm.end(ev, st);
+        if (time_it) {
+          GCU(cudaEventRecord(ix->tm_ev1, st));
+          ix->tm_pending = true;
+          ix->tm_ml = sML;
+          ix->tm_pairs = (double)srange * (double)nq;
+          // (the whole pruned range, not this stage's share: the full bound runs without a first stage)
+          ix->tm_shape = (long long)T * 1000003LL + (long long)(prange >> 12) + 1;
+        }
+        if (want_stats) {
+          unsigned long long h[3];
+          GCU(cudaMemcpyAsync(h, dstats, sizeof(h), cudaMemcpyDeviceToHost, st));
+          GCU(cudaStreamSynchronize(st));
+          for (int i = 0; i < 3; i++) g_pstats[i] += h[i];
+          g_ppairs += (unsigned long long)srange * (unsigned long long)nq;
+          if (stage == 1) g_ppairs_main += (unsigned long long)srange * (unsigned long long)nq;
+        }
+        if (stage == 1) g_last_ml = sML;
+        // best lists so far + this stage's split lists -> best lists so far
+        DevBuf &mb = stage == 0 ? ix->merged2 : ix->merged;
+        Selector &sl = stage == 0 ? ix->sel2 : ix->sel;
+        if ((i64)(S + 1) * k <= pscan::MERGE_SMALL_MAX) {
+          GCHECK(mb.ensure((size_t)Q4 * k * sizeof(u64)));
+          GLAUNCH(pscan::merge_small_kernel, (unsigned)ceil_div(Q4, 4), 128, 0, st, ix->plists.as<u64>(), S,
+                  (i64)Q4, k, cur, cur_stride, mb.as<u64>());
+          cur = mb.as<u64>();
+          cur_stride = k;
+        } else {
+          const i64 ms = round_up((i64)(S + 1) * k, SEL_CHUNK);
+          GCHECK(mb.ensure((size_t)Q4 * ms * sizeof(u64)));
+          dim3 gg((unsigned)ceil_div(ms, 256), (unsigned)Q4);
+          GLAUNCH(pscan::gather_lists2_kernel, gg, 256, 0, st, ix->plists.as<u64>(), S, (i64)Q4, k, cur,
+                  cur_stride, mb.as<u64>(), ms);
+          GCHECK(sl.run(mb.as<u64>(), ms, Q4, k, st, &cur, &cur_stride));
+        }
+      }
+  #undef GULON_PSCAN_VARIANTS
+      res = cur;
+      rs = cur_stride;
+      return GULON_OK;
+    }
+
+      return fail(GULON_EINVAL, "internal: no fast scan implementation selected");
+    };
+    u64 *res = nullptr;
+    i64 rs = 0;
+    if (k_all <= pscan::KMAX) {
+      GCHECK(fast_pass(k_all, nullptr, res, rs));
+      return unpack(res, rs, nq, k_all, id_offset, d_ids, d_dists, d_sizes, st);
+    }
+    GREQUIRE(k_all <= KCHUNK_MAX, "the fast scans take k <= %d (k=%d): use scan_impl = simple", KCHUNK_MAX, k_all);
+    GCHECK(ix->kacc.ensure((size_t)Q4 * k_all * sizeof(u64)));
+    GCHECK(ix->kfloor.ensure((size_t)Q4 * sizeof(u64)));
+    GCU(cudaMemsetAsync(ix->kacc.p, 0xFF, (size_t)Q4 * k_all * sizeof(u64), st));
+    for (int done = 0; done < k_all; done += pscan::KMAX) {
+      const int kk = std::min(pscan::KMAX, k_all - done);
+      GCHECK(fast_pass(kk, done ? ix->kfloor.as<u64>() : nullptr, res, rs));
+      dim3 block(32, 8);
+      GLAUNCH(append_pass_kernel, (unsigned)ceil_div(Q4, 8), block, 0, st, res, rs, (i64)Q4, k_all, done, kk,
+              ix->kacc.as<u64>(), ix->kfloor.as<u64>());
+    }
+    return unpack(ix->kacc.as<u64>(), k_all, nq, k_all, id_offset, d_ids, d_dists, d_sizes, st);
   }
 
   // simple path: materialise keys for a few query groups at a time, select
@@ -2284,36 +2330,30 @@ static int pq_encode_host(gulon_codebook_t cb, const float *X, int64_t N, int64_
   const int Dp = (int)round_up(D, 4);  // 16-byte row pitch of the staged chunks (TMA)
   const i64 chunk = std::min<i64>(N, g_encode_chunk.load());
   const i64 cps = round_up(chunk, 16);
-  struct Res {
-    cudaStream_t st[2] = {nullptr, nullptr};
-    float *dx[2] = {nullptr, nullptr};
-    CodeT *dc[2] = {nullptr, nullptr};
-    ~Res() {
-      for (int i = 0; i < 2; i++) {
-        if (dx[i]) cudaFree(dx[i]);
-        if (dc[i]) cudaFree(dc[i]);
-        if (st[i]) cudaStreamDestroy(st[i]);
-      }
-    }
-  } r;
+  std::lock_guard<std::mutex> lock(cb->mu);   // the staging buffers live in the codebook handle
+  float *dx[2];
+  CodeT *dc[2];
   for (int i = 0; i < 2; i++) {
-    GCU(cudaStreamCreateWithFlags(&r.st[i], cudaStreamNonBlocking));
-    GCU(cudaMalloc(&r.dx[i], (size_t)chunk * Dp * sizeof(float)));
-    if (Dp != D) GCU(cudaMemset(r.dx[i], 0, (size_t)chunk * Dp * sizeof(float)));
-    GCU(cudaMalloc(&r.dc[i], (size_t)M * cps * sizeof(CodeT)));
+    if (!cb->enc_st[i]) GCU(cudaStreamCreateWithFlags(&cb->enc_st[i], cudaStreamNonBlocking));
+    const bool grew = cb->enc_x[i].cap < (size_t)chunk * Dp * sizeof(float);
+    GCHECK(cb->enc_x[i].ensure((size_t)chunk * Dp * sizeof(float)));
+    GCHECK(cb->enc_c[i].ensure((size_t)M * cps * sizeof(CodeT)));
+    dx[i] = cb->enc_x[i].template as<float>();
+    dc[i] = cb->enc_c[i].template as<CodeT>();
+    if (Dp != D && grew) GCU(cudaMemset(dx[i], 0, cb->enc_x[i].cap));   // the pad columns stay zero
   }
   int b = 0;
   for (i64 r0 = 0; r0 < N; r0 += chunk, b ^= 1) {
     const i64 n = std::min<i64>(chunk, N - r0);
-    GCU(copy2d(r.dx[b], (size_t)Dp * 4, X + r0 * ld, (size_t)ld * 4, (size_t)D * 4,
-                          (size_t)n, cudaMemcpyHostToDevice, r.st[b], true));
-    GCHECK(encode_dev(cb, r.dx[b], n, Dp, r.dc[b], cps, r.st[b]));
-    GCU(copy2d(codes + r0, (size_t)N * sizeof(CodeT), r.dc[b], (size_t)cps * sizeof(CodeT),
-                          (size_t)n * sizeof(CodeT), (size_t)M, cudaMemcpyDeviceToHost, r.st[b], true));
+    GCU(copy2d(dx[b], (size_t)Dp * 4, X + r0 * ld, (size_t)ld * 4, (size_t)D * 4, (size_t)n,
+               cudaMemcpyHostToDevice, cb->enc_st[b], true));
+    GCHECK(encode_dev(cb, dx[b], n, Dp, dc[b], cps, cb->enc_st[b]));
+    GCU(copy2d(codes + r0, (size_t)N * sizeof(CodeT), dc[b], (size_t)cps * sizeof(CodeT),
+               (size_t)n * sizeof(CodeT), (size_t)M, cudaMemcpyDeviceToHost, cb->enc_st[b], true));
     // buffer pair b is reused two chunks later on the same stream, so reuse is stream-ordered
   }
-  GCU(cudaStreamSynchronize(r.st[0]));
-  GCU(cudaStreamSynchronize(r.st[1]));
+  GCU(cudaStreamSynchronize(cb->enc_st[0]));
+  GCU(cudaStreamSynchronize(cb->enc_st[1]));
   return GULON_OK;
 }
 
@@ -2708,6 +2748,65 @@ int gulon_synth_rows_dev(const gulon_synth_params_t *prm, int64_t stream_id, int
   GLAUNCH(synth::rows_kernel, grid, 256, 0, (cudaStream_t)stream, p, (i64)stream_id, (i64)lo, (i64)n,
           d_centres, d_map, d_out, (i64)ld);
   return GULON_OK;
+}
+
+int gulon_grouped_query_dev(gulon_index_t ix, const float *dqueries, int64_t nq, int64_t ldq,
+                            const float *d_centroids, int32_t n_partitions, const int32_t *d_bounds,
+                            const int32_t *d_pair_query, const int32_t *d_pair_partition,
+                            const int32_t *d_pair_slot, int64_t n_pairs, int32_t slots, int32_t k,
+                            int32_t *d_ids, float *d_dists, int32_t *d_sizes, void *stream) {
+  GREQUIRE(ix, "null handle");
+  GREQUIRE(!ix->codes16, "the grouped scan serves 8-bit indexes");
+  GREQUIRE(nq >= 0 && n_pairs >= 0 && slots >= 0 && n_partitions >= 0, "bad grouped-query shape");
+  GREQUIRE(k >= 1 && k <= gscan::GS_CHUNK / 2, "the grouped scan takes 1 <= k <= %d (k=%d)", gscan::GS_CHUNK / 2, k);
+  GREQUIRE(ldq >= ix->cb->D, "query leading dimension %lld < dimension %d", (long long)ldq, ix->cb->D);
+  GREQUIRE((dqueries && d_ids && d_dists) || nq == 0, "null argument");
+  GREQUIRE((d_centroids && d_bounds && d_pair_query && d_pair_partition && d_pair_slot) || n_pairs == 0,
+           "null work list");
+  GCHECK(need_device());
+  if (nq == 0) return GULON_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  gulon_codebook_t cb = ix->cb;
+  const int D = cb->D, M = cb->M;
+  if (n_pairs == 0 || slots == 0) return fill_empty(nq, k, d_ids, d_dists, d_sizes, st);
+  const size_t smem = (size_t)gscan::GS_CHUNK * 8 + ((size_t)((D + 3) & ~3) + (size_t)M * 256) * sizeof(float);
+  GREQUIRE(smem <= 227 * 1024, "D=%d, M=%d do not fit the shared memory of the grouped scan", D, M);
+  GOPTIN(gscan::grouped_pairs_kernel, 227 * 1024);
+  std::lock_guard<std::mutex> lock(ix->mu);
+  GCHECK(ix->chain.enter(st));
+  const int rc = [&]() -> int {
+    // keys [nq][stride]: slot s of query q at [q][s * k ..); unused slots stay empty
+    const i64 want = (i64)slots * k;
+    const bool small = want <= MERGE_WARP_MAX;
+    i64 stride = SEL_CHUNK;
+    if (small) {
+      stride = 2;
+      while (stride < want) stride <<= 1;
+    } else {
+      stride = round_up(want, SEL_CHUNK);
+    }
+    GCHECK(ix->keys.ensure((size_t)nq * stride * sizeof(u64)));
+    GCU(cudaMemsetAsync(ix->keys.p, 0xFF, (size_t)nq * stride * sizeof(u64), st));
+    for (i64 p0 = 0; p0 < n_pairs; p0 += 1 << 30) {
+      const i64 np = std::min<i64>(1 << 30, n_pairs - p0);
+      GLAUNCH(gscan::grouped_pairs_kernel, (unsigned)np, gscan::NT, smem, st, ix->codes, ix->ps, dqueries,
+              (i64)ldq, d_centroids, D, d_bounds, d_pair_query + p0, d_pair_partition + p0, d_pair_slot + p0,
+              cb->cb.as<float>(), cb->dfrom.as<int32_t>(), cb->ddim.as<int32_t>(), M, cb->K, cb->dmax, k,
+              ix->keys.as<u64>(), stride);
+    }
+    // TopKHeap#merge of a query's partition heaps
+    if (small) {
+      GLAUNCH(sort_rows_small_kernel, (unsigned)ceil_div(nq, 4), 128, (size_t)4 * stride * sizeof(u64), st,
+              ix->keys.as<u64>(), (int)stride, (i64)nq);
+      return unpack(ix->keys.as<u64>(), stride, nq, k, 0, d_ids, d_dists, d_sizes, st);
+    }
+    u64 *res;
+    i64 rs;
+    GCHECK(ix->sel.run(ix->keys.as<u64>(), stride, nq, k, st, &res, &rs));
+    return unpack(res, rs, nq, k, 0, d_ids, d_dists, d_sizes, st);
+  }();
+  GCHECK(ix->chain.leave(st));
+  return rc;
 }
 
 int gulon_exact_topk(gulon_points_t p, const float *queries, int64_t nq, int64_t ldq, int32_t k,

@@ -86,6 +86,7 @@ struct Params {
   const float4 *lutI;     // [T*QT/4][M][256] exact tables (scan.cuh layout)
   const QParam *qp;       // [T*QT]
   const u64 *boot_tail;   // [T*QT] key of the boot list tail (KEY_SENT: none)
+  const u64 *floor;       // [T*QT] k-chunked scans: only keys > floor enter the lists (null: none)
   u64 *lists;             // [S][T*QT][k]
   unsigned long long *stats;  // [0] survivors, [1] list candidates, [2] slow-path items
   i64 nq;
@@ -596,7 +597,7 @@ __global__ void __launch_bounds__(NT, 1) pruned_scan_kernel(const Params p) {
     auto drain = [&](int n) {
       for (int b0s = 0; b0s < n; b0s += NT) {
         bool pending = false;
-        u64 key = KEY_SENT;
+        u64 key = KEY_SENT, floor_q = 0ull;
         int q = 0;
         if (b0s + tid < n) {
           const uint32_t code = surv[b0s + tid];
@@ -608,6 +609,7 @@ __global__ void __launch_bounds__(NT, 1) pruned_scan_kernel(const Params p) {
                                  p.lutI + ((i64)ts * (QT / 4) + (q >> 2)) * M * 256) + (q & 3);
           const float *suf = p.sufmin + ((i64)ts * QT + q) * (M + 1);
           const u64 pol_keep = l2_policy_evict_last();
+          floor_q = p.floor ? p.floor[(i64)ts * QT + q] : 0ull;
           const u64 thr = s_thr[q];
           double tau_hi = 1.0e300;   // no early exit without a finite threshold
           if (thr != KEY_SENT) {
@@ -649,7 +651,7 @@ __global__ void __launch_bounds__(NT, 1) pruned_scan_kernel(const Params p) {
           }
           if (!out) {
             key = make_key(d, (uint32_t)row);
-            pending = true;
+            pending = key > floor_q;   // rows an earlier pass of a k-chunked scan already reported stay out
           }
         }
         for (;;) {

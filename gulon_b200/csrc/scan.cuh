@@ -165,6 +165,74 @@ __global__ void __launch_bounds__(256) adc_keys_wide_kernel(const uint16_t *__re
   keys[q * n_pad + t] = key;
 }
 
+// ---- grouped (IVF) index: one launch for every probed (query, partition) pair ------------------------
+// GroupedIndex#query, G/Index.scala:267-283: for each probed partition the query is made relative to the
+// partition's centroid (MathUtils.subtract), its lookup table is rebuilt (prepareQuery) and the
+// partition's rows [from, until) are scanned into a TopKHeap; the heaps are merged per query.  Here one
+// CTA owns one (query, partition) pair of a device-resident work list:
+//   1. residual r = fl(q - c_p) into shared memory;
+//   2. the M x 256 lookup table of r in shared memory (thread = code; the arithmetic of lut_build_kernel);
+//   3. thread = row: ds = (((0 + LUT[0][code_0]) + LUT[1][code_1]) + ...), fp32, quantizer order;
+//   4. the pair's k best (distance, id) keys: chunks of GS_CHUNK keys sorted in shared memory, the
+//      running best carried in the first k slots.
+// The keys land at keys[query][slot * k ..) -- `slot` = probe rank of the pair -- ready for the per-query
+// merge.  As in the reference the table rebuild dominates for small partitions (M * 256 * dsub * 3 flops
+// against M gathers per row).  grid n_pairs, block 256, dynamic shared memory (D + M * 256) * 4 + GS_CHUNK * 8.
+namespace gscan {
+constexpr int NT = 256;
+constexpr int GS_CHUNK = 2048;
+__global__ void __launch_bounds__(NT) grouped_pairs_kernel(
+    const uint8_t *__restrict__ codes, i64 ps, const float *__restrict__ Q, i64 ldq,
+    const float *__restrict__ cents, int D, const int32_t *__restrict__ bounds,  // [P + 1] first row of every partition
+    const int32_t *__restrict__ pair_q, const int32_t *__restrict__ pair_part,
+    const int32_t *__restrict__ pair_slot, const float *__restrict__ cb, const int32_t *__restrict__ from,
+    const int32_t *__restrict__ dim, int M, int K, int dmax, int k, u64 *__restrict__ keys, i64 key_stride) {
+  extern __shared__ __align__(16) unsigned char gs_smem[];
+  u64 *sk = reinterpret_cast<u64 *>(gs_smem);                       // [GS_CHUNK]
+  float *r = reinterpret_cast<float *>(gs_smem + GS_CHUNK * 8);     // [D]
+  float *lut = r + ((D + 3) & ~3);                                  // [M][256]
+  const int tid = threadIdx.x;
+  const i64 pr = blockIdx.x;
+  const int q = pair_q[pr], part = pair_part[pr], slot = pair_slot[pr];
+  const float *qv = Q + (i64)q * ldq, *cv = cents + (i64)part * D;
+  for (int j = tid; j < D; j += NT) r[j] = __fsub_rn(qv[j], cv[j]);
+  for (int i = tid; i < GS_CHUNK; i += NT) sk[i] = KEY_SENT;
+  __syncthreads();
+  for (int m = 0; m < M; m++) {
+    float s = 0.0f;
+    if (tid < K) {
+      const float *c = cb + ((i64)m * K + tid) * dmax;
+      const float *rv = r + from[m];
+      const int dm = dim[m];
+      for (int t = 0; t < dm; t++) {
+        const float d = __fsub_rn(rv[t], c[t]);
+        s = __fadd_rn(s, __fmul_rn(d, d));
+      }
+    }
+    lut[m * 256 + tid] = s;
+  }
+  __syncthreads();
+  const i64 lo = bounds[part], hi = bounds[part + 1];
+  const int step = GS_CHUNK - k;            // new keys per round; the first k slots carry the best so far
+  for (i64 base = lo; base < hi; base += step) {
+    for (int i = tid; i < step; i += NT) {
+      const i64 row = base + i;
+      u64 key = KEY_SENT;
+      if (row < hi) {
+        float ds = 0.0f;
+        for (int m = 0; m < M; m++) ds = __fadd_rn(ds, lut[m * 256 + codes[(i64)m * ps + row]]);
+        key = make_key(ds, (uint32_t)row);
+      }
+      sk[k + i] = key;
+    }
+    __syncthreads();
+    block_bitonic_sort(sk, GS_CHUNK, tid, NT);
+  }
+  u64 *dst = keys + (i64)q * key_stride + (i64)slot * k;
+  for (int i = tid; i < k; i += NT) dst[i] = sk[i];
+}
+}  // namespace gscan
+
 // ---- fused scan ---------------------------------------------------------------------------------
 // Persistent kernel, one 512-thread CTA per SM.  Work item = (chunk of 8192 rows, group of 4
 // queries).  For each quantizer m the group's 256-entry float4 table slice is replicated 8x in
@@ -199,6 +267,9 @@ struct Params {
   const float4 *lutI;
   int M, G, k, S, Bs;
   u64 *lists;        // [S][G*4][k]
+  // k-chunked scans (k > KMAX): keys already reported by earlier passes, one per query [G*4], or null.
+  // Only keys strictly greater enter the lists, so a pass returns the NEXT k of the (distance, id) order.
+  const u64 *floor;
 };
 
 __device__ __forceinline__ uint4 ldg_stream_u4(const void *p) {
@@ -285,9 +356,12 @@ __global__ void __launch_bounds__(NT, 1) fused_scan_kernel(const Params p) {
 
     // list tails of the 4 queries (issued early; consumed after the quantizer loop)
     u64 *L0 = p.lists + ((i64)s * p.G * 4 + (i64)g * 4) * k;
-    u64 tail[4];
+    u64 tail[4], fl[4];
 #pragma unroll
-    for (int q = 0; q < 4; q++) tail[q] = ldcg_u64(L0 + (i64)q * k + (k - 1));
+    for (int q = 0; q < 4; q++) {
+      tail[q] = ldcg_u64(L0 + (i64)q * k + (k - 1));
+      fl[q] = p.floor ? p.floor[(i64)g * 4 + q] : 0ull;   // every real key is > 0 (distances are >= +0)
+    }
 
     float acc[RPT][4];
 #pragma unroll
@@ -342,7 +416,7 @@ __global__ void __launch_bounds__(NT, 1) fused_scan_kernel(const Params p) {
         for (int i = 0; i < RPT; i++) {
           if (acc[i][q] <= tau && i >= vlo && i < vhi) {
             const u64 key = make_key(acc[i][q], (uint32_t)(row0 + i));
-            if (key < tail[q]) {
+            if (key < tail[q] && key > fl[q]) {
               int pos = atomicAdd(&s_cnt[q], 1);
               if (pos < CAP) sortbuf[q * SORTN + k + pos] = key;
             }
@@ -383,7 +457,7 @@ __global__ void __launch_bounds__(NT, 1) fused_scan_kernel(const Params p) {
             for (int i = 0; i < RPT; i++) {
               if (i >= vlo && i < vhi) {
                 const u64 key = make_key(acc[i][q], (uint32_t)(row0 + i));
-                if (key < tl) {
+                if (key < tl && key > fl[q]) {
                   int pos = atomicAdd(&s_cnt[q], 1);
                   if (pos < CAP) sortbuf[q * SORTN + k + pos] = key;
                 }

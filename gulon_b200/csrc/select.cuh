@@ -162,6 +162,31 @@ __global__ void __launch_bounds__(128) merge_results_small_kernel(const int32_t 
   if (out_sizes && lane == 0) out_sizes[q] = cnt;
 }
 
+// k-chunked scans: the kk keys of a pass (rows of `cur`, ascending) go behind the `done` keys already in
+// acc [rows][k]; the last key becomes the next pass's floor (KEY_SENT when the pass came back short: no
+// row is left).  grid ceil(rows / 8), block (32, 8).
+__global__ void append_pass_kernel(const u64 *__restrict__ cur, i64 cur_stride, i64 rows, int k, int done,
+                                   int kk, u64 *__restrict__ acc, u64 *__restrict__ floor) {
+  const i64 q = (i64)blockIdx.x * blockDim.y + threadIdx.y;
+  if (q >= rows) return;
+  for (int i = threadIdx.x; i < kk; i += 32) acc[q * k + done + i] = cur[q * cur_stride + i];
+  if (threadIdx.x == 0) floor[q] = cur[q * cur_stride + kk - 1];
+}
+
+// rows of P <= 1024 keys (a power of two) sorted in place, one warp per row.  grid ceil(rows / 4), block 128,
+// dynamic shared memory 4 * P * 8 bytes.
+__global__ void __launch_bounds__(128) sort_rows_small_kernel(u64 *__restrict__ keys, int P, i64 rows) {
+  extern __shared__ __align__(16) unsigned char srs_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  u64 *sb = reinterpret_cast<u64 *>(srs_smem) + (size_t)warp * P;
+  const i64 q = (i64)blockIdx.x * 4 + warp;
+  if (q >= rows) return;
+  for (int t = lane; t < P; t += 32) sb[t] = keys[q * P + t];
+  __syncwarp();
+  warp_bitonic_sort(sb, P, lane);
+  for (int t = lane; t < P; t += 32) keys[q * P + t] = sb[t];
+}
+
 // empty result rows: id -1, distance +inf, size 0
 __global__ void fill_empty_kernel(i64 nq, int k, int32_t *__restrict__ ids,
                                   float *__restrict__ dists, int32_t *__restrict__ sizes) {

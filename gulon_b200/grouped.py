@@ -104,7 +104,9 @@ class GroupedVectors:
         else:
             if len(keys) != n:
                 raise ValueError("one key per row expected")
-            by_key = np.argsort(np.asarray(keys, dtype=object), kind="stable")
+            # sortBy(word(_)): java.lang.String#compareTo order = UTF-16 code units
+            k16 = [w.encode("utf-16-be", "surrogatepass") if isinstance(w, str) else w for w in keys]
+            by_key = np.asarray(sorted(range(n), key=lambda i: k16[i]), dtype=np.int64)
         order = by_key[np.argsort(a[by_key], kind="stable")].astype(np.int64)
         if n > 0:
             a_sorted = a[order]

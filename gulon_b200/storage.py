@@ -297,6 +297,7 @@ class SortedIndex:
         self.words = list(words)
         self.vector_index = vector_index
         self.normalized = bool(normalized)
+        self._keys = None      # UTF-16 sort keys, built on the first lookup
 
     @property
     def size(self):
@@ -312,12 +313,19 @@ class SortedIndex:
     def query(self, k, vector):
         return self.batch_query(k, np.asarray(vector, np.float32).reshape(1, -1))[0]
 
-    def lookup(self, word):
+    def position(self, word):
+        """KeyIndex.Sorted#lookup: binary search in java.lang.String#compareTo order (UTF-16 code units; it
+        differs from Python's code-point order for supplementary-plane characters)."""
         import bisect
-        i = bisect.bisect_left(self.words, word)
-        if i >= len(self.words) or self.words[i] != word:
-            return None
-        return self.vector_index.decode(i)
+        if self._keys is None:
+            self._keys = [w.encode("utf-16-be", "surrogatepass") for w in self.words]
+        key = word.encode("utf-16-be", "surrogatepass")
+        i = bisect.bisect_left(self._keys, key)
+        return i if i < len(self._keys) and self._keys[i] == key else None
+
+    def lookup(self, word):
+        i = self.position(word)
+        return None if i is None else self.vector_index.decode(i)
 
     # -- Index.sorted, G/Index.scala:107-113 ---------------------------------------------------------
     @staticmethod
@@ -330,8 +338,10 @@ class SortedIndex:
         words = list(words)
         if len(words) != m.rows:
             raise ValueError("one word per row expected")
-        if any(a > b for a, b in zip(words[:-1], words[1:])):
-            raise ValueError("words must be sorted (KeyIndex.Sorted looks them up by binary search)")
+        keys = [w.encode("utf-16-be", "surrogatepass") for w in words]
+        if any(a > b for a, b in zip(keys[:-1], keys[1:])):
+            raise ValueError("words must be sorted (KeyIndex.Sorted looks them up by binary search, in "
+                             "java.lang.String#compareTo order)")
         return SortedIndex(words, PQIndex(quantizer, quantizer.encode(m)), normalized)
 
     def query_by_word(self, k, word):

@@ -294,6 +294,23 @@ int gulon_pq_query_sharded(gulon_index_t ix, const gulon_comm_t *row_comm,
                            int64_t ldq, int32_t k, int32_t normalize, int64_t row_offset,
                            int32_t *out_ids, float *out_dists, int32_t *out_sizes);
 
+/*
+ * GroupedIndex#query, G/Index.scala:267-283, for a whole batch in ONE launch: the host decides which
+ * partitions every query probes (GroupedIndex#searchSpace, :285-299, e.g. with gulon_exact_topk over
+ * the coarse centroids) and hands over the work list of (query, partition, probe rank) triples; one
+ * CTA per pair subtracts the partition's centroid from the query (MathUtils.subtract), rebuilds the
+ * lookup table (Index.prepareQuery), scans the partition's rows [bounds[p], bounds[p+1]) and keeps the
+ * pair's k best; the pairs of a query are merged by (distance, id) (TopKHeap#merge).  Row ids are
+ * positions in the grouped order.  d_centroids [n_partitions][D]; d_bounds [n_partitions + 1];
+ * pair_slot < slots is the place of the pair among its query's probes.  Queries must already be
+ * normalised for a cosine index.  1 <= k <= 1024.
+ */
+int gulon_grouped_query_dev(gulon_index_t ix, const float *dqueries, int64_t nq, int64_t ldq,
+                            const float *d_centroids, int32_t n_partitions, const int32_t *d_bounds,
+                            const int32_t *d_pair_query, const int32_t *d_pair_partition,
+                            const int32_t *d_pair_slot, int64_t n_pairs, int32_t slots, int32_t k,
+                            int32_t *d_ids, float *d_dists, int32_t *d_sizes, void *stream);
+
 /* Index.exactNearestNeighbours, G/Index.scala:209-229 (+ MathUtils.distanceSq, G/MathUtils.scala:85-95). */
 int gulon_exact_topk(gulon_points_t p, const float *queries, int64_t nq, int64_t ldq, int32_t k,
                      int64_t from, int64_t until, int32_t *out_ids, float *out_dists,

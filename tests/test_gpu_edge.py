@@ -172,3 +172,21 @@ def test_index_rejects_centroid_ids_beyond_k(g):
     t[:, :n] = torch.from_numpy(bad).cuda()
     with pytest.raises(ValueError):
         g.PQIndex.from_device_codes(pq, t, n)
+
+
+@pytest.mark.parametrize("impl", ["fused", "pruned8", "pruned16", "pruned8w2"])
+@pytest.mark.parametrize("k", [129, 300, 1000])
+def test_k_chunked_passes_through_the_fast_kernels(g, oracle, impl, k):
+    """k > 128 through the fused / pruned kernels in passes of <= 128 (each pass admits only keys greater
+    than the last key of the previous one), heavy ties included: equal to the oracle's canonical top-k."""
+    rng = np.random.default_rng(k)
+    n, D, M = 280_000, 24, 3
+    pq, cb, _, _ = build_index(g, rng, 10, D, M)
+    codes = rng.integers(0, 256, (M, n)).astype(np.uint8)
+    codes[:, 1000:1400] = codes[:, 999:1000]          # 400 rows with one code: a tie group larger than a pass
+    ix = g.PQIndex(pq, g.EncodedMatrix(g.Coder8(n), codes))
+    Q = clustered(rng, 6, D)
+    Q[0] = pq.decode(g.EncodedMatrix(g.Coder8(1), codes[:, 999:1000])).data[0]   # the tie group is the nearest
+    got = run_query(g, ix, Q, k, 3, n - 5, impl_id(g, impl))
+    ids, ds, sz = oracle.pq_query(Q, cb, codes, k, 3, n - 5, topk_mode=oracle.TOPK_CANONICAL)
+    assert_same(got, ids, ds, sz)

@@ -203,7 +203,7 @@ def test_encode_chunked_host_path(g, oracle):
     try:
         got = pq.encode(X).codes
     finally:
-        g.set_option("encode_chunk_rows", 1 << 20)
+        g.set_option("encode_chunk_rows", 1 << 18)
     assert np.array_equal(got, oracle.pq_encode(X, cb, tie_mode=oracle.TIE_LOWEST))
 
 
