@@ -22,6 +22,7 @@ Besides the headline the line carries, each with its own roofline / CPU baseline
               rows, NCCL all-gather + (distance, id) merge of every rank's k candidates, checked
               against the oracle on a query sample
   rerank_c5   configs[4]-shaped: 1M x 1000-d, m = 100, PQ top-R candidates + exact fp32 re-rank
+  grouped_ivf the reference's partitioned index at its CLI defaults (rows / 1000 partitions, 5 % probed)
 
 The reference arm (`--impl reference`) rebuilds THE SAME index on host cores -- same synthetic rows,
 the oracle's k-means and encode (bit-identical to the GPU's by the parity tests; `index_digest` in
@@ -78,6 +79,8 @@ def parse():
     ap.add_argument("--c5-rows", type=int, default=1_000_000)
     ap.add_argument("--c5-queries", type=int, default=10_000)
     ap.add_argument("--c5-candidates", type=int, default=100)
+    ap.add_argument("--gp-rows", type=int, default=1_000_000)
+    ap.add_argument("--gp-queries", type=int, default=4_000)
     return ap.parse_args()
 
 
@@ -649,6 +652,55 @@ def leg_rerank_c5(cx):
     return line
 
 
+def leg_grouped(cx):
+    """The reference's partitioned index at its CLI defaults (C/BuildIndex.scala:98-108: rows / 1000
+    partitions, probe 5 % of them): WordVectors#grouped + Index.grouped + GroupedIndex#batchQuery on
+    gp_rows x 300-d rows.  One launch covers every probed (query, partition) pair
+    (gulon_grouped_query_dev); the per-pair lookup-table rebuild dominates, as it does in the
+    reference (M * 256 * dsub * 3 flops against M gathers per row of a ~1000-row partition)."""
+    torch, g, N, a = cx.torch, cx.g, cx.N, cx.a
+    from gulon_b200.synth import Mixture
+    D, M, k = a.dim, a.m, a.k
+    rows, Q = a.gp_rows, a.gp_queries
+    P = max(rows // 1000, 1)
+    limit = max(int(P * 0.05), 5)
+    mix = Mixture(D, seed=SEED, device=cx.dev)
+    X = mix.rows(0, rows)
+    xh = X.cpu().numpy()
+    t0 = time.perf_counter()
+    coarse = g.KMeans.compute_clusters(g.Vectors(g.Matrix(xh[:min(rows, 200_000)])), g.KMeansConfig(P, 3, seed=0))
+    gv = g.GroupedVectors.group(g.Matrix(xh), coarse, device=cx.dev)
+    res = gv.residuals_dev()
+    pq = g.ProductQuantizer.train(g.DevicePoints.from_torch(res[:min(rows, a.train_rows)].contiguous()),
+                                  g.ProductQuantizerConfig(256, M, 4))
+    ix = g.GroupedIndex.build(gv, pq, strategy=g.LimitGroups(limit))
+    torch.cuda.synchronize()
+    build_s = time.perf_counter() - t0
+    qh = mix.rows(0, Q, stream_seed=1).cpu().numpy()
+    ix.batch_query(k, qh[:256])                      # warm-up
+    t0 = time.perf_counter()
+    r = ix.batch_query(k, qh)
+    dt = time.perf_counter() - t0
+    line = {"config": "%d x %d-d rows, %d partitions (rows / 1000), LimitGroups(%d) = 5 %% of the partitions, residual "
+                      "PQ m=%dx256, %d queries, top-%d" % (rows, D, P, limit, M, Q, k),
+            "value": Q / dt, "unit": UNIT, "e2e": True, "build_seconds": build_s,
+            "pairs_per_query": limit, "note": "host queries in, host answers out (search space + one device launch)"}
+    if not a.no_cpu_baseline:
+        from oracle import oracle as o
+        nqc = 8
+        codes = ix.vector_index._keepalive[:, :rows].cpu().numpy()
+        t0 = time.perf_counter()
+        wi, wd, ws = o.grouped_query(qh[:nqc], gv.centroids, gv.offsets, gv.size, pq.codebook(), codes, k,
+                                     ("groups", limit))
+        dtc = time.perf_counter() - t0
+        line["matches_oracle"] = bool(np.array_equal(wi, r.keys[:nqc]) and
+                                      np.array_equal(wd.view(np.uint32), r.values[:nqc].view(np.uint32)))
+        line["cpu_baseline"] = {"value": nqc / dtc, "unit": UNIT, "cores": 1, "kind": "port",
+                                "sample": "%d queries, GroupedIndex#query restated (one thread, as the reference's "
+                                          "query path is sequential per query)" % nqc}
+    return line
+
+
 def main():
     a = parse()
     if a.impl == "reference":
@@ -842,10 +894,10 @@ def main():
         torch.cuda.empty_cache()
         if world > 1:
             legs["row_sharded"] = leg_row_sharded(cx, clk)
-        try:
-            legs["rerank_c5"] = leg_rerank_c5(cx)
-        except ImportError as e:      # pragma: no cover
-            legs["rerank_c5"] = {"unavailable": str(e)}
+        legs["rerank_c5"] = leg_rerank_c5(cx)
+        if rank == 0:
+            legs["grouped_ivf"] = leg_grouped(cx)
+        cx.barrier()
 
     if rank == 0:
         line = {

@@ -150,6 +150,7 @@ class GroupedIndex:
         self.normalized = bool(normalized)
         self.strategy = strategy
         self._cent_points = None
+        self.work_list = True     # one launch per batch (gulon_grouped_query_dev); False: one ranged scan per partition
 
     # -- Index.grouped, G/Index.scala:133-145 --------------------------------------------------------
     @staticmethod
@@ -257,6 +258,44 @@ class GroupedIndex:
         out_sz = np.zeros(nq, np.int32)
         if S == 0 or k == 0 or nq == 0:
             return out_ids, out_ds, out_sz
+        if self.work_list and 1 <= k <= 1024 and self.vector_index.product_quantizer.num_clusters <= 256:
+            return self._query_batch_work_list(k, q, cent_dev, probes, S)
+        return self._query_batch_ranged(k, q, cent_dev, probes, S)
+
+    def _query_batch_work_list(self, k, q, cent_dev, probes, S):
+        """ONE launch for every probed (query, partition) pair: gulon_grouped_query_dev."""
+        import torch
+        dev = cent_dev.device
+        nq = q.shape[0]
+        P = self.grouped.centroids.shape[0]
+        pair_q = np.concatenate([np.full(len(p), i, np.int32) for i, p in enumerate(probes)])
+        pair_part = np.concatenate(probes).astype(np.int32)
+        pair_slot = np.concatenate([np.arange(len(p), dtype=np.int32) for p in probes])
+        bounds = np.concatenate(([0], self.grouped.offsets, [self.size])).astype(np.int32)
+        # pairs of one partition next to each other: its code rows stay in L2 while they are scanned
+        o = np.argsort(pair_part, kind="stable")
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        d_pq, d_pp, d_ps, d_b = t(pair_q[o]), t(pair_part[o]), t(pair_slot[o]), t(bounds)
+        qd = t(q)
+        ids = torch.empty((nq, k), dtype=torch.int32, device=dev)
+        ds = torch.empty((nq, k), dtype=torch.float32, device=dev)
+        sz = torch.empty((nq,), dtype=torch.int32, device=dev)
+        N.check(N.lib().gulon_grouped_query_dev(
+            self.vector_index.handle, qd.data_ptr(), nq, q.shape[1], cent_dev.data_ptr(), P, d_b.data_ptr(),
+            d_pq.data_ptr(), d_pp.data_ptr(), d_ps.data_ptr(), len(pair_q), S, k, ids.data_ptr(), ds.data_ptr(),
+            sz.data_ptr(), torch.cuda.current_stream(dev).cuda_stream))
+        torch.cuda.synchronize(dev)
+        return ids.cpu().numpy(), ds.cpu().numpy(), sz.cpu().numpy()
+
+    def _query_batch_ranged(self, k, q, cent_dev, probes, S):
+        """The same through one ranged PQIndex#batchQuery per probed partition (any k, K > 256; the
+        cross-check of the work-list kernel)."""
+        import torch
+        dev = cent_dev.device
+        nq = q.shape[0]
+        out_ids = np.full((nq, k), -1, np.int32)
+        out_ds = np.full((nq, k), np.inf, np.float32)
+        out_sz = np.zeros(nq, np.int32)
         # (query, partition, probe rank) triples, grouped by partition
         qi = np.concatenate([np.full(len(p), i, np.int64) for i, p in enumerate(probes)])
         part = np.concatenate(probes).astype(np.int32)

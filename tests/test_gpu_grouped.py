@@ -60,9 +60,13 @@ def test_grouping_matches_reference_literally(g, oracle):
 @pytest.mark.parametrize("strategy", [("groups", 1), ("groups", 3), ("groups", 50), ("vectors", 1),
                                       ("vectors", 1500), ("vectors", 10 ** 9), ("groups", 0)])
 @pytest.mark.parametrize("normalized", [False, True])
-def test_grouped_query_matches_oracle(g, oracle, strategy, normalized):
+@pytest.mark.parametrize("work_list", [True, False])
+def test_grouped_query_matches_oracle(g, oracle, strategy, normalized, work_list):
+    """work_list: gulon_grouped_query_dev, one launch for every (query, partition) pair of the batch;
+    otherwise one ranged PQIndex#batchQuery per probed partition.  Both equal the oracle."""
     rng = np.random.default_rng(7)
     X, coarse, ks, gv, res, pq, ix = build(g, oracle, rng, normalized=normalized)
+    ix.work_list = work_list
     ix.strategy = g.LimitGroups(strategy[1]) if strategy[0] == "groups" else g.LimitVectors(strategy[1])
     Q = np.concatenate((X[rng.integers(0, X.shape[0], 20)] + 0.01,
                         clustered(rng, 21, X.shape[1]))).astype(np.float32)
@@ -112,6 +116,17 @@ def test_grouped_index_large_batch_recall_vs_full_scan(g, oracle):
     r8 = ix.batch_query(10, Q)
     assert np.all(r8.values[:, 0] <= r2.values[:, 0])
     assert np.all(r8.size == 10)
+    # partitions of ~3000 rows (several sort rounds per pair) and k beyond one warp's list: the work-list
+    # kernel against the ranged scans, bit for bit
+    for k in (10, 200):
+        a = ix.batch_query(k, Q[:64])
+        ix.work_list = False
+        try:
+            b = ix.batch_query(k, Q[:64])
+        finally:
+            ix.work_list = True
+        assert np.array_equal(a.keys, b.keys) and np.array_equal(a.values.view(np.uint32), b.values.view(np.uint32))
+        assert np.array_equal(a.size, b.size)
     # a query that is a stored row finds its own position among the nearest
     pos = rng.integers(0, n, 50)
     own = ix.batch_query(5, gv.matrix_dev[pos].cpu().numpy())
