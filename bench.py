@@ -23,6 +23,7 @@ Besides the headline the line carries, each with its own roofline / CPU baseline
               against the oracle on a query sample
   rerank_c5   configs[4]-shaped: 1M x 1000-d, m = 100, PQ top-R candidates + exact fp32 re-rank
   grouped_ivf the reference's partitioned index at its CLI defaults (rows / 1000 partitions, 5 % probed)
+  other_shapes (1 GPU) configs[0] and one configs[3] shard: queries/s, encode rate, oracle check
 
 The reference arm (`--impl reference`) rebuilds THE SAME index on host cores -- same synthetic rows,
 the oracle's k-means and encode (bit-identical to the GPU's by the parity tests; `index_digest` in
@@ -565,8 +566,10 @@ def leg_row_sharded(cx, clk_unused):
             "value": value, "unit": UNIT, "ms_per_step": ms / K, "steps": K, "warmup": W, "scaling": "weak (rows per GPU fixed)",
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": cx.world * Q * D * 4,
                     "d2h_bytes_per_step": cx.world * Q * (k * 8 + 4), "ids_equal_device_path": same},
-            "local_scan_ms": ms_local / K, "exchange_ms": (ms - ms_local) / K,
+            "local_scan_ms": ms_local / K, "exchange_ms": (ms_ag + ms_mg) / K,
             "allgather_ms": ms_ag / K, "allgather_bytes_per_rank": 2 * Q * k * 4, "merge_ms": ms_mg / K,
+            "exchange_note": "all-gather and merge timed in isolation on the same shapes; the step itself is "
+                             "%.1f ms against %.1f ms for the local scan alone (separate runs)" % (ms / K, ms_local / K),
             "roofline": roof,
             "encode": {"value": enc_rows / (enc_ns * 1e-9) if enc_ns else None, "unit": "vectors/s per GPU",
                        "aggregate": cx.world * enc_rows / (enc_ns * 1e-9) if enc_ns else None}}
@@ -650,6 +653,45 @@ def leg_rerank_c5(cx):
                                 "sample": "%d queries: oracle PQ top-%d over %d rows + exact distances of the candidates"
                                           % (nqc, R, rows)}
     return line
+
+
+def leg_shapes(cx):
+    """The other BASELINE shapes on one GPU, each with its own oracle check: configs[0] (1M x 100-d iid rows,
+    m = 10: no cluster structure, the lower bound prunes least) and one configs[3] shard (12.5M x 128-d
+    SIFT-shaped, m = 16).  Resident queries, 2 timed steps after one warm-up step."""
+    torch, g, N, a = cx.torch, cx.g, cx.N, cx.a
+    from gulon_b200.synth import Mixture
+    out = {}
+    for name, rows, D, M, kw, Q in (("c1_1Mx100_m10_iid", 1_000_000, 100, 10, dict(centres=0), 10_000),
+                                    ("c4_shard_12.5Mx128_m16", a.rs_rows_per_gpu, 128, 16,
+                                     dict(centres=16384, nonneg=True, span=40.0), 20_000)):
+        mix = Mixture(D, seed=SEED + (1 if D == 100 else 4), device=cx.dev, **kw)
+        xt = mix.rows(0, min(65_536, rows))
+        pq = g.ProductQuantizer.train(g.DevicePoints.from_torch(xt), g.ProductQuantizerConfig(256, M, 4))
+        del xt
+        codes, stride, enc_ns, enc_rows = encode_shard(cx, pq, mix, 0, rows)
+        ix = g.PQIndex.from_device_codes(pq, codes, rows)
+        queries = mix.rows(0, Q, stream_seed=1)
+        ms, _, res = cx.timed(lambda: ix.batch_query_dev(a.k, queries), 2, 1)
+        line = {"rows": rows, "dim": D, "m": M, "queries": Q, "value": Q * 2 / (ms * 1e-3), "unit": UNIT,
+                "lower_bound_quantizers": N.counter("pscan_lb_quantizers"),
+                "encode_vectors_per_s": enc_rows / (enc_ns * 1e-9) if enc_ns else None}
+        if not a.no_cpu_baseline:
+            from oracle import oracle as o
+            T = o.host_cores()
+            nqc = 8
+            t0 = time.perf_counter()
+            ci, cd, _ = o.pq_query(queries[:nqc].cpu().numpy(), pq.codebook(), codes[:, :rows].cpu().numpy(), a.k,
+                                   topk_mode=o.TOPK_CANONICAL, nthreads=T)
+            dt = time.perf_counter() - t0
+            line["matches_oracle"] = bool(np.array_equal(ci, res[0][:nqc].cpu().numpy()) and
+                                          np.array_equal(cd.view(np.uint32), res[1][:nqc].cpu().numpy().view(np.uint32)))
+            line["cpu_baseline"] = {"value": nqc / dt, "unit": UNIT, "cores": T, "kind": "port",
+                                    "sample": "%d queries x the full index" % nqc}
+        out[name] = line
+        del ix, codes, queries
+        torch.cuda.empty_cache()
+    return out
 
 
 def leg_grouped(cx):
@@ -897,6 +939,8 @@ def main():
         legs["rerank_c5"] = leg_rerank_c5(cx)
         if rank == 0:
             legs["grouped_ivf"] = leg_grouped(cx)
+            if world == 1:
+                legs["other_shapes"] = leg_shapes(cx)
         cx.barrier()
 
     if rank == 0:

@@ -49,17 +49,35 @@ def _stale():
 
 
 def build(force=False, verbose=False):
-    """Compile csrc/*.cu into gulon_b200/libgulon_b200.so for sm_100a (nvcc cross-compiles)."""
+    """Compile csrc/*.cu into gulon_b200/libgulon_b200.so for sm_100a (nvcc cross-compiles).
+
+    Several processes may get here at once (one rank per GPU under torchrun, each finding the library
+    older than a source): the build runs under a file lock, writes to a temporary name and renames it
+    into place, and a process that waited for the lock re-checks before compiling again."""
     if not force and not _stale():
         return SO_PATH
-    nvcc = os.environ.get("NVCC") or "/usr/local/cuda/bin/nvcc"
-    if not os.path.exists(nvcc):
-        nvcc = "nvcc"
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", SO_PATH] + [os.path.join(_SRC_DIR, s) for s in _SOURCES]
-    if verbose:
-        cmd += ["-Xptxas", "-v"]
-        print(" ".join(cmd), file=sys.stderr)
-    subprocess.check_call(cmd, cwd=_SRC_DIR)
+    import fcntl
+    with open(SO_PATH + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not _stale():
+                return SO_PATH          # another process built it while this one waited
+            nvcc = os.environ.get("NVCC") or "/usr/local/cuda/bin/nvcc"
+            if not os.path.exists(nvcc):
+                nvcc = "nvcc"
+            tmp = SO_PATH + ".%d.tmp" % os.getpid()
+            cmd = [nvcc] + NVCC_FLAGS + ["-o", tmp] + [os.path.join(_SRC_DIR, s) for s in _SOURCES]
+            if verbose:
+                cmd += ["-Xptxas", "-v"]
+                print(" ".join(cmd), file=sys.stderr)
+            try:
+                subprocess.check_call(cmd, cwd=_SRC_DIR)
+                os.replace(tmp, SO_PATH)
+            finally:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return SO_PATH
 
 

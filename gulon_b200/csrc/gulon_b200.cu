@@ -1753,8 +1753,8 @@ int rerank_dev(gulon_points_t p, const float *dq, i64 nq, i64 ldq, const int32_t
   if (R <= RERANK_RMAX) {
     int P = 2;
     while (P < R) P <<= 1;
-    const size_t smem = (size_t)P * sizeof(u64) + (size_t)D * sizeof(float);
-    GOPTIN(rerank_topk_kernel, 64 * 1024);
+    const size_t smem = (size_t)P * sizeof(u64) + ((size_t)((D + 3) & ~3) + 4 * RERANK_TILE) * sizeof(float);
+    GOPTIN(rerank_topk_kernel, 96 * 1024);
     for (i64 q0 = 0; q0 < nq; q0 += 1 << 30) {
       const i64 nb = std::min<i64>(1 << 30, nq - q0);
       GLAUNCH(rerank_topk_kernel, (unsigned)nb, 128, smem, st, p->d, p->ld, D, p->N, id_lo, dq + q0 * ldq,

@@ -474,17 +474,16 @@ __global__ void __launch_bounds__(128) rerank_keys_kernel(const float *__restric
 // Fused re-rank: exact distances of a query's R candidates and their k best, one CTA per query, no key
 // materialisation in global memory.  cand [nq][R] holds GLOBAL row ids; this device owns rows
 // [id_lo, id_lo + N) (X row 0 = global row id_lo); ids outside (other shards' rows, or -1) are skipped.
-// Each thread walks whole rows -- the reference's sequential fp32 sum (G/MathUtils.scala:85-95) cannot
-// be split -- with 32-byte loads (one full sector per request, streamed past L1).  The keys are
-// sorted in shared memory; the k smallest go out as (global id, distance), (distance, id) ascending.
-// grid nq, block 128; dynamic shared memory: D floats + P u64, P = power of two >= R, R <= 1024.
+// The reference's distance is a SEQUENTIAL fp32 sum over the D coordinates (G/MathUtils.scala:85-95), so
+// one thread must walk a whole row -- but rows are 4 KB apart, and a lane that reads its own row
+// touches one sector per request.  Loads are therefore warp-cooperative: for each of its 32 candidates the
+// warp reads a 128-byte stretch of the row (one coalesced request), parks it in a padded shared-memory
+// tile, and then every lane sums ITS candidate's 32 coordinates from the tile in order.  (Round 2: the
+// lane-per-row loads ran at 11 % of HBM.)  The keys are sorted in shared memory; the k smallest go
+// out as (global id, distance), (distance, id) ascending.
+// grid nq, block 128; dynamic shared memory: P u64 + D floats + 4 x 32 x 33 floats; P = power of two >= R, R <= 1024.
 constexpr int RERANK_RMAX = 1024;
-__device__ __forceinline__ float4 ldg_nc_stream_f4(const float *p) {
-  float4 r;
-  asm("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-      : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
-  return r;
-}
+constexpr int RERANK_TILE = 32 * 33;
 __global__ void __launch_bounds__(128) rerank_topk_kernel(const float *__restrict__ X, i64 ld, int D,
                                                           i64 N, i64 id_lo,
                                                           const float *__restrict__ Q, i64 ldq,
@@ -495,57 +494,54 @@ __global__ void __launch_bounds__(128) rerank_topk_kernel(const float *__restric
   extern __shared__ __align__(16) unsigned char rr_smem[];
   u64 *keys = reinterpret_cast<u64 *>(rr_smem);
   float *sq = reinterpret_cast<float *>(rr_smem + (size_t)P * sizeof(u64));
+  float *tiles = sq + ((D + 3) & ~3);
   const i64 q = blockIdx.x;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float *tile = tiles + warp * RERANK_TILE;
   for (int j = tid; j < D; j += 128) sq[j] = Q[q * ldq + j];
+  for (int t = tid; t < P; t += 128) keys[t] = KEY_SENT;
   __syncthreads();
-  const bool vec = (ld & 7) == 0 && (reinterpret_cast<uintptr_t>(X) & 31) == 0;
-  for (int t = tid; t < P; t += 128) {
-    u64 key = KEY_SENT;
-    if (t < R) {
-      const i64 gid = cand[q * R + t];
-      const i64 row = gid - id_lo;
-      if (gid >= 0 && row >= 0 && row < N) {
-        const float *x = X + row * ld;
-        float s = 0.0f;
-        int j = 0;
-        if (vec) {
-          // 128 bytes (four sectors) of the row in flight per thread and step; the loads are plain
-          // (non-volatile) so that the compiler issues a step's loads ahead of the previous step's sums
-#pragma unroll 1
-          for (; j + 32 <= D; j += 32) {
-            float4 v[8];
-#pragma unroll
-            for (int u = 0; u < 8; u++) v[u] = ldg_nc_stream_f4(x + j + 4 * u);
-#pragma unroll
-            for (int u = 0; u < 8; u++) {
-              const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-#pragma unroll
-              for (int t = 0; t < 4; t++) {
-                const float dx = __fsub_rn(sq[j + 4 * u + t], e[t]);
-                s = __fadd_rn(s, __fmul_rn(dx, dx));
-              }
-            }
-          }
-          for (; j + 8 <= D; j += 8) {
-            const float4 a = ldg_nc_stream_f4(x + j), b4 = ldg_nc_stream_f4(x + j + 4);
-            const float e[8] = {a.x, a.y, a.z, a.w, b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-            for (int u = 0; u < 8; u++) {
-              const float dx = __fsub_rn(sq[j + u], e[u]);
-              s = __fadd_rn(s, __fmul_rn(dx, dx));
-            }
-          }
-        }
-        for (; j < D; j++) {
-          const float dx = __fsub_rn(sq[j], x[j]);
-          s = __fadd_rn(s, __fmul_rn(dx, dx));
-        }
-        key = make_key(s, (uint32_t)gid);
-      }
+  for (int c0 = warp * 32; c0 < R; c0 += 128) {
+    const int ci = c0 + lane;
+    i64 gid = -1, row = -1;
+    if (ci < R) {
+      gid = cand[q * R + ci];
+      row = gid - id_lo;
+      if (gid < 0 || row < 0 || row >= N) row = -1;
     }
-    keys[t] = key;
+    const unsigned live = __ballot_sync(0xffffffffu, row >= 0);
+    float s = 0.0f;
+    for (int j0 = 0; j0 < D; j0 += 32) {
+      // cooperative loads: candidate c's coordinates [j0, j0 + 32) -> tile[c][0..32)
+      unsigned todo = live;
+      while (todo) {
+        const int c = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const i64 rc = __shfl_sync(0xffffffffu, row, c);
+        if (j0 + lane < D) tile[c * 33 + lane] = __ldg(X + rc * ld + j0 + lane);
+      }
+      __syncwarp();
+      if (row >= 0) {
+        const int w = D - j0 < 32 ? D - j0 : 32;
+        const float *mine = tile + lane * 33;
+        if (w == 32) {
+#pragma unroll
+          for (int t = 0; t < 32; t++) {
+            const float dx = __fsub_rn(sq[j0 + t], mine[t]);
+            s = __fadd_rn(s, __fmul_rn(dx, dx));
+          }
+        } else {
+          for (int t = 0; t < w; t++) {
+            const float dx = __fsub_rn(sq[j0 + t], mine[t]);
+            s = __fadd_rn(s, __fmul_rn(dx, dx));
+          }
+        }
+      }
+      __syncwarp();
+    }
+    if (row >= 0) keys[ci] = make_key(s, (uint32_t)gid);
   }
+  __syncthreads();
   block_bitonic_sort(keys, P, tid, 128);
   int cnt = 0;
   for (int i = tid; i < k; i += 128) {
@@ -556,7 +552,6 @@ __global__ void __launch_bounds__(128) rerank_topk_kernel(const float *__restric
     cnt += ok;
   }
   if (sizes) {
-    // block-wide count of valid slots
     __shared__ int s_cnt;
     if (tid == 0) s_cnt = 0;
     __syncthreads();

@@ -20,8 +20,18 @@ TOPK_LITERAL, TOPK_CANONICAL = 0, 1
 def build(force=False):
     srcs = [os.path.join(_HERE, f) for f in ("gulon_oracle.c", "go_codes.inc", "synth.c",
                                              "../gulon_b200/csrc/synth_spec.h")]
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(f) for f in srcs):
-        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+    def stale():
+        return not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(f) for f in srcs)
+
+    if force or stale():
+        import fcntl
+        with open(_SO + ".lock", "w") as lock:          # several processes may find it stale at once
+            fcntl.flock(lock, fcntl.LOCK_EX)
+            try:
+                if force or stale():
+                    subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+            finally:
+                fcntl.flock(lock, fcntl.LOCK_UN)
     return _SO
 
 

@@ -258,3 +258,24 @@ def test_fused_single_window_with_offset_and_duplicates(g, oracle):
             g.set_option("train_fused", 1)
         out.append((km.centroids.copy(), info))
     assert np.array_equal(out[0][0].view(np.uint32), out[1][0].view(np.uint32)) and out[0][1] == out[1][1]
+
+
+def test_fixed_sum_precision_is_relative_to_the_window_maximum(g):
+    """the fixed-point sum keeps 2^-28 of the window's largest |x|, not of each value: with one
+    outlier of 1e3 among coordinates of ~1e-3 the centroid error is bounded by 2^-29 * 1e3 per coordinate
+    (absolute), which is what the header documents; without the outlier it is ~1e-9 relative."""
+    rng = np.random.default_rng(2)
+    n, dim, K = 20000, 8, 4
+    X = (rng.normal(size=(n, dim)) * 1e-3).astype(np.float32)
+    a = rng.integers(0, K, n).astype(np.int32)
+    exact = np.stack([X[a == k].astype(np.float64).mean(axis=0) for k in range(K)])
+    km = g.KMeans.from_assignment(K, dim, g.Vectors(g.Matrix(X)), a, g.UPDATE_SUM)
+    # unit = 2^(e - 28) with 2^e > max|x| >= 2^(e-1): half a unit is at most 2^-28 max|x|
+    assert np.abs(km.centroids - exact).max() <= 2.0 ** -28 * np.abs(X).max() + 1e-12
+    Xo = X.copy()
+    Xo[0, 0] = 1e3
+    exact_o = np.stack([Xo[a == k].astype(np.float64).mean(axis=0) for k in range(K)])
+    km_o = g.KMeans.from_assignment(K, dim, g.Vectors(g.Matrix(Xo)), a, g.UPDATE_SUM)
+    err = np.abs(km_o.centroids - exact_o)
+    assert err.max() <= 2.0 ** -28 * 1e3 + 0.25 * 2.0 ** -23              # the documented bound (+ the fp32 result rounding)
+    assert err.max() > 1e-9                                                # ... and it is really that coarse
