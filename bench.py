@@ -191,7 +191,8 @@ def build_index_cpu(a, o, T):
     ProductQuantizer.apply (seed = quantizer index, running mean, lowest-index ties) and #encode.
     Cached under the temp directory: the driver runs this arm once per GPU count on the same box."""
     rows, D, M = a.rows, a.dim, a.m
-    tag = "gulon_ref_index_%dx%d_m%d_t%dx%d_s%d" % (rows, D, M, a.train_rows, a.train_iters, SEED)
+    # (v2: bump when csrc/synth_spec.h or the oracle's training / encode change -- a cached index must be THE index)
+    tag = "gulon_ref_index_v2_%dx%d_m%d_t%dx%d_s%d" % (rows, D, M, a.train_rows, a.train_iters, SEED)
     for base in ("/dev/shm", tempfile.gettempdir()):
         path = os.path.join(base, tag + ".npz")
         if os.path.exists(path):
@@ -625,8 +626,10 @@ def leg_rerank_c5(cx):
             "rerank": {"ms_per_step": ms_r / K,
                        "roofline": {"bound": "hbm", "unit": "GB/s", "peak": cx.peak * cx.world,
                                     "algorithmic_bytes_per_query": R * D * 4,
-                                    "achieved": Q * R * D * 4 / (ms_r / K * 1e-3) / 1e9,
-                                    "frac": Q * R * D * 4 / (ms_r / K * 1e-3) / 1e9 / (cx.peak * cx.world)}}}
+                                    "achieved": cx.world * Q * R * D * 4 / (ms_r / K * 1e-3) / 1e9,
+                                    "frac": Q * R * D * 4 / (ms_r / K * 1e-3) / 1e9 / cx.peak,
+                                    "note": "the exact-distance kernel alone on a fixed candidate list: every rank "
+                                            "scores R candidates of its own rows for all Q queries"}}}
     nqc = 16
     if cx.world == 1 and not a.no_cpu_baseline:
         from oracle import oracle as o

@@ -509,17 +509,20 @@ __global__ void __launch_bounds__(128) rerank_topk_kernel(const float *__restric
       row = gid - id_lo;
       if (gid < 0 || row < 0 || row >= N) row = -1;
     }
-    const unsigned live = __ballot_sync(0xffffffffu, row >= 0);
+    if (!__any_sync(0xffffffffu, row >= 0)) continue;
     float s = 0.0f;
     for (int j0 = 0; j0 < D; j0 += 32) {
-      // cooperative loads: candidate c's coordinates [j0, j0 + 32) -> tile[c][0..32)
-      unsigned todo = live;
-      while (todo) {
-        const int c = __ffs(todo) - 1;
-        todo &= todo - 1;
+      // cooperative loads: candidate c's coordinates [j0, j0 + 32) -> tile[c][0..32); all 32 requests of
+      // the warp are issued before the first one is stored (32 x 128 bytes in flight per warp)
+      float v[32];
+      const bool in = j0 + lane < D;
+#pragma unroll
+      for (int c = 0; c < 32; c++) {
         const i64 rc = __shfl_sync(0xffffffffu, row, c);
-        if (j0 + lane < D) tile[c * 33 + lane] = __ldg(X + rc * ld + j0 + lane);
+        v[c] = (in && rc >= 0) ? __ldg(X + rc * ld + j0 + lane) : 0.0f;
       }
+#pragma unroll
+      for (int c = 0; c < 32; c++) tile[c * 33 + lane] = v[c];
       __syncwarp();
       if (row >= 0) {
         const int w = D - j0 < 32 ? D - j0 : 32;
