@@ -105,6 +105,11 @@ struct gulon_index_s {
   DevBuf qlut, mins, qp, boot_tail, plists, pstats, boot_keys, spread, msel, merged2, sufmin;
   DevBuf rowcodes;            // row-major copy of the planes, built by the first pruned scan
   DevBuf kacc, kfloor;        // k-chunked scans: accumulated keys [Q4][k], last key of the previous pass [Q4]
+  // wide indexes (16-bit ids): 8-bit GROUP planes for the lower-bound scan (pscan.cuh), built by the first
+  // pruned scan: gmap [M][K] group of every centroid, members / start = the groups' member lists
+  DevBuf gmap, gmembers, gstart, gcodes, rowcodes16;
+  i64 gps = 0, rcs16 = 0;
+  int wide_state = 0;         // 0 not tried, 1 ready, -1 unavailable
   i64 rcs = 0;
   int rowcodes_state = 0;     // 0 not tried, 1 ready, -1 unavailable (no memory): planes are used
   Selector sel, sel_boot, sel2;
@@ -126,6 +131,7 @@ struct gulon_index_s {
     qlut.release(); mins.release(); qp.release(); boot_tail.release(); plists.release();
     pstats.release(); boot_keys.release(); spread.release(); msel.release(); merged2.release();
     sel2.release(); sufmin.release(); rowcodes.release(); kacc.release(); kfloor.release();
+    gmap.release(); gmembers.release(); gstart.release(); gcodes.release(); rowcodes16.release();
     if (tm_ev0) cudaEventDestroy(tm_ev0);
     if (tm_ev1) cudaEventDestroy(tm_ev1);
     h_q.release(); h_ids.release(); h_dists.release(); h_sizes.release();
@@ -1223,6 +1229,70 @@ int collapse_lists(DevBuf &lists, int S, int Q4, int k, DevBuf &merged, Selector
   return sel.run(merged.as<u64>(), ms, Q4, k, st, keys, stride);
 }
 
+// Wide index (256 < K <= 65536): the data the lower-bound scan needs.  Every quantizer's K centroids are
+// clustered into 256 groups (a small k-means over the centroid table itself, on the device, seed = the
+// quantizer index); the planes of group ids feed the 8-bit bound pass, whose tables hold each group's
+// minimum; a row-major copy of the 16-bit ids serves the survivor evaluation.  Built once per index.
+int prepare_wide(gulon_index_t ix, cudaStream_t st) {
+  if (ix->wide_state != 0) return GULON_OK;
+  ix->wide_state = -1;
+  gulon_codebook_t cb = ix->cb;
+  const int M = cb->M, K = cb->K, dmax = cb->dmax;
+  std::vector<uint8_t> h_map((size_t)M * K);
+  std::vector<int32_t> h_members((size_t)M * K), h_start((size_t)M * 257), h_a(K);
+  DevBuf a;
+  struct Guard {
+    DevBuf &b;
+    ~Guard() { b.release(); }
+  } guard{a};
+  GCHECK(a.ensure((size_t)K * sizeof(int32_t)));
+  for (int m = 0; m < M; m++) {
+    gulon_points_s pts;
+    pts.d = cb->cb.as<float>() + (size_t)m * K * dmax;
+    pts.N = K;
+    pts.D = dmax;
+    pts.ld = dmax;
+    Problems pr;
+    const int32_t zero = 0, dm = cb->dim[m], seed = m;
+    GCHECK(pr.setup(1, 256, &zero, &dm, st));
+    GCHECK(train_problems(pr, &pts, &seed, 4, GULON_UPDATE_RUNNING_MEAN, nullptr, 0, 0, nullptr, nullptr, 0,
+                          nullptr, nullptr, st));
+    GCHECK(pr.assign(pts.d, K, pts.ld, {0}, a.as<int32_t>(), K, st));
+    GCU(cudaMemcpyAsync(h_a.data(), a.p, (size_t)K * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    GCU(cudaStreamSynchronize(st));
+    int cnt[257] = {0};
+    for (int c = 0; c < K; c++) {
+      const int g = h_a[c] & 255;
+      h_map[(size_t)m * K + c] = (uint8_t)g;
+      cnt[g + 1]++;
+    }
+    for (int g = 0; g < 256; g++) cnt[g + 1] += cnt[g];
+    for (int g = 0; g <= 256; g++) h_start[(size_t)m * 257 + g] = cnt[g];
+    std::vector<int> at(cnt, cnt + 256);
+    for (int c = 0; c < K; c++) h_members[(size_t)m * K + at[h_map[(size_t)m * K + c]]++] = c;
+  }
+  GCHECK(upload(ix->gmap, h_map, st));
+  GCHECK(upload(ix->gmembers, h_members, st));
+  GCHECK(upload(ix->gstart, h_start, st));
+  ix->gps = round_up(std::max<i64>(ix->N, 1), 16);
+  ix->rcs16 = round_up(M, 8);
+  if (ix->gcodes.ensure((size_t)M * ix->gps) != GULON_OK ||
+      ix->rowcodes16.ensure((size_t)std::max<i64>(ix->N, 1) * ix->rcs16 * sizeof(uint16_t)) != GULON_OK) {
+    cudaGetLastError();
+    return GULON_OK;   // no memory for the copies: the plain-table scan keeps serving this index
+  }
+  GCU(cudaMemsetAsync(ix->gcodes.p, 0, (size_t)M * ix->gps, st));
+  if (ix->N > 0) {
+    dim3 gg((unsigned)ceil_div(ix->N, 256), (unsigned)M);
+    GLAUNCH(pscan::group_codes_kernel, gg, 256, 0, st, ix->codes16, ix->ps, ix->N, M, K, ix->gmap.as<uint8_t>(),
+            ix->gcodes.as<uint8_t>(), ix->gps);
+    GLAUNCH(pscan::rowcodes16_kernel, (unsigned)ceil_div(ix->N, 256), 256, 0, st, ix->codes16, ix->ps, ix->N, M,
+            ix->rcs16, ix->rowcodes16.as<uint16_t>());
+  }
+  ix->wide_state = 1;
+  return GULON_OK;
+}
+
 // k beyond the in-kernel list size (128) runs the fast kernels in passes of <= 128: a pass only admits keys
 // greater than the last key of the previous pass (`floor`), so it returns the NEXT 128 of the (distance,
 // id) order.  The reference's recall harness defaults reach k = 1000 (G/Tests.scala:53): 8 passes.
@@ -1235,8 +1305,20 @@ int scan_batch(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 fr
   gulon_codebook_t cb = ix->cb;
   const int M = cb->M, K = cb->K;
   const i64 range = until - from;
+  bool wide = false;
   if (ix->codes16) {
-    // wide index: plain tables, materialised keys, selection (any k the selector takes)
+    // wide index.  Long ranges and k <= 128: the lower-bound scan over 8-bit group ids (prepare_wide);
+    // everything else: plain tables, materialised keys, selection (any k the selector takes)
+    const long long want = g_scan_impl.load();
+    if ((want == GULON_SCAN_AUTO || want == GULON_SCAN_PRUNED) && k <= pscan::KMAX && M <= 1024 &&
+        range >= g_pruned_min_rows.load() && (double)nq * M * K * 4.0 <= 8e9) {
+      GCHECK(prepare_wide(ix, st));
+      wide = ix->wide_state == 1;
+    }
+    GREQUIRE(want != GULON_SCAN_PRUNED || wide, "scan_impl = pruned on a wide index needs k <= %d, a range of at least "
+             "pruned_min_rows and room for the group planes", pscan::KMAX);
+  }
+  if (ix->codes16 && !wide) {
     const i64 n_pad = round_up(range, SEL_CHUNK);
     i64 qb = std::min<i64>(g_simple_scratch.load() / (8 * n_pad), (512LL << 20) / ((i64)M * K * 4));
     qb = std::max<i64>(1, std::min<i64>(std::min<i64>(qb, nq), 32768));
@@ -1258,7 +1340,7 @@ int scan_batch(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 fr
     }
     return GULON_OK;
   }
-  long long impl = g_scan_impl.load();
+  long long impl = wide ? (long long)GULON_SCAN_PRUNED : g_scan_impl.load();
   if (impl == GULON_SCAN_AUTO) {
     if (k <= KCHUNK_MAX && M <= 1024 && range >= g_pruned_min_rows.load())
       impl = GULON_SCAN_PRUNED;
@@ -1308,13 +1390,25 @@ int scan_batch(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 fr
   int W = (int)g_pruned_words.load();
   if (W == 0) W = nq * FB > 64 ? 4 : (nq * FB > 32 ? 2 : 1);
   if (FB == 16 && W == 1) W = 2;  // a tile is made of whole query groups of 4
+  if (wide) W = 4;                // the wide kernels are instantiated for full-width entries only
   const int QT = W * 32 / FB;
   const int G = impl == GULON_SCAN_PRUNED ? (QT / 4) * (int)ceil_div(nq, QT) : (int)ceil_div(nq, 4);
   const int Q4 = G * 4;
   GCHECK(ix->lutI.ensure((size_t)G * M * 256 * sizeof(float4)));
   dim3 lg((unsigned)G, (unsigned)M);
-  GLAUNCH(lut_build_kernel, lg, 256, 0, st, dQ, ldq, nq, cb->cb.as<float>(),
-          cb->dfrom.as<int32_t>(), cb->ddim.as<int32_t>(), M, K, cb->dmax, ix->lutI.as<float4>());
+  if (wide) {
+    // exact tables [nq][M][K], then the groups' minima in the layout of the 8-bit kernels
+    GCHECK(ix->lutW.ensure((size_t)nq * M * K * sizeof(float)));
+    dim3 wg((unsigned)ceil_div(K, 256), (unsigned)M, (unsigned)nq);
+    GLAUNCH(lut_wide_kernel, wg, 256, 0, st, dQ, ldq, cb->cb.as<float>(), cb->dfrom.as<int32_t>(),
+            cb->ddim.as<int32_t>(), M, K, cb->dmax, ix->lutW.as<float>());
+    GLAUNCH(pscan::lut_group_min_kernel, lg, 256, 0, st, ix->lutW.as<float>(), nq, M, K,
+            ix->gmembers.as<int32_t>(), ix->gstart.as<int32_t>(), ix->lutI.as<float4>());
+  } else {
+    GLAUNCH(lut_build_kernel, lg, 256, 0, st, dQ, ldq, nq, cb->cb.as<float>(),
+            cb->dfrom.as<int32_t>(), cb->ddim.as<int32_t>(), M, K, cb->dmax, ix->lutI.as<float4>());
+  }
+  const int Kb = wide ? 256 : K;   // entries per table of the bound pass
 
   if (impl == GULON_SCAN_FUSED || impl == GULON_SCAN_PRUNED) {
     const int k_all = k;
@@ -1340,6 +1434,16 @@ int scan_batch(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 fr
     }
       GULON_PSCAN_VARIANTS(GULON_X)
   #undef GULON_X
+      if (wide) {
+        GREQUIRE(W == 4, "internal: wide pruned scan with %d-word entries", W);
+        if (FB == 8) {
+          auto kern = pscan::pruned_scan_kernel<8, 4, true>;
+          GOPTIN(kern, (pscan::Cfg<8, 4>::SMEM_BYTES));
+        } else {
+          auto kern = pscan::pruned_scan_kernel<16, 4, true>;
+          GOPTIN(kern, (pscan::Cfg<16, 4>::SMEM_BYTES));
+        }
+      }
       const int T = G / (QT / 4);
       const int RI = pscan::NT * (64 / W);  // rows per work item
       g_last_qt = QT;
@@ -1349,12 +1453,24 @@ int scan_batch(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 fr
       i64 boot_want = g_boot_rows.load();
       // whole 8192-row chunks: the exact kernel pays for a chunk's table fills however few rows it holds
       if (boot_want <= 0) boot_want = std::min<i64>(32768, std::max<i64>(8192, (range / 64) & ~8191LL));
+      if (wide) boot_want = std::min<i64>(boot_want, 8192);   // materialised keys: 8 bytes per (boot row, query)
       const i64 boot = std::min<i64>(range, std::max<i64>(boot_want, k));
       int Sb = 1;
-      GCHECK(fused_lists(ix, from, from + boot, G, k, ix->lists, &Sb, st, floor));
       u64 *bkeys;
       i64 bstride;
-      GCHECK(collapse_lists(ix->lists, Sb, Q4, k, ix->boot_keys, ix->sel_boot, &bkeys, &bstride, st));
+      if (wide) {
+        // boot rows of a wide index: exact keys from the plain tables, selection
+        const i64 n_pad = round_up(boot, SEL_CHUNK);
+        GCHECK(ix->keys.ensure((size_t)Q4 * n_pad * sizeof(u64)));
+        GCU(cudaMemsetAsync(ix->keys.p, 0xFF, (size_t)Q4 * n_pad * sizeof(u64), st));   // padding queries: empty
+        dim3 kg((unsigned)(n_pad / 256), (unsigned)nq);
+        GLAUNCH(adc_keys_wide_kernel, kg, 256, 0, st, ix->codes16, ix->ps, from, from + boot, ix->lutW.as<float>(),
+                M, K, ix->keys.as<u64>(), n_pad);
+        GCHECK(ix->sel_boot.run(ix->keys.as<u64>(), n_pad, Q4, k, st, &bkeys, &bstride));
+      } else {
+        GCHECK(fused_lists(ix, from, from + boot, G, k, ix->lists, &Sb, st, floor));
+        GCHECK(collapse_lists(ix->lists, Sb, Q4, k, ix->boot_keys, ix->sel_boot, &bkeys, &bstride, st));
+      }
       if (boot == range) {
         res = bkeys;
         rs = bstride;
@@ -1363,7 +1479,7 @@ int scan_batch(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 fr
       GCHECK(ix->mins.ensure((size_t)Q4 * M * sizeof(float)));
       GCHECK(ix->spread.ensure((size_t)Q4 * M * sizeof(float)));
       GCHECK(ix->sufmin.ensure((size_t)Q4 * (M + 1) * sizeof(float)));
-      if (ix->rowcodes_state == 0 && g_pruned_rowcodes.load() != 0) {
+      if (!wide && ix->rowcodes_state == 0 && g_pruned_rowcodes.load() != 0) {
         // the codes of a row side by side: what the survivor evaluation gathers (built once; the code
         // planes of an index must not change after its first query)
         ix->rcs = round_up(M, 16);
@@ -1407,7 +1523,7 @@ int scan_batch(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 fr
         const int sML = stage == 1 ? ML : (FB == 8 ? std::min(M, std::max(ML, 42)) : M);
         GCHECK(ix->qlut.ensure((size_t)T * sML * 256 * W * sizeof(uint32_t)));
         GCHECK(ix->msel.ensure((size_t)T * sML * sizeof(int32_t)));
-        GLAUNCH(pscan::qparams_kernel, (unsigned)G, 256, 0, st, ix->lutI.as<float4>(), M, K, nq, cur,
+        GLAUNCH(pscan::qparams_kernel, (unsigned)G, 256, 0, st, ix->lutI.as<float4>(), M, Kb, nq, cur,
                 cur_stride, k, pscan::t0_units(FB, sML), ix->mins.as<float>(), ix->spread.as<float>(),
                 ix->sufmin.as<float>(), ix->qp.as<pscan::QParam>(), ix->boot_tail.as<u64>());
         GLAUNCH(pscan::qselect_kernel, (unsigned)T, 256, 0, st, ix->spread.as<float>(),
@@ -1418,7 +1534,7 @@ int scan_batch(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 fr
     if (FB == FB_ && W == W_) {                                                                   \
       auto kern = pscan::qlut_build_kernel<FB_, W_>;                                              \
       GLAUNCH(kern, qg, 256, 0, st, ix->lutI.as<float4>(), ix->mins.as<float>(),                  \
-              ix->qp.as<pscan::QParam>(), ix->msel.as<int32_t>(), M, sML, K,                      \
+              ix->qp.as<pscan::QParam>(), ix->msel.as<int32_t>(), M, sML, Kb,                     \
               ix->qlut.as<uint32_t>());                                                           \
       built = true;                                                                               \
     }
@@ -1436,9 +1552,13 @@ int scan_batch(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 fr
         unsigned long long *dstats = ix->pstats.as<unsigned long long>() + 4 * stage;
         GCU(cudaMemsetAsync(dstats, 0, 3 * sizeof(unsigned long long), st));
         pscan::Params prm;
-        prm.codes = ix->codes;
-        prm.ps = ix->ps;
-        const bool use_rows = ix->rowcodes_state == 1 && g_pruned_rowcodes.load() != 0;
+        prm.codes = wide ? ix->gcodes.as<uint8_t>() : ix->codes;
+        prm.ps = wide ? ix->gps : ix->ps;
+        prm.rowcodes16 = wide ? ix->rowcodes16.as<uint16_t>() : nullptr;
+        prm.rcs16 = ix->rcs16;
+        prm.lutW = wide ? ix->lutW.as<float>() : nullptr;
+        prm.K = K;
+        const bool use_rows = !wide && ix->rowcodes_state == 1 && g_pruned_rowcodes.load() != 0;
         prm.rowcodes = use_rows ? ix->rowcodes.as<uint8_t>() : nullptr;
         prm.rcs = ix->rcs;
         prm.sufmin = ix->sufmin.as<float>();
@@ -1465,13 +1585,20 @@ int scan_batch(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 fr
         KernelTimer &ktm = stage == 1 ? g_t_pscan : g_t_pscan_first;
         cudaEvent_t ev = ktm.begin(st);
   #define GULON_X(FB_, W_)                                                                        \
-    if (FB == FB_ && W == W_) {                                                                   \
+    if (!wide && FB == FB_ && W == W_) {                                                          \
       auto kern = pscan::pruned_scan_kernel<FB_, W_>;                                             \
       using CfgT = pscan::Cfg<FB_, W_>;                                                           \
       GLAUNCH(kern, (unsigned)(S * Bs), pscan::NT, CfgT::SMEM_BYTES, st, prm);                    \
     }
         GULON_PSCAN_VARIANTS(GULON_X)
   #undef GULON_X
+        if (wide && FB == 8) {
+          auto kern = pscan::pruned_scan_kernel<8, 4, true>;
+          GLAUNCH(kern, (unsigned)(S * Bs), pscan::NT, (pscan::Cfg<8, 4>::SMEM_BYTES), st, prm);
+        } else if (wide) {
+          auto kern = pscan::pruned_scan_kernel<16, 4, true>;
+          GLAUNCH(kern, (unsigned)(S * Bs), pscan::NT, (pscan::Cfg<16, 4>::SMEM_BYTES), st, prm);
+        }
         ktm.end(ev, st);
         if (time_it) {
           GCU(cudaEventRecord(ix->tm_ev1, st));

@@ -87,6 +87,13 @@ struct Params {
   const QParam *qp;       // [T*QT]
   const u64 *boot_tail;   // [T*QT] key of the boot list tail (KEY_SENT: none)
   const u64 *floor;       // [T*QT] k-chunked scans: only keys > floor enter the lists (null: none)
+  // WIDE indexes (256 < K <= 65536, 16-bit centroid ids): `codes` / `lutI` / `qlut` are the planes and
+  // tables of the 8-bit GROUP ids (every centroid belongs to one of 256 groups; a group's table entry is
+  // the minimum over its members: still a lower bound); survivors are evaluated with the real ids
+  const uint16_t *rowcodes16;  // [N][rcs16] row-major 16-bit ids
+  i64 rcs16;                   // elements per row (a multiple of 8)
+  const float *lutW;           // [T*QT][M][K] exact tables
+  int K;
   u64 *lists;             // [S][T*QT][k]
   unsigned long long *stats;  // [0] survivors, [1] list candidates, [2] slow-path items
   i64 nq;
@@ -287,6 +294,54 @@ __global__ void __launch_bounds__(256) rowcodes_kernel(const uint8_t *__restrict
   }
 }
 
+// ---- wide indexes: group ids ------------------------------------------------------------------------
+// planes of 16-bit ids [M][ps16] -> planes of 8-bit group ids [M][ps8] through gmap [M][K]
+__global__ void __launch_bounds__(256) group_codes_kernel(const uint16_t *__restrict__ codes16, i64 ps16, i64 N,
+                                                          int M, int K, const uint8_t *__restrict__ gmap,
+                                                          uint8_t *__restrict__ gcodes, i64 ps8) {
+  const i64 r = (i64)blockIdx.x * 256 + threadIdx.x;
+  const int m = blockIdx.y;
+  if (r >= N) return;
+  const int c = codes16[(i64)m * ps16 + r];
+  gcodes[(i64)m * ps8 + r] = c < K ? gmap[(i64)m * K + c] : 0;
+}
+// planes [M][ps16] -> rows [N][rcs16]
+__global__ void __launch_bounds__(256) rowcodes16_kernel(const uint16_t *__restrict__ codes16, i64 ps16, i64 N,
+                                                         int M, i64 rcs16, uint16_t *__restrict__ rows) {
+  const i64 r = (i64)blockIdx.x * 256 + threadIdx.x;
+  if (r >= N) return;
+  for (int m = 0; m < rcs16; m++) rows[r * rcs16 + m] = m < M ? codes16[(i64)m * ps16 + r] : (uint16_t)0;
+}
+// exact tables lutW [nq][M][K] -> group-minimum tables in the interleaved layout of the scan kernels:
+// lutG[(g4 * M + m) * 256 + g] = float4 of queries 4 g4 .. 4 g4 + 3, entry = min over the members of group g
+// (+inf for an empty group; 0 for queries past nq).  members [M][K] centroid ids sorted by group, start [M][257].
+// grid (G4, M), block 256 (thread = group).
+__global__ void __launch_bounds__(256) lut_group_min_kernel(const float *__restrict__ lutW, i64 nq, int M, int K,
+                                                            const int32_t *__restrict__ members,
+                                                            const int32_t *__restrict__ start,
+                                                            float4 *__restrict__ lutG) {
+  const int g4 = blockIdx.x, m = blockIdx.y, g = threadIdx.x;
+  const int b = start[m * 257 + g], e = start[m * 257 + g + 1];
+  float r[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const i64 q = (i64)g4 * 4 + j;
+    float mn = 0.0f;
+    if (q < nq) {
+      mn = __int_as_float(0x7f800000);
+      const float *l = lutW + (q * M + m) * K;
+      for (int i = b; i < e; i++) {
+        const float v = l[members[(i64)m * K + i]];
+        // a NaN entry must not hide behind fminf: it keeps the group at the minimum of the others, which
+        // is still a lower bound of every finite member and the NaN member is re-evaluated exactly anyway
+        mn = fminf(mn, v);
+      }
+    }
+    r[j] = mn;
+  }
+  lutG[((i64)g4 * M + m) * 256 + g] = make_float4(r[0], r[1], r[2], r[3]);
+}
+
 // The code planes stream through L2 once per pass: evict-first keeps them from displacing the exact
 // tables (tens of MB, re-read at random by the survivor evaluation), which are loaded evict-last.
 __device__ __forceinline__ u64 l2_policy_evict_first() {
@@ -383,7 +438,7 @@ __device__ __forceinline__ uint4 ldg_entry(const uint32_t *p) {
 // so that the address of a row's table entry is ONE byte-permute of (code word, per-lane base):
 // PRMT puts the row's code byte into address bits 8..15.  After the region: per-query sort areas,
 // then the survivor queue.
-template <int FB, int W>
+template <int FB, int W, bool WIDE = false>
 __global__ void __launch_bounds__(NT, 1) pruned_scan_kernel(const Params p) {
   using C = Cfg<FB, W>;
   constexpr int QT = C::QT, RPT = C::RPT, R = C::R, QSH = C::QSH, RSH = C::RSH;
@@ -618,6 +673,25 @@ __global__ void __launch_bounds__(NT, 1) pruned_scan_kernel(const Params p) {
           }
           float d = 0.0f;
           bool out = false;
+          if constexpr (WIDE) {
+            // 16-bit ids from the row-major copy (8 per 16-byte load), exact tables [M][K] of the query
+            const float *lw = p.lutW + ((i64)ts * QT + q) * M * p.K;
+            for (int mb = 0; mb < M && !out; mb += 8) {
+              const uint4 c4 = *reinterpret_cast<const uint4 *>(p.rowcodes16 + row * p.rcs16 + mb);
+              const uint32_t cw8[4] = {c4.x, c4.y, c4.z, c4.w};
+              float v[8];
+#pragma unroll
+              for (int u = 0; u < 8; u++) {
+                const int c = (int)((cw8[u >> 1] >> (16 * (u & 1))) & 0xffffu);
+                v[u] = mb + u < M ? ldg_keep_f32(lw + (i64)(mb + u) * p.K + c, pol_keep) : 0.0f;
+              }
+#pragma unroll
+              for (int u = 0; u < 8; u++)
+                if (mb + u < M) d = __fadd_rn(d, v[u]);
+              const int done = mb + 8 < M ? mb + 8 : M;
+              if ((double)d + (double)suf[done] > tau_hi) out = true;
+            }
+          } else {
           for (int m0 = 0; m0 < M && !out; m0 += 16) {
             uint32_t cw[4];
             if (p.rowcodes) {
@@ -648,6 +722,7 @@ __global__ void __launch_bounds__(NT, 1) pruned_scan_kernel(const Params p) {
                 if ((double)d + (double)suf[done] > tau_hi) out = true;
               }
             }
+          }
           }
           if (!out) {
             key = make_key(d, (uint32_t)row);

@@ -127,6 +127,20 @@ __device__ __forceinline__ bool mb_try(uint64_t *b, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// the same without the suspend-time hint (the instruction still blocks for a hardware-defined time)
+__device__ __forceinline__ bool mb_try_nohint(uint64_t *b, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(sa(b)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // A hand-off that never arrives is a bug in the pipeline: trap (the launch fails with an error and
 // the breadcrumbs) instead of hanging the device.  Legitimate waits are microseconds long.
 //
@@ -138,8 +152,13 @@ __device__ __forceinline__ bool mb_try(uint64_t *b, uint32_t parity) {
 // two-accumulator pipeline; a pure test_wait spin 484 M -- the spinners take the issue slots.  The
 // suspend-hint wait below gives 737 M.
 __device__ __forceinline__ void mb_wait(uint64_t *b, uint32_t parity) {
+#ifdef GULON_TC_WAIT_NOHINT
+  for (uint32_t spins = 0; !mb_try_nohint(b, parity); spins++)
+    if (spins > (1u << 26)) __trap();
+#else
   for (uint32_t spins = 0; !mb_try(b, parity); spins++)
     if (spins > (1u << 22)) __trap();
+#endif
 }
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sa(dst)),

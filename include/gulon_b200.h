@@ -232,7 +232,11 @@ int gulon_index_create_dev(gulon_codebook_t cb, const uint8_t *dcodes, int64_t N
                            int64_t plane_stride, gulon_index_t *out);
 /* Wide indexes: 256 < K <= 65536, the reference's BytePlus coders (G/Coder.scala:142-168).  The ids
  * cross the boundary unpacked, one uint16 per (quantizer, row); plane_stride counts elements.  Queries
- * go through gulon_pq_query / gulon_pq_query_dev like any index (plain-table scan + selection). */
+ * go through gulon_pq_query / gulon_pq_query_dev like any index.  Ranges of >= pruned_min_rows rows with
+ * k <= 128 take the lower-bound scan: on first use the index clusters every quantizer's K centroids into
+ * 256 groups and keeps 8-bit group planes (N x M bytes) plus a row-major copy of the ids (N x 2M bytes);
+ * the bound pass runs over group ids with per-group minimum tables, survivors are evaluated with the
+ * real ids -- same bits as the plain-table scan + selection that serves every other case. */
 int gulon_index_create16(gulon_codebook_t cb, const uint16_t *codes, int64_t N, int64_t plane_stride,
                          gulon_index_t *out);
 int gulon_index_create16_dev(gulon_codebook_t cb, const uint16_t *dcodes, int64_t N,

@@ -89,3 +89,41 @@ def test_wide_train_and_file_round_trip(g, oracle, tmp_path):
     a, b = ix.batch_query(10, Q), back.batch_query(10, Q)
     assert np.array_equal(a.keys, b.keys) and np.array_equal(a.values.view(np.uint32), b.values.view(np.uint32))
     assert storage.to_protobuf(back) == path.read_bytes()
+
+
+@pytest.mark.parametrize("K,M,n,k", [(1000, 4, 300_000, 10), (4096, 3, 280_000, 100), (300, 8, 270_000, 1)])
+def test_wide_lower_bound_scan_matches_oracle(g, oracle, K, M, n, k):
+    """Ranges of >= 262 144 rows on a wide index take the lower-bound scan (round 2): the bound pass runs
+    over 8-bit GROUP ids (the K centroids of a quantizer clustered into 256 groups, a group's table entry
+    = the minimum over its members), survivors are evaluated with the real 16-bit ids.  Same answer as the
+    plain-table scan and as the oracle, ids and distance bits."""
+    rng = np.random.default_rng(K + M)
+    D = 6 * M - 1                                          # ragged windows
+    X = clustered(rng, n, D, centres=60)
+    cb = codebook_from_rows(rng, X, M, K)
+    pq = g.ProductQuantizer.from_codebook(cb, D)
+    enc = pq.encode(g.Matrix(X))
+    ix = g.PQIndex(pq, enc)
+    Q = np.concatenate((X[rng.integers(0, n, 9)] + 0.01, clustered(rng, 12, D, centres=60))).astype(np.float32)
+    launches0 = g.kernel_launches()
+    got = ix.batch_query(k, Q, 5, n - 11)                  # automatic: the pruned path
+    assert g._native.counter("pscan_lb_quantizers") >= 1
+    wi, wd, ws = oracle.pq_query(Q, cb, enc.codes, k, 5, n - 11)
+    assert np.array_equal(got.size, ws)
+    assert np.array_equal(got.keys, wi) and np.array_equal(got.values.view(np.uint32), wd.view(np.uint32))
+    g.set_option("scan_impl", g.SCAN_SIMPLE)               # the plain-table scan, same index
+    try:
+        plain = ix.batch_query(k, Q, 5, n - 11)
+    finally:
+        g.set_option("scan_impl", g.SCAN_AUTO)
+    assert np.array_equal(plain.keys, got.keys) and np.array_equal(plain.values.view(np.uint32), got.values.view(np.uint32))
+    # 16-bit fields and a pinned subset of the quantizers
+    for bits, lb in ((16, 0), (8, max(1, M // 2))):
+        g.set_option("pruned_bits", bits)
+        g.set_option("pruned_lb_quantizers", lb)
+        try:
+            again = ix.batch_query(k, Q[:5], 5, n - 11)
+        finally:
+            g.set_option("pruned_bits", 0)
+            g.set_option("pruned_lb_quantizers", 0)
+        assert np.array_equal(again.keys, wi[:5]) and np.array_equal(again.values.view(np.uint32), wd[:5].view(np.uint32))
