@@ -463,7 +463,7 @@ def leg_train_c3(cx, mix, X_full):
         bytes0 = dict(comm.bytes) if comm else {}
         ms, wall, pq = cx.timed(run, 1, 0)
         secs.append(max(ms, wall) * 1e-3)
-    sec = float(np.mean(secs))
+    sec = float(np.median(secs))
     updates = N.counter("train_updates")
     alg = (updates + 1) * rows * D * 4.0      # the matrix is read at least once per Lloyd iteration
     out = {"config": "configs[2]: %dx%d-d, m=%dx256, max %d Lloyd iterations, sum-mode update" % (rows, D, M, a.c3_iters),
@@ -875,33 +875,36 @@ def main():
         T = o.host_cores()
     full_codes = cx.gather_codes(codes, n_local, bounds) if not a.no_cpu_baseline else None
     if o is not None:
-        # ~10 s of host work at the c2 shape on one GPU (about 7 queries/s per core); 16 queries at world > 1
-        per_s = 3e8 / max(1.0, float(a.rows) * M)
-        nq = a.cpu_queries or (max(64, int(64 * T * per_s)) if world == 1 else 16)
-        nq = min(Q, nq)
-        cb = pq.codebook()
-        digest = index_digest(cb, full_codes)
-        t0 = time.perf_counter()
-        ci, cd, _ = o.pq_query(q_np[:nq], cb, full_codes, k, topk_mode=o.TOPK_CANONICAL, nthreads=T)
-        dt = time.perf_counter() - t0
-        ok = bool(np.array_equal(ci, ids_dev[:nq]) and np.array_equal(cd.view(np.uint32), dist_dev[:nq].view(np.uint32)))
-        cpu = {"value": nq / dt, "unit": UNIT, "cores": T, "kind": "port",
-               "sample": "the first %d of the %d queries x the full %d-row index" % (nq, Q, a.rows),
-               "matches_gpu": ok, "threads_from": "os.sched_getaffinity"}
-        if world > 1:      # the CPU baseline proper is an N = 1 figure; at N > 1 this is the parity check
-            extra["oracle_check"] = dict(cpu, note="sharded answer (NCCL path) against the oracle over the whole index")
-            cpu = None
-        if not a.no_extra_legs:
-            # encode on host cores: ProductQuantizer#encode over a row sample, M subspace tasks in parallel
-            ne = 100_000
-            xs = o.SynthMixture(D, seed=SEED).rows(0, min(ne, a.rows), nthreads=T)
+        try:
+            # ~10 s of host work at the c2 shape on one GPU (about 7 queries/s per core); 16 queries at world > 1
+            per_s = 3e8 / max(1.0, float(a.rows) * M)
+            nq = a.cpu_queries or (max(64, int(64 * T * per_s)) if world == 1 else 16)
+            nq = min(Q, nq)
+            cb = pq.codebook()
+            digest = index_digest(cb, full_codes)
             t0 = time.perf_counter()
-            hc = o.pq_encode(xs, cb, tie_mode=o.TIE_LOWEST, nthreads=T)
+            ci, cd, _ = o.pq_query(q_np[:nq], cb, full_codes, k, topk_mode=o.TOPK_CANONICAL, nthreads=T)
             dt = time.perf_counter() - t0
-            enc_cpu = {"value": len(xs) / dt, "unit": "vectors/s", "cores": T, "kind": "port",
-                       "sample": "rows [0, %d) of the data set" % len(xs),
-                       "matches_gpu": bool(lo == 0 and np.array_equal(hc, full_codes[:, :len(xs)]))}
-            train_cpu = leg_train_cpu(cx, o, T)
+            ok = bool(np.array_equal(ci, ids_dev[:nq]) and np.array_equal(cd.view(np.uint32), dist_dev[:nq].view(np.uint32)))
+            cpu = {"value": nq / dt, "unit": UNIT, "cores": T, "kind": "port",
+                   "sample": "the first %d of the %d queries x the full %d-row index" % (nq, Q, a.rows),
+                   "matches_gpu": ok, "threads_from": "os.sched_getaffinity"}
+            if world > 1:      # the CPU baseline proper is an N = 1 figure; at N > 1 this is the parity check
+                extra["oracle_check"] = dict(cpu, note="sharded answer (NCCL path) against the oracle over the whole index")
+                cpu = None
+            if not a.no_extra_legs:
+                # encode on host cores: ProductQuantizer#encode over a row sample, M subspace tasks in parallel
+                ne = 100_000
+                xs = o.SynthMixture(D, seed=SEED).rows(0, min(ne, a.rows), nthreads=T)
+                t0 = time.perf_counter()
+                hc = o.pq_encode(xs, cb, tie_mode=o.TIE_LOWEST, nthreads=T)
+                dt = time.perf_counter() - t0
+                enc_cpu = {"value": len(xs) / dt, "unit": "vectors/s", "cores": T, "kind": "port",
+                           "sample": "rows [0, %d) of the data set" % len(xs),
+                           "matches_gpu": bool(lo == 0 and np.array_equal(hc, full_codes[:, :len(xs)]))}
+                train_cpu = leg_train_cpu(cx, o, T)
+        except Exception as e:      # pragma: no cover -- a failing checker must not lose the measured line
+            extra["cpu_baseline_error"] = "%s: %s" % (type(e).__name__, str(e)[:300])
         del full_codes
     cx.barrier()
 
@@ -929,21 +932,42 @@ def main():
     cx.barrier()
 
     # ---- other legs ---------------------------------------------------------------------------------
+    # The headline above is complete; a leg that fails must not lose it.  A failure is recorded in the leg's
+    # slot and the remaining legs are skipped on every rank (the ranks agree on that through an all-reduce;
+    # single-rank legs run last).
     legs = {}
+
+    def run_leg(name, fn, collective=True):
+        err = None
+        try:
+            legs[name] = fn()
+        except Exception as e:      # pragma: no cover
+            err = "%s: %s" % (type(e).__name__, str(e)[:300])
+            legs[name] = {"error": err}
+        bad = 1.0 if err else 0.0
+        if collective and world > 1:
+            t = torch.tensor([bad], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            bad = float(t.item())
+            if bad and not err:
+                legs[name] = {"error": "failed on another rank"}
+        return bad == 0.0
+
     if not a.no_extra_legs:
         del ix, sh
-        legs["train_c3"] = leg_train_c3(cx, mix, X)
-        if train_cpu:
+        ok = run_leg("train_c3", lambda: leg_train_c3(cx, mix, X))
+        if ok and train_cpu:
             legs["train_c3"]["cpu_baseline"] = train_cpu
         X = None
         torch.cuda.empty_cache()
-        if world > 1:
-            legs["row_sharded"] = leg_row_sharded(cx, clk)
-        legs["rerank_c5"] = leg_rerank_c5(cx)
+        if ok and world > 1:
+            ok = run_leg("row_sharded", lambda: leg_row_sharded(cx, clk))
+        if ok:
+            ok = run_leg("rerank_c5", lambda: leg_rerank_c5(cx))
         if rank == 0:
-            legs["grouped_ivf"] = leg_grouped(cx)
+            run_leg("grouped_ivf", lambda: leg_grouped(cx), collective=False)
             if world == 1:
-                legs["other_shapes"] = leg_shapes(cx)
+                run_leg("other_shapes", lambda: leg_shapes(cx), collective=False)
         cx.barrier()
 
     if rank == 0:
