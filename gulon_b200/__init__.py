@@ -4,7 +4,7 @@ reference's Scala API (G/KMeans.scala, G/ProductQuantizer.scala, G/Index.scala) 
 hand-written CUDA kernels through the C ABI in include/gulon_b200.h.  No CPU fallback.
 """
 from . import _native
-from ._native import (GulonError, NoDeviceError, SCAN_AUTO, SCAN_FUSED, SCAN_PRUNED, SCAN_SIMPLE, TIE_LOWEST,
+from ._native import (GulonError, NoDeviceError, SCAN_AUTO, SCAN_FUSED, SCAN_PRUNED, SCAN_SIMPLE, SCAN_TENSOR, TIE_LOWEST,
                       UPDATE_RUNNING_MEAN, UPDATE_SUM, build, device_count, kernel_launches,
                       set_option)
 from .grouped import GroupedIndex, GroupedVectors, LimitGroups, LimitVectors
@@ -22,7 +22,7 @@ from .recall import SummaryStats, Tests
 from .vectors import DevicePoints, Matrix, Vectors, normalize, subvector_windows
 
 __all__ = [
-    "GulonError", "NoDeviceError", "SCAN_AUTO", "SCAN_FUSED", "SCAN_PRUNED", "SCAN_SIMPLE", "TIE_LOWEST",
+    "GulonError", "NoDeviceError", "SCAN_AUTO", "SCAN_FUSED", "SCAN_PRUNED", "SCAN_SIMPLE", "SCAN_TENSOR", "TIE_LOWEST",
     "UPDATE_RUNNING_MEAN", "UPDATE_SUM", "build", "device_count", "kernel_launches", "set_option",
     "GroupedIndex", "GroupedVectors", "LimitGroups", "LimitVectors", "PQIndex", "TopK", "exact_nearest_neighbours", "prepare_query", "KMeans", "KMeansConfig",
     "KMeansProgressReport", "Coder8", "EncodedMatrix", "ProductQuantizer", "Quantizer",

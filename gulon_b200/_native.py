@@ -14,13 +14,13 @@ _ROOT = os.path.dirname(_HERE)
 SO_PATH = os.path.join(_HERE, "libgulon_b200.so")
 _SRC_DIR = os.path.join(_HERE, "csrc")
 _SOURCES = ["gulon_b200.cu"]
-_HEADERS = ["common.cuh", "kmeans.cuh", "scan.cuh", "select.cuh", "pscan.cuh", "tcassign.cuh", "kupdate.cuh", "mlctl.h",
+_HEADERS = ["common.cuh", "kmeans.cuh", "scan.cuh", "select.cuh", "pscan.cuh", "tcassign.cuh", "tscan.cuh", "kupdate.cuh", "mlctl.h",
             "synth.cuh", "synth_spec.h"]
 
 OK, EINVAL, ECUDA, ENOMEM, ENODEVICE, ECOMM, EUNSUPPORTED, ESTATE = 0, -1, -2, -3, -4, -5, -6, -7
 TIE_LOWEST = 1
 UPDATE_RUNNING_MEAN, UPDATE_SUM = 0, 1
-SCAN_AUTO, SCAN_SIMPLE, SCAN_FUSED, SCAN_PRUNED = 0, 1, 2, 3
+SCAN_AUTO, SCAN_SIMPLE, SCAN_FUSED, SCAN_PRUNED, SCAN_TENSOR = 0, 1, 2, 3, 4
 ASSIGN_AUTO, ASSIGN_EXACT, ASSIGN_TENSOR = 0, 1, 2
 
 NVCC_FLAGS = [
@@ -130,6 +130,7 @@ SIGNATURES = {
     "gulon_shutdown": (C.c_int, []),
     "gulon_set_option": (C.c_int, [C.c_char_p, i64]),
     "gulon_get_counter": (C.c_int, [C.c_char_p, C.POINTER(i64)]),
+    "gulon_debug_tscan": (C.c_int, [vp, vp, i64, i64, vp, i64, i64, vp, vp, vp, C.POINTER(i32)]),
     "gulon_subvectors": (C.c_int, [i32, i32, vp, vp]),
     "gulon_points_create": (C.c_int, [vp, i64, i32, i64, C.POINTER(vp)]),
     "gulon_points_wrap_dev": (C.c_int, [vp, i64, i32, i64, C.POINTER(vp)]),

@@ -20,6 +20,7 @@
 #include "scan.cuh"
 #include "select.cuh"
 #include "tcassign.cuh"
+#include "tscan.cuh"
 #include "kupdate.cuh"
 #include "synth.cuh"
 
@@ -105,6 +106,11 @@ struct gulon_index_s {
   DevBuf qlut, mins, qp, boot_tail, plists, pstats, boot_keys, spread, msel, merged2, sufmin;
   DevBuf rowcodes;            // row-major copy of the planes, built by the first pruned scan
   DevBuf kacc, kfloor;        // k-chunked scans: accumulated keys [Q4][k], last key of the previous pass [Q4]
+  // tensor scan (tscan.cuh): xb = the decoded rows as bf16 operand rows [N][tensor_kp], built by the first
+  // tensor scan; the rest is per-batch scratch
+  DevBuf xb, tcol, tqb, tsurv, tscount, tcand, tccount, tcur0, tcur1, tflag, tstats;
+  int tensor_state = 0;       // 0 not tried, 1 ready, -1 unavailable (shape, memory, non-finite rows)
+  int tensor_kp = 0;
   // wide indexes (16-bit ids): 8-bit GROUP planes for the lower-bound scan (pscan.cuh), built by the first
   // pruned scan: gmap [M][K] group of every centroid, members / start = the groups' member lists
   DevBuf gmap, gmembers, gstart, gcodes, rowcodes16;
@@ -132,6 +138,8 @@ struct gulon_index_s {
     pstats.release(); boot_keys.release(); spread.release(); msel.release(); merged2.release();
     sel2.release(); sufmin.release(); rowcodes.release(); kacc.release(); kfloor.release();
     gmap.release(); gmembers.release(); gstart.release(); gcodes.release(); rowcodes16.release();
+    xb.release(); tcol.release(); tqb.release(); tsurv.release(); tscount.release(); tcand.release();
+    tccount.release(); tcur0.release(); tcur1.release(); tflag.release(); tstats.release();
     if (tm_ev0) cudaEventDestroy(tm_ev0);
     if (tm_ev1) cudaEventDestroy(tm_ev1);
     h_q.release(); h_ids.release(); h_dists.release(); h_sizes.release();
@@ -156,6 +164,15 @@ std::atomic<long long> g_pruned_words{0};        // 0 = auto, 1/2/4: 32-bit word
 std::atomic<long long> g_pruned_lb{0};           // 0 = auto (feedback), else quantizers in the lower bound
 std::atomic<long long> g_pruned_stage_div{32};   // first stage = range / div rows with the full bound; 0 = one stage
 std::atomic<long long> g_pruned_rowcodes{1};     // keep a row-major copy of the codes for the survivor evaluation
+std::atomic<long long> g_tensor_min_rows{1 << 20};    // GULON_SCAN_AUTO: shorter ranges keep the pruned scan
+std::atomic<long long> g_tensor_min_queries{2048};    // ... and smaller batches
+std::atomic<long long> g_tensor_query_batch{0};       // queries per pass of the tensor scan; 0 = auto
+std::atomic<long long> g_tensor_ratio{0};             // a stage scans ratio x the rows seen so far; 0 = auto from k
+std::atomic<long long> g_tensor_boot{0};              // rows scanned exactly first; 0 = 8192
+std::atomic<long long> g_tensor_max_bytes{64LL << 30};  // largest decoded copy of an index
+std::atomic<long long> g_tensor_pair{1};                  // the filter on CTA pairs (cta_group::2) or on single CTAs
+std::atomic<long long> g_tensor_chunk_bytes{16LL << 20};  // operand rows of one row split (L2 working set)
+std::atomic<unsigned long long> g_tstats[8];          // tiles, slow paths, survivors, candidates, pairs, fallbacks, batches, stages
 std::atomic<long long> g_last_ml{0};             // quantizers in the lower bound of the last main stage
 std::atomic<long long> g_assign_impl{GULON_ASSIGN_AUTO};  // exact CUDA-core kernel or tcgen05 filter + exact recheck
 std::atomic<long long> g_assign_tc_min_rows{4096};
@@ -218,6 +235,7 @@ struct KernelTimer {
     launches = 0;
   }
 };
+KernelTimer g_t_tscan;  // tscan::filter_kernel
 KernelTimer g_t_scan, g_t_assign, g_t_pscan, g_t_pscan_first;  // pscan: main stage; first: the short full-bound stage
 
 int need_device() {
@@ -1229,6 +1247,24 @@ int collapse_lists(DevBuf &lists, int S, int Q4, int k, DevBuf &merged, Selector
   return sel.run(merged.as<u64>(), ms, Q4, k, st, keys, stride);
 }
 
+// The codes of a row side by side: what the survivor evaluations gather (built once; the code planes of
+// an index must not change after its first query).  rowcodes_state: 1 ready, -1 no memory.
+int ensure_rowcodes(gulon_index_t ix, cudaStream_t st) {
+  if (ix->rowcodes_state != 0 || !ix->codes) return GULON_OK;
+  const int M = ix->cb->M;
+  ix->rcs = round_up(M, 16);
+  if (ix->rowcodes.ensure((size_t)std::max<i64>(ix->N, 1) * (size_t)ix->rcs) == GULON_OK) {
+    if (ix->N > 0)
+      GLAUNCH(pscan::rowcodes_kernel, (unsigned)ceil_div(ix->N, 256), 256, 0, st, ix->codes, ix->ps, ix->N, M,
+              ix->rcs, ix->rowcodes.as<uint8_t>());
+    ix->rowcodes_state = 1;
+  } else {
+    cudaGetLastError();
+    ix->rowcodes_state = -1;
+  }
+  return GULON_OK;
+}
+
 // Wide index (256 < K <= 65536): the data the lower-bound scan needs.  Every quantizer's K centroids are
 // clustered into 256 groups (a small k-means over the centroid table itself, on the device, seed = the
 // quantizer index); the planes of group ids feed the 8-bit bound pass, whose tables hold each group's
@@ -1309,7 +1345,8 @@ int scan_batch(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 fr
   if (ix->codes16) {
     // wide index.  Long ranges and k <= 128: the lower-bound scan over 8-bit group ids (prepare_wide);
     // everything else: plain tables, materialised keys, selection (any k the selector takes)
-    const long long want = g_scan_impl.load();
+    long long want = g_scan_impl.load();
+    if (want == GULON_SCAN_TENSOR) want = GULON_SCAN_AUTO;
     if ((want == GULON_SCAN_AUTO || want == GULON_SCAN_PRUNED) && k <= pscan::KMAX && M <= 1024 &&
         range >= g_pruned_min_rows.load() && (double)nq * M * K * 4.0 <= 8e9) {
       GCHECK(prepare_wide(ix, st));
@@ -1341,6 +1378,7 @@ int scan_batch(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 fr
     return GULON_OK;
   }
   long long impl = wide ? (long long)GULON_SCAN_PRUNED : g_scan_impl.load();
+  if (impl == GULON_SCAN_TENSOR) impl = GULON_SCAN_AUTO;   // a batch the tensor scan handed back
   if (impl == GULON_SCAN_AUTO) {
     if (k <= KCHUNK_MAX && M <= 1024 && range >= g_pruned_min_rows.load())
       impl = GULON_SCAN_PRUNED;
@@ -1479,19 +1517,7 @@ int scan_batch(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 fr
       GCHECK(ix->mins.ensure((size_t)Q4 * M * sizeof(float)));
       GCHECK(ix->spread.ensure((size_t)Q4 * M * sizeof(float)));
       GCHECK(ix->sufmin.ensure((size_t)Q4 * (M + 1) * sizeof(float)));
-      if (!wide && ix->rowcodes_state == 0 && g_pruned_rowcodes.load() != 0) {
-        // the codes of a row side by side: what the survivor evaluation gathers (built once; the code
-        // planes of an index must not change after its first query)
-        ix->rcs = round_up(M, 16);
-        if (ix->rowcodes.ensure((size_t)ix->N * (size_t)ix->rcs) == GULON_OK) {
-          GLAUNCH(pscan::rowcodes_kernel, (unsigned)ceil_div(ix->N, 256), 256, 0, st, ix->codes, ix->ps,
-                  ix->N, M, ix->rcs, ix->rowcodes.as<uint8_t>());
-          ix->rowcodes_state = 1;
-        } else {
-          cudaGetLastError();
-          ix->rowcodes_state = -1;
-        }
-      }
+      if (!wide && g_pruned_rowcodes.load() != 0) GCHECK(ensure_rowcodes(ix, st));
       GCHECK(ix->qp.ensure((size_t)Q4 * sizeof(pscan::QParam)));
       GCHECK(ix->boot_tail.ensure((size_t)Q4 * sizeof(u64)));
       GCHECK(ix->pstats.ensure(8 * sizeof(unsigned long long)));
@@ -1687,6 +1713,229 @@ int scan_batch(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 fr
   return GULON_OK;
 }
 
+// ---- tensor scan (tscan.cuh) --------------------------------------------------------------------
+int make_bf16_map(const void *base, i64 rows, int KP, int box_rows, CUtensorMap *map) {
+  tensor_map_encode_fn enc = tensor_map_encoder();
+  GREQUIRE(enc, "cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t gdim[2] = {(cuuint64_t)KP, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)KP * 2};
+  cuuint32_t box[2] = {(cuuint32_t)tscan::KC, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(GULON_ECUDA, "cuTensorMapEncodeTiled failed (%d) for a bf16 operand of %lld rows x %d", (int)r,
+                (long long)rows, KP);
+  return GULON_OK;
+}
+
+// Can this index ever take the tensor scan?  (shape only; prepare_tensor decides about memory and data)
+bool tensor_shape_ok(gulon_index_t ix) {
+  gulon_codebook_t cb = ix->cb;
+  return ix->codes && !ix->codes16 && cb->K <= 256 && cb->M <= 1024 && tscan::padded_k(cb->D) <= tscan::KP_MAX &&
+         ix->N < (1LL << 31) && ix->N > 0 && tensor_map_encoder() != nullptr;
+}
+
+// Builds the A operand of the filter: every row decoded to bf16 plus its norm terms.  Once per index.
+int prepare_tensor(gulon_index_t ix, cudaStream_t st) {
+  if (ix->tensor_state != 0) return GULON_OK;
+  ix->tensor_state = -1;
+  if (!tensor_shape_ok(ix)) return GULON_OK;
+  gulon_codebook_t cb = ix->cb;
+  const int D = cb->D, M = cb->M, KP = tscan::padded_k(D);
+  if ((long long)ix->N * KP * 2 > g_tensor_max_bytes.load()) return GULON_OK;
+  GCHECK(ensure_rowcodes(ix, st));
+  if (ix->rowcodes_state != 1) return GULON_OK;
+  std::vector<int16_t> col(2 * (size_t)D, 0);
+  for (int m = 0; m < M; m++)
+    for (int t = 0; t < cb->dim[m]; t++) {
+      const int j = cb->from[m] + t;
+      if (j < 0 || j >= D) return GULON_OK;
+      col[j] = (int16_t)m;
+      col[D + j] = (int16_t)t;
+    }
+  GCHECK(upload(ix->tcol, col, st));
+  if (ix->xb.ensure((size_t)ix->N * KP * 2) != GULON_OK) {
+    cudaGetLastError();
+    return GULON_OK;   // no memory for the decoded copy: the pruned scan keeps serving this index
+  }
+  GCHECK(ix->tflag.ensure(4 * sizeof(int)));
+  GCU(cudaMemsetAsync(ix->tflag.p, 0, 4 * sizeof(int), st));
+  GLAUNCH(tscan::decode_rows_kernel, (unsigned)ceil_div(ix->N, 8), 256, 0, st, ix->rowcodes.as<uint8_t>(), ix->rcs,
+          ix->N, cb->cb.as<float>(), cb->K, cb->dmax, ix->tcol.as<int16_t>(), ix->tcol.as<int16_t>() + D, D, KP,
+          ix->xb.as<uint16_t>(), ix->tflag.as<int>());
+  int bad = 0;
+  GCU(cudaMemcpyAsync(&bad, ix->tflag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  GCU(cudaStreamSynchronize(st));
+  if (bad) {
+    ix->xb.release();
+    return GULON_OK;   // non-finite or huge rows: not for a bf16 bound
+  }
+  ix->tensor_kp = KP;
+  ix->tensor_state = 1;
+  return GULON_OK;
+}
+
+// One stage of the filter over rows [sfrom, suntil) for NB blocks of 256 query slots (operand rows in ix->tqb).
+int launch_filter(gulon_index_t ix, i64 sfrom, i64 suntil, int NB, unsigned capb, float *dump, cudaStream_t st) {
+  const int KP = ix->tensor_kp, sms = sm_count();
+  const bool pair = g_tensor_pair.load() != 0 && sms >= 2;
+  CUtensorMap mapA, mapB;
+  GCHECK(make_bf16_map(ix->xb.p, ix->N, KP, tscan::TM, &mapA));
+  GCHECK(make_bf16_map(ix->tqb.p, (i64)NB * tscan::TN, KP, pair ? tscan::TN / 2 : tscan::TN, &mapB));
+  const i64 len = suntil - sfrom;
+  const i64 units = pair ? sms / 2 : sms;               // CTAs, or CTA pairs, that take items
+  const i64 tile_rows = pair ? 2 * tscan::TM : tscan::TM;
+  // Items are ordered split-major, so the CTAs of the grid work on the same row split (or two adjacent
+  // ones) at any time, each for another query block: the operand rows of a split are read from HBM once
+  // and served to the other CTAs from L2.  Short stages: ~8 items per unit, at least 64 tiles per item
+  // (the item's B operand is reloaded for every item).
+  i64 chunk_rows = std::max<i64>(64 * tile_rows, (g_tensor_chunk_bytes.load() / (KP * 2)) / tile_rows * tile_rows);
+  i64 S = std::max<i64>(1, (8 * units) / NB);
+  S = std::max<i64>(S, ceil_div(len, chunk_rows));
+  S = std::max<i64>(1, std::min<i64>(S, len / (64 * tile_rows)));
+  const i64 split_len = round_up(ceil_div(len, S), tile_rows);
+  S = ceil_div(len, split_len);
+  tscan::FParams fp;
+  fp.sfrom = sfrom;
+  fp.suntil = suntil;
+  fp.split_len = split_len;
+  fp.S = (int)S;
+  fp.NB = NB;
+  fp.nkc = (int)ceil_div(KP, tscan::KC);
+  fp.ksteps = KP / 16;
+  fp.surv = ix->tsurv.as<u64>();
+  fp.scount = ix->tscount.as<unsigned>();
+  fp.capb = capb;
+  fp.flag = ix->tflag.as<int>();
+  fp.dump = dump;
+  fp.stats = g_profile.load() ? ix->tstats.as<unsigned long long>() : nullptr;
+  const i64 n_items = (i64)NB * S;
+  cudaEvent_t ev = g_t_tscan.begin(st);
+  if (pair) {
+    GOPTIN(tscan::filter2_kernel, tscan::SMEM2_BYTES);
+    const unsigned grid = 2u * (unsigned)std::min<i64>(n_items, units);
+    GLAUNCH(tscan::filter2_kernel, grid, tscan::NT, tscan::SMEM2_BYTES, st, mapA, mapB, fp);
+  } else {
+    GOPTIN(tscan::filter_kernel, tscan::SMEM_BYTES);
+    const unsigned grid = (unsigned)std::min<i64>(n_items, units);
+    GLAUNCH(tscan::filter_kernel, grid, tscan::NT, tscan::SMEM_BYTES, st, mapA, mapB, fp);
+  }
+  g_t_tscan.end(ev, st);
+  return GULON_OK;
+}
+
+constexpr unsigned TENSOR_CAPQ = 1024;                 // exact candidates per query and stage
+constexpr unsigned TENSOR_CAPB = 256 * TENSOR_CAPQ;    // survivors per query block and stage
+
+// One batch of queries over [from, until) by the tensor scan.  *redo is set when the batch has to be
+// answered by the pruned scan instead (a query the bound cannot serve, or an overflowing list: adversarial
+// data such as millions of identical rows); the outputs are then unspecified.  Caller holds ix->mu.
+int tensor_scan_batch(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 from, i64 until,
+                      i64 id_offset, int32_t *d_ids, float *d_dists, int32_t *d_sizes, cudaStream_t st,
+                      bool *redo) {
+  gulon_codebook_t cb = ix->cb;
+  const int M = cb->M, K = cb->K, D = cb->D, KP = ix->tensor_kp;
+  const i64 range = until - from;
+  *redo = false;
+  const int G = (int)ceil_div(nq, 4), Q4 = G * 4;
+  GCHECK(ix->lutI.ensure((size_t)G * M * 256 * sizeof(float4)));
+  dim3 lg((unsigned)G, (unsigned)M);
+  GLAUNCH(lut_build_kernel, lg, 256, 0, st, dQ, ldq, nq, cb->cb.as<float>(), cb->dfrom.as<int32_t>(),
+          cb->ddim.as<int32_t>(), M, K, cb->dmax, ix->lutI.as<float4>());
+  // 1. the first rows exactly (fused kernel): every query gets k keys and a threshold
+  i64 boot = g_tensor_boot.load();
+  if (boot <= 0) boot = fscan::R;
+  boot = std::min<i64>(range, std::max<i64>(boot, k));
+  int Sb = 1;
+  u64 *cur;
+  i64 cur_stride;
+  GCHECK(fused_lists(ix, from, from + boot, G, k, ix->lists, &Sb, st));
+  GCHECK(collapse_lists(ix->lists, Sb, Q4, k, ix->boot_keys, ix->sel_boot, &cur, &cur_stride, st));
+  if (boot < range) {
+    const int NB = (int)ceil_div(nq, tscan::TN);
+    const i64 nslots = (i64)NB * tscan::TN;
+    const unsigned capq = TENSOR_CAPQ, capb = TENSOR_CAPB;
+    static_assert(fscan::KMAX + TENSOR_CAPQ <= tscan::MERGE_SORTN, "merge area too small");
+    GCHECK(ix->tqb.ensure((size_t)nslots * KP * 2));
+    GCHECK(ix->tsurv.ensure((size_t)NB * capb * sizeof(u64)));
+    GCHECK(ix->tscount.ensure((size_t)NB * sizeof(unsigned)));
+    GCHECK(ix->tcand.ensure((size_t)nq * capq * sizeof(u64)));
+    GCHECK(ix->tccount.ensure((size_t)nq * sizeof(unsigned)));
+    GCHECK(ix->tcur0.ensure((size_t)nq * k * sizeof(u64)));
+    GCHECK(ix->tcur1.ensure((size_t)nq * k * sizeof(u64)));
+    GCHECK(ix->tflag.ensure(4 * sizeof(int)));
+    GCHECK(ix->tstats.ensure(8 * sizeof(unsigned long long)));
+    GCU(cudaMemsetAsync(ix->tccount.p, 0, (size_t)nq * sizeof(unsigned), st));
+    GCU(cudaMemsetAsync(ix->tflag.p, 0, 4 * sizeof(int), st));
+    GCU(cudaMemsetAsync(ix->tstats.p, 0, 8 * sizeof(unsigned long long), st));
+    // a stage scans `ratio` x the rows seen so far: ~ratio * k rows per query beat the threshold it
+    // starts with (plus the bound's slack), which the candidate lists must hold several times over
+    i64 ratio = g_tensor_ratio.load();
+    if (ratio <= 0) ratio = std::max<i64>(2, std::min<i64>(16, (i64)capq / (6 * (i64)k)));
+    const auto merge = tscan::merge_kernel;
+    GOPTIN(merge, tscan::MERGE_WARPS * tscan::MERGE_SORTN * sizeof(u64));
+    const bool want_stats = g_profile.load() != 0;
+    i64 done = boot;
+    int pp = 0, stages = 0;
+    while (done < range) {
+      i64 len = std::min<i64>(range - done, round_up(done * ratio, tscan::TM));
+      if (range - done - len < len / 4) len = range - done;   // no short last stage
+      const i64 sfrom = from + done, suntil = sfrom + len;
+      GLAUNCH(tscan::qprep_kernel, (unsigned)ceil_div(nslots, 8), 256, 0, st, dQ, ldq, nq, nslots, D, KP, cur,
+              cur_stride, k, ix->tqb.as<uint16_t>(), ix->tflag.as<int>());
+      GCU(cudaMemsetAsync(ix->tscount.p, 0, (size_t)NB * sizeof(unsigned), st));
+      GCHECK(launch_filter(ix, sfrom, suntil, NB, capb, nullptr, st));
+      tscan::EParams ep;
+      ep.surv = ix->tsurv.as<u64>();
+      ep.scount = ix->tscount.as<unsigned>();
+      ep.capb = capb;
+      ep.rowcodes = ix->rowcodes.as<uint8_t>();
+      ep.rcs = ix->rcs;
+      ep.lutI = ix->lutI.as<float4>();
+      ep.M = M;
+      ep.nq = nq;
+      ep.cur = cur;
+      ep.stride = cur_stride;
+      ep.k = k;
+      ep.cand = ix->tcand.as<u64>();
+      ep.ccount = ix->tccount.as<unsigned>();
+      ep.capq = capq;
+      ep.flag = ix->tflag.as<int>();
+      ep.stats = want_stats ? ix->tstats.as<unsigned long long>() : nullptr;
+      dim3 eg(16, (unsigned)NB);
+      GLAUNCH(tscan::eval_kernel, eg, 256, 0, st, ep);
+      u64 *nxt = (pp ? ix->tcur1 : ix->tcur0).as<u64>();
+      GLAUNCH(merge, (unsigned)ceil_div(nq, tscan::MERGE_WARPS), 32 * tscan::MERGE_WARPS,
+              tscan::MERGE_WARPS * tscan::MERGE_SORTN * sizeof(u64), st, cur, cur_stride, nq, k, ix->tcand.as<u64>(),
+              ix->tccount.as<unsigned>(), capq, nxt);
+      cur = nxt;
+      cur_stride = k;
+      pp ^= 1;
+      done += len;
+      stages++;
+    }
+    int flag = 0;
+    unsigned long long hs[4] = {0, 0, 0, 0};
+    GCU(cudaMemcpyAsync(&flag, ix->tflag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (want_stats) GCU(cudaMemcpyAsync(hs, ix->tstats.p, sizeof(hs), cudaMemcpyDeviceToHost, st));
+    GCU(cudaStreamSynchronize(st));
+    if (want_stats) {
+      for (int i = 0; i < 4; i++) g_tstats[i] += hs[i];
+      g_tstats[4] += (unsigned long long)(range - boot) * (unsigned long long)nq;
+      g_tstats[6] += 1;
+      g_tstats[7] += (unsigned long long)stages;
+    }
+    if (flag) {
+      g_tstats[5] += 1;
+      *redo = true;
+      return GULON_OK;
+    }
+  }
+  return unpack(cur, cur_stride, nq, k, id_offset, d_ids, d_dists, d_sizes, st);
+}
+
 int query_dev(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 from, i64 until,
               int normalize, i64 id_offset, int32_t *d_ids, float *d_dists, int32_t *d_sizes,
               cudaStream_t st) {
@@ -1705,19 +1954,60 @@ int query_dev(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 fro
   i64 qb = g_query_batch.load();
   if (qb <= 0) qb = (i64)sm_count() * 16;
   qb = std::min<i64>(round_up(qb, 16), 32768);
+  // the tensor scan takes large batches on long ranges (tscan.cuh); everything else, and the batches it
+  // hands back, go through scan_batch in passes of `qb`
+  const long long want = g_scan_impl.load();
+  bool tensor = false;
+  if (want == GULON_SCAN_TENSOR ||
+      (want == GULON_SCAN_AUTO && nq >= g_tensor_min_queries.load() && until - from >= g_tensor_min_rows.load())) {
+    if (k <= fscan::KMAX && tensor_shape_ok(ix)) {
+      GCHECK(prepare_tensor(ix, st));
+      tensor = ix->tensor_state == 1;
+    }
+    if (want == GULON_SCAN_TENSOR && !tensor)
+      return fail(GULON_EUNSUPPORTED, "scan_impl = tensor needs an 8-bit index with D <= %d, k <= %d, finite rows and "
+                  "room for the decoded copy (D=%d K=%d k=%d)", tscan::KP_MAX - tscan::NEXTRA, fscan::KMAX, D,
+                  ix->cb->K, k);
+  }
+  i64 tb = nq;
+  if (tensor) {
+    // queries per pass: all of them while the tables (M KB per query), the candidate lists (8 KB) and the
+    // survivor lists (8 KB) fit a few GB; passes of equal size, whole blocks of 256
+    tb = g_tensor_query_batch.load();
+    if (tb <= 0) tb = std::max<i64>(4096, (12LL << 30) / ((i64)ix->cb->M * 1024 + 16384 + 2 * tscan::KP_MAX));
+    const i64 passes = ceil_div(nq, tb);
+    tb = round_up(ceil_div(nq, passes), tscan::TN);
+  }
   const int rc = [&]() -> int {
-    for (i64 q0 = 0; q0 < nq; q0 += qb) {
-      const i64 nb = std::min<i64>(qb, nq - q0);
-      const float *q = dQ + q0 * ldq;
-      i64 ql = ldq;
-      if (normalize) {
-        GCHECK(ix->qbuf.ensure((size_t)nb * D * sizeof(float)));
-        GCHECK(normalize_dev(q, nb, D, ldq, ix->qbuf.as<float>(), D, st));
-        q = ix->qbuf.as<float>();
-        ql = D;
+    for (i64 t0 = 0; t0 < nq; t0 += tb) {
+      const i64 tn = std::min<i64>(tb, nq - t0);
+      bool redo = !tensor;
+      if (tensor) {
+        const float *q = dQ + t0 * ldq;
+        i64 ql = ldq;
+        if (normalize) {
+          GCHECK(ix->qbuf.ensure((size_t)tn * D * sizeof(float)));
+          GCHECK(normalize_dev(q, tn, D, ldq, ix->qbuf.as<float>(), D, st));
+          q = ix->qbuf.as<float>();
+          ql = D;
+        }
+        GCHECK(tensor_scan_batch(ix, q, tn, ql, k, from, until, id_offset, d_ids + t0 * k, d_dists + t0 * k,
+                                 d_sizes ? d_sizes + t0 : nullptr, st, &redo));
       }
-      GCHECK(scan_batch(ix, q, nb, ql, k, from, until, id_offset, d_ids + q0 * k, d_dists + q0 * k,
-                        d_sizes ? d_sizes + q0 : nullptr, st));
+      if (!redo) continue;
+      for (i64 q0 = t0; q0 < t0 + tn; q0 += qb) {
+        const i64 nb = std::min<i64>(qb, t0 + tn - q0);
+        const float *q = dQ + q0 * ldq;
+        i64 ql = ldq;
+        if (normalize) {
+          GCHECK(ix->qbuf.ensure((size_t)nb * D * sizeof(float)));
+          GCHECK(normalize_dev(q, nb, D, ldq, ix->qbuf.as<float>(), D, st));
+          q = ix->qbuf.as<float>();
+          ql = D;
+        }
+        GCHECK(scan_batch(ix, q, nb, ql, k, from, until, id_offset, d_ids + q0 * k, d_dists + q0 * k,
+                          d_sizes ? d_sizes + q0 : nullptr, st));
+      }
     }
     return GULON_OK;
   }();
@@ -2036,7 +2326,7 @@ int gulon_set_option(const char *name, int64_t value) {
   GREQUIRE(name, "null option name");
   std::string s(name);
   if (s == "scan_impl") {
-    GREQUIRE(value >= GULON_SCAN_AUTO && value <= GULON_SCAN_PRUNED, "scan_impl must be 0..3");
+    GREQUIRE(value >= GULON_SCAN_AUTO && value <= GULON_SCAN_TENSOR, "scan_impl must be 0..4");
     g_scan_impl = value;
   } else if (s == "query_batch") {
     GREQUIRE(value >= 0, "query_batch must be >= 0");
@@ -2064,6 +2354,8 @@ int gulon_set_option(const char *name, int64_t value) {
     g_t_assign.reset();
     g_t_pscan.reset();
     g_t_pscan_first.reset();
+    g_t_tscan.reset();
+    for (int i = 0; i < 8; i++) g_tstats[i] = 0;
     for (int i = 0; i < 3; i++) g_pstats[i] = 0;
     g_ppairs = 0;
     g_ppairs_main = 0;
@@ -2088,6 +2380,15 @@ int gulon_set_option(const char *name, int64_t value) {
   } else if (s == "pruned_min_rows") {
     GREQUIRE(value >= 0, "pruned_min_rows must be >= 0");
     g_pruned_min_rows = value;
+  } else if (s == "tensor_min_rows" || s == "tensor_min_queries" || s == "tensor_query_batch" ||
+             s == "tensor_stage_ratio" || s == "tensor_boot_rows" || s == "tensor_max_bytes" ||
+             s == "tensor_chunk_bytes" || s == "tensor_pair") {
+    GREQUIRE(value >= 0, "%s must be >= 0", name);
+    (s == "tensor_min_rows" ? g_tensor_min_rows : s == "tensor_min_queries" ? g_tensor_min_queries
+     : s == "tensor_query_batch" ? g_tensor_query_batch : s == "tensor_stage_ratio" ? g_tensor_ratio
+     : s == "tensor_boot_rows" ? g_tensor_boot : s == "tensor_chunk_bytes" ? g_tensor_chunk_bytes
+     : s == "tensor_pair" ? g_tensor_pair
+     : g_tensor_max_bytes) = value;
   } else if (s == "fused_min_rows") {
     GREQUIRE(value >= 0, "fused_min_rows must be >= 0");
     g_fused_min_rows = value;
@@ -2118,6 +2419,20 @@ int gulon_get_counter(const char *name, int64_t *value) {
     g_t_pscan_first.drain();
     *value = s == "pscan_first_kernel_ns" ? (int64_t)g_t_pscan_first.ns : g_t_pscan_first.launches;
     return GULON_OK;
+  }
+  if (s == "tscan_kernel_ns" || s == "tscan_kernel_launches") {
+    g_t_tscan.drain();
+    *value = s == "tscan_kernel_ns" ? (int64_t)g_t_tscan.ns : g_t_tscan.launches;
+    return GULON_OK;
+  }
+  {
+    static const char *tn[8] = {"tscan_tiles", "tscan_slow_paths", "tscan_survivors", "tscan_candidates",
+                                "tscan_pairs", "tscan_fallbacks", "tscan_batches", "tscan_stages"};
+    for (int i = 0; i < 8; i++)
+      if (s == tn[i]) {
+        *value = (int64_t)g_tstats[i].load();
+        return GULON_OK;
+      }
   }
   if (s == "pscan_main_pairs") {
     *value = (int64_t)g_ppairs_main.load();
@@ -2724,6 +3039,50 @@ int gulon_prepare_query(gulon_codebook_t cb, const float *queries, int64_t nq, i
                         cudaMemcpyDeviceToHost, 0));
     GCU(cudaStreamSynchronize(0));
   }
+  return GULON_OK;
+}
+
+int gulon_debug_tscan(gulon_index_t ix, const float *dqueries, int64_t nq, int64_t ldq, const float *taus,
+                      int64_t from, int64_t until, uint16_t *xb, uint16_t *qb, float *acc, int32_t *kp) {
+  GCHECK(need_device());
+  GREQUIRE(ix && dqueries && taus, "null argument");
+  GREQUIRE(nq >= 1 && nq <= tscan::TN, "gulon_debug_tscan takes 1..%d queries", tscan::TN);
+  GREQUIRE(from >= 0 && from < until && until <= ix->N && until - from <= (1 << 20), "bad row range");
+  GREQUIRE(ldq >= ix->cb->D, "query leading dimension %lld < dimension %d", (long long)ldq, ix->cb->D);
+  std::lock_guard<std::mutex> lock(ix->mu);
+  cudaStream_t st = nullptr;
+  GCHECK(prepare_tensor(ix, st));
+  if (ix->tensor_state != 1) return fail(GULON_EUNSUPPORTED, "this index cannot take the tensor scan");
+  const int KP = ix->tensor_kp, D = ix->cb->D;
+  const i64 rows = until - from;
+  if (kp) *kp = KP;
+  std::vector<u64> keys((size_t)nq);
+  for (i64 q = 0; q < nq; q++) keys[q] = make_key(taus[q], 0);
+  DevBuf dk, dacc;
+  struct Guard {
+    DevBuf &a, &b;
+    ~Guard() {
+      a.release();
+      b.release();
+    }
+  } guard{dk, dacc};
+  GCHECK(upload(dk, keys, st));
+  GCHECK(dacc.ensure((size_t)rows * tscan::TN * sizeof(float)));
+  GCU(cudaMemsetAsync(dacc.p, 0, (size_t)rows * tscan::TN * sizeof(float), st));
+  GCHECK(ix->tqb.ensure((size_t)tscan::TN * KP * 2));
+  GCHECK(ix->tsurv.ensure((size_t)TENSOR_CAPB * sizeof(u64)));
+  GCHECK(ix->tscount.ensure(sizeof(unsigned)));
+  GCHECK(ix->tflag.ensure(4 * sizeof(int)));
+  GCHECK(ix->tstats.ensure(8 * sizeof(unsigned long long)));
+  GCU(cudaMemsetAsync(ix->tscount.p, 0, sizeof(unsigned), st));
+  GCU(cudaMemsetAsync(ix->tflag.p, 0, 4 * sizeof(int), st));
+  GLAUNCH(tscan::qprep_kernel, (unsigned)ceil_div(tscan::TN, 8), 256, 0, st, dqueries, (i64)ldq, (i64)nq,
+          (i64)tscan::TN, D, KP, dk.as<u64>(), (i64)1, 1, ix->tqb.as<uint16_t>(), ix->tflag.as<int>());
+  GCHECK(launch_filter(ix, from, until, 1, TENSOR_CAPB, dacc.as<float>(), st));
+  if (xb) GCU(cudaMemcpyAsync(xb, ix->xb.as<uint16_t>() + (size_t)from * KP, (size_t)rows * KP * 2, cudaMemcpyDeviceToHost, st));
+  if (qb) GCU(cudaMemcpyAsync(qb, ix->tqb.p, (size_t)tscan::TN * KP * 2, cudaMemcpyDeviceToHost, st));
+  if (acc) GCU(cudaMemcpyAsync(acc, dacc.p, (size_t)rows * tscan::TN * sizeof(float), cudaMemcpyDeviceToHost, st));
+  GCU(cudaStreamSynchronize(st));
   return GULON_OK;
 }
 

@@ -153,6 +153,27 @@ class PQIndex:
         return out
 
 
+def debug_tscan(index, q_dev, taus, from_, until):
+    """Diagnostics of the tensor scan (gulon_debug_tscan): operands and raw accumulators of one filter
+    launch for <= 256 device queries with the given thresholds -> (xb [rows][KP] uint16, qb [256][KP] uint16,
+    acc [rows][256] float32)."""
+    nq = q_dev.shape[0]
+    rows = until - from_
+    taus = np.ascontiguousarray(taus, np.float32)
+    kp = N.i32(0)
+    acc = np.zeros((rows, 256), np.float32)
+    # KP is only known after the call: size the operand buffers for the largest contraction (320)
+    xb = np.zeros((rows, 320), np.uint16)
+    qb = np.zeros((256, 320), np.uint16)
+    N.check(N.lib().gulon_debug_tscan(index.handle, q_dev.data_ptr(), nq, q_dev.stride(0), taus.ctypes.data,
+                                      from_, until, xb.ctypes.data, qb.ctypes.data, acc.ctypes.data,
+                                      C.byref(kp)))
+    KP = int(kp.value)
+    xb = xb.reshape(-1)[:rows * KP].reshape(rows, KP)
+    qb = qb.reshape(-1)[:256 * KP].reshape(256, KP)
+    return xb, qb, acc
+
+
 def rerank(vectors, queries, cand_ids, k):
     """Exact fp32 re-rank of PQ candidates (distanceSq of G/MathUtils.scala:85-95 over the raw
     vectors, as the recall harness G/Tests.scala:24-37 scores returned keys)."""

@@ -67,6 +67,10 @@ extern "C" {
 #define GULON_SCAN_SIMPLE 1 /* distance materialisation + selection (any k, slow, cross-check path) */
 #define GULON_SCAN_FUSED  2 /* replicated-LUT gather kernel with in-kernel top-k (k <= 128)        */
 #define GULON_SCAN_PRUNED 3 /* 16-bit lower-bound pass + exact fp32 re-evaluation of survivors      */
+#define GULON_SCAN_TENSOR 4 /* tcgen05 lower bound over the decoded rows (bf16 contraction with a
+                             * rigorous error term) + exact fp32 re-evaluation of survivors; large
+                             * query batches on long ranges, D <= 313, K <= 256, k <= 128.  Forced on an
+                             * index / batch it cannot serve it fails with GULON_EUNSUPPORTED.          */
 
 /* assignment / encode implementation selector for gulon_set_option("assign_impl", ...).
  * Both produce the same bits: the tensor path only discards centroids that provably cannot win. */
@@ -131,10 +135,24 @@ int gulon_shutdown(void);
  * (0 auto | 1 | 2 | 4), "pruned_lb_quantizers" (0 = measured-cost feedback per index, else the
  * number of quantizers the lower bound sums), "pruned_stage_div" (first stage = range / div rows,
  * 0 = one stage), "pruned_rowcodes" (row-major copy of the codes for the survivor evaluation).
+ * Tensor scan: "tensor_min_rows" (default 2^20) and "tensor_min_queries" (default 2048): smaller ranges /
+ * batches keep the pruned scan under GULON_SCAN_AUTO; "tensor_query_batch" (queries per pass, 0 = auto),
+ * "tensor_stage_ratio" (a stage scans ratio x the rows seen so far, 0 = auto from k), "tensor_boot_rows"
+ * (rows scanned exactly first, 0 = 8192), "tensor_max_bytes" (the decoded bf16 copy of the index is built
+ * only below this size; default 64 GiB), "tensor_chunk_bytes" (operand rows per row split = the L2 working
+ * set shared by the CTAs; default 16 MiB), "tensor_pair" (1: the filter runs on CTA pairs with
+ * tcgen05 cta_group::2, the default; 0: on single CTAs).
  * Assignment: "assign_impl", "assign_tc_min_rows", "update_fixed".  "profile" = 1 turns the kernel
  * timers and counters of gulon_get_counter on. */
 int gulon_set_option(const char *name, int64_t value);
 int gulon_get_counter(const char *name, int64_t *value); /* e.g. "kernel_launches" */
+/* Diagnostics of the tensor scan (tests): runs the operand builders and the filter kernel of
+ * GULON_SCAN_TENSOR for nq <= 256 device queries over rows [from, until) with the given per-query
+ * thresholds (host array), and returns the operands and the raw accumulators: xb [until - from][KP]
+ * and qb [256][KP] bf16 bit patterns, acc [until - from][256] fp32 (host buffers, any may be NULL);
+ * *kp receives KP.  A survivor is an accumulator <= 0. */
+int gulon_debug_tscan(gulon_index_t ix, const float *dqueries, int64_t nq, int64_t ldq, const float *taus,
+                      int64_t from, int64_t until, uint16_t *xb, uint16_t *qb, float *acc, int32_t *kp);
 
 /* Vectors.subvectors split rule, G/Vectors.scala:84-104.  Returns dmax (>0) or a status (<0). */
 int gulon_subvectors(int32_t D, int32_t M, int32_t *from, int32_t *dim);
