@@ -379,7 +379,59 @@ def encode_shard(cx, pq, mix, lo, hi, keep=None, time_it=True):
     return codes, stride, ns, rows
 
 
-def scan_roofline(cx, M, Q, steps, n_local, clk, prof_ms, shape_key=None):
+def tensor_roofline(cx, D, M, Q, steps, n_local, prof_ms, shape_key, t_ns, t_l, boot_ns):
+    """Roofline of tscan::filter2_kernel (the tensor scan's lower-bound contraction): the tensor pipe.
+    FLOPs = 2 * 128 * 256 * KP per accumulator tile (counted by the kernel), against the SUSTAINED cuBLAS bf16
+    figure of MEASURED_PEAKS.json (the kernel runs for hundreds of milliseconds under the power cap)."""
+    N = cx.N
+    KP = (D + 4 + 15) // 16 * 16
+    st = {nm: N.counter("tscan_" + nm) for nm in ("tiles", "slow_paths", "survivors", "candidates", "pairs", "fallbacks",
+                                                   "batches", "stages")}
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    flop = 2.0 * 128 * 256 * KP * st["tiles"]
+    sec = t_ns * 1e-9
+    ach = flop / sec / 1e12
+    # SURVEY 8d's byte figure for the same work, for continuity with the pruned kernel's line: one pass over all
+    # M code planes per tile of 16 queries
+    alg_bytes = -(-Q // 16) * float(n_local) * M * steps
+    roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+            "kernel": "tscan::filter2_kernel (tcgen05 lower bound over the decoded rows, cta_group::2)",
+            "peak_source": ("measured, sustained cuBLAS bf16 (MEASURED_PEAKS.json; burst %.0f)" % peaks.get("bf16_tflops", 0))
+            if peaks else "fallback (B200_PROFILING.md: ~1400 sustained)",
+            "flop_per_launch": flop / t_l, "launch_seconds": sec / t_l, "launches": t_l,
+            "contraction": "M128 x N256 x K%d per tile (D = %d coordinates + 4 bound columns), bf16 in, fp32 accumulate" % (KP, D),
+            "kernel_share_of_step": t_ns * 1e-6 / prof_ms,
+            "other_kernels_share_of_step": {"exact_kernel_boot_rows": boot_ns * 1e-6 / prof_ms},
+            "timed_in": "a repeat of the K steps with the kernel timers on (%.1f ms per step; the timed region "
+                        "runs without them)" % (prof_ms / steps),
+            "hbm_algorithmic": {"unit": "GB/s", "bytes_per_step": alg_bytes / steps,
+                                "achieved": alg_bytes / (prof_ms * 1e-3) / 1e9, "peak": cx.peak,
+                                "frac": alg_bytes / (prof_ms * 1e-3) / 1e9 / cx.peak,
+                                "note": "SURVEY 8d bytes (ceil(Q/16) passes over the M code planes) / whole step time: what the "
+                                        "byte-gather formulation of this scan would have to move per second to keep up; the "
+                                        "tensor scan itself reads the decoded rows from L2, not the code planes"},
+            "filter": {"survivor_rate": st["survivors"] / max(st["pairs"], 1), "survivors": st["survivors"],
+                       "list_candidates": st["candidates"], "stages_per_batch": st["stages"] / max(st["batches"], 1),
+                       "batches": st["batches"], "handed_back_batches": st["fallbacks"]}}
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "scan_traffic.json")))
+        key = "%s_tensor" % shape_key
+        if cx.world == 1 and shape_key and key in tr:
+            t = tr[key]
+            roof["traffic"] = t["dram_bytes_per_launch"]
+            roof["traffic_source"] = t["source"]
+            roof["traffic_note"] = t.get("note")
+    except Exception:
+        pass
+    return roof
+
+
+def scan_roofline(cx, M, Q, steps, n_local, clk, prof_ms, shape_key=None, D=None):
     """Roofline of the dominant scan kernel from the library's per-launch event timers (profile = 1)."""
     N = cx.N
     scan_ns, scan_l = N.counter("scan_kernel_ns"), N.counter("scan_kernel_launches")
@@ -387,6 +439,9 @@ def scan_roofline(cx, M, Q, steps, n_local, clk, prof_ms, shape_key=None):
     f_ns, f_l = N.counter("pscan_first_kernel_ns"), N.counter("pscan_first_kernel_launches")
     pst = {nm: N.counter("pscan_" + nm) for nm in ("survivors", "candidates", "slow_items", "pairs", "main_pairs")}
     ml = N.counter("pscan_lb_quantizers") or M
+    t_ns, t_l = N.counter("tscan_kernel_ns"), N.counter("tscan_kernel_launches")
+    if t_l > 0 and t_ns >= max(p_ns, scan_ns):
+        return tensor_roofline(cx, D or cx.a.dim, M, Q, steps, n_local, prof_ms, shape_key, t_ns, t_l, scan_ns)
     use_p = p_l > 0 and p_ns >= scan_ns
     k_ns, k_l = (p_ns, p_l) if use_p else (scan_ns, scan_l)
     if k_l <= 0:
@@ -552,7 +607,7 @@ def leg_row_sharded(cx, clk_unused):
     # roofline of the main-stage kernel on this rank (every rank runs the same shapes)
     g.set_option("profile", 1)
     pms, _, _ = cx.timed(lambda: sh.batch_query(k, queries), K, 0)
-    roof = scan_roofline(cx, M, Q, K, hi - lo, None, pms)
+    roof = scan_roofline(cx, M, Q, K, hi - lo, None, pms, D=D)
     g.set_option("profile", 0)
     # end to end: host queries in, host answers out on every rank
     q_host = torch.empty((Q, D), dtype=torch.float32, pin_memory=True)
@@ -677,7 +732,8 @@ def leg_shapes(cx):
         queries = mix.rows(0, Q, stream_seed=1)
         ms, _, res = cx.timed(lambda: ix.batch_query_dev(a.k, queries), 2, 1)
         line = {"rows": rows, "dim": D, "m": M, "queries": Q, "value": Q * 2 / (ms * 1e-3), "unit": UNIT,
-                "lower_bound_quantizers": N.counter("pscan_lb_quantizers"),
+                "scan": {4: "tensor", 3: "pruned", 2: "fused", 1: "simple"}.get(N.counter("scan_last_impl"), "?"),
+                "lower_bound_quantizers": N.counter("pscan_lb_quantizers") if N.counter("scan_last_impl") == 3 else None,
                 "encode_vectors_per_s": enc_rows / (enc_ns * 1e-9) if enc_ns else None}
         if not a.no_cpu_baseline:
             from oracle import oracle as o

@@ -170,9 +170,11 @@ std::atomic<long long> g_tensor_query_batch{0};       // queries per pass of the
 std::atomic<long long> g_tensor_ratio{0};             // a stage scans ratio x the rows seen so far; 0 = auto from k
 std::atomic<long long> g_tensor_boot{0};              // rows scanned exactly first; 0 = 8192
 std::atomic<long long> g_tensor_max_bytes{64LL << 30};  // largest decoded copy of an index
+std::atomic<long long> g_tensor_epi_wait{2};              // tscan::mb_wait_epi
 std::atomic<long long> g_tensor_pair{1};                  // the filter on CTA pairs (cta_group::2) or on single CTAs
 std::atomic<long long> g_tensor_chunk_bytes{16LL << 20};  // operand rows of one row split (L2 working set)
 std::atomic<unsigned long long> g_tstats[8];          // tiles, slow paths, survivors, candidates, pairs, fallbacks, batches, stages
+std::atomic<long long> g_last_scan{0};           // GULON_SCAN_* that answered the last batch
 std::atomic<long long> g_last_ml{0};             // quantizers in the lower bound of the last main stage
 std::atomic<long long> g_assign_impl{GULON_ASSIGN_AUTO};  // exact CUDA-core kernel or tcgen05 filter + exact recheck
 std::atomic<long long> g_assign_tc_min_rows{4096};
@@ -1387,6 +1389,7 @@ int scan_batch(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 fr
     else
       impl = GULON_SCAN_SIMPLE;
   }
+  g_last_scan = impl;
   // query groups of 4 (float4 tables); the pruned scan works on tiles of QT = 16 queries
   // (8-bit lower-bound fields, used while they keep >= 3 levels per quantizer) or 8 (16-bit fields).
   // The lower bound of the main stage sums ML <= M quantizers (see pscan::qselect_kernel).
@@ -1811,6 +1814,7 @@ int launch_filter(gulon_index_t ix, i64 sfrom, i64 suntil, int NB, unsigned capb
   fp.flag = ix->tflag.as<int>();
   fp.dump = dump;
   fp.stats = g_profile.load() ? ix->tstats.as<unsigned long long>() : nullptr;
+  fp.epi_wait = (int)g_tensor_epi_wait.load();
   const i64 n_items = (i64)NB * S;
   cudaEvent_t ev = g_t_tscan.begin(st);
   if (pair) {
@@ -1873,7 +1877,7 @@ int tensor_scan_batch(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k,
     // a stage scans `ratio` x the rows seen so far: ~ratio * k rows per query beat the threshold it
     // starts with (plus the bound's slack), which the candidate lists must hold several times over
     i64 ratio = g_tensor_ratio.load();
-    if (ratio <= 0) ratio = std::max<i64>(2, std::min<i64>(16, (i64)capq / (6 * (i64)k)));
+    if (ratio <= 0) ratio = std::max<i64>(2, std::min<i64>(4, (i64)capq / (6 * (i64)k)));
     const auto merge = tscan::merge_kernel;
     GOPTIN(merge, tscan::MERGE_WARPS * tscan::MERGE_SORTN * sizeof(u64));
     const bool want_stats = g_profile.load() != 0;
@@ -1994,7 +1998,10 @@ int query_dev(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 fro
         GCHECK(tensor_scan_batch(ix, q, tn, ql, k, from, until, id_offset, d_ids + t0 * k, d_dists + t0 * k,
                                  d_sizes ? d_sizes + t0 : nullptr, st, &redo));
       }
-      if (!redo) continue;
+      if (!redo) {
+        g_last_scan = GULON_SCAN_TENSOR;
+        continue;
+      }
       for (i64 q0 = t0; q0 < t0 + tn; q0 += qb) {
         const i64 nb = std::min<i64>(qb, t0 + tn - q0);
         const float *q = dQ + q0 * ldq;
@@ -2382,12 +2389,12 @@ int gulon_set_option(const char *name, int64_t value) {
     g_pruned_min_rows = value;
   } else if (s == "tensor_min_rows" || s == "tensor_min_queries" || s == "tensor_query_batch" ||
              s == "tensor_stage_ratio" || s == "tensor_boot_rows" || s == "tensor_max_bytes" ||
-             s == "tensor_chunk_bytes" || s == "tensor_pair") {
+             s == "tensor_chunk_bytes" || s == "tensor_pair" || s == "tensor_epi_wait") {
     GREQUIRE(value >= 0, "%s must be >= 0", name);
     (s == "tensor_min_rows" ? g_tensor_min_rows : s == "tensor_min_queries" ? g_tensor_min_queries
      : s == "tensor_query_batch" ? g_tensor_query_batch : s == "tensor_stage_ratio" ? g_tensor_ratio
      : s == "tensor_boot_rows" ? g_tensor_boot : s == "tensor_chunk_bytes" ? g_tensor_chunk_bytes
-     : s == "tensor_pair" ? g_tensor_pair
+     : s == "tensor_pair" ? g_tensor_pair : s == "tensor_epi_wait" ? g_tensor_epi_wait
      : g_tensor_max_bytes) = value;
   } else if (s == "fused_min_rows") {
     GREQUIRE(value >= 0, "fused_min_rows must be >= 0");
@@ -2433,6 +2440,10 @@ int gulon_get_counter(const char *name, int64_t *value) {
         *value = (int64_t)g_tstats[i].load();
         return GULON_OK;
       }
+  }
+  if (s == "scan_last_impl") {
+    *value = g_last_scan.load();
+    return GULON_OK;
   }
   if (s == "pscan_main_pairs") {
     *value = (int64_t)g_ppairs_main.load();

@@ -10,12 +10,13 @@
 // from below with 8-bit table gathers from shared memory -- one byte through the 128 B/clk crossbar per
 // (row, query, quantizer), the roof it sits on.  This path bounds it with ONE dense contraction instead:
 //
-//   A[row][.]   = [ bf16(x^_0 .. x^_{D-1}) | a1 a2 a3 | nb | 1 1 1 | 0.. ]      (rows of the index, built once)
-//   B[query][.] = [ -2 bf16(q_0 .. q_{D-1}) | 1  1  1 | -e |c1 c2 c3| 0.. ]      (per stage: holds tau)
-//   D = A B^T   =  (|x^|^2)'' - 2 qb.xb - e nb + (|q|^2 - tau')''               (fp32 accumulate in TMEM)
+//   A[row][.]   = [ bf16(x^_0 .. x^_{D-1}) | a1 a2 | nb | 1 | 0.. ]      (rows of the index, built once)
+//   B[query][.] = [ -2 bf16(q_0 .. q_{D-1}) | 1  1 | -e | c | 0.. ]      (per stage: holds tau)
+//   D = A B^T   =  (|x^|^2)'' - 2 qb.xb - e nb + (|q|^2 - tau')''        (fp32 accumulate in TMEM)
 //
-// a1+a2+a3 <= |x^|^2 (1 - EPS_ACC), nb >= |x^|, e >= COEF |q|, c1+c2+c3 <= C - 2 EPS_ACC |C| with
-// C = |q|^2 - tau' and tau' = tau (1 + 2^-11) (the fp32 summation error of the reference, as in pscan.cuh).
+// a1+a2 <= |x^|^2 (1 - EPS_ACC), nb >= |x^|, e >= COEF |q|, c <= C - 2 EPS_ACC |C| (every piece rounded
+// towards the safe side) with C = |q|^2 - tau' and tau' = tau (1 + 2^-11) (the fp32 summation error of the
+// reference, as in pscan.cuh).  Four extra columns: D = 300 contracts over KP = 304 = 19 K16 steps.
 // With the operand rounding |q.x^ - qb.xb| <= (2^-8 + 2^-18) |q||x^| and an accumulation error of the
 // tensor core of at most EPS_ACC times the sum of the absolute products (EPS_ACC = 2^-12; measured
 // ~2^-21, tests/test_gpu_tscan.py), COEF = 2^-7 + 2^-17 + 2.03 EPS_ACC gives
@@ -62,7 +63,7 @@ constexpr int TN = 256;            // queries per block (UMMA N)
 constexpr int KC = 64;             // bf16 per K chunk = one 128-byte swizzle span
 constexpr int NKC_MAX = 5;         // resident B chunks: KP <= 320
 constexpr int KP_MAX = NKC_MAX * KC;
-constexpr int NEXTRA = 7;          // a1 a2 a3 | nb | 1 1 1   /   1 1 1 | -e | c1 c2 c3
+constexpr int NEXTRA = 4;          // a1 a2 | nb | 1   /   1 1 | -e | c   (D = 300 -> KP = 304: 19 K16 steps)
 constexpr int NSTAGE = 3;          // A ring
 constexpr int A_BYTES = TM * KC * 2;   // 16384
 constexpr int B_BYTES = TN * KC * 2;   // 32768
@@ -97,13 +98,11 @@ __device__ __forceinline__ uint16_t bf_ru(float f) {
   if ((u & 0xFFFFu) && !(u & 0x80000000u)) b++;  // positive with dropped bits: one step up
   return b;
 }
-// v as three bf16 pieces with p1 + p2 + p3 <= v (the first two truncate, the last rounds down)
-__device__ __forceinline__ void split3_down(double v, uint16_t &p1, uint16_t &p2, uint16_t &p3) {
+// v as two bf16 pieces with p1 + p2 <= v and v - (p1 + p2) <= 2^-15 |v| (the first truncates, the second rounds down)
+__device__ __forceinline__ void split2_down(double v, uint16_t &p1, uint16_t &p2) {
   p1 = bf_rz(__double2float_rz(v));
   const double r1 = v - (double)bf_val(p1);
-  p2 = bf_rz(__double2float_rz(r1));
-  const double r2 = r1 - (double)bf_val(p2);
-  p3 = bf_rd(__double2float_rd(r2));
+  p2 = bf_rd(__double2float_rd(r1));
 }
 
 // ---- A operand: the decoded rows, built once per index ---------------------------------------------
@@ -131,20 +130,17 @@ __global__ void __launch_bounds__(256) decode_rows_kernel(const uint8_t *__restr
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
   if (lane == 0) {
-    uint16_t a1 = 0, a2 = 0, a3 = 0, nb = 0;
+    uint16_t a1 = 0, a2 = 0, nb = 0;
     if (!(nrm <= (double)FINITE_MAX)) {
       atomicExch(bad, 1);
     } else {
-      split3_down(nrm * (1.0 - EPS_ACC - 1e-9), a1, a2, a3);
+      split2_down(nrm * (1.0 - EPS_ACC - 1e-9), a1, a2);
       nb = bf_ru(__double2float_ru(sqrt(nrm) * (1.0 + 1e-9)));
     }
     out[D + 0] = a1;
     out[D + 1] = a2;
-    out[D + 2] = a3;
-    out[D + 3] = nb;
-    out[D + 4] = 0x3F80;   // 1.0
-    out[D + 5] = 0x3F80;
-    out[D + 6] = 0x3F80;
+    out[D + 2] = nb;
+    out[D + 3] = 0x3F80;   // 1.0
   }
   for (int j = D + NEXTRA + lane; j < KP; j += 32) out[j] = 0;
 }
@@ -184,21 +180,16 @@ __global__ void __launch_bounds__(256) qprep_kernel(const float *__restrict__ Q,
       if (lane == 0) {
         const double taup = (double)tau * (1.0 + TAU_SLACK);
         const double c = nrm * (1.0 - 1e-9) - taup;
-        uint16_t c1, c2, c3;
-        split3_down(c - 2.0 * EPS_ACC * fabs(c) - 1e-300, c1, c2, c3);
         out[D + 0] = 0x3F80;
         out[D + 1] = 0x3F80;
-        out[D + 2] = 0x3F80;
-        out[D + 3] = bf_ru(__double2float_ru(COEF * sqrt(nrm) * (1.0 + 1e-9))) | 0x8000u;   // -e
-        out[D + 4] = c1;
-        out[D + 5] = c2;
-        out[D + 6] = c3;
+        out[D + 2] = bf_ru(__double2float_ru(COEF * sqrt(nrm) * (1.0 + 1e-9))) | 0x8000u;   // -e
+        out[D + 3] = bf_rd(__double2float_rd(c - 2.0 * EPS_ACC * fabs(c) - 1e-300));          // one piece, rounded down
       }
     }
   }
   if (!ok) {
     for (int j = lane; j < D + NEXTRA; j += 32) out[j] = 0;
-    if (lane == 0) out[D + 4] = 0x7E80;   // c1 = 2^126: D = 2^126 > 0 for every row, nothing survives
+    if (lane == 0) out[D + 3] = 0x7E80;   // c = 2^126: D = 2^126 > 0 for every row, nothing survives
   }
   for (int j = D + NEXTRA + lane; j < KP; j += 32) out[j] = 0;
 }
@@ -217,6 +208,7 @@ struct FParams {
   int *flag;             // [0] |= 2 on overflow
   float *dump;           // diagnostics: D of every (row - sfrom, query slot) [rows][NB * 256], or null
   unsigned long long *stats;  // [0] tiles, [1] warp slow paths
+  int epi_wait;          // see mb_wait_epi
 };
 
 // shared-memory matrix descriptor: K-major, 128-byte swizzle, 8-row groups 1024 bytes apart
@@ -261,6 +253,19 @@ __device__ __forceinline__ void commit1_elect(uint64_t *bar) {
 // every tile pays two such wake-ups in series (ncu, round 2: the MMA warp waited for `tempty`, the
 // epilogue warps for `tfull`, the tensor pipe was 59 % active).  The CTA has 18 warps on four schedulers
 // and little else to issue, so spinning costs nothing that matters.
+__device__ __forceinline__ void mb_spin(uint64_t *b, uint32_t parity);
+// how the epilogue warps wait for an accumulator (FParams::epi_wait): 0 spin, 1 try_wait without the
+// suspend hint, 2 try_wait with it
+__device__ __forceinline__ void mb_wait_epi(uint64_t *b, uint32_t parity, int mode) {
+  if (mode == 0) {
+    mb_spin(b, parity);
+  } else if (mode == 1) {
+    for (uint32_t spins = 0; !tca::mb_try_nohint(b, parity); spins++)
+      if (spins > (1u << 26)) __trap();
+  } else {
+    mb_wait(b, parity);
+  }
+}
 __device__ __forceinline__ void mb_spin(uint64_t *b, uint32_t parity) {
   const uint32_t addr = sa(b);
   for (uint32_t spins = 0;; spins++) {
@@ -279,20 +284,23 @@ __device__ __forceinline__ void mb_spin(uint64_t *b, uint32_t parity) {
   }
 }
 
-// One epilogue warp, one accumulator tile: thread = row = TMEM lane, COLS columns (queries) starting at
-// taddr (column c0 of the query block).  Per 32 columns: minimum; a warp that saw D <= 0 lists its
-// survivors straight from the registers.
+// One epilogue warp, one accumulator tile: thread = row = TMEM lane, COLS = 64 columns (queries) starting
+// at column c0 of the query block.  sweep_load brings the columns into registers -- after it the
+// accumulator can be handed back to the MMA warp -- and sweep_scan works on the registers: per 32
+// columns the minimum; a warp that saw D <= 0 appends its survivors (one atomic per warp and 32 columns).
 template <int COLS>
-__device__ __forceinline__ void sweep_tile(const FParams &p, uint32_t taddr, i64 row, i64 r1, int qb, int c0,
-                                           int lane) {
-  constexpr int NLD = COLS / 32;
-  uint32_t v[2][32];
-  tc_ld32_issue(taddr, v[0]);
-  if (NLD > 1) tc_ld32_issue(taddr + 32, v[1]);
+__device__ __forceinline__ void sweep_load(uint32_t taddr, uint32_t (&v)[COLS / 32][32]) {
 #pragma unroll
-  for (int j = 0; j < NLD; j++) {
-    uint32_t(&x)[32] = v[j & 1];
-    tc_ld_wait(x);
+  for (int j = 0; j < COLS / 32; j++) tc_ld32_issue(taddr + j * 32, v[j]);
+#pragma unroll
+  for (int j = 0; j < COLS / 32; j++) tc_ld_wait(v[j]);
+}
+template <int COLS>
+__device__ __forceinline__ void sweep_scan(const FParams &p, const uint32_t (&v)[COLS / 32][32], i64 row, i64 r1, int qb,
+                                           int c0, int lane) {
+#pragma unroll
+  for (int j = 0; j < COLS / 32; j++) {
+    const uint32_t(&x)[32] = v[j];
     float m[8];
 #pragma unroll
     for (int i = 0; i < 8; i++)
@@ -301,26 +309,41 @@ __device__ __forceinline__ void sweep_tile(const FParams &p, uint32_t taddr, i64
     const float mn = fminf(fminf(fminf(m[0], m[1]), fminf(m[2], m[3])), fminf(fminf(m[4], m[5]), fminf(m[6], m[7])));
     const bool hit = mn <= 0.0f && row < r1;
     if (__any_sync(0xffffffffu, hit) || p.dump) {
-      if (lane == 0 && p.stats) atomicAdd(p.stats + 1, 1ull);
       if (p.dump && row < r1) {
         float *dst = p.dump + (row - p.sfrom) * ((i64)p.NB * TN) + (i64)qb * TN + c0 + j * 32;
 #pragma unroll
         for (int c = 0; c < 32; c++) dst[c] = __uint_as_float(x[c]);
       }
+      uint32_t mask = 0;
       if (hit) {
 #pragma unroll
-        for (int c = 0; c < 32; c++) {
-          if (__uint_as_float(x[c]) <= 0.0f) {
-            const unsigned pos = atomicAdd(p.scount + qb, 1u);
-            if (pos < p.capb)
-              p.surv[(size_t)qb * p.capb + pos] = ((u64)(uint32_t)(c0 + j * 32 + c) << 32) | (u64)(uint32_t)row;
-            else
-              atomicOr(p.flag, 2);
-          }
-        }
+        for (int c = 0; c < 32; c++) mask |= (__uint_as_float(x[c]) <= 0.0f ? 1u : 0u) << c;
+      }
+      // the warp's entries go to consecutive slots: exclusive prefix of the lanes' counts, one atomic
+      const uint32_t n = __popc(mask);
+      uint32_t incl = n;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+      uint32_t base = 0;
+      if (lane == 0) {
+        base = atomicAdd(p.scount + qb, total);
+        if (p.stats) atomicAdd(p.stats + 1, 1ull);
+      }
+      base = __shfl_sync(0xffffffffu, base, 0) + incl - n;
+      while (mask) {
+        const int c = __ffs(mask) - 1;
+        mask &= mask - 1;
+        if (base < p.capb)
+          p.surv[(size_t)qb * p.capb + base] = ((u64)(uint32_t)(c0 + j * 32 + c) << 32) | (u64)(uint32_t)row;
+        else
+          atomicOr(p.flag, 2);
+        base++;
       }
     }
-    if (j + 2 < NLD) tc_ld32_issue(taddr + (j + 2) * 32, x);
   }
 }
 
@@ -448,13 +471,15 @@ __global__ void __launch_bounds__(NT, 1) filter_kernel(const __grid_constant__ C
       i64 row = r0 + quad * 32 + lane;
       for (uint32_t t = 0; t < n_tiles; t++, tcnt++, row += TM) {
         const uint32_t acc = tcnt & 1u;
-        mb_spin(tfull + acc, (tcnt >> 1) & 1u);
+        mb_wait_epi(tfull + acc, (tcnt >> 1) & 1u, p.epi_wait);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * TN + (uint32_t)c0;
-        sweep_tile<COLS>(p, taddr, row, r1, qb, c0, lane);
+        uint32_t v[COLS / 32][32];
+        sweep_load<COLS>(taddr, v);
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mb_arrive(tempty + acc);
+        if (lane == 0) mb_arrive(tempty + acc);   // the columns are in registers: the accumulator is free
+        sweep_scan<COLS>(p, v, row, r1, qb, c0, lane);
       }
       if (ew == 0 && lane == 0 && p.stats) atomicAdd(p.stats, (unsigned long long)n_tiles);
     }
@@ -688,13 +713,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1)
       i64 row = my0 + quad * 32 + lane;
       for (uint32_t t = 0; t < n_tiles; t++, tcnt++, row += 2 * TM) {
         const uint32_t acc = tcnt & 1u;
-        mb_spin(tfull + acc, (tcnt >> 1) & 1u);
+        mb_wait_epi(tfull + acc, (tcnt >> 1) & 1u, p.epi_wait);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * TN + (uint32_t)c0;
-        sweep_tile<COLS>(p, taddr, row, r1, qb, c0, lane);
+        uint32_t v[COLS / 32][32];
+        sweep_load<COLS>(taddr, v);
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mb_arrive_cluster(tempty0 + acc * 8u);
+        if (lane == 0) mb_arrive_cluster(tempty0 + acc * 8u);   // the columns are in registers: the accumulator is free
+        sweep_scan<COLS>(p, v, row, r1, qb, c0, lane);
       }
       if (ew == 0 && lane == 0 && p.stats) atomicAdd(p.stats, (unsigned long long)n_tiles);
     }

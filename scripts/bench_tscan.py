@@ -33,14 +33,16 @@ def main():
     ix = g.PQIndex.from_device_codes(pq, codes, rows)
     Q = mix.rows(0, nq, stream_seed=1)
     res = {}
-    for name, impl in (("tensor", g.SCAN_TENSOR), ("pruned", g.SCAN_PRUNED)):
+    import os
+    only = os.environ.get("TSCAN_ONLY")
+    for name, impl in ((("tensor", g.SCAN_TENSOR),) if only else (("tensor", g.SCAN_TENSOR), ("pruned", g.SCAN_PRUNED))):
         g.set_option("scan_impl", impl)
         g.set_option("profile", 1)
         t0 = time.perf_counter()
         out = ix.batch_query_dev(k, Q)
         torch.cuda.synchronize()
         first = time.perf_counter() - t0
-        reps = 3 if name == "tensor" else 1
+        reps = 1 if only else (3 if name == "tensor" else 1)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(reps):
@@ -54,17 +56,16 @@ def main():
             c = {n: N.counter("tscan_" + n) for n in ("kernel_ns", "kernel_launches", "tiles", "slow_paths", "survivors",
                                                      "candidates", "pairs", "fallbacks", "batches", "stages")}
             line.update(c)
-            KP = (D + 7 + 15) // 16 * 16
+            KP = (D + 4 + 15) // 16 * 16
             flop = 2.0 * 128 * 256 * KP * c["tiles"]
             line["filter_tflops"] = flop / max(c["kernel_ns"], 1) * 1e-3
             line["survivor_rate"] = c["survivors"] / max(c["pairs"], 1)
         print(line, flush=True)
         g.set_option("profile", 0)
-    import os
     if os.environ.get("TSCAN_SWEEP"):
         g.set_option("scan_impl", g.SCAN_TENSOR)
-        for name, vals in (("tensor_pair", [0, 1]), ("tensor_chunk_bytes", [4 << 20, 64 << 20, 16 << 20]),
-                           ("tensor_stage_ratio", [3, 4, 6, 8, 0]), ("tensor_boot_rows", [16384, 0])):
+        for name, vals in (("tensor_pair", [0, 1]), ("tensor_epi_wait", [1, 2, 0]), ("tensor_pair", [0]), ("tensor_epi_wait", [1, 2, 0]), ("tensor_pair", [1]),
+                           ("tensor_stage_ratio", [3, 5, 8, 16, 0])):
             for v in vals:
                 g.set_option(name, v)
                 g.set_option("profile", 1)
@@ -82,6 +83,8 @@ def main():
                        "survivors": N.counter("tscan_survivors") // 3, "same": bool(same)}, flush=True)
                 g.set_option("profile", 0)
     g.set_option("scan_impl", g.SCAN_AUTO)
+    if only:
+        return
     same = np.array_equal(res["tensor"][0], res["pruned"][0]) and np.array_equal(res["tensor"][1].view(np.uint32), res["pruned"][1].view(np.uint32))
     print({"tensor_equals_pruned": bool(same)}, flush=True)
 

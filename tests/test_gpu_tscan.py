@@ -53,9 +53,10 @@ def pair(request, g):
 @pytest.mark.parametrize("n,D,M,frm,until", [
     (3000, 300, 30, 0, 3000),        # c2 shape: KP = 320, five chunks
     (2500, 128, 16, 37, 2401),       # c4 shape: KP = 144 (last chunk partly outside the operand), ragged range
+    (1800, 60, 6, 0, 1800),          # KP = 64: exactly one chunk
     (2000, 100, 10, 1, 1999),        # c1 shape: KP = 112
     (1500, 37, 5, 0, 1500),          # ragged windows: KP = 48
-    (1100, 313, 31, 0, 1100),        # the widest index the filter takes
+    (1100, 316, 31, 0, 1100),        # the widest index the filter takes
 ])
 def test_filter_accumulators_and_bound(g, pair, n, D, M, frm, until):
     import torch
@@ -74,15 +75,15 @@ def test_filter_accumulators_and_bound(g, pair, n, D, M, frm, until):
     xb, qb, acc = debug_tscan(ix, torch.from_numpy(Q).cuda(), taus, frm, until)
     rows = until - frm
     KP = xb.shape[1]
-    assert KP == (D + 7 + 15) // 16 * 16 and acc.shape == (rows, 256)
+    assert KP == (D + 4 + 15) // 16 * 16 and acc.shape == (rows, 256)
     A, B = bf16_to_f64(xb), bf16_to_f64(qb)
     # operand rows: coordinates rounded to nearest, the norm terms on the safe side
     x32 = pq.decode(enc).data[frm:until]
     assert np.array_equal(A[:, :D], bf16_to_f64((x32.view(np.uint32) + 0x7FFF + ((x32.view(np.uint32) >> 16) & 1) >> 16).astype(np.uint16)))
     n2 = (dec[frm:until] ** 2).sum(axis=1)
-    assert np.all(A[:, D:D + 3].sum(axis=1) <= n2 * (1 - EPS_ACC)) and np.all(A[:, D:D + 3].sum(axis=1) >= n2 * (1 - 2 * EPS_ACC))
-    assert np.all(A[:, D + 3] >= np.sqrt(n2)) and np.all(A[:, D + 4:D + 7] == 1.0) and np.all(A[:, D + 7:] == 0.0)
-    assert np.all(B[nq:, :D] == 0) and np.all(B[nq:, D + 4] > 1e37)     # padding slots: nothing survives
+    assert np.all(A[:, D:D + 2].sum(axis=1) <= n2 * (1 - EPS_ACC)) and np.all(A[:, D:D + 2].sum(axis=1) >= n2 * (1 - 2 * EPS_ACC))
+    assert np.all(A[:, D + 2] >= np.sqrt(n2)) and np.all(A[:, D + 3] == 1.0) and np.all(A[:, D + 4:] == 0.0)
+    assert np.all(B[nq:, :D] == 0) and np.all(B[nq:, D + 3] > 1e37)     # padding slots: nothing survives
     # 1. the tensor core's accumulation: far inside the allowance
     ref = A @ B.T
     mag = np.abs(A) @ np.abs(B).T
@@ -108,7 +109,7 @@ SHAPES = [
     (150000, 128, 16, 257, 100, 5, 149990, 0, 4096),    # c4 shape, large k (ratio 2), one query past a block
     (120000, 37, 5, 33, 1, 0, None, 16, 16),            # ragged windows, k = 1, boot shorter than a tile
     (90000, 24, 3, 5, 128, 100, 89000, 2, 4096),        # k at the limit
-    (50000, 313, 31, 9, 10, 0, None, 3, 8192),          # widest index
+    (50000, 316, 31, 9, 10, 0, None, 3, 8192),          # widest index
     (20000, 64, 8, 12, 10, 0, 8192, 0, 0),              # range == boot: no stage at all
     (20000, 64, 8, 12, 10, 3, 8400, 0, 0),              # one short stage (< 2 tiles)
 ]
@@ -204,7 +205,7 @@ def test_tensor_scan_overflowing_ties_fall_back(g, oracle):
     n, D, M = 400000, 16, 2
     codes = rng.integers(0, 2, (M, n)).astype(np.uint8)
     pq, cb, codes, ix = build_index(g, rng, n, D, M, codes=codes)
-    Q = clustered(rng, 5, D)
+    Q = clustered(rng, 40, D)
     g.set_option("profile", 1)
     try:
         check_query(g, oracle, ix, cb, codes, Q, 25, 3, n - 1, (g.SCAN_TENSOR, 0, 0))
@@ -223,7 +224,7 @@ def test_tensor_scan_refuses_what_it_cannot_serve(g):
             ix.batch_query(129, Q, 0, 20000)          # k beyond the in-kernel lists
         pq2, cb2, codes2, ix2 = build_index(g, rng, 5000, 400, 40)
         with pytest.raises(Exception):
-            ix2.batch_query(10, clustered(rng, 3, 400), 0, 5000)   # D + 7 > 320
+            ix2.batch_query(10, clustered(rng, 3, 400), 0, 5000)   # D + 4 > 320
     finally:
         g.set_option("scan_impl", g.SCAN_AUTO)
     r = ix.batch_query(129, Q, 0, 20000)              # automatic: served by the k-chunked scans
