@@ -164,7 +164,7 @@ std::atomic<long long> g_pruned_words{0};        // 0 = auto, 1/2/4: 32-bit word
 std::atomic<long long> g_pruned_lb{0};           // 0 = auto (feedback), else quantizers in the lower bound
 std::atomic<long long> g_pruned_stage_div{32};   // first stage = range / div rows with the full bound; 0 = one stage
 std::atomic<long long> g_pruned_rowcodes{1};     // keep a row-major copy of the codes for the survivor evaluation
-std::atomic<long long> g_tensor_min_rows{1 << 20};    // GULON_SCAN_AUTO: shorter ranges keep the pruned scan
+std::atomic<long long> g_tensor_min_rows{1 << 19};    // GULON_SCAN_AUTO: shorter ranges keep the pruned scan
 std::atomic<long long> g_tensor_min_queries{2048};    // ... and smaller batches
 std::atomic<long long> g_tensor_query_batch{0};       // queries per pass of the tensor scan; 0 = auto
 std::atomic<long long> g_tensor_ratio{0};             // a stage scans ratio x the rows seen so far; 0 = auto from k
@@ -2391,6 +2391,7 @@ int gulon_set_option(const char *name, int64_t value) {
              s == "tensor_stage_ratio" || s == "tensor_boot_rows" || s == "tensor_max_bytes" ||
              s == "tensor_chunk_bytes" || s == "tensor_pair" || s == "tensor_epi_wait") {
     GREQUIRE(value >= 0, "%s must be >= 0", name);
+    GREQUIRE(s != "tensor_epi_wait" || value <= 7, "tensor_epi_wait must be 0..7");
     (s == "tensor_min_rows" ? g_tensor_min_rows : s == "tensor_min_queries" ? g_tensor_min_queries
      : s == "tensor_query_batch" ? g_tensor_query_batch : s == "tensor_stage_ratio" ? g_tensor_ratio
      : s == "tensor_boot_rows" ? g_tensor_boot : s == "tensor_chunk_bytes" ? g_tensor_chunk_bytes

@@ -68,7 +68,7 @@ constexpr int NSTAGE = 3;          // A ring
 constexpr int A_BYTES = TM * KC * 2;   // 16384
 constexpr int B_BYTES = TN * KC * 2;   // 32768
 constexpr int NEPI = 16;           // epilogue warps: 4 per TMEM lane quadrant, 64 columns each
-constexpr int NT = 32 * (2 + NEPI);
+constexpr int NT = 32 * (2 + NEPI + 1);   // TMA, MMA, epilogue warps, sentinel
 constexpr int BAR_BYTES = 256;
 constexpr int SMEM_BYTES = NKC_MAX * B_BYTES + NSTAGE * A_BYTES + BAR_BYTES;
 static_assert(SMEM_BYTES <= 232448, "the filter must fit the 227 KB of an sm_100 CTA");
@@ -255,7 +255,7 @@ __device__ __forceinline__ void commit1_elect(uint64_t *bar) {
 // and little else to issue, so spinning costs nothing that matters.
 __device__ __forceinline__ void mb_spin(uint64_t *b, uint32_t parity);
 // how the epilogue warps wait for an accumulator (FParams::epi_wait): 0 spin, 1 try_wait without the
-// suspend hint, 2 try_wait with it
+// suspend hint, 2 try_wait with it, 3 (default) a named barrier released by the sentinel warp
 __device__ __forceinline__ void mb_wait_epi(uint64_t *b, uint32_t parity, int mode) {
   if (mode == 0) {
     mb_spin(b, parity);
@@ -282,6 +282,19 @@ __device__ __forceinline__ void mb_spin(uint64_t *b, uint32_t parity) {
     if (ok) return;
     if (spins > (1u << 28)) __trap();
   }
+}
+
+// Waking the epilogue warps (FParams::epi_wait == 3, the default): a suspended mbarrier waiter wakes up
+// ~1 us after the phase completes, and with two accumulators that latency sits on the critical path of
+// every other tile (M + wake-up + sweep must fit into 2 M; at KP = 144 it did not: tensor pipe 62 %).
+// Spinning in all 16 epilogue warps takes the issue slots the MMA warp needs.  So ONE extra warp (the
+// sentinel) spins on `tfull` and releases the epilogue warps through a named hardware barrier, which wakes
+// its waiters within tens of cycles and costs no issue slots while they wait.
+__device__ __forceinline__ void epi_bar_arrive(uint32_t id) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"((NEPI + 1) * 32) : "memory");
+}
+__device__ __forceinline__ void epi_bar_sync(uint32_t id) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "n"((NEPI + 1) * 32) : "memory");
 }
 
 // One epilogue warp, one accumulator tile: thread = row = TMEM lane, COLS = 64 columns (queries) starting
@@ -416,7 +429,7 @@ __global__ void __launch_bounds__(NT, 1) filter_kernel(const __grid_constant__ C
         // the first A chunks only need ring slots of the previous item, not its B operand
         for (uint32_t ci = 0; ci < n_chunks; ci++) {
           if (ci == n_pre) load_b();
-          mb_wait(empty + rs, rph ^ 1u);
+          if (p.epi_wait & 4) mb_wait(empty + rs, rph ^ 1u); else mb_spin(empty + rs, rph ^ 1u);
           mb_expect_tx(full + rs, A_BYTES);
           tma_box(a_s + rs * A_BYTES, &mapA, (int)(kc * KC), row, full + rs);
           if (++kc == nkc) {
@@ -464,14 +477,26 @@ __global__ void __launch_bounds__(NT, 1) filter_kernel(const __grid_constant__ C
         }
       }
       commit1_elect(bempty);   // the item's B operand is no longer read
+    } else if (warp == 2 + NEPI) {
+      // ================= sentinel: spins on `tfull`, releases the epilogue warps through a named barrier =================
+      if ((p.epi_wait & 3) == 3) {
+        for (uint32_t t = 0; t < n_tiles; t++, tcnt++) {
+          const uint32_t acc = tcnt & 1u;
+          mb_spin(tfull + acc, (tcnt >> 1) & 1u);
+          epi_bar_arrive(1u + acc);
+        }
+      }
     } else {
-      // ================= epilogue: thread = row = TMEM lane, 128 of the 256 columns =================
+      // ================= epilogue: thread = row = TMEM lane, 64 of the 256 columns =================
       constexpr int COLS = TN / (NEPI / 4);
       const int ew = warp - 2, quad = warp & 3, c0 = (ew >> 2) * COLS;
       i64 row = r0 + quad * 32 + lane;
       for (uint32_t t = 0; t < n_tiles; t++, tcnt++, row += TM) {
         const uint32_t acc = tcnt & 1u;
-        mb_wait_epi(tfull + acc, (tcnt >> 1) & 1u, p.epi_wait);
+        if ((p.epi_wait & 3) == 3)
+          epi_bar_sync(1u + acc);
+        else
+          mb_wait_epi(tfull + acc, (tcnt >> 1) & 1u, p.epi_wait & 3);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * TN + (uint32_t)c0;
         uint32_t v[COLS / 32][32];
@@ -654,7 +679,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1)
         // the first A chunks only need ring slots of the previous item, not its B operand
         for (uint32_t ci = 0; ci < n_chunks; ci++) {
           if (ci == n_pre) load_b();
-          mb_wait(empty + rs, rph ^ 1u);
+          if (p.epi_wait & 4) mb_wait(empty + rs, rph ^ 1u); else mb_spin(empty + rs, rph ^ 1u);
           if (leader) mb_expect_tx(full + rs, 2 * A_BYTES);   // both CTAs' boxes
           tma_box2(a_s + rs * A_BYTES, &mapA, (int)(kc * KC), row, full0 + rs * 8u);
           if (++kc == nkc) {
@@ -706,6 +731,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1)
         // the last item's multicast arrivals must have landed before either CTA may exit
         if (item + n_pairs >= n_items) mb_wait(bempty, it & 1u);
       }
+    } else if (warp == 2 + NEPI) {
+      // ================= sentinel (both CTAs): spins on `tfull`, releases the epilogue warps =================
+      if ((p.epi_wait & 3) == 3) {
+        for (uint32_t t = 0; t < n_tiles; t++, tcnt++) {
+          const uint32_t acc = tcnt & 1u;
+          mb_spin(tfull + acc, (tcnt >> 1) & 1u);
+          epi_bar_arrive(1u + acc);
+        }
+      }
     } else {
       // ================= epilogue: this CTA's 128 rows of every tile =================
       constexpr int COLS = TN / (NEPI / 4);
@@ -713,7 +747,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1)
       i64 row = my0 + quad * 32 + lane;
       for (uint32_t t = 0; t < n_tiles; t++, tcnt++, row += 2 * TM) {
         const uint32_t acc = tcnt & 1u;
-        mb_wait_epi(tfull + acc, (tcnt >> 1) & 1u, p.epi_wait);
+        if ((p.epi_wait & 3) == 3)
+          epi_bar_sync(1u + acc);
+        else
+          mb_wait_epi(tfull + acc, (tcnt >> 1) & 1u, p.epi_wait & 3);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * TN + (uint32_t)c0;
         uint32_t v[COLS / 32][32];

@@ -21,7 +21,11 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_ld.sum",
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_atom.sum",
         "lts__t_sectors_srcunit_tex_op_read.sum", "lts__t_sector_hit_rate.pct",
-        "sm__warps_active.avg.per_cycle_active", "smsp__warps_eligible.avg.per_cycle_active"]
+        "sm__warps_active.avg.per_cycle_active", "smsp__warps_eligible.avg.per_cycle_active",
+        "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg", "sm__cycles_elapsed.avg.per_second",
+        "l1tex__m_xbar2l1tex_read_bytes.sum", "l1tex__m_xbar2l1tex_read_bytes.sum.per_second",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed"]
 
 
 def main():
@@ -35,7 +39,7 @@ def main():
         w.writerow(["kernel", "metric", "value", "unit"])
         for r in rows[2:]:
             for h, u, v in zip(hdr, units, r):
-                if h in KEYS or ("issue_stalled" in h and h.endswith("per_issue_active.ratio")) or \
+                if h in KEYS or h.split(".TriageCompute.")[-1] in KEYS or ("issue_stalled" in h and h.endswith("per_issue_active.ratio")) or \
                         ("tensor" in h and h.endswith("pct_of_peak_sustained_active")):
                     w.writerow([r[ki][:80], h, v, u])
 
