@@ -68,7 +68,7 @@ constexpr int NSTAGE = 3;          // A ring
 constexpr int A_BYTES = TM * KC * 2;   // 16384
 constexpr int B_BYTES = TN * KC * 2;   // 32768
 constexpr int NEPI = 16;           // epilogue warps: 4 per TMEM lane quadrant, 64 columns each
-constexpr int NT = 32 * (2 + NEPI + 1);   // TMA, MMA, epilogue warps, sentinel
+constexpr int NT = 32 * (2 + NEPI + 2);   // TMA, MMA, epilogue warps, sentinel, second MMA warp (pair kernel)
 constexpr int BAR_BYTES = 256;
 constexpr int SMEM_BYTES = NKC_MAX * B_BYTES + NSTAGE * A_BYTES + BAR_BYTES;
 static_assert(SMEM_BYTES <= 232448, "the filter must fit the 227 KB of an sm_100 CTA");
@@ -486,7 +486,7 @@ __global__ void __launch_bounds__(NT, 1) filter_kernel(const __grid_constant__ C
           epi_bar_arrive(1u + acc);
         }
       }
-    } else {
+    } else if (warp < 2 + NEPI) {
       // ================= epilogue: thread = row = TMEM lane, 64 of the 256 columns =================
       constexpr int COLS = TN / (NEPI / 4);
       const int ew = warp - 2, quad = warp & 3, c0 = (ew >> 2) * COLS;
@@ -626,7 +626,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1)
       mb_init(empty + i, 1);
     }
     mb_init(bfull, 1);
-    mb_init(bempty, 1);
+    mb_init(bempty, 2);   // both issuing warps commit it
     for (int i = 0; i < 2; i++) {
       mb_init(tfull + i, 1);
       mb_init(tempty + i, 2 * NEPI);
@@ -694,12 +694,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1)
         if (n_pre == n_chunks) load_b();
       }
       __syncwarp();
-    } else if (warp == 1) {
-      // ================= MMA issue (the leader's warp 1, one elected lane) =================
+    } else if (warp == 1 || warp == 3 + NEPI) {
+      // ================= MMA issue (the leader's warps 1 and 3 + NEPI, one elected lane each) =================
+      // Two issuing warps on alternate tiles (warp 1: accumulator 0, the other: accumulator 1).  At KP = 144
+      // a tile is 9 MMAs = 1152 cycles of tensor time, and one thread's instruction stream (~15 per MMA,
+      // ~40 per ring hand-off) took ~1535 (timing experiment in profiles/README.md).  tcgen05.commit tracks
+      // the MMAs of the committing thread, so each warp frees its own ring slots and publishes its own tiles;
+      // both commit `bempty` (count 2).
       if (leader) {
+        const uint32_t mine = warp == 1 ? 0u : 1u;
         mb_wait(bfull, it & 1u);
         for (uint32_t t = 0; t < n_tiles; t++, tcnt++) {
           const uint32_t acc = tcnt & 1u;
+          if (acc != mine) {   // the other warp's tile: skip its ring slots
+            rs += nkc;
+            if (rs >= (uint32_t)NSTAGE2) {
+              rs -= (uint32_t)NSTAGE2;
+              rph ^= 1u;
+            }
+            continue;
+          }
           mb_spin(tempty + acc, ((tcnt >> 1) & 1u) ^ 1u);
           tc_fence_after();
           const uint32_t d_addr = tmem_base + acc * TN;
@@ -729,7 +743,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1)
         }
         commit2_elect(bempty);
         // the last item's multicast arrivals must have landed before either CTA may exit
-        if (item + n_pairs >= n_items) mb_wait(bempty, it & 1u);
+        if (warp == 1 && item + n_pairs >= n_items) mb_wait(bempty, it & 1u);
       }
     } else if (warp == 2 + NEPI) {
       // ================= sentinel (both CTAs): spins on `tfull`, releases the epilogue warps =================
@@ -740,7 +754,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1)
           epi_bar_arrive(1u + acc);
         }
       }
-    } else {
+    } else if (warp < 2 + NEPI) {
       // ================= epilogue: this CTA's 128 rows of every tile =================
       constexpr int COLS = TN / (NEPI / 4);
       const int ew = warp - 2, quad = warp & 3, c0 = (ew >> 2) * COLS;
