@@ -165,7 +165,7 @@ std::atomic<long long> g_pruned_lb{0};           // 0 = auto (feedback), else qu
 std::atomic<long long> g_pruned_stage_div{32};   // first stage = range / div rows with the full bound; 0 = one stage
 std::atomic<long long> g_pruned_rowcodes{1};     // keep a row-major copy of the codes for the survivor evaluation
 std::atomic<long long> g_tensor_min_rows{1 << 19};    // GULON_SCAN_AUTO: shorter ranges keep the pruned scan
-std::atomic<long long> g_tensor_min_queries{2048};    // ... and smaller batches
+std::atomic<long long> g_tensor_min_queries{256};    // ... and smaller batches
 std::atomic<long long> g_tensor_query_batch{0};       // queries per pass of the tensor scan; 0 = auto
 std::atomic<long long> g_tensor_ratio{0};             // a stage scans ratio x the rows seen so far; 0 = auto from k
 std::atomic<long long> g_tensor_boot{0};              // rows scanned exactly first; 0 = 8192
@@ -1908,7 +1908,8 @@ int tensor_scan_batch(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k,
       ep.capq = capq;
       ep.flag = ix->tflag.as<int>();
       ep.stats = want_stats ? ix->tstats.as<unsigned long long>() : nullptr;
-      dim3 eg(16, (unsigned)NB);
+      // 128 CTAs per query block: ~9 query blocks (70 MB of tables) are in flight at a time and stay in L2
+      dim3 eg(128, (unsigned)NB);
       GLAUNCH(tscan::eval_kernel, eg, 256, 0, st, ep);
       u64 *nxt = (pp ? ix->tcur1 : ix->tcur0).as<u64>();
       GLAUNCH(merge, (unsigned)ceil_div(nq, tscan::MERGE_WARPS), 32 * tscan::MERGE_WARPS,

@@ -162,8 +162,8 @@ def test_tensor_scan_auto_selection_and_cosine(g, oracle):
         assert N.counter("tscan_batches") == 1
     finally:
         g.set_option("profile", 0)
-        g.set_option("tensor_min_rows", 1 << 20)
-        g.set_option("tensor_min_queries", 2048)
+        g.set_option("tensor_min_rows", 1 << 19)
+        g.set_option("tensor_min_queries", 256)
     assert np.array_equal(small.keys, got.keys[:100]) and np.array_equal(small.values.view(np.uint32), got.values[:100].view(np.uint32))
     g.set_option("scan_impl", g.SCAN_FUSED)
     try:
