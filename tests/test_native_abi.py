@@ -61,6 +61,29 @@ def test_coder_width():
         coder_width(65537)   # "too many clusters", G/ProductQuantizer.scala:13-15
 
 
+def test_tensor_scan_options_and_counters(native):
+    """The tensor scan's knobs (header: gulon_set_option) exist, validate their ranges and never need a device."""
+    import gulon_b200 as g
+    from gulon_b200 import _native as N
+    assert g.SCAN_TENSOR == 4
+    defaults = {"tensor_min_rows": 1 << 19, "tensor_min_queries": 256, "tensor_query_batch": 0, "tensor_stage_ratio": 0,
+                "tensor_boot_rows": 0, "tensor_max_bytes": 64 << 30, "tensor_chunk_bytes": 16 << 20, "tensor_pair": 1,
+                "tensor_epi_wait": 2}
+    for name, v in defaults.items():
+        g.set_option(name, v)
+        with pytest.raises(ValueError):
+            g.set_option(name, -1)
+    with pytest.raises(ValueError):
+        g.set_option("tensor_epi_wait", 8)
+    g.set_option("scan_impl", g.SCAN_TENSOR)
+    g.set_option("scan_impl", g.SCAN_AUTO)
+    with pytest.raises(ValueError):
+        g.set_option("scan_impl", 5)
+    for c in ("tscan_kernel_ns", "tscan_kernel_launches", "tscan_tiles", "tscan_survivors", "tscan_candidates",
+              "tscan_pairs", "tscan_fallbacks", "tscan_batches", "tscan_stages", "scan_last_impl"):
+        assert N.counter(c) >= 0
+
+
 def test_no_cpu_fallback(native):
     import gulon_b200 as g
     if g.device_count() > 0:
