@@ -110,8 +110,13 @@ def config_of(a, world):
             "sharding": ("%d row shard(s) of the code planes x %d query group(s); all-gather + (distance,id) "
                          "merge inside a group, all-gather of the slices across groups" % (R, Cq))
             if world > 1 else "single GPU",
-            "l2": "inputs larger than L2: code planes (%d MB) + per-tile lookup tables > 126 MB; no flush "
-                  "needed" % (a.rows * a.m // 1_000_000)}
+            "l2": "inputs larger than L2: code planes (%d MB), their decoded bf16 copy (%d MB, the tensor scan's "
+                  "operand) and the per-query lookup tables (%d MB) all exceed 126 MB; no flush needed"
+                  % (a.rows * a.m // 1_000_000, a.rows * ((a.dim + 4 + 15) // 16 * 16) * 2 // 1_000_000,
+                     a.queries * a.m * 1024 // 1_000_000),
+            "arithmetic": "every returned distance is the reference's sequential fp32 table sum (dtype f32); the "
+                          "tensor scan's lower bound, which only discards pairs, contracts bf16 operands with fp32 "
+                          "accumulation"}
 
 
 def index_digest(codebook, codes):

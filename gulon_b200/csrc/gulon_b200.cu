@@ -170,6 +170,7 @@ std::atomic<long long> g_tensor_query_batch{0};       // queries per pass of the
 std::atomic<long long> g_tensor_ratio{0};             // a stage scans ratio x the rows seen so far; 0 = auto from k
 std::atomic<long long> g_tensor_boot{0};              // rows scanned exactly first; 0 = 8192
 std::atomic<long long> g_tensor_max_bytes{64LL << 30};  // largest decoded copy of an index
+std::atomic<long long> g_tensor_eval_blocks{16};          // CTAs per query block in tscan::eval_kernel
 std::atomic<long long> g_tensor_epi_wait{2};              // tscan::mb_wait_epi
 std::atomic<long long> g_tensor_pair{1};                  // the filter on CTA pairs (cta_group::2) or on single CTAs
 std::atomic<long long> g_tensor_chunk_bytes{16LL << 20};  // operand rows of one row split (L2 working set)
@@ -1820,7 +1821,16 @@ int launch_filter(gulon_index_t ix, i64 sfrom, i64 suntil, int NB, unsigned capb
   if (pair) {
     GOPTIN(tscan::filter2_kernel, tscan::SMEM2_BYTES);
     const unsigned grid = 2u * (unsigned)std::min<i64>(n_items, units);
-    GLAUNCH(tscan::filter2_kernel, grid, tscan::NT, tscan::SMEM2_BYTES, st, mapA, mapB, fp);
+    tscan::filter2_kernel<<<grid, tscan::NT, tscan::SMEM2_BYTES, st>>>(mapA, mapB, fp);
+    launch_counter().fetch_add(1, std::memory_order_relaxed);
+    const cudaError_t le = cudaGetLastError();
+    if (le != cudaSuccess) {
+      // a context that cannot co-schedule 2-CTA clusters with 227 KB each (MPS partitions, odd SM masks):
+      // the single-CTA form serves from now on
+      g_tensor_pair = 0;
+      g_t_tscan.end(ev, st);
+      return launch_filter(ix, sfrom, suntil, NB, capb, dump, st);
+    }
   } else {
     GOPTIN(tscan::filter_kernel, tscan::SMEM_BYTES);
     const unsigned grid = (unsigned)std::min<i64>(n_items, units);
@@ -1908,8 +1918,9 @@ int tensor_scan_batch(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k,
       ep.capq = capq;
       ep.flag = ix->tflag.as<int>();
       ep.stats = want_stats ? ix->tstats.as<unsigned long long>() : nullptr;
-      // 128 CTAs per query block: ~9 query blocks (70 MB of tables) are in flight at a time and stay in L2
-      dim3 eg(128, (unsigned)NB);
+      // CTAs per query block: with few, many query blocks' tables (7.7 MB each at M = 30) are in flight at a
+      // time; with many, they stay in L2 but most threads find no survivor
+      dim3 eg((unsigned)std::max<long long>(1, std::min<long long>(1024, g_tensor_eval_blocks.load())), (unsigned)NB);
       GLAUNCH(tscan::eval_kernel, eg, 256, 0, st, ep);
       u64 *nxt = (pp ? ix->tcur1 : ix->tcur0).as<u64>();
       GLAUNCH(merge, (unsigned)ceil_div(nq, tscan::MERGE_WARPS), 32 * tscan::MERGE_WARPS,
@@ -1996,8 +2007,16 @@ int query_dev(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 fro
           q = ix->qbuf.as<float>();
           ql = D;
         }
-        GCHECK(tensor_scan_batch(ix, q, tn, ql, k, from, until, id_offset, d_ids + t0 * k, d_dists + t0 * k,
-                                 d_sizes ? d_sizes + t0 : nullptr, st, &redo));
+        const int trc = tensor_scan_batch(ix, q, tn, ql, k, from, until, id_offset, d_ids + t0 * k, d_dists + t0 * k,
+                                          d_sizes ? d_sizes + t0 : nullptr, st, &redo);
+        if (trc == GULON_ENOMEM && want != GULON_SCAN_TENSOR) {
+          // no room for this batch's tables / lists: the pruned scan works in passes of a few thousand queries
+          cudaGetLastError();
+          g_tstats[5] += 1;
+          redo = true;
+        } else if (trc != GULON_OK) {
+          return trc;
+        }
       }
       if (!redo) {
         g_last_scan = GULON_SCAN_TENSOR;
@@ -2390,13 +2409,14 @@ int gulon_set_option(const char *name, int64_t value) {
     g_pruned_min_rows = value;
   } else if (s == "tensor_min_rows" || s == "tensor_min_queries" || s == "tensor_query_batch" ||
              s == "tensor_stage_ratio" || s == "tensor_boot_rows" || s == "tensor_max_bytes" ||
-             s == "tensor_chunk_bytes" || s == "tensor_pair" || s == "tensor_epi_wait") {
+             s == "tensor_chunk_bytes" || s == "tensor_pair" || s == "tensor_epi_wait" || s == "tensor_eval_blocks") {
     GREQUIRE(value >= 0, "%s must be >= 0", name);
     GREQUIRE(s != "tensor_epi_wait" || value <= 7, "tensor_epi_wait must be 0..7");
     (s == "tensor_min_rows" ? g_tensor_min_rows : s == "tensor_min_queries" ? g_tensor_min_queries
      : s == "tensor_query_batch" ? g_tensor_query_batch : s == "tensor_stage_ratio" ? g_tensor_ratio
      : s == "tensor_boot_rows" ? g_tensor_boot : s == "tensor_chunk_bytes" ? g_tensor_chunk_bytes
      : s == "tensor_pair" ? g_tensor_pair : s == "tensor_epi_wait" ? g_tensor_epi_wait
+     : s == "tensor_eval_blocks" ? g_tensor_eval_blocks
      : g_tensor_max_bytes) = value;
   } else if (s == "fused_min_rows") {
     GREQUIRE(value >= 0, "fused_min_rows must be >= 0");

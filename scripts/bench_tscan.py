@@ -64,7 +64,7 @@ def main():
         g.set_option("profile", 0)
     if os.environ.get("TSCAN_SWEEP"):
         g.set_option("scan_impl", g.SCAN_TENSOR)
-        for name, vals in (("tensor_pair", [0, 1]), ("tensor_epi_wait", [6, 3, 2]),):
+        for name, vals in (("tensor_eval_blocks", [8, 32, 64, 128, 16]), ("tensor_stage_ratio", [3, 6, 8, 0]), ("tensor_boot_rows", [16384, 0]),):
             for v in vals:
                 g.set_option(name, v)
                 g.set_option("profile", 1)
@@ -80,7 +80,7 @@ def main():
                 same = np.array_equal(out[0].cpu().numpy(), res["tensor"][0])
                 if name == "tensor_epi_wait" and v >= 8:
                     N.lib().gulon_set_option(b"tensor_epi_wait", 2)
-                print({name: v, "ms": ms, "qps": nq / ms * 1e3, "filter_ms": N.counter("tscan_kernel_ns") / 3e6,
+                print({name: v, "ms": ms, "qps": nq / ms * 1e3, "filter_ms": N.counter("tscan_kernel_ns") / 3e6, "other_ms": ms - N.counter("tscan_kernel_ns") / 3e6,
                        "survivors": N.counter("tscan_survivors") // 3, "same": bool(same)}, flush=True)
                 g.set_option("profile", 0)
     g.set_option("scan_impl", g.SCAN_AUTO)
