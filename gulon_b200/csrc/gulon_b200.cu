@@ -1737,7 +1737,7 @@ int make_bf16_map(const void *base, i64 rows, int KP, int box_rows, CUtensorMap 
 // Can this index ever take the tensor scan?  (shape only; prepare_tensor decides about memory and data)
 bool tensor_shape_ok(gulon_index_t ix) {
   gulon_codebook_t cb = ix->cb;
-  return ix->codes && !ix->codes16 && cb->K <= 256 && cb->M <= 1024 && tscan::padded_k(cb->D) <= tscan::KP_MAX &&
+  return ix->codes && !ix->codes16 && cb->K <= 256 && cb->M <= 1024 && tscan::padded_k(cb->D) <= tscan::KP_STREAM_MAX &&
          ix->N < (1LL << 31) && ix->N > 0 && tensor_map_encoder() != nullptr;
 }
 
@@ -1784,7 +1784,9 @@ int prepare_tensor(gulon_index_t ix, cudaStream_t st) {
 // One stage of the filter over rows [sfrom, suntil) for NB blocks of 256 query slots (operand rows in ix->tqb).
 int launch_filter(gulon_index_t ix, i64 sfrom, i64 suntil, int NB, unsigned capb, float *dump, cudaStream_t st) {
   const int KP = ix->tensor_kp, sms = sm_count();
-  const bool pair = g_tensor_pair.load() != 0 && sms >= 2;
+  const bool sb = KP > tscan::KP_MAX;   // the query block does not fit shared memory: streamed with the rows (pair kernel only)
+  const bool pair = (g_tensor_pair.load() != 0 || sb) && sms >= 2;
+  GREQUIRE(pair || !sb, "the tensor scan of an index with D > %d needs CTA pairs", tscan::KP_MAX - tscan::NEXTRA);
   CUtensorMap mapA, mapB;
   GCHECK(make_bf16_map(ix->xb.p, ix->N, KP, tscan::TM, &mapA));
   GCHECK(make_bf16_map(ix->tqb.p, (i64)NB * tscan::TN, KP, pair ? tscan::TN / 2 : tscan::TN, &mapB));
@@ -1819,11 +1821,20 @@ int launch_filter(gulon_index_t ix, i64 sfrom, i64 suntil, int NB, unsigned capb
   const i64 n_items = (i64)NB * S;
   cudaEvent_t ev = g_t_tscan.begin(st);
   if (pair) {
-    GOPTIN(tscan::filter2_kernel, tscan::SMEM2_BYTES);
     const unsigned grid = 2u * (unsigned)std::min<i64>(n_items, units);
-    tscan::filter2_kernel<<<grid, tscan::NT, tscan::SMEM2_BYTES, st>>>(mapA, mapB, fp);
+    if (sb) {
+      GOPTIN(tscan::filter2_kernel<true>, tscan::SMEM2_BYTES);
+      tscan::filter2_kernel<true><<<grid, tscan::NT, tscan::SMEM2_BYTES, st>>>(mapA, mapB, fp);
+    } else {
+      GOPTIN(tscan::filter2_kernel<false>, tscan::SMEM2_BYTES);
+      tscan::filter2_kernel<false><<<grid, tscan::NT, tscan::SMEM2_BYTES, st>>>(mapA, mapB, fp);
+    }
     launch_counter().fetch_add(1, std::memory_order_relaxed);
     const cudaError_t le = cudaGetLastError();
+    if (le != cudaSuccess && sb) {
+      g_t_tscan.end(ev, st);
+      return fail(GULON_ECUDA, "tscan::filter2_kernel<streamed B>: %s", cudaGetErrorString(le));
+    }
     if (le != cudaSuccess) {
       // a context that cannot co-schedule 2-CTA clusters with 227 KB each (MPS partitions, odd SM masks):
       // the single-CTA form serves from now on
@@ -1982,7 +1993,7 @@ int query_dev(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 fro
     }
     if (want == GULON_SCAN_TENSOR && !tensor)
       return fail(GULON_EUNSUPPORTED, "scan_impl = tensor needs an 8-bit index with D <= %d, k <= %d, finite rows and "
-                  "room for the decoded copy (D=%d K=%d k=%d)", tscan::KP_MAX - tscan::NEXTRA, fscan::KMAX, D,
+                  "room for the decoded copy (D=%d K=%d k=%d)", tscan::KP_STREAM_MAX - tscan::NEXTRA, fscan::KMAX, D,
                   ix->cb->K, k);
   }
   i64 tb = nq;
@@ -1990,7 +2001,7 @@ int query_dev(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 fro
     // queries per pass: all of them while the tables (M KB per query), the candidate lists (8 KB) and the
     // survivor lists (8 KB) fit a few GB; passes of equal size, whole blocks of 256
     tb = g_tensor_query_batch.load();
-    if (tb <= 0) tb = std::max<i64>(4096, (12LL << 30) / ((i64)ix->cb->M * 1024 + 16384 + 2 * tscan::KP_MAX));
+    if (tb <= 0) tb = std::max<i64>(4096, (12LL << 30) / ((i64)ix->cb->M * 1024 + 16384 + 2 * tscan::KP_STREAM_MAX));
     const i64 passes = ceil_div(nq, tb);
     tb = round_up(ceil_div(nq, passes), tscan::TN);
   }

@@ -18,8 +18,8 @@
 // towards the safe side) with C = |q|^2 - tau' and tau' = tau (1 + 2^-11) (the fp32 summation error of the
 // reference, as in pscan.cuh).  Four extra columns: D = 300 contracts over KP = 304 = 19 K16 steps.
 // With the operand rounding |q.x^ - qb.xb| <= (2^-8 + 2^-18) |q||x^| and an accumulation error of the
-// tensor core of at most EPS_ACC times the sum of the absolute products (EPS_ACC = 2^-12; measured
-// ~2^-21, tests/test_gpu_tscan.py), COEF = 2^-7 + 2^-17 + 2.03 EPS_ACC gives
+// tensor core of at most EPS_ACC times the sum of the absolute products (EPS_ACC = eps_acc(KP) = 2^-12 up to
+// KP = 320; measured < 2^-16, tests/test_gpu_tscan.py), COEF = 2^-7 + 2^-17 + 2.03 EPS_ACC gives
 //
 //   D_computed <= d* - tau'     for every (row, query),
 //
@@ -73,8 +73,12 @@ constexpr int BAR_BYTES = 256;
 constexpr int SMEM_BYTES = NKC_MAX * B_BYTES + NSTAGE * A_BYTES + BAR_BYTES;
 static_assert(SMEM_BYTES <= 232448, "the filter must fit the 227 KB of an sm_100 CTA");
 
-constexpr double EPS_ACC = 1.0 / 4096.0;   // allowance for the tensor core's fp32 accumulation (per unit of sum |products|)
-constexpr double COEF = 1.0 / 128.0 + 1.0 / 131072.0 + 2.03 * EPS_ACC;
+// allowance for the tensor core's fp32 accumulation, per unit of the sum of |products|: 2^-12 up to KP = 320,
+// growing with the depth of the contraction beyond (KP 2^-20: 2^-10 at KP = 1008); measured errors are
+// more than 16x smaller (tests/test_gpu_tscan.py)
+__host__ __device__ inline double eps_acc(int KP) { return KP <= 320 ? 1.0 / 4096.0 : (double)KP / 1048576.0; }
+__host__ __device__ inline double bound_coef(int KP) { return 1.0 / 128.0 + 1.0 / 131072.0 + 2.03 * eps_acc(KP); }
+constexpr int KP_STREAM_MAX = 1024;        // deepest contraction of the streamed-B form of the pair kernel
 constexpr double TAU_SLACK = 1.0 / 2048.0;  // the reference's fp32 summation error (pscan.cuh uses the same)
 constexpr float FINITE_MAX = 1e30f;         // larger norms go to the fallback path (products must not overflow)
 
@@ -134,7 +138,7 @@ __global__ void __launch_bounds__(256) decode_rows_kernel(const uint8_t *__restr
     if (!(nrm <= (double)FINITE_MAX)) {
       atomicExch(bad, 1);
     } else {
-      split2_down(nrm * (1.0 - EPS_ACC - 1e-9), a1, a2);
+      split2_down(nrm * (1.0 - eps_acc(KP) - 1e-9), a1, a2);
       nb = bf_ru(__double2float_ru(sqrt(nrm) * (1.0 + 1e-9)));
     }
     out[D + 0] = a1;
@@ -182,8 +186,8 @@ __global__ void __launch_bounds__(256) qprep_kernel(const float *__restrict__ Q,
         const double c = nrm * (1.0 - 1e-9) - taup;
         out[D + 0] = 0x3F80;
         out[D + 1] = 0x3F80;
-        out[D + 2] = bf_ru(__double2float_ru(COEF * sqrt(nrm) * (1.0 + 1e-9))) | 0x8000u;   // -e
-        out[D + 3] = bf_rd(__double2float_rd(c - 2.0 * EPS_ACC * fabs(c) - 1e-300));          // one piece, rounded down
+        out[D + 2] = bf_ru(__double2float_ru(bound_coef(KP) * sqrt(nrm) * (1.0 + 1e-9))) | 0x8000u;   // -e
+        out[D + 3] = bf_rd(__double2float_rd(c - 2.0 * eps_acc(KP) * fabs(c) - 1e-300));       // one piece, rounded down
       }
     }
   }
@@ -601,12 +605,19 @@ __device__ __forceinline__ void commit2_elect(uint64_t *bar) {
       : "memory");
 }
 
+// SB ("streamed B", KP > 320: c5's D = 1000): the query block does not fit next to the ring, so every ring slot
+// carries the A chunk AND this CTA's half of the B chunk (32 KB, 7 slots); the B block (256 queries x KP) stays
+// hot in L2, at twice the L2 -> shared-memory traffic of the resident form.
+template <bool SB>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1)
     filter2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const FParams p) {
+  constexpr int NSTAGE2 = SB ? 7 : tscan::NSTAGE2;
+  constexpr int SLOT = SB ? A_BYTES + BH_BYTES : A_BYTES;
+  static_assert(NSTAGE2 * SLOT + (SB ? 0 : NKC_MAX * BH_BYTES) + BAR_BYTES <= SMEM2_BYTES, "shared memory layout");
   extern __shared__ __align__(1024) unsigned char smem[];
-  unsigned char *b_s = smem;                                // nkc chunks of [128][128 B]: this CTA's half of B
-  unsigned char *a_s = smem + NKC_MAX * BH_BYTES;           // NSTAGE2 tiles of [128][128 B]
-  uint64_t *bars = reinterpret_cast<uint64_t *>(a_s + NSTAGE2 * A_BYTES);
+  unsigned char *b_s = smem;                                // !SB: nkc chunks of [128][128 B]: this CTA's half of B
+  unsigned char *a_s = smem + (SB ? 0 : NKC_MAX * BH_BYTES);  // NSTAGE2 slots: [128][128 B] of A (SB: + [128][128 B] of B)
+  uint64_t *bars = reinterpret_cast<uint64_t *>(a_s + NSTAGE2 * SLOT);
   uint64_t *full = bars;                   // NSTAGE2 (leader's are used)
   uint64_t *empty = bars + NSTAGE2;        // NSTAGE2
   uint64_t *bfull = bars + 2 * NSTAGE2;    // 1 (leader's)
@@ -669,6 +680,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1)
         const uint32_t n_chunks = n_tiles * nkc;
         const uint32_t n_pre = n_chunks < (uint32_t)NSTAGE2 ? n_chunks : (uint32_t)NSTAGE2;
         auto load_b = [&]() {
+          if constexpr (SB) return;
           mb_wait(bempty, (it & 1u) ^ 1u);
           if (leader) mb_expect_tx(bfull, 2u * nkc * BH_BYTES);
           for (uint32_t kc = 0; kc < nkc; kc++)
@@ -680,8 +692,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1)
         for (uint32_t ci = 0; ci < n_chunks; ci++) {
           if (ci == n_pre) load_b();
           if (p.epi_wait & 4) mb_wait(empty + rs, rph ^ 1u); else mb_spin(empty + rs, rph ^ 1u);
-          if (leader) mb_expect_tx(full + rs, 2 * A_BYTES);   // both CTAs' boxes
-          tma_box2(a_s + rs * A_BYTES, &mapA, (int)(kc * KC), row, full0 + rs * 8u);
+          if (leader) mb_expect_tx(full + rs, 2 * SLOT);   // both CTAs' boxes
+          tma_box2(a_s + rs * SLOT, &mapA, (int)(kc * KC), row, full0 + rs * 8u);
+          if constexpr (SB)
+            tma_box2(a_s + rs * SLOT + A_BYTES, &mapB, (int)(kc * KC), qb * TN + (int)rank * (TN / 2), full0 + rs * 8u);
           if (++kc == nkc) {
             kc = 0;
             row += 2 * TM;
@@ -701,14 +715,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1)
       // ~40 per ring hand-off) took ~1535 (timing experiment in profiles/README.md).  tcgen05.commit tracks
       // the MMAs of the committing thread, so each warp frees its own ring slots and publishes its own tiles;
       // both commit `bempty` (count 2).
-      if (leader) {
+      // (SB: a tile is up to 16 chunks but the ring has 7 slots, so a warp that skips a tile would look at a
+      // slot two laps ahead and a parity wait cannot tell laps apart: warp 1 issues every tile there -- with
+      // >= 21 MMAs per tile the issue stream is not the limiter anyway)
+      if (leader && (!SB || warp == 1)) {
         const uint32_t mine = warp == 1 ? 0u : 1u;
-        mb_wait(bfull, it & 1u);
+        if constexpr (!SB) mb_wait(bfull, it & 1u);
         for (uint32_t t = 0; t < n_tiles; t++, tcnt++) {
           const uint32_t acc = tcnt & 1u;
-          if (acc != mine) {   // the other warp's tile: skip its ring slots
+          if (!SB && acc != mine) {   // the other warp's tile: skip its ring slots
             rs += nkc;
-            if (rs >= (uint32_t)NSTAGE2) {
+            while (rs >= (uint32_t)NSTAGE2) {
               rs -= (uint32_t)NSTAGE2;
               rph ^= 1u;
             }
@@ -720,7 +737,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1)
           for (uint32_t kc = 0; kc < nkc; kc++) {
             mb_spin(full + rs, rph);
             tc_fence_after();
-            const uint32_t alo = desc_lo(a_base + rs * A_BYTES), blo = desc_lo(b_base + kc * BH_BYTES);
+            const uint32_t alo = desc_lo(a_base + rs * SLOT);
+            const uint32_t blo = SB ? desc_lo(a_base + rs * SLOT + A_BYTES) : desc_lo(b_base + kc * BH_BYTES);
             if (kc + 1 < nkc) {
               mma2_elect(d_addr, alo, blo, kc);
               mma2_elect(d_addr, alo + 2, blo + 2, 1u);
@@ -741,9 +759,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1)
             }
           }
         }
-        commit2_elect(bempty);
-        // the last item's multicast arrivals must have landed before either CTA may exit
-        if (warp == 1 && item + n_pairs >= n_items) mb_wait(bempty, it & 1u);
+        if constexpr (!SB) {
+          commit2_elect(bempty);
+          // the last item's multicast arrivals must have landed before either CTA may exit
+          if (warp == 1 && item + n_pairs >= n_items) mb_wait(bempty, it & 1u);
+        }
       }
     } else if (warp == 2 + NEPI) {
       // ================= sentinel (both CTAs): spins on `tfull`, releases the epilogue warps =================

@@ -162,9 +162,9 @@ def debug_tscan(index, q_dev, taus, from_, until):
     taus = np.ascontiguousarray(taus, np.float32)
     kp = N.i32(0)
     acc = np.zeros((rows, 256), np.float32)
-    # KP is only known after the call: size the operand buffers for the largest contraction (320)
-    xb = np.zeros((rows, 320), np.uint16)
-    qb = np.zeros((256, 320), np.uint16)
+    # KP is only known after the call: size the operand buffers for the largest contraction (1024)
+    xb = np.zeros((rows, 1024), np.uint16)
+    qb = np.zeros((256, 1024), np.uint16)
     N.check(N.lib().gulon_debug_tscan(index.handle, q_dev.data_ptr(), nq, q_dev.stride(0), taus.ctypes.data,
                                       from_, until, xb.ctypes.data, qb.ctypes.data, acc.ctypes.data,
                                       C.byref(kp)))

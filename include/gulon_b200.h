@@ -69,7 +69,7 @@ extern "C" {
 #define GULON_SCAN_PRUNED 3 /* 16-bit lower-bound pass + exact fp32 re-evaluation of survivors      */
 #define GULON_SCAN_TENSOR 4 /* tcgen05 lower bound over the decoded rows (bf16 contraction with a
                              * rigorous error term) + exact fp32 re-evaluation of survivors; large
-                             * query batches on long ranges, D <= 316, K <= 256, k <= 128.  Forced on an
+                             * query batches on long ranges, D <= 1020, K <= 256, k <= 128.  Forced on an
                              * index / batch it cannot serve it fails with GULON_EUNSUPPORTED.          */
 
 /* assignment / encode implementation selector for gulon_set_option("assign_impl", ...).
