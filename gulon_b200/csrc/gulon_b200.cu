@@ -1869,15 +1869,29 @@ int tensor_scan_batch(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k,
   dim3 lg((unsigned)G, (unsigned)M);
   GLAUNCH(lut_build_kernel, lg, 256, 0, st, dQ, ldq, nq, cb->cb.as<float>(), cb->dfrom.as<int32_t>(),
           cb->ddim.as<int32_t>(), M, K, cb->dmax, ix->lutI.as<float4>());
-  // 1. the first rows exactly (fused kernel): every query gets k keys and a threshold
+  // 1. the first rows exactly: every query gets k keys and a threshold.  By default the first 256 rows through
+  //    tscan::boot_kernel; "tensor_boot_rows" > 0 asks for that many rows through the exact scan kernel instead
+  //    (measured, profiles/README.md: -12 ms of a 465 ms step at c2, -12 of 329 at a c4 shard; with k = 100 the
+  //    stages grow by 2x only and the five extra ones cost more than the exact kernel's 8192 rows)
   i64 boot = g_tensor_boot.load();
-  if (boot <= 0) boot = fscan::R;
-  boot = std::min<i64>(range, std::max<i64>(boot, k));
-  int Sb = 1;
+  i64 ratio = g_tensor_ratio.load();
+  if (ratio <= 0) ratio = std::max<i64>(2, std::min<i64>(4, (i64)TENSOR_CAPQ / (6 * (i64)k)));
+  if (boot <= 0 && ratio < 4) boot = fscan::R;
   u64 *cur;
   i64 cur_stride;
-  GCHECK(fused_lists(ix, from, from + boot, G, k, ix->lists, &Sb, st));
-  GCHECK(collapse_lists(ix->lists, Sb, Q4, k, ix->boot_keys, ix->sel_boot, &cur, &cur_stride, st));
+  if (boot <= 0) {
+    boot = std::min<i64>(range, tscan::BOOT_ROWS);
+    GCHECK(ix->boot_keys.ensure((size_t)Q4 * k * sizeof(u64)));
+    GLAUNCH(tscan::boot_kernel, (unsigned)G, tscan::BOOT_ROWS, 0, st, ix->codes, ix->ps, from, (int)boot,
+            ix->lutI.as<float4>(), M, k, ix->boot_keys.as<u64>());
+    cur = ix->boot_keys.as<u64>();
+    cur_stride = k;
+  } else {
+    boot = std::min<i64>(range, std::max<i64>(boot, k));
+    int Sb = 1;
+    GCHECK(fused_lists(ix, from, from + boot, G, k, ix->lists, &Sb, st));
+    GCHECK(collapse_lists(ix->lists, Sb, Q4, k, ix->boot_keys, ix->sel_boot, &cur, &cur_stride, st));
+  }
   if (boot < range) {
     const int NB = (int)ceil_div(nq, tscan::TN);
     const i64 nslots = (i64)NB * tscan::TN;
@@ -1897,8 +1911,6 @@ int tensor_scan_batch(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k,
     GCU(cudaMemsetAsync(ix->tstats.p, 0, 8 * sizeof(unsigned long long), st));
     // a stage scans `ratio` x the rows seen so far: ~ratio * k rows per query beat the threshold it
     // starts with (plus the bound's slack), which the candidate lists must hold several times over
-    i64 ratio = g_tensor_ratio.load();
-    if (ratio <= 0) ratio = std::max<i64>(2, std::min<i64>(4, (i64)capq / (6 * (i64)k)));
     const auto merge = tscan::merge_kernel;
     GOPTIN(merge, tscan::MERGE_WARPS * tscan::MERGE_SORTN * sizeof(u64));
     const bool want_stats = g_profile.load() != 0;

@@ -40,6 +40,7 @@
 // memory, all CTAs stream the same A rows, which therefore come from L2).
 #pragma once
 #include "common.cuh"
+#include "select.cuh"
 #include "tcassign.cuh"
 
 namespace gulon {
@@ -804,6 +805,40 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1)
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
+}
+
+// ---- the first rows, exactly ---------------------------------------------------------------------------
+// PQIndex.distances (G/Index.scala:393-409) of rows [from, from + nrows), nrows <= BOOT_ROWS, for the 4 queries
+// of a table group, and their k best: the lists and thresholds the first filter stage starts from.  (The
+// exact scan kernel pays 30 shared-memory table fills per (8192-row chunk, query group) and starts from empty
+// lists -- 20-26 ms for 100 000 queries whatever the row count; this is one pass over the group's tables.)
+// grid (G), block BOOT_ROWS (thread = row: the code planes are read coalesced), out [G * 4][k].
+constexpr int BOOT_ROWS = 256;
+__global__ void __launch_bounds__(BOOT_ROWS) boot_kernel(const uint8_t *__restrict__ codes, i64 ps, i64 from, int nrows,
+                                                         const float4 *__restrict__ lutI, int M, int k,
+                                                         u64 *__restrict__ out) {
+  __shared__ u64 keys[4][BOOT_ROWS];
+  const int g = blockIdx.x, tid = threadIdx.x;
+  const i64 row = from + tid;
+  const bool valid = tid < nrows;
+  float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f, d3 = 0.0f;
+  if (valid) {
+    const float4 *lut = lutI + (i64)g * M * 256;
+    for (int m = 0; m < M; m++) {
+      const float4 t = __ldg(lut + m * 256 + codes[(i64)m * ps + row]);
+      d0 = __fadd_rn(d0, t.x);
+      d1 = __fadd_rn(d1, t.y);
+      d2 = __fadd_rn(d2, t.z);
+      d3 = __fadd_rn(d3, t.w);
+    }
+  }
+  keys[0][tid] = valid ? make_key(d0, (uint32_t)row) : KEY_SENT;
+  keys[1][tid] = valid ? make_key(d1, (uint32_t)row) : KEY_SENT;
+  keys[2][tid] = valid ? make_key(d2, (uint32_t)row) : KEY_SENT;
+  keys[3][tid] = valid ? make_key(d3, (uint32_t)row) : KEY_SENT;
+  // one warp pair per query would do; the block-wide sort is simpler and this kernel is ~1 % of a batch
+  for (int j = 0; j < 4; j++) block_bitonic_sort(keys[j], BOOT_ROWS, tid, BOOT_ROWS);
+  for (int t = tid; t < 4 * k; t += BOOT_ROWS) out[((i64)g * 4 + t / k) * k + t % k] = keys[t / k][t % k];
 }
 
 // ---- survivors -> exact distances -> per-query candidate lists --------------------------------------

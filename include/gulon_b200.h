@@ -138,8 +138,9 @@ int gulon_shutdown(void);
  * Tensor scan: "tensor_min_rows" (default 2^19) and "tensor_min_queries" (default 256): smaller ranges /
  * batches keep the pruned scan under GULON_SCAN_AUTO; "tensor_query_batch" (queries per pass, 0 = auto),
  * "tensor_stage_ratio" (a stage scans ratio x the rows seen so far, 0 = auto from k), "tensor_boot_rows"
- * (rows scanned exactly first, 0 = 8192), "tensor_max_bytes" (the decoded bf16 copy of the index is built
- * only below this size; default 64 GiB), "tensor_chunk_bytes" (operand rows per row split = the L2 working
+ * (rows scanned exactly first by the exact scan kernel; 0 = auto: the first 256 rows through a dedicated
+ * kernel when the stages grow 4x, 8192 through the exact kernel when k is large and they grow 2x),
+ * "tensor_max_bytes" (the decoded bf16 copy of the index is built only below this size; default 64 GiB), "tensor_chunk_bytes" (operand rows per row split = the L2 working
  * set shared by the CTAs; default 16 MiB), "tensor_pair" (1: the filter runs on CTA pairs with
  * tcgen05 cta_group::2, the default; 0: on single CTAs), "tensor_epi_wait" (how the filter's warps wait:
  * bits 0-1 the epilogue warps -- 0 spin, 1 try_wait, 2 try_wait with a suspend hint (default), 3 a named

@@ -64,7 +64,7 @@ def main():
         g.set_option("profile", 0)
     if os.environ.get("TSCAN_SWEEP"):
         g.set_option("scan_impl", g.SCAN_TENSOR)
-        for name, vals in (("tensor_eval_blocks", [8, 32, 64, 128, 16]), ("tensor_stage_ratio", [3, 6, 8, 0]), ("tensor_boot_rows", [16384, 0]),):
+        for name, vals in (("tensor_boot_rows", [8192, 0]), ("tensor_stage_ratio", [3, 6, 8, 0]),):
             for v in vals:
                 g.set_option(name, v)
                 g.set_option("profile", 1)

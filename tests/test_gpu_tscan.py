@@ -118,7 +118,10 @@ SHAPES = [
     (120000, 1000, 100, 300, 100, 0, None, 0, 4096),    # c5 shape (streamed B), k = 100
     (60000, 400, 40, 40, 10, 7, 59000, 0, 8192),        # streamed B, KP = 416
     (20000, 64, 8, 12, 10, 0, 8192, 0, 0),              # range == boot: no stage at all
-    (20000, 64, 8, 12, 10, 3, 8400, 0, 0),              # one short stage (< 2 tiles)
+    (20000, 64, 8, 12, 10, 3, 8400, 0, 8192),           # one short stage (< 2 tiles) after the exact kernel's boot rows
+    (20000, 64, 8, 12, 10, 100, 300, 0, 0),             # range shorter than the 256 boot rows: no stage at all
+    (5000, 16, 2, 7, 128, 10, 160, 0, 0),               # ... with k close to the range
+    (9000, 16, 2, 7, 128, 10, 400, 0, 0),               # one tiny stage after the boot rows
 ]
 
 
