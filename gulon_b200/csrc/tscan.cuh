@@ -26,18 +26,20 @@
 // so a row whose reference distance is <= tau has D <= 0: **no row that can enter a top-k list is ever
 // dropped**; rows with D <= 0 ("survivors", ~1e-5 of the pairs) are re-evaluated with the reference's
 // literal fp32 table sum and merged into the lists, which makes the result bit-identical to the exact
-// kernels and to the oracle.  tau is the k-th best distance known so far: the first rows are scanned
-// exactly (fscan), then stages of geometrically growing length run filter -> evaluate -> merge.
+// kernels and to the oracle.  tau is the k-th best distance known so far: the first 256 rows are evaluated
+// exactly (boot_kernel; for large k the first 8192 through fscan), then stages of geometrically growing length
+// run qprep -> filter -> eval -> merge.
 //
-// Filter kernel, per CTA (persistent; item = (block of 256 queries, row split)):
-//   warp 0   TMA: the item's B operand (<= 5 boxes of [256 queries][64 bf16], 128-byte swizzle) once,
-//            then the A tiles ([128 rows][64 bf16] boxes) through a ring of NSTAGE buffers.
-//   warp 1   one thread issues tcgen05.mma.cta_group::1.kind::f16 (M128 N256 K16), KP/16 per tile, into
-//            one of two 256-column TMEM accumulators; tcgen05.commit frees ring slots / publishes tiles.
-//   warps 2-9  thread = row = TMEM lane, each warp 128 of the 256 columns: tcgen05.ld, min-reduce; a
-//            warp that saw D <= 0 re-reads its columns and appends (query, row) to the block's list.
-// Roofline: the tensor pipe -- 2 * 128 * 256 * KP flop per tile; bytes are secondary (B resident in shared
-// memory, all CTAs stream the same A rows, which therefore come from L2).
+// Filter kernels (persistent; item = (block of 256 queries, row split), items ordered split-major so that all
+// CTAs stream the same rows from L2):
+//   filter_kernel            single CTAs: the whole B operand (<= 5 chunks of [256 queries][64 bf16]) resident, a
+//                            3-slot ring of A chunks ([128 rows][64 bf16]), tcgen05.mma.cta_group::1 M128 N256 K16
+//   filter2_kernel<false>    CTA pairs (the default): half of B per CTA, 9-slot ring, cta_group::2 M256 N256 K16
+//   filter2_kernel<true>     CTA pairs, D > 316: B chunks streamed with the A chunks (7 slots of 32 KB)
+// warp 0 TMA, warp 1 (pair kernel: and warp 19, alternate tiles) MMA issue, warps 2-17 epilogue (thread = row =
+// TMEM lane, 64 of the 256 columns each: two tcgen05.ld.32x32b.x32, accumulator handed back, then FMNMX tree and
+// the survivors appended with one atomic per warp and 32 columns), warp 18 optional sentinel.
+// Roofline: the tensor pipe -- 2 * 128 * 256 * KP flop per tile; bytes are secondary (DRAM < 1 % of the HBM peak).
 #pragma once
 #include "common.cuh"
 #include "select.cuh"
