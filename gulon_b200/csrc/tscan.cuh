@@ -195,8 +195,8 @@ __global__ void __launch_bounds__(256) qprep_kernel(const float *__restrict__ Q,
     }
   }
   if (!ok) {
-    for (int j = lane; j < D + NEXTRA; j += 32) out[j] = 0;
-    if (lane == 0) out[D + 3] = 0x7E80;   // c = 2^126: D = 2^126 > 0 for every row, nothing survives
+    // c = 2^126 (column D + 3 against the rows' 1.0), zeros elsewhere: D = 2^126 > 0 for every row, nothing survives
+    for (int j = lane; j < D + NEXTRA; j += 32) out[j] = j == D + 3 ? (uint16_t)0x7E80 : (uint16_t)0;
   }
   for (int j = D + NEXTRA + lane; j < KP; j += 32) out[j] = 0;
 }
