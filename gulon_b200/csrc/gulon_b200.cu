@@ -164,7 +164,8 @@ std::atomic<long long> g_pruned_words{0};        // 0 = auto, 1/2/4: 32-bit word
 std::atomic<long long> g_pruned_lb{0};           // 0 = auto (feedback), else quantizers in the lower bound
 std::atomic<long long> g_pruned_stage_div{32};   // first stage = range / div rows with the full bound; 0 = one stage
 std::atomic<long long> g_pruned_rowcodes{1};     // keep a row-major copy of the codes for the survivor evaluation
-std::atomic<long long> g_tensor_min_rows{1 << 19};    // GULON_SCAN_AUTO: shorter ranges keep the pruned scan
+std::atomic<long long> g_tensor_min_rows{1 << 16};    // GULON_SCAN_AUTO: shorter ranges keep the pruned / exact scan
+std::atomic<long long> g_tensor_min_pairs{1LL << 27}; // ... and batches with fewer (row, query) pairs
 std::atomic<long long> g_tensor_min_queries{256};    // ... and smaller batches
 std::atomic<long long> g_tensor_query_batch{0};       // queries per pass of the tensor scan; 0 = auto
 std::atomic<long long> g_tensor_ratio{0};             // a stage scans ratio x the rows seen so far; 0 = auto from k
@@ -1998,7 +1999,8 @@ int query_dev(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k, i64 fro
   const long long want = g_scan_impl.load();
   bool tensor = false;
   if (want == GULON_SCAN_TENSOR ||
-      (want == GULON_SCAN_AUTO && nq >= g_tensor_min_queries.load() && until - from >= g_tensor_min_rows.load())) {
+      (want == GULON_SCAN_AUTO && nq >= g_tensor_min_queries.load() && until - from >= g_tensor_min_rows.load() &&
+       (double)nq * (double)(until - from) >= (double)g_tensor_min_pairs.load())) {
     if (k <= fscan::KMAX && tensor_shape_ok(ix)) {
       GCHECK(prepare_tensor(ix, st));
       tensor = ix->tensor_state == 1;
@@ -2430,12 +2432,13 @@ int gulon_set_option(const char *name, int64_t value) {
   } else if (s == "pruned_min_rows") {
     GREQUIRE(value >= 0, "pruned_min_rows must be >= 0");
     g_pruned_min_rows = value;
-  } else if (s == "tensor_min_rows" || s == "tensor_min_queries" || s == "tensor_query_batch" ||
+  } else if (s == "tensor_min_rows" || s == "tensor_min_queries" || s == "tensor_min_pairs" || s == "tensor_query_batch" ||
              s == "tensor_stage_ratio" || s == "tensor_boot_rows" || s == "tensor_max_bytes" ||
              s == "tensor_chunk_bytes" || s == "tensor_pair" || s == "tensor_epi_wait" || s == "tensor_eval_blocks") {
     GREQUIRE(value >= 0, "%s must be >= 0", name);
     GREQUIRE(s != "tensor_epi_wait" || value <= 7, "tensor_epi_wait must be 0..7");
     (s == "tensor_min_rows" ? g_tensor_min_rows : s == "tensor_min_queries" ? g_tensor_min_queries
+     : s == "tensor_min_pairs" ? g_tensor_min_pairs
      : s == "tensor_query_batch" ? g_tensor_query_batch : s == "tensor_stage_ratio" ? g_tensor_ratio
      : s == "tensor_boot_rows" ? g_tensor_boot : s == "tensor_chunk_bytes" ? g_tensor_chunk_bytes
      : s == "tensor_pair" ? g_tensor_pair : s == "tensor_epi_wait" ? g_tensor_epi_wait

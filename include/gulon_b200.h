@@ -135,8 +135,8 @@ int gulon_shutdown(void);
  * (0 auto | 1 | 2 | 4), "pruned_lb_quantizers" (0 = measured-cost feedback per index, else the
  * number of quantizers the lower bound sums), "pruned_stage_div" (first stage = range / div rows,
  * 0 = one stage), "pruned_rowcodes" (row-major copy of the codes for the survivor evaluation).
- * Tensor scan: "tensor_min_rows" (default 2^19) and "tensor_min_queries" (default 256): smaller ranges /
- * batches keep the pruned scan under GULON_SCAN_AUTO; "tensor_query_batch" (queries per pass, 0 = auto),
+ * Tensor scan: "tensor_min_rows" (default 2^16), "tensor_min_queries" (default 256) and "tensor_min_pairs"
+ * (rows x queries, default 2^27): smaller ranges / batches keep the pruned or exact scan under GULON_SCAN_AUTO; "tensor_query_batch" (queries per pass, 0 = auto),
  * "tensor_stage_ratio" (a stage scans ratio x the rows seen so far, 0 = auto from k), "tensor_boot_rows"
  * (rows scanned exactly first by the exact scan kernel; 0 = auto: the first 256 rows through a dedicated
  * kernel when the stages grow 4x, 8192 through the exact kernel when k is large and they grow 2x),

@@ -168,6 +168,7 @@ def test_tensor_scan_auto_selection_and_cosine(g, oracle):
     from gulon_b200 import _native as N
     g.set_option("tensor_min_rows", 100000)
     g.set_option("tensor_min_queries", 512)
+    g.set_option("tensor_min_pairs", 0)
     g.set_option("profile", 1)
     try:
         got = ix.batch_query(10, Q, 0, 140000, normalize=True)
@@ -176,8 +177,9 @@ def test_tensor_scan_auto_selection_and_cosine(g, oracle):
         assert N.counter("tscan_batches") == 1
     finally:
         g.set_option("profile", 0)
-        g.set_option("tensor_min_rows", 1 << 19)
+        g.set_option("tensor_min_rows", 1 << 16)
         g.set_option("tensor_min_queries", 256)
+        g.set_option("tensor_min_pairs", 1 << 27)
     assert np.array_equal(small.keys, got.keys[:100]) and np.array_equal(small.values.view(np.uint32), got.values[:100].view(np.uint32))
     g.set_option("scan_impl", g.SCAN_FUSED)
     try:

@@ -66,7 +66,7 @@ def test_tensor_scan_options_and_counters(native):
     import gulon_b200 as g
     from gulon_b200 import _native as N
     assert g.SCAN_TENSOR == 4
-    defaults = {"tensor_min_rows": 1 << 19, "tensor_min_queries": 256, "tensor_query_batch": 0, "tensor_stage_ratio": 0,
+    defaults = {"tensor_min_rows": 1 << 16, "tensor_min_queries": 256, "tensor_min_pairs": 1 << 27, "tensor_query_batch": 0, "tensor_stage_ratio": 0,
                 "tensor_boot_rows": 0, "tensor_max_bytes": 64 << 30, "tensor_chunk_bytes": 16 << 20, "tensor_pair": 1,
                 "tensor_epi_wait": 2}
     for name, v in defaults.items():
