@@ -321,12 +321,19 @@ __device__ __forceinline__ void sweep_scan(const FParams &p, const uint32_t (&v)
 #pragma unroll
   for (int j = 0; j < COLS / 32; j++) {
     const uint32_t(&x)[32] = v[j];
-    float m[8];
+    // four independent chains of three-input minima (FMNMX3): 16 + 3 instructions per 32 columns where a
+    // tree of two-input minima takes 31 -- at KP = 144 the epilogue warps were 56 % busy, half of it here
+    float m0 = __uint_as_float(x[0]), m1 = __uint_as_float(x[1]), m2 = __uint_as_float(x[2]), m3 = __uint_as_float(x[3]);
 #pragma unroll
-    for (int i = 0; i < 8; i++)
-      m[i] = fminf(fminf(__uint_as_float(x[4 * i]), __uint_as_float(x[4 * i + 1])),
-                   fminf(__uint_as_float(x[4 * i + 2]), __uint_as_float(x[4 * i + 3])));
-    const float mn = fminf(fminf(fminf(m[0], m[1]), fminf(m[2], m[3])), fminf(fminf(m[4], m[5]), fminf(m[6], m[7])));
+    for (int i = 4; i < 28; i += 8) {
+      m0 = tca::min3(m0, __uint_as_float(x[i]), __uint_as_float(x[i + 1]));
+      m1 = tca::min3(m1, __uint_as_float(x[i + 2]), __uint_as_float(x[i + 3]));
+      m2 = tca::min3(m2, __uint_as_float(x[i + 4]), __uint_as_float(x[i + 5]));
+      m3 = tca::min3(m3, __uint_as_float(x[i + 6]), __uint_as_float(x[i + 7]));
+    }
+    m0 = tca::min3(m0, __uint_as_float(x[28]), __uint_as_float(x[29]));
+    m1 = tca::min3(m1, __uint_as_float(x[30]), __uint_as_float(x[31]));
+    const float mn = fminf(tca::min3(m0, m1, m2), m3);
     const bool hit = mn <= 0.0f && row < r1;
     if (__any_sync(0xffffffffu, hit) || p.dump) {
       if (p.dump && row < r1) {
