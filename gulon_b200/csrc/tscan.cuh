@@ -315,26 +315,38 @@ __device__ __forceinline__ void sweep_load(uint32_t taddr, uint32_t (&v)[COLS / 
 #pragma unroll
   for (int j = 0; j < COLS / 32; j++) tc_ld_wait(v[j]);
 }
+// minimum of 32 accumulator columns: four independent chains of three-input minima (FMNMX3): 16 + 3
+// instructions where a tree of two-input minima takes 31 -- at KP = 144 the epilogue warps were 56 % busy,
+// half of it here
+__device__ __forceinline__ float min32(const uint32_t (&x)[32]) {
+  float m0 = __uint_as_float(x[0]), m1 = __uint_as_float(x[1]), m2 = __uint_as_float(x[2]), m3 = __uint_as_float(x[3]);
+#pragma unroll
+  for (int i = 4; i < 28; i += 8) {
+    m0 = tca::min3(m0, __uint_as_float(x[i]), __uint_as_float(x[i + 1]));
+    m1 = tca::min3(m1, __uint_as_float(x[i + 2]), __uint_as_float(x[i + 3]));
+    m2 = tca::min3(m2, __uint_as_float(x[i + 4]), __uint_as_float(x[i + 5]));
+    m3 = tca::min3(m3, __uint_as_float(x[i + 6]), __uint_as_float(x[i + 7]));
+  }
+  m0 = tca::min3(m0, __uint_as_float(x[28]), __uint_as_float(x[29]));
+  m1 = tca::min3(m1, __uint_as_float(x[30]), __uint_as_float(x[31]));
+  return fminf(tca::min3(m0, m1, m2), m3);
+}
 template <int COLS>
 __device__ __forceinline__ void sweep_scan(const FParams &p, const uint32_t (&v)[COLS / 32][32], i64 row, i64 r1, int qb,
                                            int c0, int lane) {
+  float mn[COLS / 32];
+  float all = 1.0f;
+#pragma unroll
+  for (int j = 0; j < COLS / 32; j++) {
+    mn[j] = min32(v[j]);
+    all = fminf(all, mn[j]);
+  }
+  // one vote per tile and warp; the rest only runs for a warp that holds a survivor (or under the diagnostics dump)
+  if (!(__any_sync(0xffffffffu, all <= 0.0f && row < r1) || p.dump)) return;
 #pragma unroll
   for (int j = 0; j < COLS / 32; j++) {
     const uint32_t(&x)[32] = v[j];
-    // four independent chains of three-input minima (FMNMX3): 16 + 3 instructions per 32 columns where a
-    // tree of two-input minima takes 31 -- at KP = 144 the epilogue warps were 56 % busy, half of it here
-    float m0 = __uint_as_float(x[0]), m1 = __uint_as_float(x[1]), m2 = __uint_as_float(x[2]), m3 = __uint_as_float(x[3]);
-#pragma unroll
-    for (int i = 4; i < 28; i += 8) {
-      m0 = tca::min3(m0, __uint_as_float(x[i]), __uint_as_float(x[i + 1]));
-      m1 = tca::min3(m1, __uint_as_float(x[i + 2]), __uint_as_float(x[i + 3]));
-      m2 = tca::min3(m2, __uint_as_float(x[i + 4]), __uint_as_float(x[i + 5]));
-      m3 = tca::min3(m3, __uint_as_float(x[i + 6]), __uint_as_float(x[i + 7]));
-    }
-    m0 = tca::min3(m0, __uint_as_float(x[28]), __uint_as_float(x[29]));
-    m1 = tca::min3(m1, __uint_as_float(x[30]), __uint_as_float(x[31]));
-    const float mn = fminf(tca::min3(m0, m1, m2), m3);
-    const bool hit = mn <= 0.0f && row < r1;
+    const bool hit = mn[j] <= 0.0f && row < r1;
     if (__any_sync(0xffffffffu, hit) || p.dump) {
       if (p.dump && row < r1) {
         float *dst = p.dump + (row - p.sfrom) * ((i64)p.NB * TN) + (i64)qb * TN + c0 + j * 32;
