@@ -136,15 +136,17 @@ int gulon_shutdown(void);
  * number of quantizers the lower bound sums), "pruned_stage_div" (first stage = range / div rows,
  * 0 = one stage), "pruned_rowcodes" (row-major copy of the codes for the survivor evaluation).
  * Tensor scan: "tensor_min_rows" (default 2^16), "tensor_min_queries" (default 256) and "tensor_min_pairs"
- * (rows x queries, default 2^27): smaller ranges / batches keep the pruned or exact scan under GULON_SCAN_AUTO; "tensor_query_batch" (queries per pass, 0 = auto),
- * "tensor_stage_ratio" (a stage scans ratio x the rows seen so far, 0 = auto from k), "tensor_boot_rows"
- * (rows scanned exactly first by the exact scan kernel; 0 = auto: the first 256 rows through a dedicated
- * kernel when the stages grow 4x, 8192 through the exact kernel when k is large and they grow 2x),
- * "tensor_max_bytes" (the decoded bf16 copy of the index is built only below this size; default 64 GiB), "tensor_chunk_bytes" (operand rows per row split = the L2 working
- * set shared by the CTAs; default 16 MiB), "tensor_pair" (1: the filter runs on CTA pairs with
- * tcgen05 cta_group::2, the default; 0: on single CTAs), "tensor_epi_wait" (how the filter's warps wait:
- * bits 0-1 the epilogue warps -- 0 spin, 1 try_wait, 2 try_wait with a suspend hint (default), 3 a named
- * barrier released by a sentinel warp; bit 2: the TMA thread suspends instead of spinning).
+ * (rows x queries, default 2^27): smaller ranges / batches keep the pruned or exact scan under
+ * GULON_SCAN_AUTO; "tensor_query_batch" (queries per pass, 0 = auto), "tensor_stage_ratio" (a stage scans
+ * ratio x the rows seen so far, 0 = auto from k), "tensor_boot_rows" (rows scanned exactly first by the
+ * exact scan kernel; 0 = auto: the first 256 rows through a dedicated kernel when the stages grow 4x, 8192
+ * through the exact kernel when k is large and they grow 2x), "tensor_max_bytes" (the decoded bf16 copy of
+ * the index is built only below this size; default 64 GiB), "tensor_chunk_bytes" (operand rows per row
+ * split = the L2 working set shared by the CTAs; default 16 MiB), "tensor_pair" (1: the filter runs on CTA
+ * pairs with tcgen05 cta_group::2, the default; 0: on single CTAs), "tensor_eval_blocks" (CTAs per query
+ * block of the survivor evaluation; default 16), "tensor_epi_wait" (how the filter's warps wait: bits 0-1
+ * the epilogue warps -- 0 spin, 1 try_wait, 2 try_wait with a suspend hint (default), 3 a named barrier
+ * released by a sentinel warp; bit 2: the TMA thread suspends instead of spinning).
  * Assignment: "assign_impl", "assign_tc_min_rows", "update_fixed".  "profile" = 1 turns the kernel
  * timers and counters of gulon_get_counter on. */
 int gulon_set_option(const char *name, int64_t value);
