@@ -108,7 +108,7 @@ struct gulon_index_s {
   DevBuf kacc, kfloor;        // k-chunked scans: accumulated keys [Q4][k], last key of the previous pass [Q4]
   // tensor scan (tscan.cuh): xb = the decoded rows as bf16 operand rows [N][tensor_kp], built by the first
   // tensor scan; the rest is per-batch scratch
-  DevBuf xb, tcol, tqb, tsurv, tscount, tcand, tccount, tcur0, tcur1, tflag, tstats;
+  DevBuf xb, tcol, tqb, tsurv, tscount, tcand, tccount, tcur0, tcur1, tflag, tstats, tbad, tbq, tbi, tbd, tbs, tbx;
   int tensor_state = 0;       // 0 not tried, 1 ready, -1 unavailable (shape, memory, non-finite rows)
   int tensor_kp = 0;
   // wide indexes (16-bit ids): 8-bit GROUP planes for the lower-bound scan (pscan.cuh), built by the first
@@ -140,6 +140,7 @@ struct gulon_index_s {
     gmap.release(); gmembers.release(); gstart.release(); gcodes.release(); rowcodes16.release();
     xb.release(); tcol.release(); tqb.release(); tsurv.release(); tscount.release(); tcand.release();
     tccount.release(); tcur0.release(); tcur1.release(); tflag.release(); tstats.release();
+    tbad.release(); tbq.release(); tbi.release(); tbd.release(); tbs.release(); tbx.release();
     if (tm_ev0) cudaEventDestroy(tm_ev0);
     if (tm_ev1) cudaEventDestroy(tm_ev1);
     h_q.release(); h_ids.release(); h_dists.release(); h_sizes.release();
@@ -176,6 +177,7 @@ std::atomic<long long> g_tensor_epi_wait{2};              // tscan::mb_wait_epi
 std::atomic<long long> g_tensor_pair{1};                  // the filter on CTA pairs (cta_group::2) or on single CTAs
 std::atomic<long long> g_tensor_chunk_bytes{16LL << 20};  // operand rows of one row split (L2 working set)
 std::atomic<unsigned long long> g_tstats[8];          // tiles, slow paths, survivors, candidates, pairs, fallbacks, batches, stages
+std::atomic<long long> g_tscan_bad_queries{0};   // queries the tensor scan handed to the pruned scan one by one
 std::atomic<long long> g_last_scan{0};           // GULON_SCAN_* that answered the last batch
 std::atomic<long long> g_last_ml{0};             // quantizers in the lower bound of the last main stage
 std::atomic<long long> g_assign_impl{GULON_ASSIGN_AUTO};  // exact CUDA-core kernel or tcgen05 filter + exact recheck
@@ -1910,6 +1912,8 @@ int tensor_scan_batch(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k,
     GCU(cudaMemsetAsync(ix->tccount.p, 0, (size_t)nq * sizeof(unsigned), st));
     GCU(cudaMemsetAsync(ix->tflag.p, 0, 4 * sizeof(int), st));
     GCU(cudaMemsetAsync(ix->tstats.p, 0, 8 * sizeof(unsigned long long), st));
+    GCHECK(ix->tbad.ensure((size_t)nq));
+    GCU(cudaMemsetAsync(ix->tbad.p, 0, (size_t)nq, st));
     // a stage scans `ratio` x the rows seen so far: ~ratio * k rows per query beat the threshold it
     // starts with (plus the bound's slack), which the candidate lists must hold several times over
     const auto merge = tscan::merge_kernel;
@@ -1922,7 +1926,7 @@ int tensor_scan_batch(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k,
       if (range - done - len < len / 4) len = range - done;   // no short last stage
       const i64 sfrom = from + done, suntil = sfrom + len;
       GLAUNCH(tscan::qprep_kernel, (unsigned)ceil_div(nslots, 8), 256, 0, st, dQ, ldq, nq, nslots, D, KP, cur,
-              cur_stride, k, ix->tqb.as<uint16_t>(), ix->tflag.as<int>());
+              cur_stride, k, ix->tqb.as<uint16_t>(), ix->tflag.as<int>(), ix->tbad.as<uint8_t>());
       GCU(cudaMemsetAsync(ix->tscount.p, 0, (size_t)NB * sizeof(unsigned), st));
       GCHECK(launch_filter(ix, sfrom, suntil, NB, capb, nullptr, st));
       tscan::EParams ep;
@@ -1967,11 +1971,44 @@ int tensor_scan_batch(gulon_index_t ix, const float *dQ, i64 nq, i64 ldq, int k,
       g_tstats[6] += 1;
       g_tstats[7] += (unsigned long long)stages;
     }
-    if (flag) {
+    if (flag & 6) {   // a survivor or candidate list overflowed: the whole batch goes to the pruned scan
       g_tstats[5] += 1;
       *redo = true;
       return GULON_OK;
     }
+    GCHECK(unpack(cur, cur_stride, nq, k, id_offset, d_ids, d_dists, d_sizes, st));
+    if (flag & 1) {
+      // queries the bound cannot serve (non-finite coordinates, norms beyond 1e30): only THEY are answered by
+      // the pruned scan; their rows of the output are overwritten
+      std::vector<uint8_t> hb((size_t)nq);
+      GCU(cudaMemcpyAsync(hb.data(), ix->tbad.p, (size_t)nq, cudaMemcpyDeviceToHost, st));
+      GCU(cudaStreamSynchronize(st));
+      std::vector<int32_t> idx;
+      for (i64 q = 0; q < nq; q++)
+        if (hb[q]) idx.push_back((int32_t)q);
+      const i64 nb = (i64)idx.size();
+      if (nb > 0) {
+        g_tscan_bad_queries += nb;
+        GCHECK(upload(ix->tbx, idx, st));
+        GCHECK(ix->tbq.ensure((size_t)nb * D * sizeof(float)));
+        GCHECK(ix->tbi.ensure((size_t)nb * k * sizeof(int32_t)));
+        GCHECK(ix->tbd.ensure((size_t)nb * k * sizeof(float)));
+        GCHECK(ix->tbs.ensure((size_t)nb * sizeof(int32_t)));
+        GLAUNCH(tscan::gather_queries_kernel, (unsigned)nb, 128, 0, st, dQ, ldq, ix->tbx.as<int32_t>(), D,
+                ix->tbq.as<float>());
+        i64 qb = g_query_batch.load();
+        if (qb <= 0) qb = (i64)sm_count() * 16;
+        qb = std::min<i64>(round_up(qb, 16), 32768);
+        for (i64 q0 = 0; q0 < nb; q0 += qb) {
+          const i64 n1 = std::min<i64>(qb, nb - q0);
+          GCHECK(scan_batch(ix, ix->tbq.as<float>() + q0 * D, n1, D, k, from, until, id_offset,
+                            ix->tbi.as<int32_t>() + q0 * k, ix->tbd.as<float>() + q0 * k, ix->tbs.as<int32_t>() + q0, st));
+        }
+        GLAUNCH(tscan::scatter_results_kernel, (unsigned)nb, 128, 0, st, ix->tbx.as<int32_t>(), k, ix->tbi.as<int32_t>(),
+                ix->tbd.as<float>(), ix->tbs.as<int32_t>(), d_ids, d_dists, d_sizes);
+      }
+    }
+    return GULON_OK;
   }
   return unpack(cur, cur_stride, nq, k, id_offset, d_ids, d_dists, d_sizes, st);
 }
@@ -2408,6 +2445,7 @@ int gulon_set_option(const char *name, int64_t value) {
     g_t_pscan_first.reset();
     g_t_tscan.reset();
     for (int i = 0; i < 8; i++) g_tstats[i] = 0;
+    g_tscan_bad_queries = 0;
     for (int i = 0; i < 3; i++) g_pstats[i] = 0;
     g_ppairs = 0;
     g_ppairs_main = 0;
@@ -2488,6 +2526,10 @@ int gulon_get_counter(const char *name, int64_t *value) {
         *value = (int64_t)g_tstats[i].load();
         return GULON_OK;
       }
+  }
+  if (s == "tscan_handed_back_queries") {
+    *value = g_tscan_bad_queries.load();
+    return GULON_OK;
   }
   if (s == "scan_last_impl") {
     *value = g_last_scan.load();
@@ -3136,7 +3178,7 @@ int gulon_debug_tscan(gulon_index_t ix, const float *dqueries, int64_t nq, int64
   GCU(cudaMemsetAsync(ix->tscount.p, 0, sizeof(unsigned), st));
   GCU(cudaMemsetAsync(ix->tflag.p, 0, 4 * sizeof(int), st));
   GLAUNCH(tscan::qprep_kernel, (unsigned)ceil_div(tscan::TN, 8), 256, 0, st, dqueries, (i64)ldq, (i64)nq,
-          (i64)tscan::TN, D, KP, dk.as<u64>(), (i64)1, 1, ix->tqb.as<uint16_t>(), ix->tflag.as<int>());
+          (i64)tscan::TN, D, KP, dk.as<u64>(), (i64)1, 1, ix->tqb.as<uint16_t>(), ix->tflag.as<int>(), (uint8_t *)nullptr);
   GCHECK(launch_filter(ix, from, until, 1, TENSOR_CAPB, dacc.as<float>(), st));
   if (xb) GCU(cudaMemcpyAsync(xb, ix->xb.as<uint16_t>() + (size_t)from * KP, (size_t)rows * KP * 2, cudaMemcpyDeviceToHost, st));
   if (qb) GCU(cudaMemcpyAsync(qb, ix->tqb.p, (size_t)tscan::TN * KP * 2, cudaMemcpyDeviceToHost, st));

@@ -155,10 +155,11 @@ __global__ void __launch_bounds__(256) decode_rows_kernel(const uint8_t *__restr
 // ---- B operand: one row per query, rebuilt for every stage (it holds the threshold) -----------------
 // One warp per query slot (nslots = query blocks * 256).  cur [nq][stride]: the sorted best keys so far.
 // A query the filter cannot serve (non-finite coordinates, huge norm, no finite threshold yet) sets
-// flag[0]; its row -- and the rows of the padding slots -- let nothing survive.
+// bit 0 of flag[0] and bad[q]; its row -- and the rows of the padding slots -- let nothing survive.
 __global__ void __launch_bounds__(256) qprep_kernel(const float *__restrict__ Q, i64 ldq, i64 nq, i64 nslots, int D,
                                                     int KP, const u64 *__restrict__ cur, i64 stride, int k,
-                                                    uint16_t *__restrict__ qb, int *__restrict__ flag) {
+                                                    uint16_t *__restrict__ qb, int *__restrict__ flag,
+                                                    uint8_t *__restrict__ bad) {
   const i64 q = (i64)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (q >= nslots) return;
@@ -181,7 +182,10 @@ __global__ void __launch_bounds__(256) qprep_kernel(const float *__restrict__ Q,
       tau = ord2f((uint32_t)(key >> 32));
       if (key == KEY_SENT || !(tau >= 0.0f) || !(tau <= FINITE_MAX)) ok = false;
     }
-    if (!ok && lane == 0) atomicExch(flag, 1);
+    if (!ok && lane == 0) {
+      atomicOr(flag, 1);
+      if (bad) bad[q] = 1;   // this query is answered by the pruned scan afterwards (the rest of the batch stays)
+    }
     if (ok) {
       for (int j = lane; j < D; j += 32) out[j] = bf_rn(-2.0f * qv[j]);
       if (lane == 0) {
@@ -826,6 +830,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1)
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
+}
+
+// ---- queries the filter handed back: gather them for the pruned scan, scatter its answers ------------
+__global__ void gather_queries_kernel(const float *__restrict__ Q, i64 ldq, const int32_t *__restrict__ idx, int D,
+                                      float *__restrict__ out) {
+  const float *src = Q + (i64)idx[blockIdx.x] * ldq;
+  for (int j = threadIdx.x; j < D; j += blockDim.x) out[(i64)blockIdx.x * D + j] = src[j];
+}
+__global__ void scatter_results_kernel(const int32_t *__restrict__ idx, int k, const int32_t *__restrict__ ids,
+                                       const float *__restrict__ dists, const int32_t *__restrict__ sizes,
+                                       int32_t *__restrict__ d_ids, float *__restrict__ d_dists,
+                                       int32_t *__restrict__ d_sizes) {
+  const i64 q = idx[blockIdx.x];
+  for (int j = threadIdx.x; j < k; j += blockDim.x) {
+    d_ids[q * k + j] = ids[(i64)blockIdx.x * k + j];
+    d_dists[q * k + j] = dists[(i64)blockIdx.x * k + j];
+  }
+  if (threadIdx.x == 0 && d_sizes) d_sizes[q] = sizes[blockIdx.x];
 }
 
 // ---- the first rows, exactly ---------------------------------------------------------------------------

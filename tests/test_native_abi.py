@@ -80,7 +80,7 @@ def test_tensor_scan_options_and_counters(native):
     with pytest.raises(ValueError):
         g.set_option("scan_impl", 5)
     for c in ("tscan_kernel_ns", "tscan_kernel_launches", "tscan_tiles", "tscan_survivors", "tscan_candidates",
-              "tscan_pairs", "tscan_fallbacks", "tscan_batches", "tscan_stages", "scan_last_impl"):
+              "tscan_pairs", "tscan_fallbacks", "tscan_batches", "tscan_stages", "tscan_handed_back_queries", "scan_last_impl"):
         assert N.counter(c) >= 0
 
 
