@@ -422,7 +422,8 @@ def tensor_roofline(cx, D, M, Q, steps, n_local, prof_ms, shape_key, t_ns, t_l, 
                                         "tensor scan itself reads the decoded rows from L2, not the code planes"},
             "filter": {"survivor_rate": st["survivors"] / max(st["pairs"], 1), "survivors": st["survivors"],
                        "list_candidates": st["candidates"], "stages_per_batch": st["stages"] / max(st["batches"], 1),
-                       "batches": st["batches"], "handed_back_batches": st["fallbacks"]}}
+                       "batches": st["batches"], "handed_back_batches": st["fallbacks"],
+                       "handed_back_queries": N.counter("tscan_handed_back_queries")}}
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "scan_traffic.json")))
         key = "%s_tensor" % shape_key
